@@ -1,0 +1,2 @@
+/* oracle/refshim/include/ogr_srs_api.h -- TEST INFRASTRUCTURE ONLY: forwards to the shim gdal.h. */
+#include "gdal.h"
