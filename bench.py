@@ -1,0 +1,477 @@
+#!/usr/bin/env python
+"""bench.py -- GCN10 Curve Number hot path on B200: CN Gpixel/s (9 LUT variants).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one synthetic 3x3 degree block: a 36000 x 36000 uint8
+WorldCover-like tile plus its 1440 x 1440 HSG window, all nine lookup variants (p/f/g x ARC
+I/II/III) of one drainage condition written in a single fused pass (BASELINE.json configs[1]).
+1 pixel = one land-cover pixel for which all nine CN values were written.
+
+  value      whole-job Gpixel/s with inputs resident in HBM (device-side entry point
+             gcn10_cuda_block_device), CUDA events on the launching stream, max over ranks
+  e2e        the same metric through the host-buffer C-ABI call gcn10_cuda_block: pinned host
+             rasters in, nine pinned host planes out, H2D + kernels + D2H inside the timed region
+  roofline   HBM: algorithmic bytes (W*H*(1+9) + HSG window) / mean step duration vs the measured
+             copy peak in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own object code (oracle/_ref) on one host core, bounded sample
+
+`--impl reference` times the reference's CPU implementation (oracle/_ref = src/cn.c + src/raster.c
+compiled unmodified; falls back to the C restatement if that library is absent) on all host cores,
+one independent process per core exactly like the reference's MPI ranks (main.c:171), each step a
+bounded row-slab sample of the same tile.
+
+Multi-GPU: blocks are independent (no collective on the data path); every rank runs its own tile
+per step (weak scaling), value = N * pixels / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILE = 36000
+HSG = 1440
+NVAR = 9
+METRIC = "CN Gpixel/s (9 LUT variants)"
+UNIT = "Gpixel/s"
+BLOCK_ID = 2234                 # first id of /root/reference/src/test/blocks.txt: NW corner (-114, 42)
+LON0, LAT0 = -114.0, 42.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", default="worldcover", choices=["worldcover", "random", "coastal"])
+    ap.add_argument("--tile", type=int, default=TILE, help="tile edge in pixels (default 36000)")
+    ap.add_argument("--e2e-steps", type=int, default=None, help="timed end-to-end steps (default min(steps, 5))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=1800)
+    ap.add_argument("--ref-sample-rows", type=int, default=600)
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    t = args.tile
+    hs = (t * HSG + TILE - 1) // TILE
+    cfg = {
+        "workload": (f"BASELINE configs[1]: synthetic 3x3 deg WorldCover tile {t}x{t} uint8 + {hs}x{hs} "
+                     f"250 m HSG window, all 9 lookups (f/g/p x ARC I/II/III, drained) in one pass"),
+        "tile": [t, t], "hsg_window": [hs, hs], "planes": NVAR, "profile": args.profile,
+        "block_id": BLOCK_ID,
+        "l2": "per-step working set (1.3 GB in + 11.7 GB out) >> 126 MB L2, so no flush between iterations",
+        "parallelism": "one block per GPU per step, no collective (blocks are independent)",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------- CPU reference legs
+
+
+def _cpu_sample_inputs(tile, rows, profile, seed):
+    """A bounded sample of the benchmark workload: the first `rows` rows of the tile (full width)."""
+    from gcn10_b200 import synth
+    gt, sgt, hsx, hsy = synth.block_geometry(LON0, LAT0, tile, rows)
+    esa = synth.esa_tile(tile, rows, seed, profile)
+    hsg = synth.hsg_tile(hsx, hsy, seed + 1000, profile)
+    return esa, gt, hsg, sgt
+
+
+def _ref_worker(task):
+    """One 'MPI rank': run process_block() of the reference object code on its own slab."""
+    tile, rows, profile, seed, lookup_dir, reps = task
+    from oracle import oracle as O
+    esa, gt, hsg, sgt = _cpu_sample_inputs(tile, rows, profile, seed)
+    bbox = (gt[0], gt[3] + rows * gt[5], gt[0] + tile * gt[1], gt[3])
+    out = []
+    if O.Ref.available():
+        ref = O.Ref()
+        for _ in range(reps):
+            r = ref.run_block(esa, gt, hsg, sgt, bbox, lookup_dir, block_id=BLOCK_ID, keep=False)
+            if r["nplanes"] != 18 or (r["w"], r["h"]) != (tile, rows):
+                raise RuntimeError(f"reference run failed: {r['nplanes']} planes, {r['w']}x{r['h']}\n{r['log']}")
+            out.append((r["times"][8], r["times"][17]))      # time to the 9th / 18th saved plane
+        kind = "reference"
+    else:
+        port = O.Port()
+        tables = port.load_tables(lookup_dir)
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            port.block_rows(esa, gt, hsg, sgt, tables)
+            t = time.perf_counter() - t0
+            out.append((t / 2, t))
+        kind = "port"
+    return kind, out
+
+
+def cpu_baseline_one_core(args, lookup_dir):
+    rows = min(args.cpu_sample_rows, args.tile)
+    kind, times = _ref_worker((args.tile, rows, args.profile, BLOCK_ID, lookup_dir, 1))
+    t9, t18 = times[0]
+    px = args.tile * rows
+    return {
+        "value": px / t9 / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+        "sample": (f"first {rows} rows x {args.tile} px of the same tile ({px / 1e6:.1f} Mpx): "
+                   f"process_block() time to the 9th saved plane {t9:.2f} s (all 18 planes: {t18:.2f} s)"),
+        "value_18_planes": px / t18 / 1e9,
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    from gcn10_b200 import lookups
+    lookup_dir = lookups.write_default_lookups(tempfile.mkdtemp(prefix="gcn10_lookups_"))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    rows = min(args.ref_sample_rows, args.tile)
+    px_per_proc = args.tile * rows
+    ctx = mp.get_context("fork")
+    step_times = []
+    kind = "reference"
+    with ctx.Pool(cores) as pool:
+        def one_step():
+            nonlocal kind
+            tasks = [(args.tile, rows, args.profile, BLOCK_ID + i, lookup_dir, 1) for i in range(cores)]
+            t0 = time.perf_counter()
+            res = pool.map(_ref_worker, tasks)
+            wall = time.perf_counter() - t0
+            kind = res[0][0]
+            t9 = max(r[1][0][0] for r in res)       # slowest rank, time to its 9th plane
+            t18 = max(r[1][0][1] for r in res)
+            return t9, t18, wall
+        for _ in range(args.warmup):
+            one_step()
+        for _ in range(args.steps):
+            step_times.append(one_step())
+    t9 = sum(s[0] for s in step_times) / len(step_times)
+    t18 = sum(s[1] for s in step_times) / len(step_times)
+    value = cores * px_per_proc / t9 / 1e9
+    sample = (f"{cores} independent processes (= MPI ranks, main.c:171), each process_block() on a "
+              f"{rows}-row x {args.tile}-px slab of the tile ({px_per_proc / 1e6:.1f} Mpx); rate = pixels / time to "
+              f"the 9th saved plane of the slowest rank ({t9:.2f} s; all 18 planes {t18:.2f} s)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t9 * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, {"sample_rows_per_process": rows, "processes": cores}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- clocks sampler
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- our arm
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from gcn10_b200 import capi, lookups, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the Curve Number path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # lookup tables through the product's own CSV reader when the host library is built,
+    # else parsed here with the same rules (cn.c:13-85)
+    lookup_dir = lookups.write_default_lookups(tempfile.mkdtemp(prefix="gcn10_lookups_"))
+    tables = load_tables_host(lookup_dir)
+
+    ctx = capi.Context(local_rank)
+    ctx.set_luts(tables)
+
+    w = h = args.tile
+    seed = BLOCK_ID + rank                  # every rank (GPU worker) gets its own block
+    gt, sgt, hsx, hsy = synth.block_geometry(LON0, LAT0, w, h)
+    d_esa = synth.esa_tile(w, h, seed, args.profile, device=dev)
+    hsg_np = synth.hsg_tile(hsx, hsy, seed + 1000, args.profile)
+    d_hsg = torch.from_numpy(hsg_np).to(dev)
+    d_out = torch.empty((NVAR, h, w), dtype=torch.uint8, device=dev)
+    out_ptrs = [d_out[k].data_ptr() for k in range(NVAR)] + [0] * 9
+    # a dedicated (non-default) torch stream: the library launches on the stream handle it is given,
+    # and the CUDA events below are recorded on that same stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def step():
+        ctx.block_device(d_esa.data_ptr(), w, h, w, gt, d_hsg.data_ptr(), hsx, hsy, hsx, sgt,
+                         capi.MASK_DRAINED, out_ptrs, w, stream=stream.cuda_stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- kernel-resident timing: K steps, per-step events for the roofline average
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = ctx.launch_count()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for a, b in ev:
+        a.record(stream)
+        step()
+        b.record(stream)
+    t_end.record(stream)
+    barrier()
+    launches = ctx.launch_count() - l0
+    total_ms = max_over_ranks(t_start.elapsed_time(t_end))
+    step_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    mean_step_ms = sum(step_ms) / len(step_ms)
+    px = float(w) * h
+    value = world * px * args.steps / (total_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory both ways)
+    e2e = None
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 5)
+    if e2e_steps > 0:
+        e2e = run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_over_ranks, e2e_steps)
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # spot check on rank 0: one sampled row of the device result against itself through the host path
+    # (full parity lives in tests/; this only guards against timing a kernel that writes nothing)
+    chk = int(d_out[:, h // 2, : min(w, 4096)].to(torch.int64).sum().item())
+    if chk == 0 or chk == 255 * NVAR * min(w, 4096):
+        raise SystemExit("bench.py: output plane looks unwritten")
+
+    algo_bytes = px * (1 + NVAR) + hsx * hsy
+    achieved = algo_bytes / (mean_step_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": profiled_traffic(), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": algo_bytes, "mean_launch_ms": mean_step_ms,
+            "kernel": "gcn10::cn_block_kernel<9,1> (+ index_map_kernel, O(W+H))"}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_baseline_one_core(args, lookup_dir)
+            except Exception as e:  # the baseline leg must never take the benchmark down
+                cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(e)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "cpu_baseline": cpu,
+            "output_gpixel_per_s": value * NVAR,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_over_ranks, steps):
+    import numpy as np
+    import psutil
+
+    need = (1 + NVAR) * w * h
+    avail = psutil.virtual_memory().available
+    rows = h
+    note = None
+    if need * world * 1.3 > avail:
+        # not enough host RAM to pin a full tile's planes on every rank: use a row slab
+        rows = max(256, int(h * avail / (need * world * 1.3)) // 256 * 256)
+        note = f"host RAM limited: e2e measured on a {rows}-row slab"
+    lib = ctx.lib
+    esa_pin = capi.PinnedArray(lib, (rows, w))
+    out_pin = capi.PinnedArray(lib, (NVAR, rows, w))
+    try:
+        esa_pin.array[:] = d_esa[:rows].cpu().numpy()
+        planes = out_pin.array
+        # capi.Context.block wants an [18,h,w] array; build the pointer list by hand instead
+        import ctypes as C
+        ptrs = (C.c_void_p * capi.NPLANES)()
+        for k in range(NVAR):
+            ptrs[k] = planes[k].ctypes.data
+        gt6 = (C.c_double * 6)(*gt)
+        sgt6 = (C.c_double * 6)(*sgt)
+        hsy, hsx = hsg_np.shape
+
+        def step():
+            rc = lib.gcn10_cuda_block(ctx.h, esa_pin.array.ctypes.data, w, rows, w, gt6, hsg_np.ctypes.data, hsx, hsy,
+                                      hsx, sgt6, capi.MASK_DRAINED, ptrs, w)
+            if rc:
+                raise RuntimeError(lib.gcn10_cuda_last_error().decode())
+            # the device->host read of the result is part of the call; touch it like a consumer would
+            return int(planes[NVAR - 1, rows - 1, w - 1])
+
+        for _ in range(2):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        res = {"value": world * float(w) * rows * steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(w * rows + hsg_np.size), "d2h_bytes_per_step": int(NVAR * w * rows),
+               "steps": steps, "ms_per_step": dt / steps * 1e3,
+               "kernel_ms_per_step": ctx.last_kernel_ms(),
+               "path": "gcn10_cuda_block: pinned host rasters -> strip-pipelined H2D / fused kernel / D2H -> pinned host planes"}
+        if note:
+            res["note"] = note
+        return res
+    finally:
+        esa_pin.free()
+        out_pin.free()
+
+
+def load_tables_host(lookup_dir):
+    """The nine int[256][5] tables: via the host library's CSV reader when built, else the same
+    parsing rules restated here (first line skipped, '<lc>_<A|B|C|D>,<cn>', cn.c:13-85)."""
+    import numpy as np
+    try:
+        from gcn10_b200 import hostlib
+        return hostlib.load_lookup_tables(lookup_dir)
+    except Exception:
+        pass
+    from gcn10_b200 import lookups
+    t = np.full((9, 256, 5), 255, dtype=np.int32)
+    for i, v in enumerate(lookups.VARIANTS):
+        with open(os.path.join(lookup_dir, f"default_lookup_{v}.csv"), "rb") as f:
+            lines = f.read().split(b"\n")[1:]
+        for ln in lines:
+            if b"," not in ln or b"_" not in ln.split(b",")[0]:
+                continue
+            code, val = ln.split(b",")[:2]
+            lc, letter = code.split(b"_", 1)
+            sg = {b"A": 1, b"B": 2, b"C": 3}.get(letter[:1], 4)
+            t[i, int(lc), sg] = int(val.strip() or 0)
+    return t
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md), MEASURED_PEAKS.json absent"
+
+
+def profiled_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

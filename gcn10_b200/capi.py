@@ -1,0 +1,173 @@
+"""ctypes binding of libgcn10cuda.so (C ABI: include/gcn10_cuda.h).
+
+This is the thin Python mirror used by the tests and the benchmark harness; the product is the
+shared library itself and the C host program in gcn10_b200/host/.  There is no fallback: if the
+library is missing or no CUDA device is usable, loading / context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgcn10cuda.so")
+
+NVARIANTS = 9
+NPLANES = 18
+MASK_DRAINED = 0x001FF
+MASK_UNDRAINED = 0x3FE00
+MASK_ALL = 0x3FFFF
+
+# every symbol include/gcn10_cuda.h declares
+EXPORTS = (
+    "gcn10_cuda_version", "gcn10_cuda_last_error", "gcn10_cuda_device_count", "gcn10_cuda_create",
+    "gcn10_cuda_destroy", "gcn10_cuda_set_luts", "gcn10_cuda_block", "gcn10_cuda_block_device",
+    "gcn10_cuda_index_maps", "gcn10_cuda_synchronize", "gcn10_cuda_last_kernel_ms",
+    "gcn10_cuda_launch_count", "gcn10_cuda_set_option", "gcn10_cuda_host_alloc", "gcn10_cuda_host_free",
+    "gcn10_cuda_host_register", "gcn10_cuda_host_unregister",
+)
+
+_vp = C.c_void_p
+_dp = C.POINTER(C.c_double)
+
+
+class Gcn10Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gcn10cuda error {code}: {msg}")
+        self.code = code
+
+
+def load(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} not built: run `make cuda` (nvcc -gencode arch=compute_100a,code=sm_100a). "
+            "There is no CPU fallback for the Curve Number path.")
+    lib = C.CDLL(path)
+    lib.gcn10_cuda_version.restype = C.c_char_p
+    lib.gcn10_cuda_last_error.restype = C.c_char_p
+    lib.gcn10_cuda_create.argtypes = [C.c_int, C.POINTER(_vp)]
+    lib.gcn10_cuda_destroy.argtypes = [_vp]
+    lib.gcn10_cuda_destroy.restype = None
+    lib.gcn10_cuda_set_luts.argtypes = [_vp, _vp]
+    blk = [_vp, _vp, C.c_int, C.c_int, C.c_size_t, _dp, _vp, C.c_int, C.c_int, C.c_size_t, _dp,
+           C.c_uint, C.POINTER(_vp), C.c_size_t]
+    lib.gcn10_cuda_block.argtypes = blk
+    lib.gcn10_cuda_block_device.argtypes = blk + [_vp]
+    lib.gcn10_cuda_index_maps.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp, _vp, _vp]
+    lib.gcn10_cuda_synchronize.argtypes = [_vp]
+    lib.gcn10_cuda_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float)]
+    lib.gcn10_cuda_launch_count.argtypes = [_vp, C.POINTER(C.c_uint64)]
+    lib.gcn10_cuda_set_option.argtypes = [_vp, C.c_char_p, C.c_long]
+    lib.gcn10_cuda_host_alloc.argtypes = [C.c_size_t]
+    lib.gcn10_cuda_host_alloc.restype = _vp
+    lib.gcn10_cuda_host_free.argtypes = [_vp]
+    lib.gcn10_cuda_host_free.restype = None
+    lib.gcn10_cuda_host_register.argtypes = [_vp, C.c_size_t]
+    lib.gcn10_cuda_host_unregister.argtypes = [_vp]
+    return lib
+
+
+def _d6(a):
+    return (C.c_double * 6)(*[float(v) for v in a])
+
+
+class PinnedArray:
+    """uint8 numpy view over page-locked memory from gcn10_cuda_host_alloc."""
+
+    def __init__(self, lib, shape):
+        self.lib = lib
+        n = int(np.prod(shape))
+        self.ptr = lib.gcn10_cuda_host_alloc(n)
+        if not self.ptr:
+            raise Gcn10Error(-3, lib.gcn10_cuda_last_error().decode())
+        buf = (C.c_uint8 * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.uint8).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.gcn10_cuda_host_free(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One gcn10_ctx: a GPU worker (replaces one MPI rank of the reference)."""
+
+    def __init__(self, device: int = 0, lib: C.CDLL | None = None):
+        self.lib = lib or load()
+        h = _vp()
+        self._check(self.lib.gcn10_cuda_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise Gcn10Error(rc, self.lib.gcn10_cuda_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gcn10_cuda_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_luts(self, tables):
+        t = np.ascontiguousarray(tables, dtype=np.int32)
+        assert t.shape == (NVARIANTS, 256, 5), t.shape
+        self._check(self.lib.gcn10_cuda_set_luts(self.h, t.ctypes.data))
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.gcn10_cuda_set_option(self.h, key.encode(), int(value)))
+
+    def index_maps(self, w, h, gt, hsx, hsy, soil_gt):
+        ci = np.empty(w, dtype=np.int32)
+        cj = np.empty(h, dtype=np.int32)
+        self._check(self.lib.gcn10_cuda_index_maps(self.h, w, h, _d6(gt), hsx, hsy, _d6(soil_gt),
+                                                   ci.ctypes.data, cj.ctypes.data))
+        return ci, cj
+
+    def block(self, esa, gt, hsg, soil_gt, plane_mask=MASK_ALL, out=None):
+        """Host-buffer call.  esa [h,w] uint8, hsg [hsy,hsx] uint8 (numpy, any row stride).
+        Returns uint8 [18,h,w]; planes not in the mask are left untouched (zeros if allocated here)."""
+        assert esa.dtype == np.uint8 and hsg.dtype == np.uint8
+        assert esa.strides[1] == 1 and hsg.strides[1] == 1
+        h, w = esa.shape
+        hsy, hsx = hsg.shape
+        if out is None:
+            out = np.zeros((NPLANES, h, w), dtype=np.uint8)
+        ptrs = (_vp * NPLANES)()
+        for k in range(NPLANES):
+            ptrs[k] = out[k].ctypes.data if plane_mask & (1 << k) else None
+        self._check(self.lib.gcn10_cuda_block(
+            self.h, esa.ctypes.data, w, h, esa.strides[0], _d6(gt), hsg.ctypes.data, hsx, hsy,
+            hsg.strides[0], _d6(soil_gt), plane_mask, ptrs, out.strides[1]))
+        return out
+
+    def block_device(self, d_esa, w, h, esa_pitch, gt, d_hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask,
+                     d_out_ptrs, out_pitch, stream=None):
+        """Device-buffer call; pointers are integers (e.g. torch.Tensor.data_ptr())."""
+        ptrs = (_vp * NPLANES)()
+        for k in range(NPLANES):
+            ptrs[k] = d_out_ptrs[k] if (plane_mask & (1 << k)) and d_out_ptrs[k] else None
+        self._check(self.lib.gcn10_cuda_block_device(
+            self.h, d_esa, w, h, esa_pitch, _d6(gt), d_hsg, hsx, hsy, hsg_pitch, _d6(soil_gt),
+            plane_mask, ptrs, out_pitch, stream))
+
+    def synchronize(self):
+        self._check(self.lib.gcn10_cuda_synchronize(self.h))
+
+    def last_kernel_ms(self) -> float:
+        v = C.c_float()
+        self._check(self.lib.gcn10_cuda_last_kernel_ms(self.h, C.byref(v)))
+        return v.value
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        self._check(self.lib.gcn10_cuda_launch_count(self.h, C.byref(v)))
+        return v.value

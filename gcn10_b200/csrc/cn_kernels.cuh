@@ -1,0 +1,349 @@
+// gcn10_b200/csrc/cn_kernels.cuh -- sm_100a device code for GCN10's Curve Number hot path.
+//
+// What the reference does in five CPU passes per output plane (/root/reference/src/cn.c):
+//   resample (cn.c:218-232) -> memcpy (274) -> dual-HSG remap (275, 88-111) -> memset 255 (289)
+//   -> table pass (290, 114-131), 18 times per block,
+// is done here in ONE pass over the land-cover raster that writes all requested planes:
+//
+//   index_map_kernel   O(W+H) threads, fp64: the separable pixel->HSG-cell maps of cn.c:219-229,
+//                      evaluated with explicitly rounded, never-fused IEEE operations.
+//   cn_block_kernel    the streaming kernel (HBM bound, ~1 B read + NP*G B written per pixel):
+//                      one thread owns a 16-pixel column group and walks down the rows of its
+//                      CTA's row chunk.  Per row: one 16-byte load of land cover, 16 shared-memory
+//                      record fetches (one 16-byte record = the 9 CN values of a (class, soil
+//                      group) pair), a register byte-transpose (PRMT), and one 16-byte streaming
+//                      store per output plane.  The HSG cells a CTA needs (a few rows x <=256
+//                      columns of the 250 m grid) are staged into shared memory with one 2-D TMA
+//                      tensor load; a thread re-gathers its 16 soil codes only when the HSG row
+//                      changes (every ~25 raster rows).
+//   cn_bytes_kernel    byte-wise version for the <16-pixel right edge and for misaligned buffers.
+//
+// No tensor cores: the path is a byte gather with no contraction (BASELINE.json north_star).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gcn10 {
+
+constexpr int kThreads = 256;          // threads per CTA
+constexpr int kVecPx = 16;             // pixels per thread per row (one 16-byte vector)
+constexpr int kStripPx = kThreads * kVecPx;   // 4096 pixels of a row per CTA
+constexpr int kBoxCols = 256;          // TMA box: HSG columns staged per CTA (max box extent)
+constexpr int kBoxRows = 16;           // TMA box: HSG rows staged per CTA
+constexpr int kLutRecords = 256 * 8;   // (land cover, slot) -> 16-byte record
+constexpr int kLutBytes = kLutRecords * 16;
+constexpr int kSgInvalid = 5;          // soil-group slot whose record is all 255
+
+struct BlockParams {
+    const uint8_t *esa;         // first row of this launch
+    size_t esa_pitch;
+    int w, h;                   // pixels per row, rows in this launch
+    int y_base;                 // row of the block that esa row 0 corresponds to (row_idx offset)
+    const int32_t *col_idx;     // [roundup16(w)]  HSG column of each pixel column
+    const int32_t *row_idx;     // [block rows]    HSG row of each pixel row
+    const uint8_t *hsg;         // coarse window
+    size_t hsg_pitch;
+    int hsx, hsy;
+    const uint4 *lut;           // kLutRecords records, see pack_lut_records()
+    int swz_shift;              // bank swizzle: slot = sg ^ ((lc >> swz_shift) & 7)
+    int rows_per_cta;
+    int use_tma;
+    int group_drained[2];       // per output group: 1 = "drained" remap, 0 = "undrained"
+    uint8_t *out[18];           // group g, plane k at out[g*NP + k]
+    size_t out_pitch;
+};
+
+// ---------------------------------------------------------------------------------------------
+// fp64 index maps (cn.c:219-229).  Every operation is an explicitly rounded intrinsic so that
+// nvcc cannot contract a*b+c into an FMA: the reference build has no FMA (no -march,
+// src/CMakeLists.txt:68) and a fused evaluation moves up to 62 tie columns per block.
+
+__device__ __forceinline__ double c99_round(double v)
+{
+    // round half away from zero without an inexact v+0.5: v - trunc(v) is exact in fp64
+    double t = trunc(v);
+    if (fabs(__dsub_rn(v, t)) >= 0.5)
+        t = __dadd_rn(t, copysign(1.0, v));
+    return t;
+}
+
+__device__ __forceinline__ int int_from_double_x86(double v)
+{
+    // (int) as the reference's x86-64 object code performs it (cvttsd2si): INT_MIN for NaN and
+    // for values outside int range.  v is already integral here.
+    if (!(v > -2147483649.0 && v < 2147483648.0))
+        return INT_MIN;
+    return (int)v;
+}
+
+__device__ __forceinline__ int clamp_index(int i, int n)
+{
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);       // cn.c:228-229
+}
+
+__global__ void index_map_kernel(int w, int w_pad, int h,
+                                 double g0, double g1, double g3, double g5,
+                                 double s0, double s1, double s3, double s5,
+                                 int hsx, int hsy, int32_t *__restrict__ col_idx, int32_t *__restrict__ row_idx)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w_pad) {
+        int x = i < w ? i : w - 1;                  // padding repeats the last column
+        double px = __dadd_rn(g0, __dmul_rn(__dadd_rn((double)x, 0.5), g1));      // cn.c:222
+        double dc = __ddiv_rn(__dsub_rn(px, s0), s1);                             // cn.c:223
+        col_idx[i] = clamp_index(int_from_double_x86(c99_round(dc)), hsx);        // cn.c:225,228
+    }
+    int j = i - w_pad;
+    if (j >= 0 && j < h) {
+        double py = __dadd_rn(g3, __dmul_rn(__dadd_rn((double)j, 0.5), g5));      // cn.c:219
+        double dr = __ddiv_rn(__dsub_rn(s3, py), fabs(s5));                       // cn.c:224
+        row_idx[j] = clamp_index(int_from_double_x86(c99_round(dr)), hsy);        // cn.c:226,229
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small PTX helpers
+
+__device__ __forceinline__ uint4 ldg_stream16(const void *p)
+{
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void stg_stream16(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// soil code -> LUT slot, both drainage conditions (cn.c:88-111 + the sg<5 test of cn.c:123-124)
+__device__ __forceinline__ uint32_t soil_slot(uint32_t hv, int drained)
+{
+    uint32_t d = hv - 11u;
+    uint32_t s = (d <= 3u) ? (drained ? 4u : d + 1u) : hv;
+    return s < (uint32_t)kSgInvalid ? s : (uint32_t)kSgInvalid;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The streaming kernel.  NP = planes per group (1..9), G = groups (1 or 2 drainage conditions).
+//
+// Shared memory: [0, 32 KB) LUT records, then the kBoxRows x kBoxCols HSG tile, then one mbarrier.
+
+constexpr int kSmemHsgOff = kLutBytes;
+constexpr int kSmemBarOff = kSmemHsgOff + kBoxRows * kBoxCols;
+constexpr int kSmemBytes = kSmemBarOff + 16;
+
+template <int NP>
+__device__ __forceinline__ void transpose_store_word(const uint4 (&r)[4], uint32_t (&ow)[NP][4], int j)
+{
+    const uint32_t a[3] = { r[0].x, r[0].y, r[0].z };
+    const uint32_t b[3] = { r[1].x, r[1].y, r[1].z };
+    const uint32_t c[3] = { r[2].x, r[2].y, r[2].z };
+    const uint32_t d[3] = { r[3].x, r[3].y, r[3].z };
+#pragma unroll
+    for (int wd = 0; wd < (NP + 3) / 4; wd++) {
+        // 4x4 byte transpose: rows = pixels a,b,c,d; columns = planes 4wd..4wd+3
+        uint32_t t0 = __byte_perm(a[wd], b[wd], 0x5140);    // a0 b0 a1 b1
+        uint32_t t1 = __byte_perm(c[wd], d[wd], 0x5140);    // c0 d0 c1 d1
+        if (4 * wd + 0 < NP) ow[4 * wd + 0][j] = __byte_perm(t0, t1, 0x5410);
+        if (4 * wd + 1 < NP) ow[4 * wd + 1][j] = __byte_perm(t0, t1, 0x7632);
+        if (4 * wd + 2 < NP) {
+            uint32_t t2 = __byte_perm(a[wd], b[wd], 0x7362);    // a2 b2 a3 b3
+            uint32_t t3 = __byte_perm(c[wd], d[wd], 0x7362);
+            ow[4 * wd + 2][j] = __byte_perm(t2, t3, 0x5410);
+            if (4 * wd + 3 < NP) ow[4 * wd + 3][j] = __byte_perm(t2, t3, 0x7632);
+        }
+    }
+}
+
+template <int NP, int G>
+__global__ void __launch_bounds__(kThreads)
+cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ CUtensorMap hsg_map)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t s_hsg = smem_u32(smem + kSmemHsgOff);
+    const uint32_t s_bar = smem_u32(smem + kSmemBarOff);
+
+    const int tid = threadIdx.x;
+    const int x_first = blockIdx.x * kStripPx;
+    const int x0 = x_first + tid * kVecPx;
+    const int w16 = p.w & ~(kVecPx - 1);            // the right edge (< 16 px) is cn_bytes_kernel's
+    const int y_begin = blockIdx.y * p.rows_per_cta;
+    const int y_end = min(p.h, y_begin + p.rows_per_cta);
+
+    // HSG footprint of this CTA.  Both index maps are monotone (each fp64 step of cn.c:219-229
+    // is monotone in x / y), so the end points bound the range.
+    const int x_last = min(w16, x_first + kStripPx) - 1;
+    const int ca = __ldg(p.col_idx + x_first), cb = __ldg(p.col_idx + x_last);
+    const int ra = __ldg(p.row_idx + p.y_base + y_begin), rb = __ldg(p.row_idx + p.y_base + y_end - 1);
+    // the box start is rounded down to a 16-element boundary: TMA moves 16-byte granules and
+    // faults on an inner coordinate whose byte address is not 16-byte aligned
+    const int ci_min = min(ca, cb) & ~15, cj_min = min(ra, rb);
+    const bool staged = p.use_tma && (max(ca, cb) - ci_min < kBoxCols) && (max(ra, rb) - cj_min < kBoxRows);
+
+    if (staged && tid == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(s_bar, kBoxRows * kBoxCols);
+        tma_load_2d(s_hsg, &hsg_map, ci_min, cj_min, s_bar);
+    }
+    // LUT records -> shared memory (32 KB, L2 resident after the first CTA)
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+#pragma unroll
+        for (int i = 0; i < kLutRecords / kThreads; i++)
+            dst[tid + i * kThreads] = __ldg(p.lut + tid + i * kThreads);
+    }
+    __syncthreads();
+    if (staged)
+        mbar_wait(s_bar, 0);
+
+    if (x0 >= w16)
+        return;
+
+    const uint32_t swz_mask = 0x07070707u;
+    uint32_t slot[G][4];            // per pixel: (slot << 4) in one byte, 4 pixels per word
+    int cj_cur = INT_MIN;           // row_idx is clamped to >= 0, so this never matches
+#pragma unroll
+    for (int g = 0; g < G; g++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            slot[g][j] = 0;
+
+    const uint8_t *esa_ptr = p.esa + (size_t)y_begin * p.esa_pitch + x0;
+    size_t out_off = (size_t)y_begin * p.out_pitch + x0;
+    uint4 e = ldg_stream16(esa_ptr);
+
+    for (int y = y_begin; y < y_end; y++) {
+        // prefetch the next row's land cover while this row is looked up
+        uint4 e_next = e;
+        if (y + 1 < y_end)
+            e_next = ldg_stream16(esa_ptr + p.esa_pitch);
+
+        const int cj = __ldg(p.row_idx + p.y_base + y);
+        if (cj != cj_cur) {
+            // new HSG row: gather this thread's 16 soil codes (cn.c:230) and turn them into
+            // LUT slots for each drainage condition (cn.c:88-111)
+            cj_cur = cj;
+            const int4 *cp = reinterpret_cast<const int4 *>(p.col_idx + x0);
+            const uint8_t *row_g = p.hsg + (size_t)cj * p.hsg_pitch;
+            const int row_s = kSmemHsgOff + (cj - cj_min) * kBoxCols - ci_min;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int4 c4 = __ldg(cp + j);
+                const int cc[4] = { c4.x, c4.y, c4.z, c4.w };
+                uint32_t acc[G];
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    acc[g] = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t hv = staged ? (uint32_t)smem[row_s + cc[q]] : (uint32_t)__ldg(row_g + cc[q]);
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        acc[g] |= (soil_slot(hv, p.group_drained[g]) << 4) << (8 * q);
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    slot[g][j] = acc[g];
+            }
+        }
+
+        const uint32_t ew[4] = { e.x, e.y, e.z, e.w };
+        // bank swizzle term per pixel: ((lc >> swz_shift) & 7) << 4, byte-parallel
+        uint32_t fz[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            fz[j] = ((ew[j] >> p.swz_shift) & swz_mask) << 4;
+
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            uint32_t ow[NP][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t sx = slot[g][j] ^ fz[j];
+                uint4 r[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    // record offset = lc*128 + (slot ^ swizzle)*16
+                    const uint32_t lc = __byte_perm(ew[j], 0, 0x4440 | q);
+                    const uint32_t sb = __byte_perm(sx, 0, 0x4440 | q);
+                    r[q] = *reinterpret_cast<const uint4 *>(smem + (lc * 128u + sb));
+                }
+                transpose_store_word<NP>(r, ow, j);
+            }
+#pragma unroll
+            for (int k = 0; k < NP; k++)
+                stg_stream16(p.out[g * NP + k] + out_off, ow[k][0], ow[k][1], ow[k][2], ow[k][3]);
+        }
+
+        e = e_next;
+        esa_ptr += p.esa_pitch;
+        out_off += p.out_pitch;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Byte-wise kernel for columns [x_begin, w) of every row: the right edge the vector kernel leaves
+// (w % 16 pixels) or, with x_begin = 0, whole blocks whose buffers are not 16-byte aligned.
+// Planes are addressed through the same compacted out[] list; NP and G are runtime values here.
+
+__global__ void cn_bytes_kernel(const __grid_constant__ BlockParams p, int x_begin, int np, int groups)
+{
+    const int cols = p.w - x_begin;
+    const long long n = (long long)cols * p.h;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / cols);
+        const int x = x_begin + (int)(i - (long long)y * cols);
+        const uint32_t lc = p.esa[(size_t)y * p.esa_pitch + x];
+        const int ci = __ldg(p.col_idx + x);
+        const int cj = __ldg(p.row_idx + p.y_base + y);
+        const uint32_t hv = __ldg(p.hsg + (size_t)cj * p.hsg_pitch + ci);
+        for (int g = 0; g < groups; g++) {
+            const uint32_t s = soil_slot(hv, p.group_drained[g]) ^ ((lc >> p.swz_shift) & 7u);
+            const uint8_t *rec = reinterpret_cast<const uint8_t *>(p.lut + (lc * 8u + s));
+            for (int k = 0; k < np; k++)
+                p.out[g * np + k][(size_t)y * p.out_pitch + x] = __ldg(rec + k);
+        }
+    }
+}
+
+}  // namespace gcn10

@@ -1,0 +1,678 @@
+// gcn10_b200/csrc/gcn10_cuda.cu -- host side of libgcn10cuda.so (C ABI in include/gcn10_cuda.h).
+//
+// Replaces the per-pixel part of the reference's process_block() (/root/reference/src/cn.c:208-290):
+// upload of the two windows that load_raster() produced, the fp64 index maps, the fused
+// resample + remap + lookup kernel, and download of the planes that go to save_raster().
+//
+// There is deliberately no CPU implementation in this file: if CUDA is unavailable every
+// compute entry point returns an error.
+#include "../../include/gcn10_cuda.h"
+#include "cn_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace gcn10;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(e_ == cudaErrorMemoryAllocation ? GCN10_ENOMEM : GCN10_ECUDA,        \
+                        "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);\
+    } while (0)
+
+constexpr int kMaxStreams = 8;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct StripSlot {
+    DevBuf esa;
+    DevBuf out;                 // nplanes * strip_rows * pitch
+    cudaEvent_t k0 = nullptr, k1 = nullptr, done = nullptr;
+    bool timed = false;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct gcn10_ctx {
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t streams[kMaxStreams] = {};
+    int nstreams = 4;
+    int strip_rows = 512;
+    int rows_per_cta = 128;
+    int use_tma = 1;
+    EncodeTiledFn encode_tiled = nullptr;
+
+    bool have_lut = false;
+    int host_tables[GCN10_NVARIANTS][256][5];
+    DevBuf lut;                 // packed records for the current plane selection
+    unsigned lut_mask[2] = { 0xFFFFFFFFu, 0xFFFFFFFFu };   // variant masks the records were packed for
+    int swz_shift = 1;
+
+    DevBuf col_idx, row_idx, hsg;
+    StripSlot slots[kMaxStreams];
+    float last_kernel_ms = 0.f;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int ensure(DevBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes && b.p)
+        return GCN10_OK;
+    if (b.p)
+        cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    CUDA_TRY(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return GCN10_OK;
+}
+
+void release(DevBuf &b)
+{
+    if (b.p)
+        cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// (uint8_t)v when v < 255, else 255: what calculate_cn() leaves in a plane prefilled with 255
+// (cn.c:126-128,289)
+inline uint8_t cn_byte(int v) { return v < 255 ? (uint8_t)v : (uint8_t)GCN10_NODATA; }
+
+// Pick the bank-swizzle shift: spread the land-cover classes that actually have table rows over
+// the 8 16-byte bank groups of shared memory, so that neighbouring pixels of different classes
+// (same soil group) do not serialise their record fetches.
+int choose_swizzle(const int tables[GCN10_NVARIANTS][256][5])
+{
+    bool live[256];
+    for (int lc = 0; lc < 256; lc++) {
+        live[lc] = false;
+        for (int t = 0; t < GCN10_NVARIANTS && !live[lc]; t++)
+            for (int s = 0; s < 5; s++)
+                if (tables[t][lc][s] < 255) {
+                    live[lc] = true;
+                    break;
+                }
+    }
+    int best = 0, best_cost = 1 << 30;
+    for (int sh = 0; sh <= 5; sh++) {
+        int cnt[8] = { 0 };
+        for (int lc = 0; lc < 256; lc++)
+            if (live[lc])
+                cnt[(lc >> sh) & 7]++;
+        int cost = 0;
+        for (int g = 0; g < 8; g++)
+            cost += cnt[g] * cnt[g];
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = sh;
+        }
+    }
+    return best;
+}
+
+// Record (lc, slot') = the CN bytes of the selected variants, in selection order, for land cover
+// lc and soil-group slot s = slot' ^ ((lc >> shift) & 7).  Slots 5..7 (invalid soil group, cn.c:123-124)
+// hold 255 everywhere.
+void pack_lut_records(const int tables[GCN10_NVARIANTS][256][5], unsigned variant_mask, int shift,
+                      std::vector<uint8_t> &rec)
+{
+    rec.assign((size_t)kLutBytes, (uint8_t)GCN10_NODATA);
+    for (int lc = 0; lc < 256; lc++) {
+        for (int s = 0; s < 5; s++) {
+            int slot = s ^ ((lc >> shift) & 7);
+            uint8_t *r = &rec[((size_t)lc * 8 + slot) * 16];
+            int k = 0;
+            for (int t = 0; t < GCN10_NVARIANTS; t++)
+                if (variant_mask & (1u << t))
+                    r[k++] = cn_byte(tables[t][lc][s]);
+        }
+    }
+}
+
+int popcount9(unsigned m) { return __builtin_popcount(m & 0x1FFu); }
+
+// ---- kernel dispatch ------------------------------------------------------------------------
+
+typedef void (*BlockKernel)(const BlockParams, const CUtensorMap);
+
+template <int NP>
+BlockKernel pick_g(int groups)
+{
+    return groups == 2 ? (BlockKernel)cn_block_kernel<NP, 2> : (BlockKernel)cn_block_kernel<NP, 1>;
+}
+
+BlockKernel pick_kernel(int np, int groups)
+{
+    switch (np) {
+    case 1: return pick_g<1>(groups);
+    case 2: return pick_g<2>(groups);
+    case 3: return pick_g<3>(groups);
+    case 4: return pick_g<4>(groups);
+    case 5: return pick_g<5>(groups);
+    case 6: return pick_g<6>(groups);
+    case 7: return pick_g<7>(groups);
+    case 8: return pick_g<8>(groups);
+    case 9: return pick_g<9>(groups);
+    }
+    return nullptr;
+}
+
+struct LaunchPlan {
+    int np = 0, groups = 0;     // planes per group, number of groups in this launch
+    int drained[2] = { 1, 0 };
+    unsigned variant_mask = 0;  // variants (bits 0..8) the LUT records must be packed for
+    int plane_ids[18];          // original plane index of each compacted output
+};
+
+// Split a plane mask into launches.  Both drainage conditions share one launch (one read of the
+// land cover) when they ask for the same variants; otherwise each condition gets its own.
+int plan_launches(unsigned plane_mask, LaunchPlan plans[2])
+{
+    unsigned md = plane_mask & 0x1FFu, mu = (plane_mask >> 9) & 0x1FFu;
+    int n = 0;
+    auto fill = [](LaunchPlan &lp, unsigned vm, int g0_drained, int groups) {
+        lp.np = popcount9(vm);
+        lp.groups = groups;
+        lp.variant_mask = vm;
+        lp.drained[0] = g0_drained;
+        lp.drained[1] = 0;
+        int k = 0;
+        for (int g = 0; g < groups; g++) {
+            int cond = (groups == 2) ? g : (g0_drained ? 0 : 1);
+            for (int t = 0; t < 9; t++)
+                if (vm & (1u << t))
+                    lp.plane_ids[k++] = cond * 9 + t;
+        }
+    };
+    if (md && md == mu) {
+        fill(plans[n++], md, 1, 2);
+    }
+    else {
+        if (md)
+            fill(plans[n++], md, 1, 1);
+        if (mu)
+            fill(plans[n++], mu, 0, 1);
+    }
+    return n;
+}
+
+int upload_lut(gcn10_ctx *c, unsigned variant_mask, int slot, cudaStream_t st)
+{
+    // two cached record sets (one per launch of a split plan)
+    if (c->lut_mask[slot] == variant_mask)
+        return GCN10_OK;
+    int rc = ensure(c->lut, 2 * (size_t)kLutBytes);
+    if (rc)
+        return rc;
+    std::vector<uint8_t> rec;
+    pack_lut_records(c->host_tables, variant_mask, c->swz_shift, rec);
+    // synchronous w.r.t. the host vector's lifetime
+    CUDA_TRY(cudaMemcpyAsync((uint8_t *)c->lut.p + (size_t)slot * kLutBytes, rec.data(), kLutBytes,
+                             cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    c->lut_mask[slot] = variant_mask;
+    return GCN10_OK;
+}
+
+int make_hsg_map(gcn10_ctx *c, const uint8_t *d_hsg, int hsx, int hsy, size_t pitch, CUtensorMap *map, int *usable)
+{
+    *usable = 0;
+    memset(map, 0, sizeof(*map));
+    if (!c->use_tma || !c->encode_tiled)
+        return GCN10_OK;
+    if (((uintptr_t)d_hsg & 15u) || (pitch & 15u) || hsy < 1 || hsx < 1)
+        return GCN10_OK;        // TMA needs a 16-byte aligned base and row stride
+    cuuint64_t dims[2] = { (cuuint64_t)hsx, (cuuint64_t)hsy };
+    cuuint64_t strides[1] = { (cuuint64_t)pitch };
+    cuuint32_t box[2] = { (cuuint32_t)kBoxCols, (cuuint32_t)kBoxRows };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = c->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)d_hsg, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+        *usable = 1;
+    return GCN10_OK;
+}
+
+int launch_index_maps(gcn10_ctx *c, int w, int h, const double gt[6], int hsx, int hsy, const double sgt[6],
+                      cudaStream_t st)
+{
+    int w_pad = (int)round_up((size_t)w, kVecPx);
+    int rc = ensure(c->col_idx, sizeof(int32_t) * (size_t)w_pad);
+    if (rc)
+        return rc;
+    rc = ensure(c->row_idx, sizeof(int32_t) * (size_t)h);
+    if (rc)
+        return rc;
+    int n = w_pad + h;
+    index_map_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, w_pad, h, gt[0], gt[1], gt[3], gt[5],
+                                                      sgt[0], sgt[1], sgt[3], sgt[5], hsx, hsy,
+                                                      (int32_t *)c->col_idx.p, (int32_t *)c->row_idx.p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return GCN10_OK;
+}
+
+// Launch the fused kernel(s) for `rows` rows starting at block row y_base.  d_out holds the 18
+// plane pointers already offset to the first row of this launch.
+int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t *d_esa, size_t esa_pitch, int w,
+                int rows, int y_base, const uint8_t *d_hsg, size_t hsg_pitch, int hsx, int hsy,
+                const CUtensorMap &map, int tma_ok, uint8_t *const d_out[GCN10_NPLANES], size_t out_pitch,
+                cudaStream_t st)
+{
+    BlockParams p;
+    memset(&p, 0, sizeof(p));
+    p.esa = d_esa;
+    p.esa_pitch = esa_pitch;
+    p.w = w;
+    p.h = rows;
+    p.y_base = y_base;
+    p.col_idx = (const int32_t *)c->col_idx.p;
+    p.row_idx = (const int32_t *)c->row_idx.p;
+    p.hsg = d_hsg;
+    p.hsg_pitch = hsg_pitch;
+    p.hsx = hsx;
+    p.hsy = hsy;
+    p.lut = (const uint4 *)((const uint8_t *)c->lut.p + (size_t)lut_slot * kLutBytes);
+    p.swz_shift = c->swz_shift;
+    p.rows_per_cta = c->rows_per_cta;
+    p.use_tma = tma_ok;
+    p.group_drained[0] = lp.drained[0];
+    p.group_drained[1] = lp.drained[1];
+    p.out_pitch = out_pitch;
+    bool aligned = (((uintptr_t)d_esa | esa_pitch | out_pitch) & 15u) == 0;
+    for (int k = 0; k < lp.np * lp.groups; k++) {
+        p.out[k] = d_out[lp.plane_ids[k]];
+        if (!p.out[k])
+            return fail(GCN10_EINVAL, "output plane %d selected by the mask but its pointer is NULL", lp.plane_ids[k]);
+        if ((uintptr_t)p.out[k] & 15u)
+            aligned = false;
+    }
+
+    int x_bytes = 0;
+    if (aligned && (w & ~(kVecPx - 1)) > 0) {
+        int w16 = w & ~(kVecPx - 1);
+        dim3 grid((w16 + kStripPx - 1) / kStripPx, (rows + c->rows_per_cta - 1) / c->rows_per_cta);
+        BlockKernel k = pick_kernel(lp.np, lp.groups);
+        k<<<grid, kThreads, kSmemBytes, st>>>(p, map);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        x_bytes = w16;
+    }
+    if (x_bytes < w) {
+        long long n = (long long)(w - x_bytes) * rows;
+        int blocks = (int)std::min<long long>((n + 255) / 256, (long long)c->sm_count * 16);
+        cn_bytes_kernel<<<blocks, 256, 0, st>>>(p, x_bytes, lp.np, lp.groups);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return GCN10_OK;
+}
+
+int check_geometry(const void *esa, int w, int h, size_t esa_pitch, const double *gt, const void *hsg, int hsx,
+                   int hsy, size_t hsg_pitch, const double *sgt, unsigned mask, const void *out, size_t out_pitch)
+{
+    if (!esa || !hsg || !gt || !sgt || !out)
+        return fail(GCN10_EINVAL, "NULL argument");
+    if (w <= 0 || h <= 0 || hsx <= 0 || hsy <= 0)
+        return fail(GCN10_EINVAL, "non-positive raster size (%d x %d, hsg %d x %d)", w, h, hsx, hsy);
+    if (esa_pitch < (size_t)w || out_pitch < (size_t)w || hsg_pitch < (size_t)hsx)
+        return fail(GCN10_EINVAL, "pitch smaller than row width");
+    if ((mask & GCN10_MASK_ALL) == 0 || (mask & ~GCN10_MASK_ALL))
+        return fail(GCN10_EINVAL, "plane mask 0x%x selects nothing or unknown planes", mask);
+    return GCN10_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+
+extern "C" {
+
+const char *gcn10_cuda_version(void) { return "gcn10cuda 0.1.0 (sm_100a)"; }
+
+const char *gcn10_cuda_last_error(void) { return g_err; }
+
+int gcn10_cuda_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess)
+        return fail(GCN10_ENODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int gcn10_cuda_create(int device, gcn10_ctx **out)
+{
+    if (!out)
+        return fail(GCN10_EINVAL, "NULL out pointer");
+    *out = nullptr;
+    int n = gcn10_cuda_device_count();
+    if (n < 0)
+        return n;
+    if (device < 0 || device >= n)
+        return fail(GCN10_ENODEV, "device %d out of range (%d visible)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    gcn10_ctx *c = new (std::nothrow) gcn10_ctx();
+    if (!c)
+        return fail(GCN10_ENOMEM, "context allocation failed");
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete c;
+        return fail(GCN10_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    }
+    for (int i = 0; i < kMaxStreams; i++)
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxStreams; i++) {
+        CUDA_TRY(cudaEventCreate(&c->slots[i].k0));
+        CUDA_TRY(cudaEventCreate(&c->slots[i].k1));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->slots[i].done, cudaEventDisableTiming));
+    }
+    // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        c->encode_tiled = (EncodeTiledFn)fn;
+    for (int np = 1; np <= 9; np++)
+        for (int g = 1; g <= 2; g++)
+            CUDA_TRY(cudaFuncSetAttribute((const void *)pick_kernel(np, g),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    *out = c;
+    return GCN10_OK;
+}
+
+void gcn10_cuda_destroy(gcn10_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    release(c->lut);
+    release(c->col_idx);
+    release(c->row_idx);
+    release(c->hsg);
+    for (int i = 0; i < kMaxStreams; i++) {
+        release(c->slots[i].esa);
+        release(c->slots[i].out);
+        if (c->slots[i].k0) cudaEventDestroy(c->slots[i].k0);
+        if (c->slots[i].k1) cudaEventDestroy(c->slots[i].k1);
+        if (c->slots[i].done) cudaEventDestroy(c->slots[i].done);
+        if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    }
+    delete c;
+}
+
+int gcn10_cuda_set_luts(gcn10_ctx *c, const int tables[GCN10_NVARIANTS][256][5])
+{
+    if (!c || !tables)
+        return fail(GCN10_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    memcpy(c->host_tables, tables, sizeof(c->host_tables));
+    c->swz_shift = choose_swizzle(c->host_tables);
+    c->lut_mask[0] = c->lut_mask[1] = 0xFFFFFFFFu;
+    c->have_lut = true;
+    return GCN10_OK;
+}
+
+int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
+{
+    if (!c || !key)
+        return fail(GCN10_EINVAL, "NULL argument");
+    if (!strcmp(key, "strip_rows") && value >= 1) c->strip_rows = (int)value;
+    else if (!strcmp(key, "streams") && value >= 1 && value <= kMaxStreams) c->nstreams = (int)value;
+    else if (!strcmp(key, "rows_per_cta") && value >= 1) c->rows_per_cta = (int)value;
+    else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
+    else return fail(GCN10_EINVAL, "unknown option or bad value: %s=%ld", key, value);
+    return GCN10_OK;
+}
+
+int gcn10_cuda_synchronize(gcn10_ctx *c)
+{
+    if (!c)
+        return fail(GCN10_EINVAL, "NULL context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (int i = 0; i < kMaxStreams; i++)
+        CUDA_TRY(cudaStreamSynchronize(c->streams[i]));
+    return GCN10_OK;
+}
+
+int gcn10_cuda_last_kernel_ms(gcn10_ctx *c, float *ms)
+{
+    if (!c || !ms)
+        return fail(GCN10_EINVAL, "NULL argument");
+    *ms = c->last_kernel_ms;
+    return GCN10_OK;
+}
+
+int gcn10_cuda_launch_count(gcn10_ctx *c, uint64_t *launches)
+{
+    if (!c || !launches)
+        return fail(GCN10_EINVAL, "NULL argument");
+    *launches = c->launches;
+    return GCN10_OK;
+}
+
+int gcn10_cuda_index_maps(gcn10_ctx *c, int w, int h, const double gt[6], int hsx, int hsy,
+                          const double soil_gt[6], int32_t *col_index, int32_t *row_index)
+{
+    if (!c || !gt || !soil_gt || !col_index || !row_index)
+        return fail(GCN10_EINVAL, "NULL argument");
+    if (w <= 0 || h <= 0 || hsx <= 0 || hsy <= 0)
+        return fail(GCN10_EINVAL, "non-positive size");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->streams[0];
+    int rc = launch_index_maps(c, w, h, gt, hsx, hsy, soil_gt, st);
+    if (rc)
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(col_index, c->col_idx.p, sizeof(int32_t) * (size_t)w, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(row_index, c->row_idx.p, sizeof(int32_t) * (size_t)h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GCN10_OK;
+}
+
+int gcn10_cuda_block_device(gcn10_ctx *c,
+                            const uint8_t *d_esa, int w, int h, size_t esa_pitch, const double gt[6],
+                            const uint8_t *d_hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                            unsigned plane_mask, uint8_t *const d_out[GCN10_NPLANES], size_t out_pitch,
+                            void *stream)
+{
+    if (!c)
+        return fail(GCN10_EINVAL, "NULL context");
+    int rc = check_geometry(d_esa, w, h, esa_pitch, gt, d_hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask, d_out,
+                            out_pitch);
+    if (rc)
+        return rc;
+    if (!c->have_lut)
+        return fail(GCN10_ENOLUT, "gcn10_cuda_set_luts() has not been called");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->streams[0];
+
+    LaunchPlan plans[2];
+    int nplans = plan_launches(plane_mask, plans);
+    for (int i = 0; i < nplans; i++)
+        if ((rc = upload_lut(c, plans[i].variant_mask, i, st)))
+            return rc;
+    if ((rc = launch_index_maps(c, w, h, gt, hsx, hsy, soil_gt, st)))
+        return rc;
+    CUtensorMap map;
+    int tma_ok = 0;
+    make_hsg_map(c, d_hsg, hsx, hsy, hsg_pitch, &map, &tma_ok);
+    for (int i = 0; i < nplans; i++)
+        if ((rc = launch_rows(c, plans[i], i, d_esa, esa_pitch, w, h, 0, d_hsg, hsg_pitch, hsx, hsy, map, tma_ok,
+                              d_out, out_pitch, st)))
+            return rc;
+    return GCN10_OK;
+}
+
+int gcn10_cuda_block(gcn10_ctx *c,
+                     const uint8_t *esa, int w, int h, size_t esa_pitch, const double gt[6],
+                     const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                     unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch)
+{
+    if (!c)
+        return fail(GCN10_EINVAL, "NULL context");
+    int rc = check_geometry(esa, w, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask, out, out_pitch);
+    if (rc)
+        return rc;
+    if (!c->have_lut)
+        return fail(GCN10_ENOLUT, "gcn10_cuda_set_luts() has not been called");
+    for (int k = 0; k < GCN10_NPLANES; k++)
+        if ((plane_mask & (1u << k)) && !out[k])
+            return fail(GCN10_EINVAL, "output plane %d selected by the mask but its pointer is NULL", k);
+    CUDA_TRY(cudaSetDevice(c->device));
+
+    LaunchPlan plans[2];
+    const int nplans = plan_launches(plane_mask, plans);
+    int nplanes = 0;
+    for (int i = 0; i < nplans; i++)
+        nplanes += plans[i].np * plans[i].groups;
+
+    cudaStream_t s0 = c->streams[0];
+    for (int i = 0; i < nplans; i++)
+        if ((rc = upload_lut(c, plans[i].variant_mask, i, s0)))
+            return rc;
+
+    // whole-block state: index maps and the coarse HSG window (<= a few MB), on stream 0
+    const size_t hsg_dpitch = round_up((size_t)hsx, 256);
+    if ((rc = ensure(c->hsg, hsg_dpitch * (size_t)hsy)))
+        return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(c->hsg.p, hsg_dpitch, hsg, hsg_pitch, (size_t)hsx, (size_t)hsy,
+                               cudaMemcpyHostToDevice, s0));
+    if ((rc = launch_index_maps(c, w, h, gt, hsx, hsy, soil_gt, s0)))
+        return rc;
+    CUtensorMap map;
+    int tma_ok = 0;
+    make_hsg_map(c, (const uint8_t *)c->hsg.p, hsx, hsy, hsg_dpitch, &map, &tma_ok);
+    CUDA_TRY(cudaStreamSynchronize(s0));
+
+    // row strips, round-robin over the streams; each stream owns one staging slot
+    const size_t dpitch = round_up((size_t)w, 256);
+    const int ns = c->nstreams;
+    const int strip = std::max(1, std::min(c->strip_rows, h));
+    for (int i = 0; i < ns; i++) {
+        if ((rc = ensure(c->slots[i].esa, dpitch * (size_t)strip)))
+            return rc;
+        if ((rc = ensure(c->slots[i].out, dpitch * (size_t)strip * (size_t)nplanes)))
+            return rc;
+        c->slots[i].timed = false;
+    }
+    float kernel_ms = 0.f;
+    int si = 0;
+    for (int y0 = 0; y0 < h; y0 += strip, si = (si + 1) % ns) {
+        const int rows = std::min(strip, h - y0);
+        StripSlot &sl = c->slots[si];
+        cudaStream_t st = c->streams[si];
+        if (sl.timed) {
+            // the slot's previous strip: its D2H copies must be complete before the buffers are reused
+            CUDA_TRY(cudaEventSynchronize(sl.done));
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, sl.k0, sl.k1));
+            kernel_ms += ms;
+        }
+        CUDA_TRY(cudaMemcpy2DAsync(sl.esa.p, dpitch, esa + (size_t)y0 * esa_pitch, esa_pitch, (size_t)w,
+                                   (size_t)rows, cudaMemcpyHostToDevice, st));
+        uint8_t *d_out[GCN10_NPLANES] = { nullptr };
+        int k = 0;
+        for (int i = 0; i < nplans; i++)
+            for (int j = 0; j < plans[i].np * plans[i].groups; j++, k++)
+                d_out[plans[i].plane_ids[j]] = (uint8_t *)sl.out.p + (size_t)k * dpitch * (size_t)strip;
+        CUDA_TRY(cudaEventRecord(sl.k0, st));
+        for (int i = 0; i < nplans; i++)
+            if ((rc = launch_rows(c, plans[i], i, (const uint8_t *)sl.esa.p, dpitch, w, rows, y0,
+                                  (const uint8_t *)c->hsg.p, hsg_dpitch, hsx, hsy, map, tma_ok, d_out, dpitch, st)))
+                return rc;
+        CUDA_TRY(cudaEventRecord(sl.k1, st));
+        for (int p = 0; p < GCN10_NPLANES; p++)
+            if (d_out[p])
+                CUDA_TRY(cudaMemcpy2DAsync(out[p] + (size_t)y0 * out_pitch, out_pitch, d_out[p], dpitch, (size_t)w,
+                                           (size_t)rows, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(sl.done, st));
+        sl.timed = true;
+    }
+    for (int i = 0; i < ns; i++) {
+        StripSlot &sl = c->slots[i];
+        if (!sl.timed)
+            continue;
+        CUDA_TRY(cudaEventSynchronize(sl.done));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, sl.k0, sl.k1));
+        kernel_ms += ms;
+        sl.timed = false;
+    }
+    c->last_kernel_ms = kernel_ms;
+    return GCN10_OK;
+}
+
+void *gcn10_cuda_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        fail(GCN10_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+
+void gcn10_cuda_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+int gcn10_cuda_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes)
+        return fail(GCN10_EINVAL, "NULL or empty range");
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return GCN10_OK;
+}
+
+int gcn10_cuda_host_unregister(void *p)
+{
+    if (!p)
+        return fail(GCN10_EINVAL, "NULL pointer");
+    CUDA_TRY(cudaHostUnregister(p));
+    return GCN10_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+/* include/gcn10_cuda.h -- C ABI of libgcn10cuda.so, the B200 (sm_100a) implementation of
+ * GCN10's per-block Curve Number hot path.
+ *
+ * The reference (clawrim/gcn10) has no plugin or FFI interface; its only seam around the
+ * hot path is the plain C function
+ *
+ *     void process_block(int block_id, bool overwrite, int total_blocks);
+ *                                            -- /root/reference/src/global.h:58
+ *
+ * whose body (/root/reference/src/cn.c:134-384) loads two byte rasters with load_raster()
+ * (global.h:54-55), runs five full-raster CPU passes per output (cn.c:218-232, 274, 275,
+ * 289, 290) and hands 18 byte planes to save_raster() (global.h:56-57).  This library
+ * replaces exactly the part between "load_raster returned" and "save_raster is called":
+ * the entry points below take the same byte rasters and geotransforms that load_raster()
+ * produces and return the same byte planes that save_raster() consumes.  INTEGRATION.md shows
+ * the replacement cn.c that a maintainer of the reference would write on top of it, and
+ * gcn10_b200/host/ holds this repository's own host program built that way.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no CUDA, C++ or torch types in any signature
+ *     (a stream is passed as an opaque void*: a cudaStream_t / CUstream value, NULL = the
+ *     context's own stream);
+ *   - every function that can fail returns int: 0 = GCN10_OK, negative = error code, and
+ *     gcn10_cuda_last_error() returns a human-readable message for the calling thread;
+ *   - a gcn10_ctx is bound to one GPU and must be used by one host thread at a time
+ *     (one context per worker thread per GPU, mirroring one MPI rank per process in the
+ *     reference, /root/reference/src/main.c:80-82,171);
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point fails
+ *     with GCN10_ENODEV / GCN10_ECUDA.
+ *
+ * Plane numbering (the reference's save order, cn.c:145-147,236,258-259,308):
+ *     plane = cond * 9 + hc * 3 + arc,  cond: 0 drained, 1 undrained
+ *                                       hc:   0 p, 1 f, 2 g       arc: 0 i, 1 ii, 2 iii
+ * A plane mask selects planes by bit (1u << plane).
+ */
+#ifndef GCN10_CUDA_H
+#define GCN10_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCN10_NVARIANTS 9           /* lookup tables per drainage condition             */
+#define GCN10_NPLANES   18          /* rasters per block (cn.c:236,258-259)             */
+#define GCN10_NODATA    255         /* cn.c:38,289                                       */
+
+#define GCN10_MASK_DRAINED   0x001FFu       /* planes 0..8   (cn_rasters_drained/)      */
+#define GCN10_MASK_UNDRAINED 0x3FE00u       /* planes 9..17  (cn_rasters_undrained/)    */
+#define GCN10_MASK_ALL       0x3FFFFu
+
+enum {
+    GCN10_OK      = 0,
+    GCN10_EINVAL  = -1,     /* bad argument (NULL, non-positive size, pitch < width, ...) */
+    GCN10_ECUDA   = -2,     /* a CUDA runtime/driver call failed                          */
+    GCN10_ENOMEM  = -3,     /* host or device allocation failed                           */
+    GCN10_ENOLUT  = -4,     /* gcn10_cuda_set_luts() has not been called                  */
+    GCN10_ENODEV  = -5      /* no CUDA device / device index out of range                 */
+};
+
+typedef struct gcn10_ctx gcn10_ctx;
+
+/* Library identification, e.g. "gcn10cuda 0.1.0 (sm_100a)". */
+const char *gcn10_cuda_version(void);
+
+/* Message describing the last failure on the calling thread ("" if none). */
+const char *gcn10_cuda_last_error(void);
+
+/* Number of CUDA devices visible to the process; negative error code on failure.
+ * Replaces MPI_Comm_size() as the worker count (main.c:82). */
+int gcn10_cuda_device_count(void);
+
+/* Create / destroy a per-GPU context (streams, LUT storage, staging buffers). */
+int gcn10_cuda_create(int device, gcn10_ctx **out);
+void gcn10_cuda_destroy(gcn10_ctx *ctx);
+
+/* Install the nine lookup tables.  Element layout and order are exactly those of the
+ * reference: int table[256][5] indexed [land cover][soil group] as filled by
+ * load_lookup_table() (cn.c:13-85, declared cn.c:148), tables in loop order
+ * p_i, p_ii, p_iii, f_i, f_ii, f_iii, g_i, g_ii, g_iii (cn.c:146-147,258-259).
+ * A value v is emitted as (uint8_t)v when v < 255 and as 255 otherwise (cn.c:126-128,289). */
+int gcn10_cuda_set_luts(gcn10_ctx *ctx, const int tables[GCN10_NVARIANTS][256][5]);
+
+/* One block, inputs and outputs in HOST memory (replaces cn.c:208-290 and the buffers that
+ * flow into save_raster at cn.c:363).  Synchronous.  Internally the block is cut into row
+ * strips that are pipelined host->device copy / kernel / device->host copy over several
+ * streams.  Copies are asynchronous when the buffers are page-locked
+ * (gcn10_cuda_host_alloc / gcn10_cuda_host_register), otherwise staged by the driver.
+ *
+ *   esa, w, h, esa_pitch   land cover window from load_raster (cn.c:187); row y starts at
+ *                          esa + y*esa_pitch (the reference has esa_pitch == w)
+ *   gt                     its clipped geotransform (raster.c:157-162)
+ *   hsg, hsx, hsy,         coarse HYSOGs window (cn.c:195-196) and its geotransform
+ *   hsg_pitch, soil_gt
+ *   plane_mask             which of the 18 planes to produce
+ *   out[18], out_pitch     destination of plane k = out[k] (ignored where the mask bit is 0)
+ */
+int gcn10_cuda_block(gcn10_ctx *ctx,
+                     const uint8_t *esa, int w, int h, size_t esa_pitch, const double gt[6],
+                     const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                     unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch);
+
+/* Same computation with every buffer already in DEVICE memory; asynchronous on `stream`
+ * (NULL = the context's own non-blocking stream; to use the legacy default stream pass
+ * cudaStreamLegacy, i.e. (void *)1).  Fast path requirements: esa, every selected out[k], and
+ * both pitches 16-byte aligned; otherwise a slower byte-wise kernel is used.  hsg may have
+ * any alignment (16-byte aligned base and pitch enable the TMA staging path). */
+int gcn10_cuda_block_device(gcn10_ctx *ctx,
+                            const uint8_t *d_esa, int w, int h, size_t esa_pitch, const double gt[6],
+                            const uint8_t *d_hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                            unsigned plane_mask, uint8_t *const d_out[GCN10_NPLANES], size_t out_pitch,
+                            void *stream);
+
+/* The separable pixel -> HSG cell maps of cn.c:219-229, evaluated on the GPU in fp64 with
+ * the reference's exact operation order; copies col_index[w] and row_index[h] to the host.
+ * Diagnostic / test entry point (the block calls compute these maps internally). */
+int gcn10_cuda_index_maps(gcn10_ctx *ctx, int w, int h, const double gt[6],
+                          int hsx, int hsy, const double soil_gt[6],
+                          int32_t *col_index, int32_t *row_index);
+
+/* Wait for everything queued on the context's streams. */
+int gcn10_cuda_synchronize(gcn10_ctx *ctx);
+
+/* Device time of the fused kernels of the most recent gcn10_cuda_block() call (sum over its
+ * strips), measured with CUDA events on the launching streams. */
+int gcn10_cuda_last_kernel_ms(gcn10_ctx *ctx, float *ms);
+
+/* Number of kernels this context has launched since it was created. */
+int gcn10_cuda_launch_count(gcn10_ctx *ctx, uint64_t *launches);
+
+/* Tunables: "strip_rows" (rows per pipelined strip in gcn10_cuda_block), "streams"
+ * (1..8), "rows_per_cta", "tma" (0 = always use the gather fallback for HSG staging). */
+int gcn10_cuda_set_option(gcn10_ctx *ctx, const char *key, long value);
+
+/* Page-locked host memory for rasters, so that the strip copies run asynchronously
+ * (replaces malloc at raster.c:169 / cn.c:278 in a host program built on this library). */
+void *gcn10_cuda_host_alloc(size_t bytes);
+void gcn10_cuda_host_free(void *p);
+int gcn10_cuda_host_register(void *p, size_t bytes);
+int gcn10_cuda_host_unregister(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCN10_CUDA_H */

@@ -192,7 +192,7 @@ void cn_oracle_apply_table(const uint8_t *esa, const uint8_t *hsg, size_t n,
     }
 }
 
-int cn_oracle_block_rows(const uint8_t *esa, int w, int h, const double gt[6],
+int cn_oracle_block_rows(const uint8_t *esa_rows, int w, int h, const double gt[6],
                          const uint8_t *coarse, int hsx, int hsy, const double soil_gt[6],
                          const int tables[9][256][5], int y0, int y1,
                          uint8_t *out, size_t plane_stride)
@@ -211,7 +211,7 @@ int cn_oracle_block_rows(const uint8_t *esa, int w, int h, const double gt[6],
         for (int t = 0; t < 9; t++) {                       /* cn.c:258-259 */
             memcpy(adjusted, resampled, n);                 /* cn.c:274 */
             cn_oracle_remap_hsg(adjusted, n, cond == 0);    /* cn.c:275 */
-            cn_oracle_apply_table(esa + (size_t)y0 * w, adjusted, n, tables[t],
+            cn_oracle_apply_table(esa_rows, adjusted, n, tables[t],
                                   out + (size_t)(cond * 9 + t) * plane_stride);
         }
     }

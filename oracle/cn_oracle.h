@@ -46,11 +46,12 @@ void cn_oracle_remap_hsg(uint8_t *hsg, size_t n, int drained);
 void cn_oracle_apply_table(const uint8_t *esa, const uint8_t *hsg, size_t n,
                            const int table[256][5], uint8_t *out);
 
-/* src/cn.c:218-290 for rows [y0,y1) of a block: writes the 18 planes in the
+/* src/cn.c:218-290 for rows [y0,y1) of a w x h block: writes the 18 planes in the
  * reference's save order (cond-major: drained p_i..g_iii, undrained p_i..g_iii),
  * plane k at out + k*plane_stride, each (y1-y0)*w bytes, row-major.
- * esa points at row 0 of the block window (w x h).  0 ok, -1 allocation failure */
-int cn_oracle_block_rows(const uint8_t *esa, int w, int h, const double gt[6],
+ * esa_rows points at row y0 of the land-cover window (so a caller that only holds
+ * a few rows of a large block can still check them).  0 ok, -1 allocation failure */
+int cn_oracle_block_rows(const uint8_t *esa_rows, int w, int h, const double gt[6],
                          const uint8_t *coarse, int hsx, int hsy, const double soil_gt[6],
                          const int tables[9][256][5], int y0, int y1,
                          uint8_t *out, size_t plane_stride);

@@ -109,16 +109,26 @@ class Port:
         self.lib.cn_oracle_row_index(h, _d6(gt), _d6(soil_gt), hsy, out.ctypes.data)
         return out
 
-    def block_rows(self, esa, gt, hsg, soil_gt, tables, y0=0, y1=None) -> np.ndarray:
-        """18 planes for rows [y0,y1) of a block; returns uint8 [18, y1-y0, w]."""
+    def block_rows(self, esa, gt, hsg, soil_gt, tables, y0=0, y1=None, h=None) -> np.ndarray:
+        """18 planes for rows [y0,y1) of a block; returns uint8 [18, y1-y0, w].
+
+        ``esa`` is either the whole window [h, w] (default) or, when ``h`` (the block's row
+        count) is given, just the rows [y0,y1) -- for spot checks of very large blocks."""
         esa = np.ascontiguousarray(esa, dtype=np.uint8)
         hsg = np.ascontiguousarray(hsg, dtype=np.uint8)
         tables = np.ascontiguousarray(tables, dtype=np.int32)
-        h, w = esa.shape
+        w = esa.shape[1]
         hh, hw = hsg.shape
-        y1 = h if y1 is None else y1
+        if h is None:
+            h = esa.shape[0]
+            y1 = h if y1 is None else y1
+            rows = esa[y0:y1]
+        else:
+            assert y1 is not None and esa.shape[0] == y1 - y0
+            rows = esa
+        rows = np.ascontiguousarray(rows)
         out = np.empty((NPLANES, y1 - y0, w), dtype=np.uint8)
-        rc = self.lib.cn_oracle_block_rows(_u8(esa), w, h, _d6(gt), _u8(hsg), hw, hh, _d6(soil_gt),
+        rc = self.lib.cn_oracle_block_rows(_u8(rows), w, h, _d6(gt), _u8(hsg), hw, hh, _d6(soil_gt),
                                            tables.ctypes.data, y0, y1, _u8(out), (y1 - y0) * w)
         if rc:
             raise MemoryError("cn_oracle_block_rows")

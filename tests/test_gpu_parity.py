@@ -1,0 +1,174 @@
+"""GPU parity: libgcn10cuda (through its C ABI) against the CPU oracle, bit for bit.
+
+The oracle (oracle/cn_oracle.c) is itself pinned to the reference's object code in
+tests/test_oracle_pinned.py.  Tolerance: none -- uint8 planes and int32 index maps must be equal.
+"""
+import numpy as np
+import pytest
+
+from gcn10_b200 import capi, synth
+from tests.cases import SMALL_CASES, make_block, PX, PX_VRT, HSG_PX
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,kw", SMALL_CASES, ids=[c[0] for c in SMALL_CASES])
+def test_block_host_api_all_planes(name, kw, gpu_ctx, port, tables):
+    b = make_block(**kw)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    for k in range(18):
+        assert np.array_equal(got[k], want[k]), f"{name}: plane {k} differs in {(got[k] != want[k]).sum()} px"
+
+
+@pytest.mark.parametrize("tma", [0, 1])
+@pytest.mark.parametrize("rows_per_cta", [7, 128, 1000])
+def test_tma_and_gather_staging_agree(tma, rows_per_cta, gpu_ctx, port, tables):
+    b = make_block(w=4500, h=700, seed=21, shift=(0.0003, 0.0007), margin=1)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    gpu_ctx.set_option("tma", tma)
+    gpu_ctx.set_option("rows_per_cta", rows_per_cta)
+    try:
+        got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    finally:
+        gpu_ctx.set_option("tma", 1)
+        gpu_ctx.set_option("rows_per_cta", 128)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("strip_rows,streams", [(1, 1), (37, 3), (512, 4), (100000, 2)])
+def test_strip_pipeline_shapes(strip_rows, streams, gpu_ctx, port, tables):
+    b = make_block(w=1234, h=999, seed=5)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    gpu_ctx.set_option("strip_rows", strip_rows)
+    gpu_ctx.set_option("streams", streams)
+    try:
+        got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    finally:
+        gpu_ctx.set_option("strip_rows", 512)
+        gpu_ctx.set_option("streams", 4)
+    assert np.array_equal(got, want)
+
+
+MASKS = {
+    "g_ii_only_drained": 1 << 7,                      # BASELINE config 1
+    "nine_drained": capi.MASK_DRAINED,                # BASELINE config 2
+    "nine_undrained": capi.MASK_UNDRAINED,
+    "same_three_both": (0b000010101) | (0b000010101 << 9),
+    "different_per_condition": 0b000000110 | (0b101000000 << 9),
+    "single_undrained": 1 << 17,
+}
+
+
+@pytest.mark.parametrize("mname", list(MASKS))
+def test_plane_masks(mname, gpu_ctx, port, tables):
+    mask = MASKS[mname]
+    b = make_block(w=2100, h=333, seed=8, profile="coastal")
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    out = np.full((18, 333, 2100), 7, dtype=np.uint8)
+    got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"], plane_mask=mask, out=out)
+    for k in range(18):
+        if mask & (1 << k):
+            assert np.array_equal(got[k], want[k]), (mname, k)
+        else:
+            assert (got[k] == 7).all(), f"{mname}: unselected plane {k} was written"
+
+
+def test_lut_edge_values(gpu_ctx, port, tables):
+    """cn >= 255 -> nodata, negative cn wraps through (uint8_t), column 0 honoured (cn.c:123-128)."""
+    t = tables.copy()
+    rng = np.random.default_rng(3)
+    t[:, :, :] = rng.integers(-300, 600, size=t.shape)
+    t[2, 40, 1] = 255
+    t[3, 40, 2] = 254
+    t[4, 40, 3] = -1
+    t[5, 40, 4] = 256
+    b = make_block(w=1500, h=200, seed=9, profile="random")
+    b["esa"] = rng.integers(0, 256, size=b["esa"].shape, dtype=np.uint8)      # every byte value
+    b["hsg"] = rng.integers(0, 256, size=b["hsg"].shape, dtype=np.uint8)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], t)
+    try:
+        gpu_ctx.set_luts(t)
+        got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    finally:
+        gpu_ctx.set_luts(tables)
+    assert np.array_equal(got, want)
+
+
+GEOMS = [
+    # (w, h, gt, hsx, hsy, soil_gt)
+    (36000, 36000, (-114.0, PX, 0, 42.0, 0, -PX), 1440, 1440, (-114.0, HSG_PX, 0, 42.0, 0, -HSG_PX)),
+    (36001, 36001, (-3.0, PX_VRT, 0, 3.0, 0, -PX_VRT), 1441, 1441, (-3.0, HSG_PX, 0, 3.0, 0, -HSG_PX)),
+    (36001, 36001, (33.0, PX_VRT, 0, -57.0, 0, -PX_VRT), 1442, 1442, (32.9993, HSG_PX, 0, -56.9989, 0, -HSG_PX)),
+    (36000, 36000, (0.0, PX, 0, 0.0, 0, -PX), 1440, 1440, (0.0, HSG_PX, 0, 0.0, 0, -HSG_PX)),
+    (36000, 36000, (177.0, PX, 0, 84.0, 0, -PX), 1440, 1440, (177.0, HSG_PX, 0, 84.0, 0, -HSG_PX)),
+    # degenerate / absurd transforms: zero and negative HSG pixel, huge offsets, NaN
+    (500, 400, (10.0, PX, 0, 5.0, 0, -PX), 30, 20, (10.0, 0.0, 0, 5.0, 0, -HSG_PX)),
+    (500, 400, (10.0, PX, 0, 5.0, 0, -PX), 30, 20, (10.0, -HSG_PX, 0, 5.0, 0, HSG_PX)),
+    (500, 400, (1e300, PX, 0, -1e300, 0, -PX), 30, 20, (10.0, 1e-300, 0, 5.0, 0, -1e-300)),
+    (500, 400, (float("nan"), PX, 0, 5.0, 0, -PX), 30, 20, (10.0, HSG_PX, 0, float("inf"), 0, -HSG_PX)),
+    (500, 400, (10.0, -PX, 0, 5.0, 0, PX), 30, 20, (10.0 - 500 * PX, HSG_PX, 0, 5.0 + 400 * PX, 0, -HSG_PX)),
+]
+
+
+@pytest.mark.parametrize("g", range(len(GEOMS)))
+def test_index_maps_match_reference_arithmetic(g, gpu_ctx, port):
+    w, h, gt, hsx, hsy, sgt = GEOMS[g]
+    ci, cj = gpu_ctx.index_maps(w, h, gt, hsx, hsy, sgt)
+    assert np.array_equal(ci, port.col_index(w, gt, sgt, hsx))
+    assert np.array_equal(cj, port.row_index(h, gt, sgt, hsy))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+@pytest.mark.parametrize("w,h,pitch_extra", [(4096, 300, 0), (4111, 257, 0), (4111, 257, 5), (1000, 100, 3)])
+def test_block_device_api(w, h, pitch_extra, gpu_ctx, port, tables):
+    """Device-resident entry point; odd pitches exercise the byte-wise kernel."""
+    torch = _torch()
+    b = make_block(w=w, h=h, seed=31)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    pitch = (w + 15) // 16 * 16 + pitch_extra
+    d_esa = torch.zeros((h, pitch), dtype=torch.uint8, device="cuda")
+    d_esa[:, :w] = torch.from_numpy(b["esa"]).cuda()
+    hsy, hsx = b["hsg"].shape
+    d_hsg = torch.from_numpy(b["hsg"]).cuda().contiguous()
+    d_out = torch.full((18, h, pitch), 3, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream or 1      # 0 would mean "the context's stream"; 1 = cudaStreamLegacy
+    gpu_ctx.block_device(d_esa.data_ptr(), w, h, pitch, b["gt"], d_hsg.data_ptr(), hsx, hsy, hsx, b["soil_gt"],
+                         capi.MASK_ALL, [d_out[k].data_ptr() for k in range(18)], pitch, stream=st)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy()
+    assert np.array_equal(got[:, :, :w], want)
+    assert (got[:, :, w:] == 3).all(), "padding columns were written"
+
+
+def test_full_tile_sampled_rows(gpu_ctx, port, tables):
+    """BASELINE config 2 size: 36000 x 36000, 9 drained planes in one pass, device resident.
+    Bit-exact check of sampled rows against the oracle plus a whole-plane invariant."""
+    torch = _torch()
+    w = h = 36000
+    gt, sgt, hsx, hsy = synth.block_geometry(-114.0, 42.0, w, h)
+    dev = torch.device("cuda:0")
+    d_esa = synth.esa_tile(w, h, seed=2234, device=dev)
+    hsg = synth.hsg_tile(hsx, hsy, seed=3234)
+    d_hsg = torch.from_numpy(hsg).to(dev)
+    d_out = torch.empty((9, h, w), dtype=torch.uint8, device=dev)
+    ptrs = [d_out[k].data_ptr() for k in range(9)] + [0] * 9
+    gpu_ctx.block_device(d_esa.data_ptr(), w, h, w, gt, d_hsg.data_ptr(), hsx, hsy, hsx, sgt,
+                         capi.MASK_DRAINED, ptrs, w, stream=torch.cuda.current_stream().cuda_stream or 1)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(0)
+    rows = sorted(set([0, 1, 11, 12, 13, 24, 25, 37, h - 38, h - 13, h - 12, h - 1] +
+                      list(rng.integers(0, h, size=40))))
+    for y in rows:
+        esa_row = d_esa[y:y + 1].cpu().numpy()
+        want = port.block_rows(esa_row, gt, hsg, sgt, tables, y0=y, y1=y + 1, h=h)[:9]
+        got = d_out[:, y:y + 1].cpu().numpy()
+        assert np.array_equal(got, want), f"row {y}"
+    # size-independent invariant: nodata placement is identical in all 9 planes of a condition
+    # for the default tables (a pixel is 255 iff its class/soil pair has no row)
+    nod = (d_out == 255)
+    assert bool((nod[0] == nod[8]).all())
