@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgcn10cuda.so")
+LIB_PATH = os.environ.get("GCN10_CUDA_LIB") or os.path.join(HERE, "libgcn10cuda.so")
 
 NVARIANTS = 9
 NPLANES = 18

@@ -35,6 +35,13 @@ constexpr int kBoxRows = 16;           // TMA box: HSG rows staged per CTA
 constexpr int kLutRecords = 256 * 8;   // (land cover, slot) -> 16-byte record
 constexpr int kLutBytes = kLutRecords * 16;
 constexpr int kSgInvalid = 5;          // soil-group slot whose record is all 255
+#ifndef GCN10_PREFETCH
+#define GCN10_PREFETCH 2
+#endif
+#ifndef GCN10_STORE_POLICY
+#define GCN10_STORE_POLICY 0
+#endif
+constexpr int kPrefetch = GCN10_PREFETCH;   // rows of land cover in flight per thread
 
 struct BlockParams {
     const uint8_t *esa;         // first row of this launch
@@ -116,7 +123,15 @@ __device__ __forceinline__ uint4 ldg_stream16(const void *p)
 
 __device__ __forceinline__ void stg_stream16(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
+#if GCN10_STORE_POLICY == 0
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#elif GCN10_STORE_POLICY == 1
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#elif GCN10_STORE_POLICY == 2
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#else
+    asm volatile("st.global.wt.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+#endif
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -193,8 +208,11 @@ __device__ __forceinline__ void transpose_store_word(const uint4 (&r)[4], uint32
     }
 }
 
+#ifndef GCN10_MIN_CTAS
+#define GCN10_MIN_CTAS 1
+#endif
 template <int NP, int G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, GCN10_MIN_CTAS)
 cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ CUtensorMap hsg_map)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -249,15 +267,32 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
 
     const uint8_t *esa_ptr = p.esa + (size_t)y_begin * p.esa_pitch + x0;
     size_t out_off = (size_t)y_begin * p.out_pitch + x0;
-    uint4 e = ldg_stream16(esa_ptr);
+    // software pipeline: the land-cover vectors (and HSG row indices) of the next kPrefetch rows
+    // are in flight while the current row is looked up and stored
+    const int32_t *rowp = p.row_idx + p.y_base + y_begin;
+    uint4 eq[kPrefetch];
+    int cq[kPrefetch];
+#pragma unroll
+    for (int s = 0; s < kPrefetch; s++) {
+        const bool in = y_begin + s < y_end;
+        eq[s] = in ? ldg_stream16(esa_ptr + (size_t)s * p.esa_pitch) : make_uint4(0, 0, 0, 0);
+        cq[s] = in ? __ldg(rowp + s) : 0;
+    }
 
     for (int y = y_begin; y < y_end; y++) {
-        // prefetch the next row's land cover while this row is looked up
-        uint4 e_next = e;
-        if (y + 1 < y_end)
-            e_next = ldg_stream16(esa_ptr + p.esa_pitch);
+        const uint4 e = eq[0];
+        const int cj = cq[0];
+#pragma unroll
+        for (int s = 0; s + 1 < kPrefetch; s++) {
+            eq[s] = eq[s + 1];
+            cq[s] = cq[s + 1];
+        }
+        if (y + kPrefetch < y_end) {
+            eq[kPrefetch - 1] = ldg_stream16(esa_ptr + (size_t)kPrefetch * p.esa_pitch);
+            cq[kPrefetch - 1] = __ldg(rowp + kPrefetch);
+        }
+        rowp++;
 
-        const int cj = __ldg(p.row_idx + p.y_base + y);
         if (cj != cj_cur) {
             // new HSG row: gather this thread's 16 soil codes (cn.c:230) and turn them into
             // LUT slots for each drainage condition (cn.c:88-111)
@@ -314,7 +349,6 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
                 stg_stream16(p.out[g * NP + k] + out_off, ow[k][0], ow[k][1], ow[k][2], ow[k][3]);
         }
 
-        e = e_next;
         esa_ptr += p.esa_pitch;
         out_off += p.out_pitch;
     }

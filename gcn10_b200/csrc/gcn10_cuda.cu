@@ -66,8 +66,8 @@ struct gcn10_ctx {
     int sm_count = 148;
     cudaStream_t streams[kMaxStreams] = {};
     int nstreams = 4;
-    int strip_rows = 512;
-    int rows_per_cta = 128;
+    int strip_rows = 2048;
+    int rows_per_cta = 0;       // 0 = auto (see auto_rows_per_cta)
     int use_tma = 1;
     EncodeTiledFn encode_tiled = nullptr;
 
@@ -162,6 +162,11 @@ void pack_lut_records(const int tables[GCN10_NVARIANTS][256][5], unsigned varian
         }
     }
 }
+
+// Rows each CTA walks.  Measured on B200 (profiles/r01_kernel_sweeps.md): short chunks keep the
+// co-resident CTAs inside a narrow band of rows and leave no tail wave; 12 rows is best for <= 9
+// planes, 16 for 18 planes; below 8 the per-CTA prologue (LUT copy, HSG box) starts to show.
+int auto_rows_per_cta(int planes) { return planes > 9 ? 16 : 12; }
 
 int popcount9(unsigned m) { return __builtin_popcount(m & 0x1FFu); }
 
@@ -309,7 +314,7 @@ int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t 
     p.hsy = hsy;
     p.lut = (const uint4 *)((const uint8_t *)c->lut.p + (size_t)lut_slot * kLutBytes);
     p.swz_shift = c->swz_shift;
-    p.rows_per_cta = c->rows_per_cta;
+    p.rows_per_cta = c->rows_per_cta > 0 ? c->rows_per_cta : auto_rows_per_cta(lp.np * lp.groups);
     p.use_tma = tma_ok;
     p.group_drained[0] = lp.drained[0];
     p.group_drained[1] = lp.drained[1];
@@ -326,7 +331,7 @@ int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t 
     int x_bytes = 0;
     if (aligned && (w & ~(kVecPx - 1)) > 0) {
         int w16 = w & ~(kVecPx - 1);
-        dim3 grid((w16 + kStripPx - 1) / kStripPx, (rows + c->rows_per_cta - 1) / c->rows_per_cta);
+        dim3 grid((w16 + kStripPx - 1) / kStripPx, (rows + p.rows_per_cta - 1) / p.rows_per_cta);
         BlockKernel k = pick_kernel(lp.np, lp.groups);
         k<<<grid, kThreads, kSmemBytes, st>>>(p, map);
         c->launches++;
@@ -459,7 +464,7 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
         return fail(GCN10_EINVAL, "NULL argument");
     if (!strcmp(key, "strip_rows") && value >= 1) c->strip_rows = (int)value;
     else if (!strcmp(key, "streams") && value >= 1 && value <= kMaxStreams) c->nstreams = (int)value;
-    else if (!strcmp(key, "rows_per_cta") && value >= 1) c->rows_per_cta = (int)value;
+    else if (!strcmp(key, "rows_per_cta") && value >= 0) c->rows_per_cta = (int)value;
     else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
     else return fail(GCN10_EINVAL, "unknown option or bad value: %s=%ld", key, value);
     return GCN10_OK;

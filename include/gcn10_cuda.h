@@ -131,7 +131,8 @@ int gcn10_cuda_last_kernel_ms(gcn10_ctx *ctx, float *ms);
 int gcn10_cuda_launch_count(gcn10_ctx *ctx, uint64_t *launches);
 
 /* Tunables: "strip_rows" (rows per pipelined strip in gcn10_cuda_block), "streams"
- * (1..8), "rows_per_cta", "tma" (0 = always use the gather fallback for HSG staging). */
+ * (1..8), "rows_per_cta" (0 = automatic), "tma" (0 = always use the gather fallback for HSG
+ * staging). */
 int gcn10_cuda_set_option(gcn10_ctx *ctx, const char *key, long value);
 
 /* Page-locked host memory for rasters, so that the strip copies run asynchronously

@@ -32,7 +32,7 @@ def test_tma_and_gather_staging_agree(tma, rows_per_cta, gpu_ctx, port, tables):
         got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
     finally:
         gpu_ctx.set_option("tma", 1)
-        gpu_ctx.set_option("rows_per_cta", 128)
+        gpu_ctx.set_option("rows_per_cta", 0)
     assert np.array_equal(got, want)
 
 
@@ -45,7 +45,7 @@ def test_strip_pipeline_shapes(strip_rows, streams, gpu_ctx, port, tables):
     try:
         got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
     finally:
-        gpu_ctx.set_option("strip_rows", 512)
+        gpu_ctx.set_option("strip_rows", 2048)
         gpu_ctx.set_option("streams", 4)
     assert np.array_equal(got, want)
 
