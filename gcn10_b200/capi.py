@@ -23,7 +23,8 @@ MASK_ALL = 0x3FFFF
 # every symbol include/gcn10_cuda.h declares
 EXPORTS = (
     "gcn10_cuda_version", "gcn10_cuda_last_error", "gcn10_cuda_device_count", "gcn10_cuda_create",
-    "gcn10_cuda_destroy", "gcn10_cuda_set_luts", "gcn10_cuda_block", "gcn10_cuda_block_device",
+    "gcn10_cuda_destroy", "gcn10_cuda_set_luts", "gcn10_cuda_block", "gcn10_cuda_block_rows",
+    "gcn10_cuda_block_device",
     "gcn10_cuda_index_maps", "gcn10_cuda_synchronize", "gcn10_cuda_last_kernel_ms",
     "gcn10_cuda_launch_count", "gcn10_cuda_set_option", "gcn10_cuda_host_alloc", "gcn10_cuda_host_free",
     "gcn10_cuda_host_register", "gcn10_cuda_host_unregister",
@@ -54,6 +55,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     blk = [_vp, _vp, C.c_int, C.c_int, C.c_size_t, _dp, _vp, C.c_int, C.c_int, C.c_size_t, _dp,
            C.c_uint, C.POINTER(_vp), C.c_size_t]
     lib.gcn10_cuda_block.argtypes = blk
+    lib.gcn10_cuda_block_rows.argtypes = blk[:4] + [C.c_int, C.c_int] + blk[4:]
     lib.gcn10_cuda_block_device.argtypes = blk + [_vp]
     lib.gcn10_cuda_index_maps.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp, _vp, _vp]
     lib.gcn10_cuda_synchronize.argtypes = [_vp]
@@ -147,6 +149,19 @@ class Context:
         self._check(self.lib.gcn10_cuda_block(
             self.h, esa.ctypes.data, w, h, esa.strides[0], _d6(gt), hsg.ctypes.data, hsx, hsy,
             hsg.strides[0], _d6(soil_gt), plane_mask, ptrs, out.strides[1]))
+        return out
+
+    def block_rows(self, esa_rows, h, row0, gt, hsg, soil_gt, plane_mask=MASK_ALL):
+        """Band call: esa_rows holds rows [row0, row0+len) of a block that is h rows tall."""
+        nrows, w = esa_rows.shape
+        hsy, hsx = hsg.shape
+        out = np.zeros((NPLANES, nrows, w), dtype=np.uint8)
+        ptrs = (_vp * NPLANES)()
+        for k in range(NPLANES):
+            ptrs[k] = out[k].ctypes.data if plane_mask & (1 << k) else None
+        self._check(self.lib.gcn10_cuda_block_rows(
+            self.h, esa_rows.ctypes.data, w, h, row0, nrows, esa_rows.strides[0], _d6(gt), hsg.ctypes.data,
+            hsx, hsy, hsg.strides[0], _d6(soil_gt), plane_mask, ptrs, out.strides[1]))
         return out
 
     def block_device(self, d_esa, w, h, esa_pitch, gt, d_hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask,

@@ -553,11 +553,23 @@ int gcn10_cuda_block(gcn10_ctx *c,
                      const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
                      unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch)
 {
+    return gcn10_cuda_block_rows(c, esa, w, h, 0, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask,
+                                 out, out_pitch);
+}
+
+int gcn10_cuda_block_rows(gcn10_ctx *c,
+                          const uint8_t *esa, int w, int h, int row0, int nrows, size_t esa_pitch,
+                          const double gt[6],
+                          const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                          unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch)
+{
     if (!c)
         return fail(GCN10_EINVAL, "NULL context");
     int rc = check_geometry(esa, w, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask, out, out_pitch);
     if (rc)
         return rc;
+    if (row0 < 0 || nrows <= 0 || row0 > h - nrows)
+        return fail(GCN10_EINVAL, "row range [%d, %d+%d) outside the block's %d rows", row0, row0, nrows, h);
     if (!c->have_lut)
         return fail(GCN10_ENOLUT, "gcn10_cuda_set_luts() has not been called");
     for (int k = 0; k < GCN10_NPLANES; k++)
@@ -592,7 +604,7 @@ int gcn10_cuda_block(gcn10_ctx *c,
     // row strips, round-robin over the streams; each stream owns one staging slot
     const size_t dpitch = round_up((size_t)w, 256);
     const int ns = c->nstreams;
-    const int strip = std::max(1, std::min(c->strip_rows, h));
+    const int strip = std::max(1, std::min(c->strip_rows, nrows));
     for (int i = 0; i < ns; i++) {
         if ((rc = ensure(c->slots[i].esa, dpitch * (size_t)strip)))
             return rc;
@@ -602,8 +614,9 @@ int gcn10_cuda_block(gcn10_ctx *c,
     }
     float kernel_ms = 0.f;
     int si = 0;
-    for (int y0 = 0; y0 < h; y0 += strip, si = (si + 1) % ns) {
-        const int rows = std::min(strip, h - y0);
+    // y0 counts rows of the caller's band: esa / out row 0 is block row `row0`
+    for (int y0 = 0; y0 < nrows; y0 += strip, si = (si + 1) % ns) {
+        const int rows = std::min(strip, nrows - y0);
         StripSlot &sl = c->slots[si];
         cudaStream_t st = c->streams[si];
         if (sl.timed) {
@@ -622,7 +635,7 @@ int gcn10_cuda_block(gcn10_ctx *c,
                 d_out[plans[i].plane_ids[j]] = (uint8_t *)sl.out.p + (size_t)k * dpitch * (size_t)strip;
         CUDA_TRY(cudaEventRecord(sl.k0, st));
         for (int i = 0; i < nplans; i++)
-            if ((rc = launch_rows(c, plans[i], i, (const uint8_t *)sl.esa.p, dpitch, w, rows, y0,
+            if ((rc = launch_rows(c, plans[i], i, (const uint8_t *)sl.esa.p, dpitch, w, rows, row0 + y0,
                                   (const uint8_t *)c->hsg.p, hsg_dpitch, hsx, hsy, map, tma_ok, d_out, dpitch, st)))
                 return rc;
         CUDA_TRY(cudaEventRecord(sl.k1, st));

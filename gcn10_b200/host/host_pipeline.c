@@ -1,0 +1,406 @@
+/* gcn10_b200/host/host_pipeline.c -- the per-block pipeline and the per-GPU block queue.
+ *
+ * gh_process_block() is this program's process_block() (/root/reference/src/cn.c:134-384): same
+ * inputs (block id -> bbox -> two raster windows), same 18 outputs with the same names, same log
+ * lines and the same two-tier error convention (recoverable: log ERROR and skip the block; fatal:
+ * exit(1) where the reference calls MPI_Abort).  What changes is the middle: instead of five CPU
+ * passes per raster (cn.c:218-290) the block is streamed band by band (1024 rows, a multiple of the
+ * 256-row GeoTIFF tiles) through gcn10_cuda_block_rows(), and while the GPU works on band i+1 the
+ * DEFLATE threads encode band i.
+ *
+ * gh_run_blocks() replaces the MPI round-robin of main.c:171: one worker thread and one gcn10_ctx
+ * per GPU, block ids popped from a shared atomic counter; the join of the workers is the barrier
+ * (main.c:187).  No data moves between workers, exactly as no data moves between ranks.
+ */
+#define _GNU_SOURCE
+#include "gcn10_host.h"
+#include "host_tiff.h"
+#include "../../include/gcn10_cuda.h"
+
+#include <errno.h>
+#include <limits.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+
+enum { BAND_ROWS = 1024, NPLANES = GCN10_NPLANES };
+
+static const char *const k_conds[2] = { "drained", "undrained" };      /* cn.c:145 */
+static const char *const k_hcs[3] = { "p", "f", "g" };                 /* cn.c:146 */
+static const char *const k_arcs[3] = { "i", "ii", "iii" };             /* cn.c:147 */
+
+typedef struct {
+    uint8_t *esa;                   /* pinned: BAND_ROWS x pitch */
+    uint8_t *planes[NPLANES];       /* pinned: BAND_ROWS x pitch each */
+    int y0, rows;
+    int state;                      /* 0 free, 1 filled (waiting for the encoder) */
+} band_buf;
+
+typedef struct worker {
+    int index;                      /* GPU / worker number: the "rank" of the log lines */
+    const gh_run_options *opt;
+    gh_blocks *blocks;
+    const int (*tables)[256][5];
+    const int *ids;
+    int n_ids;
+    atomic_int *next;               /* shared queue head */
+    atomic_int *done;               /* blocks that produced all 18 rasters */
+    gh_log *log;                    /* rank_<index>.log */
+    gh_log *log0;                   /* worker 0's log: progress lines go there (log.c:199-207) */
+    gcn10_ctx *ctx;
+    size_t pitch_cap;
+    band_buf bands[2];
+    /* encoder hand-off */
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    gh_tiffw *writers[NPLANES];
+    size_t pitch;
+    int encode_failed;
+    int encoder_quit;
+} worker;
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void fatal(worker *wk, const char *msg)
+{
+    /* the reference's MPI_Abort(MPI_COMM_WORLD, 1) tier */
+    gh_log_message(wk->log, "ERROR", msg, 1);
+    exit(1);
+}
+
+static int ensure_bands(worker *wk, size_t pitch)
+{
+    if (wk->pitch_cap >= pitch)
+        return 0;
+    for (int b = 0; b < 2; b++) {
+        gcn10_cuda_host_free(wk->bands[b].esa);
+        wk->bands[b].esa = gcn10_cuda_host_alloc(pitch * BAND_ROWS);
+        for (int k = 0; k < NPLANES; k++) {
+            gcn10_cuda_host_free(wk->bands[b].planes[k]);
+            wk->bands[b].planes[k] = gcn10_cuda_host_alloc(pitch * BAND_ROWS);
+            if (!wk->bands[b].planes[k])
+                return -1;
+        }
+        if (!wk->bands[b].esa)
+            return -1;
+        wk->bands[b].state = 0;
+    }
+    wk->pitch_cap = pitch;
+    return 0;
+}
+
+/* encoder thread: compresses and appends filled bands in order */
+static void *encoder_main(void *arg)
+{
+    worker *wk = arg;
+    int turn = 0;
+    for (;;) {
+        pthread_mutex_lock(&wk->mu);
+        while (wk->bands[turn].state != 1 && !wk->encoder_quit)
+            pthread_cond_wait(&wk->cv, &wk->mu);
+        if (wk->bands[turn].state != 1 && wk->encoder_quit) {
+            pthread_mutex_unlock(&wk->mu);
+            return NULL;
+        }
+        pthread_mutex_unlock(&wk->mu);
+        band_buf *bb = &wk->bands[turn];
+        for (int k = 0; k < NPLANES; k++)
+            if (gh_tiffw_write_rows(wk->writers[k], bb->planes[k], wk->pitch, bb->y0, bb->rows, wk->opt->io_threads))
+                wk->encode_failed = 1;
+        pthread_mutex_lock(&wk->mu);
+        bb->state = 0;
+        pthread_cond_broadcast(&wk->cv);
+        pthread_mutex_unlock(&wk->mu);
+        turn ^= 1;
+    }
+}
+
+/* cn.c:293-360: "<outdir>/cn_<hc>_<arc>_<id>.tif", or "..._<id>_.tif" when the file exists and
+ * overwrite is off */
+static void output_path(const worker *wk, int cond, int hi, int ai, int block_id, char *path, size_t n)
+{
+    const char *root = (wk->opt->out_root && *wk->opt->out_root) ? wk->opt->out_root : ".";
+    snprintf(path, n, "%s/cn_rasters_%s/cn_%s_%s_%d.tif", root, k_conds[cond], k_hcs[hi], k_arcs[ai], block_id);
+    if (!wk->opt->overwrite) {
+        FILE *f = fopen(path, "r");
+        if (f) {
+            fclose(f);
+            snprintf(path, n, "%s/cn_rasters_%s/cn_%s_%s_%d_.tif", root, k_conds[cond], k_hcs[hi], k_arcs[ai],
+                     block_id);
+        }
+    }
+}
+
+static int gh_process_block(worker *wk, int block_id, int total_blocks)
+{
+    char msg[8192], err[GH_ERRLEN] = "";
+    double bbox[4];
+    double t_start = now_s();
+
+    /* block geometry (cn.c:155-184) */
+    if (gh_blocks_bbox(wk->blocks, block_id, bbox)) {
+        snprintf(msg, sizeof msg, "block %d not found", block_id);                  /* cn.c:173 */
+        gh_log_message(wk->log, "ERROR", msg, 1);
+        return -1;
+    }
+
+    /* land cover window (cn.c:187 -> raster.c:106-189) */
+    gh_tiff *esa_ds = NULL, *hsg_ds = NULL;
+    gh_window we, wh;
+    int rw, rh;
+    double t[6];
+    if (gh_tiff_open(wk->opt->cfg.esa_data_path, &esa_ds, err, sizeof err)) {
+        gh_log_message(wk->log, "ERROR", err, 1);
+        goto esa_failed;
+    }
+    gh_tiff_size(esa_ds, &rw, &rh);
+    gh_tiff_geotransform(esa_ds, t);
+    if (gh_raster_window(rw, rh, t, bbox, &we)) {
+        snprintf(msg, sizeof msg, "invalid raster bounds for %s", wk->opt->cfg.esa_data_path);   /* raster.c:143 */
+        gh_log_message(wk->log, "ERROR", msg, 1);
+        goto esa_failed;
+    }
+
+    /* soil window (cn.c:195-196) */
+    if (gh_tiff_open(wk->opt->cfg.hysogs_data_path, &hsg_ds, err, sizeof err)) {
+        gh_log_message(wk->log, "ERROR", err, 1);
+        goto hsg_failed;
+    }
+    gh_tiff_size(hsg_ds, &rw, &rh);
+    gh_tiff_geotransform(hsg_ds, t);
+    if (gh_raster_window(rw, rh, t, bbox, &wh)) {
+        snprintf(msg, sizeof msg, "invalid raster bounds for %s", wk->opt->cfg.hysogs_data_path);
+        gh_log_message(wk->log, "ERROR", msg, 1);
+        goto hsg_failed;
+    }
+    uint8_t *hsg = malloc((size_t)wh.xcount * (size_t)wh.ycount);
+    if (!hsg)
+        fatal(wk, "out of memory for raster");                                      /* raster.c:171 */
+    if (gh_tiff_read_window(hsg_ds, wh.xoff, wh.yoff, wh.xcount, wh.ycount, hsg, (size_t)wh.xcount,
+                            wk->opt->io_threads, err, sizeof err)) {
+        gh_log_message(wk->log, "ERROR", err, 1);
+        free(hsg);
+        goto hsg_failed;
+    }
+    gh_tiff_close(hsg_ds);
+    hsg_ds = NULL;
+
+    const int w = we.xcount, h = we.ycount;
+    const size_t pitch = ((size_t)w + 255) / 256 * 256;
+    if (ensure_bands(wk, pitch)) {
+        snprintf(msg, sizeof msg, "pinned allocation failed for block %d: %s", block_id, gcn10_cuda_last_error());
+        fatal(wk, msg);
+    }
+    wk->pitch = pitch;
+
+    /* output directories and files (cn.c:236-256, 293-360) */
+    const char *root = (wk->opt->out_root && *wk->opt->out_root) ? wk->opt->out_root : ".";
+    char paths[NPLANES][PATH_MAX];
+    for (int c = 0; c < 2; c++) {
+        char outdir[PATH_MAX];
+        snprintf(outdir, sizeof outdir, "%s/cn_rasters_%s", root, k_conds[c]);
+        if (mkdir(outdir, 0755) != 0 && errno != EEXIST) {
+            snprintf(msg, sizeof msg, "failed to create output directory %s", outdir);   /* cn.c:250 */
+            fatal(wk, msg);
+        }
+    }
+    int opened = 0;
+    for (int k = 0; k < NPLANES; k++) {
+        output_path(wk, k / 9, (k % 9) / 3, k % 3, block_id, paths[k], sizeof paths[k]);
+        if (gh_tiffw_open(paths[k], w, h, we.gt, &wk->writers[k], err, sizeof err)) {
+            gh_log_message(wk->log, "ERROR", err, 1);                               /* raster.c:220-223 */
+            break;
+        }
+        opened++;
+    }
+    if (opened < NPLANES) {
+        for (int k = 0; k < opened; k++)
+            gh_tiffw_abort(wk->writers[k]);
+        free(hsg);
+        gh_tiff_close(esa_ds);
+        return -1;
+    }
+
+    /* band loop: decode -> GPU -> (encoder thread) DEFLATE + append */
+    wk->encode_failed = 0;
+    wk->encoder_quit = 0;
+    wk->bands[0].state = wk->bands[1].state = 0;
+    pthread_t enc;
+    if (pthread_create(&enc, NULL, encoder_main, wk) != 0)
+        fatal(wk, "cannot start the encoder thread");
+    int turn = 0, failed = 0;
+    double t_read = 0, t_gpu = 0;
+    for (int y0 = 0; y0 < h && !failed; y0 += BAND_ROWS, turn ^= 1) {
+        band_buf *bb = &wk->bands[turn];
+        int rows = h - y0 < BAND_ROWS ? h - y0 : BAND_ROWS;
+        pthread_mutex_lock(&wk->mu);
+        while (bb->state != 0)
+            pthread_cond_wait(&wk->cv, &wk->mu);
+        pthread_mutex_unlock(&wk->mu);
+        double t0 = now_s();
+        if (gh_tiff_read_window(esa_ds, we.xoff, we.yoff + y0, w, rows, bb->esa, pitch, wk->opt->io_threads, err,
+                                sizeof err)) {
+            gh_log_message(wk->log, "ERROR", err, 1);                               /* raster.c:182-186 */
+            failed = 1;
+            break;
+        }
+        double t1 = now_s();
+        int rc = gcn10_cuda_block_rows(wk->ctx, bb->esa, w, h, y0, rows, pitch, we.gt, hsg, wh.xcount, wh.ycount,
+                                       (size_t)wh.xcount, wh.gt, GCN10_MASK_ALL, bb->planes, pitch);
+        if (rc) {
+            snprintf(msg, sizeof msg, "cuda failure on block %d: %s", block_id, gcn10_cuda_last_error());
+            fatal(wk, msg);                         /* CUDA errors are the fatal tier; there is no CPU path */
+        }
+        t_read += t1 - t0;
+        t_gpu += now_s() - t1;
+        bb->y0 = y0;
+        bb->rows = rows;
+        pthread_mutex_lock(&wk->mu);
+        bb->state = 1;
+        pthread_cond_broadcast(&wk->cv);
+        pthread_mutex_unlock(&wk->mu);
+    }
+    pthread_mutex_lock(&wk->mu);
+    wk->encoder_quit = 1;
+    pthread_cond_broadcast(&wk->cv);
+    pthread_mutex_unlock(&wk->mu);
+    pthread_join(enc, NULL);
+    free(hsg);
+    gh_tiff_close(esa_ds);
+
+    if (failed) {
+        for (int k = 0; k < NPLANES; k++)
+            gh_tiffw_abort(wk->writers[k]);
+        snprintf(msg, sizeof msg, "esa load failed for block %d", block_id);        /* cn.c:189 */
+        gh_log_message(wk->log, "ERROR", msg, 1);
+        return -1;
+    }
+    int ok = 1;
+    for (int k = 0; k < NPLANES; k++) {
+        if (gh_tiffw_close(wk->writers[k]) || wk->encode_failed) {
+            snprintf(msg, sizeof msg, "write error 3 on %s", paths[k]);             /* raster.c:221 */
+            gh_log_message(wk->log, "ERROR", msg, 1);
+            ok = 0;
+        }
+        /* the reference logs each raster and reports it to rank 0 whether or not the write worked
+         * (cn.c:363-373) */
+        snprintf(msg, sizeof msg, "completed condition for %d: %s/%s/%s", block_id, k_conds[k / 9],
+                 k_hcs[(k % 9) / 3], k_arcs[k % 3]);                                /* cn.c:366-369 */
+        gh_log_message(wk->log, "INFO", msg, 0);
+        snprintf(msg, sizeof msg, "progress: completed block %d / total %d", block_id, total_blocks);
+        gh_log_message(wk->log0, "INFO", msg, 0);                                   /* log.c:199-207 */
+    }
+    double dt = now_s() - t_start;
+    snprintf(msg, sizeof msg,
+             "block %d: %d x %d px, 18 rasters in %.2f s (%.1f Mpx/s; decode %.2f s, gpu+copies %.2f s)", block_id,
+             w, h, dt, (double)w * h / dt / 1e6, t_read, t_gpu);
+    gh_log_message(wk->log, "INFO", msg, 0);
+    return ok ? 0 : -1;
+
+hsg_failed:
+    gh_tiff_close(hsg_ds);
+    gh_tiff_close(esa_ds);
+    snprintf(msg, sizeof msg, "hysogs load failed for block %d", block_id);         /* cn.c:198-199 */
+    gh_log_message(wk->log, "ERROR", msg, 1);
+    return -1;
+esa_failed:
+    gh_tiff_close(esa_ds);
+    snprintf(msg, sizeof msg, "esa load failed for block %d", block_id);            /* cn.c:189 */
+    gh_log_message(wk->log, "ERROR", msg, 1);
+    return -1;
+}
+
+static void *worker_main(void *arg)
+{
+    worker *wk = arg;
+    char msg[256];
+    if (gcn10_cuda_create(wk->index, &wk->ctx) || gcn10_cuda_set_luts(wk->ctx, wk->tables)) {
+        snprintf(msg, sizeof msg, "cannot initialise GPU %d: %s", wk->index, gcn10_cuda_last_error());
+        fatal(wk, msg);
+    }
+    pthread_mutex_init(&wk->mu, NULL);
+    pthread_cond_init(&wk->cv, NULL);
+    for (;;) {
+        int i = atomic_fetch_add(wk->next, 1);                  /* replaces i = rank; i += size (main.c:171) */
+        if (i >= wk->n_ids)
+            break;
+        snprintf(msg, sizeof msg, "processing block %d", wk->ids[i]);              /* main.c:172-173 */
+        gh_log_message(wk->log, "INFO", msg, 1);
+        if (gh_process_block(wk, wk->ids[i], wk->n_ids) == 0)
+            atomic_fetch_add(wk->done, 1);
+    }
+    for (int b = 0; b < 2; b++) {
+        gcn10_cuda_host_free(wk->bands[b].esa);
+        for (int k = 0; k < NPLANES; k++)
+            gcn10_cuda_host_free(wk->bands[b].planes[k]);
+    }
+    gcn10_cuda_destroy(wk->ctx);
+    pthread_cond_destroy(&wk->cv);
+    pthread_mutex_destroy(&wk->mu);
+    return NULL;
+}
+
+int gh_run_blocks(const gh_run_options *opt, const int *block_ids, int n_blocks)
+{
+    char err[GH_ERRLEN] = "", msg[1024];
+    static int tables[9][256][5];
+
+    int ngpu = gcn10_cuda_device_count();
+    if (ngpu <= 0) {
+        fprintf(stderr, "gcn10: no usable CUDA device (%s); there is no CPU fallback\n", gcn10_cuda_last_error());
+        exit(1);
+    }
+    int nworkers = opt->n_gpus > 0 && opt->n_gpus < ngpu ? opt->n_gpus : ngpu;
+    if (nworkers > n_blocks)
+        nworkers = n_blocks > 0 ? n_blocks : 1;
+
+    gh_log *log0 = gh_log_open(opt->cfg.log_dir, 0);
+    /* lookup tables once per run (the reference re-reads the CSV 18 times per block, cn.c:261) */
+    if (gh_load_lookup_tables(opt->cfg.lookup_table_path, tables, err, sizeof err)) {
+        gh_log_message(log0, "ERROR", err, 1);                  /* fatal in the reference: cn.c:25,32,47 */
+        exit(1);
+    }
+    gh_blocks *blocks = NULL;
+    if (gh_blocks_open(opt->cfg.blocks_shp_path, &blocks, err, sizeof err)) {
+        gh_log_message(log0, "ERROR", err, 1);
+        exit(1);
+    }
+    snprintf(msg, sizeof msg, "processing %d blocks on %d gpu workers", n_blocks, nworkers);
+    gh_log_message(log0, "INFO", msg, 1);
+
+    atomic_int next = 0, done = 0;
+    worker *wks = calloc((size_t)nworkers, sizeof *wks);
+    pthread_t *th = calloc((size_t)nworkers, sizeof *th);
+    for (int i = 0; i < nworkers; i++) {
+        wks[i].index = i;
+        wks[i].opt = opt;
+        wks[i].blocks = blocks;
+        wks[i].tables = tables;
+        wks[i].ids = block_ids;
+        wks[i].n_ids = n_blocks;
+        wks[i].next = &next;
+        wks[i].done = &done;
+        wks[i].log0 = log0;
+        wks[i].log = i == 0 ? log0 : gh_log_open(opt->cfg.log_dir, i);
+        pthread_create(&th[i], NULL, worker_main, &wks[i]);
+    }
+    for (int i = 0; i < nworkers; i++)
+        pthread_join(th[i], NULL);              /* the barrier of main.c:187 */
+    snprintf(msg, sizeof msg, "processed %d blocks on %d ranks", n_blocks, nworkers);      /* main.c:191-193 */
+    gh_log_message(log0, "INFO", msg, 1);
+    for (int i = nworkers - 1; i >= 0; i--)
+        gh_log_close(wks[i].log);
+    gh_blocks_close(blocks);
+    free(wks);
+    free(th);
+    return atomic_load(&done);
+}

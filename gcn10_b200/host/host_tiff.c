@@ -1,0 +1,724 @@
+/* gcn10_b200/host/host_tiff.c -- minimal GeoTIFF reader / writer for the gcn10 host program.
+ *
+ * Stands in for the two GDAL calls on either side of the hot path, neither of which is available
+ * in this image (no libgdal):
+ *   load_raster()  /root/reference/src/raster.c:106-189  -> gh_tiff_open + gh_tiff_read_window
+ *   save_raster()  /root/reference/src/raster.c:192-227  -> gh_tiffw_* / gh_tiff_write
+ *
+ * Reader: single band, 8 bit, strips or tiles, classic TIFF or BigTIFF, either byte order,
+ * compression none (1), LZW (5), DEFLATE (8 / 32946), predictor 1 or 2.
+ * Writer: what GDAL's GTiff driver produces for COMPRESS=DEFLATE, TILED=YES with defaults
+ * (raster.c:206-207): 256 x 256 tiles, zlib level 6, no predictor, PixelIsArea, EPSG:4326 keys,
+ * no NoData tag.  Tiles are compressed in parallel (pthreads) and appended band by band, so a
+ * 36000 x 36000 plane never has to be resident in full.
+ */
+#define _GNU_SOURCE
+#include "gcn10_host.h"
+#include "host_tiff.h"
+
+#include <errno.h>
+#include <pthread.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <zlib.h>
+
+static void set_err(char *err, size_t errlen, const char *fmt, ...)
+{
+    if (!err || !errlen)
+        return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, errlen, fmt, ap);
+    va_end(ap);
+}
+
+/* ------------------------------------------------------------------------------- parallel for */
+
+typedef void (*job_fn)(void *arg, int index);
+
+typedef struct {
+    job_fn fn;
+    void *arg;
+    int n;
+    int next;
+    pthread_mutex_t mu;
+} job_pool;
+
+static void *job_worker(void *p)
+{
+    job_pool *jp = p;
+    for (;;) {
+        pthread_mutex_lock(&jp->mu);
+        int i = jp->next++;
+        pthread_mutex_unlock(&jp->mu);
+        if (i >= jp->n)
+            return NULL;
+        jp->fn(jp->arg, i);
+    }
+}
+
+static void parallel_for(int n, int threads, job_fn fn, void *arg)
+{
+    if (threads > n)
+        threads = n;
+    if (threads <= 1) {
+        for (int i = 0; i < n; i++)
+            fn(arg, i);
+        return;
+    }
+    job_pool jp = { fn, arg, n, 0, PTHREAD_MUTEX_INITIALIZER };
+    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)threads);
+    int started = 0;
+    for (int t = 0; t < threads - 1; t++)
+        if (pthread_create(&th[started], NULL, job_worker, &jp) == 0)
+            started++;
+    job_worker(&jp);
+    for (int t = 0; t < started; t++)
+        pthread_join(th[t], NULL);
+    free(th);
+}
+
+/* ------------------------------------------------------------------------------------- reader */
+
+struct gh_tiff {
+    int fd;
+    int big, swap;
+    int w, h;
+    int compression, predictor;
+    int tiled, tw, th;          /* tile (or strip: tw = w, th = rows per strip) geometry */
+    int tiles_x, tiles_y;
+    uint64_t *offsets, *counts;
+    uint64_t nchunks;
+    int has_gt;
+    double gt[6];
+};
+
+static uint16_t rd16(const gh_tiff *t, const unsigned char *p)
+{
+    return t->swap ? (uint16_t)(p[0] << 8 | p[1]) : (uint16_t)(p[1] << 8 | p[0]);
+}
+
+static uint32_t rd32(const gh_tiff *t, const unsigned char *p)
+{
+    return t->swap ? ((uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3])
+                   : ((uint32_t)p[3] << 24 | (uint32_t)p[2] << 16 | (uint32_t)p[1] << 8 | p[0]);
+}
+
+static uint64_t rd64(const gh_tiff *t, const unsigned char *p)
+{
+    uint64_t v = 0;
+    if (t->swap)
+        for (int i = 0; i < 8; i++) v = v << 8 | p[i];
+    else
+        for (int i = 7; i >= 0; i--) v = v << 8 | p[i];
+    return v;
+}
+
+static int pread_all(int fd, void *buf, size_t n, uint64_t off)
+{
+    unsigned char *p = buf;
+    while (n) {
+        ssize_t r = pread(fd, p, n, (off_t)off);
+        if (r <= 0)
+            return -1;
+        p += r;
+        n -= (size_t)r;
+        off += (uint64_t)r;
+    }
+    return 0;
+}
+
+static size_t type_size(int type)
+{
+    switch (type) {
+    case 1: case 2: case 6: case 7: return 1;
+    case 3: case 8: return 2;
+    case 4: case 9: case 11: case 13: return 4;
+    case 5: case 10: case 12: case 16: case 17: case 18: return 8;
+    }
+    return 0;
+}
+
+/* Fetches the values of one IFD entry as doubles or uint64 (whichever array is non-NULL). */
+static int entry_values(gh_tiff *t, int type, uint64_t count, const unsigned char *valfield, size_t valfield_len,
+                        uint64_t *u, double *d, uint64_t max)
+{
+    size_t ts = type_size(type);
+    if (!ts || count == 0)
+        return -1;
+    const int is_inline = ts * (size_t)count <= valfield_len;    /* decided by the stored count */
+    if (count > max)
+        count = max;
+    size_t bytes = ts * (size_t)count;
+    unsigned char *buf = malloc(bytes);
+    if (!buf)
+        return -1;
+    if (is_inline) {
+        memcpy(buf, valfield, bytes);
+    }
+    else {
+        uint64_t off = t->big ? rd64(t, valfield) : rd32(t, valfield);
+        if (pread_all(t->fd, buf, bytes, off)) {
+            free(buf);
+            return -1;
+        }
+    }
+    for (uint64_t i = 0; i < count; i++) {
+        const unsigned char *p = buf + ts * i;
+        uint64_t uv = 0;
+        double dv = 0;
+        switch (type) {
+        case 1: case 7: uv = p[0]; dv = (double)uv; break;
+        case 3: uv = rd16(t, p); dv = (double)uv; break;
+        case 4: case 13: uv = rd32(t, p); dv = (double)uv; break;
+        case 16: case 18: uv = rd64(t, p); dv = (double)uv; break;
+        case 12: { uint64_t b = rd64(t, p); memcpy(&dv, &b, 8); uv = (uint64_t)dv; break; }
+        case 11: { uint32_t b = rd32(t, p); float f; memcpy(&f, &b, 4); dv = f; uv = (uint64_t)dv; break; }
+        default: free(buf); return -1;
+        }
+        if (u) u[i] = uv;
+        if (d) d[i] = dv;
+    }
+    free(buf);
+    return 0;
+}
+
+int gh_tiff_open(const char *path, gh_tiff **out, char *err, size_t errlen)
+{
+    *out = NULL;
+    if (err && errlen)
+        err[0] = '\0';
+    gh_tiff *t = calloc(1, sizeof *t);
+    if (!t)
+        return -1;
+    t->fd = open(path, O_RDONLY);
+    unsigned char hdr[16];
+    if (t->fd < 0 || pread_all(t->fd, hdr, 8, 0)) {
+        set_err(err, errlen, "gdal open failed: %s", path);                 /* raster.c:121 */
+        goto fail;
+    }
+    if (hdr[0] == 'I' && hdr[1] == 'I') t->swap = 0;
+    else if (hdr[0] == 'M' && hdr[1] == 'M') t->swap = 1;
+    else { set_err(err, errlen, "gdal open failed: %s (not a TIFF)", path); goto fail; }
+    uint16_t magic = rd16(t, hdr + 2);
+    uint64_t ifd;
+    if (magic == 42) {
+        ifd = rd32(t, hdr + 4);
+    }
+    else if (magic == 43) {
+        t->big = 1;
+        if (pread_all(t->fd, hdr, 16, 0)) goto fail;
+        ifd = rd64(t, hdr + 8);
+    }
+    else { set_err(err, errlen, "gdal open failed: %s (bad TIFF magic %u)", path, magic); goto fail; }
+
+    unsigned char nb[8];
+    if (pread_all(t->fd, nb, t->big ? 8 : 2, ifd)) goto fail;
+    uint64_t nent = t->big ? rd64(t, nb) : rd16(t, nb);
+    size_t esz = t->big ? 20 : 12;
+    unsigned char *ents = malloc(esz * (size_t)nent);
+    if (!ents || pread_all(t->fd, ents, esz * (size_t)nent, ifd + (t->big ? 8 : 2))) { free(ents); goto fail; }
+
+    int bits = 1, spp = 1, rows_per_strip = 0;
+    uint64_t off_tag_count = 0;
+    const unsigned char *off_ent = NULL, *cnt_ent = NULL;
+    int off_type = 0, cnt_type = 0;
+    double scale[3] = { 0 }, tie[6] = { 0 }, xf[16] = { 0 };
+    int have_scale = 0, have_tie = 0, have_xf = 0;
+    t->compression = 1;
+    t->predictor = 1;
+    for (uint64_t i = 0; i < nent; i++) {
+        const unsigned char *e = ents + esz * i;
+        int tag = rd16(t, e), type = rd16(t, e + 2);
+        uint64_t count = t->big ? rd64(t, e + 4) : rd32(t, e + 4);
+        const unsigned char *val = e + (t->big ? 12 : 8);
+        size_t vlen = t->big ? 8 : 4;
+        uint64_t u[1] = { 0 };
+        switch (tag) {
+        case 256: entry_values(t, type, count, val, vlen, u, NULL, 1); t->w = (int)u[0]; break;
+        case 257: entry_values(t, type, count, val, vlen, u, NULL, 1); t->h = (int)u[0]; break;
+        case 258: entry_values(t, type, count, val, vlen, u, NULL, 1); bits = (int)u[0]; break;
+        case 259: entry_values(t, type, count, val, vlen, u, NULL, 1); t->compression = (int)u[0]; break;
+        case 277: entry_values(t, type, count, val, vlen, u, NULL, 1); spp = (int)u[0]; break;
+        case 278: entry_values(t, type, count, val, vlen, u, NULL, 1); rows_per_strip = (int)(u[0] > 0x7fffffff ? 0x7fffffff : u[0]); break;
+        case 317: entry_values(t, type, count, val, vlen, u, NULL, 1); t->predictor = (int)u[0]; break;
+        case 322: entry_values(t, type, count, val, vlen, u, NULL, 1); t->tw = (int)u[0]; t->tiled = 1; break;
+        case 323: entry_values(t, type, count, val, vlen, u, NULL, 1); t->th = (int)u[0]; t->tiled = 1; break;
+        case 273: case 324: off_ent = e; off_type = type; off_tag_count = count; break;
+        case 279: case 325: cnt_ent = e; cnt_type = type; break;
+        case 33550: have_scale = entry_values(t, type, count, val, vlen, NULL, scale, 3) == 0 && count >= 2; break;
+        case 33922: have_tie = entry_values(t, type, count, val, vlen, NULL, tie, 6) == 0 && count >= 6; break;
+        case 34264: have_xf = entry_values(t, type, count, val, vlen, NULL, xf, 16) == 0 && count >= 16; break;
+        default: break;
+        }
+    }
+    if (t->w <= 0 || t->h <= 0 || bits != 8 || spp != 1 || !off_ent || !cnt_ent) {
+        set_err(err, errlen, "gdal open failed: %s (need a single-band 8-bit raster; got %d bits x %d samples)",
+                path, bits, spp);
+        free(ents);
+        goto fail;
+    }
+    if (t->compression != 1 && t->compression != 5 && t->compression != 8 && t->compression != 32946) {
+        set_err(err, errlen, "gdal open failed: %s (unsupported TIFF compression %d)", path, t->compression);
+        free(ents);
+        goto fail;
+    }
+    if (!t->tiled) {
+        t->tw = t->w;
+        t->th = (rows_per_strip <= 0 || rows_per_strip > t->h) ? t->h : rows_per_strip;
+    }
+    t->tiles_x = (t->w + t->tw - 1) / t->tw;
+    t->tiles_y = (t->h + t->th - 1) / t->th;
+    t->nchunks = (uint64_t)t->tiles_x * (uint64_t)t->tiles_y;
+    if (off_tag_count < t->nchunks) {
+        set_err(err, errlen, "gdal open failed: %s (offset table shorter than the tile grid)", path);
+        free(ents);
+        goto fail;
+    }
+    t->offsets = malloc(sizeof(uint64_t) * t->nchunks);
+    t->counts = malloc(sizeof(uint64_t) * t->nchunks);
+    size_t vlen = t->big ? 8 : 4;
+    if (!t->offsets || !t->counts ||
+        entry_values(t, off_type, off_tag_count, off_ent + (t->big ? 12 : 8), vlen, t->offsets, NULL, t->nchunks) ||
+        entry_values(t, cnt_type, off_tag_count, cnt_ent + (t->big ? 12 : 8), vlen, t->counts, NULL, t->nchunks)) {
+        set_err(err, errlen, "gdal open failed: %s (cannot read the tile tables)", path);
+        free(ents);
+        goto fail;
+    }
+    free(ents);
+    if (have_scale && have_tie) {
+        /* PixelIsArea north-up: origin = tiepoint world coords minus tiepoint raster coords * scale */
+        t->gt[1] = scale[0];
+        t->gt[5] = -scale[1];
+        t->gt[0] = tie[3] - tie[0] * scale[0];
+        t->gt[3] = tie[4] + tie[1] * scale[1];
+        t->has_gt = 1;
+    }
+    else if (have_xf) {
+        t->gt[0] = xf[3]; t->gt[1] = xf[0]; t->gt[2] = xf[1];
+        t->gt[3] = xf[7]; t->gt[4] = xf[4]; t->gt[5] = xf[5];
+        t->has_gt = 1;
+    }
+    else {
+        t->gt[1] = 1.0;         /* GDAL's default for an ungeoreferenced raster */
+        t->gt[5] = 1.0;
+    }
+    *out = t;
+    return 0;
+fail:
+    if (err && !*err)
+        set_err(err, errlen, "gdal open failed: %s", path);
+    gh_tiff_close(t);
+    return -1;
+}
+
+int gh_tiff_size(const gh_tiff *t, int *w, int *h) { *w = t->w; *h = t->h; return 0; }
+int gh_tiff_geotransform(const gh_tiff *t, double gt[6]) { memcpy(gt, t->gt, sizeof t->gt); return t->has_gt ? 0 : 1; }
+
+void gh_tiff_close(gh_tiff *t)
+{
+    if (!t)
+        return;
+    if (t->fd >= 0)
+        close(t->fd);
+    free(t->offsets);
+    free(t->counts);
+    free(t);
+}
+
+/* TIFF LZW: MSB-first variable width codes (9..12 bits), 256 = clear, 257 = end of information,
+ * width grows one code early ("early change"). */
+static int lzw_decode(const unsigned char *src, size_t n, unsigned char *dst, size_t cap)
+{
+    enum { CLEAR = 256, EOI = 257, FIRST = 258, MAXC = 4096 };
+    uint16_t *prefix = malloc(sizeof(uint16_t) * MAXC);
+    unsigned char *suffix = malloc(MAXC), *first = malloc(MAXC);
+    uint16_t *length = malloc(sizeof(uint16_t) * MAXC);
+    if (!prefix || !suffix || !first || !length) { free(prefix); free(suffix); free(first); free(length); return -1; }
+    for (int i = 0; i < 256; i++) { prefix[i] = 0xFFFF; suffix[i] = first[i] = (unsigned char)i; length[i] = 1; }
+    size_t out = 0, bitpos = 0, nbits = n * 8;
+    int width = 9, next = FIRST, prev = -1, rc = 0;
+    while (bitpos + (size_t)width <= nbits) {
+        uint32_t code = 0;
+        for (int b = 0; b < width; b++) {
+            size_t bp = bitpos + (size_t)b;
+            code = code << 1 | ((src[bp >> 3] >> (7 - (bp & 7))) & 1u);
+        }
+        bitpos += (size_t)width;
+        if (code == EOI)
+            break;
+        if (code == CLEAR) {
+            width = 9;
+            next = FIRST;
+            prev = -1;
+            continue;
+        }
+        int cur = (int)code;
+        if (prev < 0) {
+            if (cur >= 256) { rc = -1; break; }
+            if (out < cap) dst[out] = (unsigned char)cur;
+            out++;
+            prev = cur;
+            continue;
+        }
+        int emit;
+        if (cur < next) {
+            emit = cur;
+        }
+        else if (cur == next) {
+            emit = -1;          /* KwKwK: prev string + its own first byte */
+        }
+        else { rc = -1; break; }
+        /* add table entry prev + first(emit string) */
+        unsigned char fb = emit >= 0 ? first[emit] : first[prev];
+        if (next < MAXC) {
+            prefix[next] = (uint16_t)prev;
+            suffix[next] = fb;
+            first[next] = first[prev];
+            length[next] = (uint16_t)(length[prev] + 1);
+            next++;
+        }
+        int s = emit >= 0 ? emit : next - 1;
+        size_t len = length[s];
+        if (out + len <= cap) {
+            size_t pos = out + len;
+            int c = s;
+            while (c != 0xFFFF && pos > out) {
+                dst[--pos] = suffix[c];
+                c = prefix[c];
+            }
+        }
+        out += len;
+        prev = cur;
+        if (next + 1 >= (1 << width) && width < 12)
+            width++;
+    }
+    free(prefix); free(suffix); free(first); free(length);
+    (void)out;
+    return rc;
+}
+
+typedef struct {
+    gh_tiff *t;
+    int xoff, yoff, xcount, ycount;
+    uint8_t *dst;
+    size_t pitch;
+    int tx0, ty0, ntx, nty;
+    int failed;
+} read_job;
+
+static void read_chunk(void *arg, int index)
+{
+    read_job *j = arg;
+    gh_tiff *t = j->t;
+    int tx = j->tx0 + index % j->ntx, ty = j->ty0 + index / j->ntx;
+    uint64_t ci = (uint64_t)ty * (uint64_t)t->tiles_x + (uint64_t)tx;
+    int rows = t->th, cols = t->tw;
+    if (!t->tiled && (ty + 1) * t->th > t->h)
+        rows = t->h - ty * t->th;           /* the last strip may be short */
+    size_t raw = (size_t)rows * (size_t)cols;
+    unsigned char *buf = malloc(raw ? raw : 1);
+    unsigned char *comp = NULL;
+    if (!buf) { j->failed = 1; return; }
+    uint64_t n = t->counts[ci];
+    if (n == 0) {
+        memset(buf, 0, raw);                /* sparse tile: GDAL serves zeros */
+    }
+    else if (t->compression == 1) {
+        size_t take = n < raw ? (size_t)n : raw;
+        if (pread_all(t->fd, buf, take, t->offsets[ci])) j->failed = 1;
+        if (take < raw) memset(buf + take, 0, raw - take);
+    }
+    else {
+        comp = malloc((size_t)n);
+        if (!comp || pread_all(t->fd, comp, (size_t)n, t->offsets[ci])) {
+            j->failed = 1;
+        }
+        else if (t->compression == 5) {
+            memset(buf, 0, raw);
+            if (lzw_decode(comp, (size_t)n, buf, raw)) j->failed = 1;
+        }
+        else {
+            uLongf dl = (uLongf)raw;
+            int zr = uncompress(buf, &dl, comp, (uLong)n);
+            if (zr != Z_OK && zr != Z_BUF_ERROR) j->failed = 1;
+            if (dl < raw) memset(buf + dl, 0, raw - dl);
+        }
+    }
+    free(comp);
+    if (t->predictor == 2) {
+        for (int r = 0; r < rows; r++) {
+            unsigned char *p = buf + (size_t)r * cols;
+            for (int c = 1; c < cols; c++)
+                p[c] = (unsigned char)(p[c] + p[c - 1]);
+        }
+    }
+    /* copy the intersection with the window */
+    int cx0 = tx * t->tw, cy0 = ty * t->th;
+    int x_lo = cx0 > j->xoff ? cx0 : j->xoff, x_hi = cx0 + cols < j->xoff + j->xcount ? cx0 + cols : j->xoff + j->xcount;
+    int y_lo = cy0 > j->yoff ? cy0 : j->yoff, y_hi = cy0 + rows < j->yoff + j->ycount ? cy0 + rows : j->yoff + j->ycount;
+    for (int y = y_lo; y < y_hi; y++)
+        memcpy(j->dst + (size_t)(y - j->yoff) * j->pitch + (size_t)(x_lo - j->xoff),
+               buf + (size_t)(y - cy0) * cols + (size_t)(x_lo - cx0), (size_t)(x_hi - x_lo));
+    free(buf);
+}
+
+int gh_tiff_read_window(gh_tiff *t, int xoff, int yoff, int xcount, int ycount, uint8_t *dst, size_t pitch,
+                        int threads, char *err, size_t errlen)
+{
+    if (xoff < 0 || yoff < 0 || xcount <= 0 || ycount <= 0 || xoff + xcount > t->w || yoff + ycount > t->h ||
+        pitch < (size_t)xcount) {
+        set_err(err, errlen, "gdalrasterio error 3 (window %d,%d %dx%d outside %dx%d)", xoff, yoff, xcount, ycount,
+                t->w, t->h);
+        return -1;
+    }
+    read_job j = { t, xoff, yoff, xcount, ycount, dst, pitch, 0, 0, 0, 0, 0 };
+    j.tx0 = xoff / t->tw;
+    j.ty0 = yoff / t->th;
+    j.ntx = (xoff + xcount - 1) / t->tw - j.tx0 + 1;
+    j.nty = (yoff + ycount - 1) / t->th - j.ty0 + 1;
+    parallel_for(j.ntx * j.nty, threads, read_chunk, &j);
+    if (j.failed) {
+        set_err(err, errlen, "gdalrasterio error 3 (tile decode failed)");
+        return -1;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------- writer */
+
+enum { TILE = 256 };
+
+struct gh_tiffw {
+    FILE *fp;
+    int w, h;
+    int tiles_x, tiles_y;
+    double gt[6];
+    uint32_t *offsets, *counts;
+    uint64_t pos;
+    int next_tile_row;
+    int level;
+    int failed;
+};
+
+typedef struct {
+    gh_tiffw *tw;
+    const uint8_t *data;        /* first row of this band */
+    size_t pitch;
+    int rows;                   /* rows available in the band */
+    int tile_row0;
+    unsigned char **comp;
+    uLongf *comp_len;
+} write_job;
+
+static void compress_tile(void *arg, int index)
+{
+    write_job *j = arg;
+    gh_tiffw *tw = j->tw;
+    int tx = index % tw->tiles_x, tr = index / tw->tiles_x;
+    unsigned char tile[TILE * TILE];
+    int x0 = tx * TILE, y0 = tr * TILE;
+    int cols = tw->w - x0 < TILE ? tw->w - x0 : TILE;
+    int rows = j->rows - y0 < TILE ? j->rows - y0 : TILE;
+    if (cols < TILE || rows < TILE)
+        memset(tile, 0, sizeof tile);       /* edge tiles are padded with zeros */
+    for (int r = 0; r < rows; r++)
+        memcpy(tile + r * TILE, j->data + (size_t)(y0 + r) * j->pitch + x0, (size_t)cols);
+    uLongf cap = compressBound(sizeof tile);
+    unsigned char *out = malloc(cap);
+    if (!out || compress2(out, &cap, tile, sizeof tile, tw->level) != Z_OK) {
+        free(out);
+        out = NULL;
+        cap = 0;
+        tw->failed = 1;
+    }
+    j->comp[index] = out;
+    j->comp_len[index] = cap;
+}
+
+int gh_tiffw_open(const char *path, int w, int h, const double gt[6], gh_tiffw **out, char *err, size_t errlen)
+{
+    *out = NULL;
+    if (w <= 0 || h <= 0) {
+        set_err(err, errlen, "write error 3 on %s (empty raster)", path);
+        return -1;
+    }
+    gh_tiffw *tw = calloc(1, sizeof *tw);
+    if (!tw)
+        return -1;
+    tw->fp = fopen(path, "wb");
+    if (!tw->fp) {
+        set_err(err, errlen, "write error 3 on %s (%s)", path, strerror(errno));     /* raster.c:221 */
+        free(tw);
+        return -1;
+    }
+    setvbuf(tw->fp, NULL, _IOFBF, 1 << 20);
+    tw->w = w;
+    tw->h = h;
+    tw->tiles_x = (w + TILE - 1) / TILE;
+    tw->tiles_y = (h + TILE - 1) / TILE;
+    tw->level = 6;              /* GDAL's default ZLEVEL */
+    memcpy(tw->gt, gt, sizeof tw->gt);
+    size_t nt = (size_t)tw->tiles_x * (size_t)tw->tiles_y;
+    tw->offsets = calloc(nt, sizeof(uint32_t));
+    tw->counts = calloc(nt, sizeof(uint32_t));
+    unsigned char hdr[8] = { 'I', 'I', 42, 0, 0, 0, 0, 0 };      /* IFD offset patched on close */
+    if (!tw->offsets || !tw->counts || fwrite(hdr, 1, 8, tw->fp) != 8) {
+        set_err(err, errlen, "write error 3 on %s", path);
+        gh_tiffw_abort(tw);
+        return -1;
+    }
+    tw->pos = 8;
+    *out = tw;
+    return 0;
+}
+
+int gh_tiffw_write_rows(gh_tiffw *tw, const uint8_t *data, size_t pitch, int y0, int nrows, int threads)
+{
+    if (tw->failed || y0 != tw->next_tile_row * TILE || y0 + nrows > tw->h ||
+        (nrows % TILE != 0 && y0 + nrows != tw->h))
+        return -1;
+    int tile_rows = (nrows + TILE - 1) / TILE;
+    int n = tile_rows * tw->tiles_x;
+    write_job j = { tw, data, pitch, nrows, tw->next_tile_row, NULL, NULL };
+    j.comp = calloc((size_t)n, sizeof(unsigned char *));
+    j.comp_len = calloc((size_t)n, sizeof(uLongf));
+    if (!j.comp || !j.comp_len) {
+        free(j.comp);
+        free(j.comp_len);
+        tw->failed = 1;
+        return -1;
+    }
+    parallel_for(n, threads, compress_tile, &j);
+    for (int i = 0; i < n; i++) {
+        size_t ti = (size_t)(tw->next_tile_row + i / tw->tiles_x) * (size_t)tw->tiles_x + (size_t)(i % tw->tiles_x);
+        if (!tw->failed && j.comp[i]) {
+            if (tw->pos + j.comp_len[i] > 0xFFFFFFF0ull || fwrite(j.comp[i], 1, j.comp_len[i], tw->fp) != j.comp_len[i])
+                tw->failed = 1;
+            tw->offsets[ti] = (uint32_t)tw->pos;
+            tw->counts[ti] = (uint32_t)j.comp_len[i];
+            tw->pos += j.comp_len[i];
+        }
+        free(j.comp[i]);
+    }
+    free(j.comp);
+    free(j.comp_len);
+    tw->next_tile_row += tile_rows;
+    return tw->failed ? -1 : 0;
+}
+
+static void put16(unsigned char **p, uint16_t v) { (*p)[0] = (unsigned char)v; (*p)[1] = (unsigned char)(v >> 8); *p += 2; }
+static void put32(unsigned char **p, uint32_t v) { for (int i = 0; i < 4; i++) (*p)[i] = (unsigned char)(v >> (8 * i)); *p += 4; }
+static void put_f64(unsigned char **p, double d) { uint64_t v; memcpy(&v, &d, 8); for (int i = 0; i < 8; i++) (*p)[i] = (unsigned char)(v >> (8 * i)); *p += 8; }
+
+static void put_entry(unsigned char **p, uint16_t tag, uint16_t type, uint32_t count, uint32_t value)
+{
+    put16(p, tag);
+    put16(p, type);
+    put32(p, count);
+    if (type == 3 && count == 1) { put16(p, (uint16_t)value); put16(p, 0); }
+    else put32(p, value);
+}
+
+int gh_tiffw_close(gh_tiffw *tw)
+{
+    if (!tw)
+        return -1;
+    int rc = -1;
+    size_t nt = (size_t)tw->tiles_x * (size_t)tw->tiles_y;
+    if (!tw->failed && tw->next_tile_row == tw->tiles_y) {
+        /* trailing data area: tile offsets, tile byte counts, pixel scale, tiepoint, geo keys, ascii */
+        static const uint16_t geokeys[] = {
+            1, 1, 0, 4,
+            1024, 0, 1, 2,          /* GTModelTypeGeoKey      = ModelTypeGeographic */
+            1025, 0, 1, 1,          /* GTRasterTypeGeoKey     = RasterPixelIsArea   */
+            2048, 0, 1, 4326,       /* GeographicTypeGeoKey   = WGS 84              */
+            2054, 0, 1, 9102,       /* GeogAngularUnitsGeoKey = degree              */
+        };
+        static const char ascii[] = "WGS 84|";
+        if (tw->pos & 1) { fputc(0, tw->fp); tw->pos++; }
+        uint64_t off_offsets = tw->pos, off_counts = off_offsets + 4 * nt, off_scale = off_counts + 4 * nt;
+        uint64_t off_tie = off_scale + 24, off_keys = off_tie + 48, off_ascii = off_keys + sizeof geokeys;
+        uint64_t off_ifd = (off_ascii + sizeof ascii + 1) & ~(uint64_t)1;
+        size_t tail = (size_t)(off_ifd - tw->pos) + 2 + 16 * 12 + 4;
+        unsigned char *buf = calloc(1, tail), *p = buf;
+        if (buf && off_ifd + 256 < 0xFFFFFFF0ull) {
+            for (size_t i = 0; i < nt; i++) put32(&p, tw->offsets[i]);
+            for (size_t i = 0; i < nt; i++) put32(&p, tw->counts[i]);
+            put_f64(&p, tw->gt[1]); put_f64(&p, -tw->gt[5]); put_f64(&p, 0.0);
+            put_f64(&p, 0.0); put_f64(&p, 0.0); put_f64(&p, 0.0);
+            put_f64(&p, tw->gt[0]); put_f64(&p, tw->gt[3]); put_f64(&p, 0.0);
+            for (size_t i = 0; i < sizeof geokeys / 2; i++) put16(&p, geokeys[i]);
+            memcpy(p, ascii, sizeof ascii);
+            p = buf + (off_ifd - tw->pos);
+            put16(&p, 16);
+            put_entry(&p, 256, 4, 1, (uint32_t)tw->w);
+            put_entry(&p, 257, 4, 1, (uint32_t)tw->h);
+            put_entry(&p, 258, 3, 1, 8);
+            put_entry(&p, 259, 3, 1, 8);                /* Adobe DEFLATE, what GDAL writes */
+            put_entry(&p, 262, 3, 1, 1);                /* BlackIsZero */
+            put_entry(&p, 277, 3, 1, 1);
+            put_entry(&p, 284, 3, 1, 1);
+            put_entry(&p, 322, 3, 1, TILE);
+            put_entry(&p, 323, 3, 1, TILE);
+            put_entry(&p, 324, 4, (uint32_t)nt, nt == 1 ? tw->offsets[0] : (uint32_t)off_offsets);
+            put_entry(&p, 325, 4, (uint32_t)nt, nt == 1 ? tw->counts[0] : (uint32_t)off_counts);
+            put_entry(&p, 339, 3, 1, 1);                /* SampleFormat = unsigned */
+            put_entry(&p, 33550, 12, 3, (uint32_t)off_scale);
+            put_entry(&p, 33922, 12, 6, (uint32_t)off_tie);
+            put_entry(&p, 34735, 3, (uint32_t)(sizeof geokeys / 2), (uint32_t)off_keys);
+            put_entry(&p, 34737, 2, (uint32_t)sizeof ascii, (uint32_t)off_ascii);
+            put32(&p, 0);
+            if (fwrite(buf, 1, tail, tw->fp) == tail && fseek(tw->fp, 4, SEEK_SET) == 0) {
+                unsigned char o[4], *q = o;
+                put32(&q, (uint32_t)off_ifd);
+                if (fwrite(o, 1, 4, tw->fp) == 4)
+                    rc = 0;
+            }
+        }
+        free(buf);
+    }
+    if (fclose(tw->fp) != 0)
+        rc = -1;
+    free(tw->offsets);
+    free(tw->counts);
+    free(tw);
+    return rc;
+}
+
+void gh_tiffw_abort(gh_tiffw *tw)
+{
+    if (!tw)
+        return;
+    if (tw->fp)
+        fclose(tw->fp);
+    free(tw->offsets);
+    free(tw->counts);
+    free(tw);
+}
+
+int gh_tiff_write(const char *path, const uint8_t *data, int w, int h, size_t pitch, const double gt[6],
+                  int threads, char *err, size_t errlen)
+{
+    gh_tiffw *tw;
+    if (gh_tiffw_open(path, w, h, gt, &tw, err, errlen))
+        return -1;
+    /* bands of 16 tile rows keep the compressed scratch small */
+    for (int y0 = 0; y0 < h; y0 += 16 * TILE) {
+        int rows = h - y0 < 16 * TILE ? h - y0 : 16 * TILE;
+        if (gh_tiffw_write_rows(tw, data + (size_t)y0 * pitch, pitch, y0, rows, threads)) {
+            set_err(err, errlen, "write error 3 on %s", path);
+            gh_tiffw_abort(tw);
+            return -1;
+        }
+    }
+    if (gh_tiffw_close(tw)) {
+        set_err(err, errlen, "write error 3 on %s", path);
+        return -1;
+    }
+    return 0;
+}

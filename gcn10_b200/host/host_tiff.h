@@ -1,0 +1,26 @@
+/* gcn10_b200/host/host_tiff.h -- incremental GeoTIFF writer used by the block pipeline
+ * (the one-shot gh_tiff_write and the reader are declared in gcn10_host.h). */
+#ifndef GCN10_HOST_TIFF_H
+#define GCN10_HOST_TIFF_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gh_tiffw gh_tiffw;
+
+/* Creates path and reserves the header; tiles are appended with gh_tiffw_write_rows. */
+int gh_tiffw_open(const char *path, int w, int h, const double gt[6], gh_tiffw **out, char *err, size_t errlen);
+/* Appends rows [y0, y0+nrows): y0 must continue where the previous call stopped and be a multiple
+ * of 256; nrows must be a multiple of 256 except for the last band of the raster. */
+int gh_tiffw_write_rows(gh_tiffw *tw, const uint8_t *data, size_t pitch, int y0, int nrows, int threads);
+/* Writes the tile tables, georeferencing and IFD; 0 ok. */
+int gh_tiffw_close(gh_tiffw *tw);
+void gh_tiffw_abort(gh_tiffw *tw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,193 @@
+"""ctypes binding of gcn10_b200/host/libgcn10host.so -- the CUDA-free part of the C host program
+(config file, lookup CSVs, window arithmetic, block list, shapefile extents, GeoTIFF I/O).
+Used by the tests and by bench.py to read lookup tables exactly as the gcn10 executable does."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "host", "libgcn10host.so")
+EXE_PATH = os.path.join(HERE, "host", "gcn10")
+ERRLEN = 512
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_vp = C.c_void_p
+
+
+class Window(C.Structure):
+    _fields_ = [("xoff", C.c_int), ("yoff", C.c_int), ("xcount", C.c_int), ("ycount", C.c_int),
+                ("gt", C.c_double * 6)]
+
+
+class Config(C.Structure):
+    _fields_ = [(k, C.c_char_p) for k in ("hysogs_data_path", "esa_data_path", "blocks_shp_path",
+                                           "lookup_table_path", "log_dir")]
+
+
+class HostError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gcn10 host error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not built: run `make host`")
+    L = C.CDLL(LIB_PATH)
+    L.gh_load_lookup_tables.argtypes = [C.c_char_p, _vp, C.c_char_p, C.c_size_t]
+    L.gh_load_lookup_table.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, _vp, C.c_char_p, C.c_size_t]
+    L.gh_raster_window.argtypes = [C.c_int, C.c_int, _dp, _dp, C.POINTER(Window)]
+    L.gh_config_parse.argtypes = [C.c_char_p, C.POINTER(Config), C.c_char_p, C.c_size_t]
+    L.gh_config_free.argtypes = [C.POINTER(Config)]
+    L.gh_read_block_list.argtypes = [C.c_char_p, C.POINTER(_ip), _ip]
+    L.gh_blocks_open.argtypes = [C.c_char_p, C.POINTER(_vp), C.c_char_p, C.c_size_t]
+    L.gh_blocks_count.argtypes = [_vp]
+    L.gh_blocks_id.argtypes = [_vp, C.c_int]
+    L.gh_blocks_bbox.argtypes = [_vp, C.c_int, _dp]
+    L.gh_blocks_close.argtypes = [_vp]
+    L.gh_blocks_close.restype = None
+    L.gh_tiff_open.argtypes = [C.c_char_p, C.POINTER(_vp), C.c_char_p, C.c_size_t]
+    L.gh_tiff_size.argtypes = [_vp, _ip, _ip]
+    L.gh_tiff_geotransform.argtypes = [_vp, _dp]
+    L.gh_tiff_read_window.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.c_int,
+                                      C.c_char_p, C.c_size_t]
+    L.gh_tiff_close.argtypes = [_vp]
+    L.gh_tiff_close.restype = None
+    L.gh_tiff_write.argtypes = [C.c_char_p, _vp, C.c_int, C.c_int, C.c_size_t, _dp, C.c_int, C.c_char_p, C.c_size_t]
+    L.gh_log_open.argtypes = [C.c_char_p, C.c_int]
+    L.gh_log_open.restype = _vp
+    L.gh_log_message.argtypes = [_vp, C.c_char_p, C.c_char_p, C.c_int]
+    L.gh_log_message.restype = None
+    L.gh_log_close.argtypes = [_vp]
+    L.gh_log_close.restype = None
+    _lib = L
+    return L
+
+
+def _err():
+    return C.create_string_buffer(ERRLEN)
+
+
+def load_lookup_tables(lookup_dir: str) -> np.ndarray:
+    """int32 [9,256,5] in the reference's order p_i..g_iii (cn.c:146-147)."""
+    L = load()
+    t = np.empty((9, 256, 5), dtype=np.int32)
+    e = _err()
+    rc = L.gh_load_lookup_tables(os.fsencode(lookup_dir), t.ctypes.data, e, ERRLEN)
+    if rc:
+        raise HostError(rc, e.value.decode())
+    return t
+
+
+def raster_window(rw, rh, t, bbox):
+    L = load()
+    w = Window()
+    rc = L.gh_raster_window(rw, rh, (C.c_double * 6)(*t), (C.c_double * 4)(*bbox), C.byref(w))
+    if rc:
+        return None
+    return w.xoff, w.yoff, w.xcount, w.ycount, tuple(w.gt)
+
+
+def parse_config(path: str) -> dict:
+    L = load()
+    cfg = Config()
+    e = _err()
+    rc = L.gh_config_parse(os.fsencode(path), C.byref(cfg), e, ERRLEN)
+    if rc:
+        raise HostError(rc, e.value.decode())
+    out = {k: getattr(cfg, k).decode() for k, _ in Config._fields_}
+    L.gh_config_free(C.byref(cfg))
+    return out
+
+
+def read_block_list(path: str):
+    L = load()
+    ids = _ip()
+    n = C.c_int()
+    rc = L.gh_read_block_list(os.fsencode(path), C.byref(ids), C.byref(n))
+    if rc:
+        raise HostError(rc, f"cannot open block list file {path}")
+    out = [ids[i] for i in range(n.value)]
+    C.CDLL(None).free(ids)
+    return out
+
+
+class Blocks:
+    def __init__(self, shp_path: str):
+        self.L = load()
+        h = _vp()
+        e = _err()
+        rc = self.L.gh_blocks_open(os.fsencode(shp_path), C.byref(h), e, ERRLEN)
+        if rc:
+            raise HostError(rc, e.value.decode())
+        self.h = h
+
+    def __len__(self):
+        return self.L.gh_blocks_count(self.h)
+
+    def ids(self):
+        return [self.L.gh_blocks_id(self.h, i) for i in range(len(self))]
+
+    def bbox(self, block_id):
+        b = (C.c_double * 4)()
+        if self.L.gh_blocks_bbox(self.h, block_id, b):
+            return None
+        return tuple(b)
+
+    def close(self):
+        if self.h:
+            self.L.gh_blocks_close(self.h)
+            self.h = None
+
+
+def tiff_write(path: str, data: np.ndarray, gt, threads: int = 4):
+    L = load()
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    h, w = data.shape
+    e = _err()
+    rc = L.gh_tiff_write(os.fsencode(path), data.ctypes.data, w, h, w, (C.c_double * 6)(*gt), threads, e, ERRLEN)
+    if rc:
+        raise HostError(rc, e.value.decode())
+
+
+class Tiff:
+    def __init__(self, path: str):
+        self.L = load()
+        h = _vp()
+        e = _err()
+        rc = self.L.gh_tiff_open(os.fsencode(path), C.byref(h), e, ERRLEN)
+        if rc:
+            raise HostError(rc, e.value.decode())
+        self.h = h
+        w, hh = C.c_int(), C.c_int()
+        self.L.gh_tiff_size(h, w, hh)
+        self.width, self.height = w.value, hh.value
+        gt = (C.c_double * 6)()
+        self.georeferenced = self.L.gh_tiff_geotransform(h, gt) == 0
+        self.gt = tuple(gt)
+
+    def read(self, xoff=0, yoff=0, xcount=None, ycount=None, threads=4) -> np.ndarray:
+        xcount = self.width - xoff if xcount is None else xcount
+        ycount = self.height - yoff if ycount is None else ycount
+        out = np.empty((ycount, xcount), dtype=np.uint8)
+        e = _err()
+        rc = self.L.gh_tiff_read_window(self.h, xoff, yoff, xcount, ycount, out.ctypes.data, xcount, threads, e, ERRLEN)
+        if rc:
+            raise HostError(rc, e.value.decode())
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.gh_tiff_close(self.h)
+            self.h = None

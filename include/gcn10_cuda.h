@@ -102,6 +102,17 @@ int gcn10_cuda_block(gcn10_ctx *ctx,
                      const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
                      unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch);
 
+/* Rows [row0, row0+nrows) of a w x h block: esa and out[k] point at row `row0` (the caller holds
+ * only that band of the rasters), while gt / soil_gt / h still describe the WHOLE block so that the
+ * fp64 index maps are the block's (a band with a shifted geotransform origin would not round the
+ * same way).  Lets a host program stream a 36000 x 36000 block through a few hundred MB of pinned
+ * memory, band by band, aligned to the 256-row tiles of the output GeoTIFFs. */
+int gcn10_cuda_block_rows(gcn10_ctx *ctx,
+                          const uint8_t *esa, int w, int h, int row0, int nrows, size_t esa_pitch,
+                          const double gt[6],
+                          const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                          unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch);
+
 /* Same computation with every buffer already in DEVICE memory; asynchronous on `stream`
  * (NULL = the context's own non-blocking stream; to use the legacy default stream pass
  * cudaStreamLegacy, i.e. (void *)1).  Fast path requirements: esa, every selected out[k], and

@@ -1,0 +1,102 @@
+"""End to end on a GPU: the gcn10 executable (C host program + libgcn10cuda) against the reference's
+own process_block() on the same rasters -- decoded planes must be identical, file names, log lines
+and the no-overwrite underscore rule must match the reference's observable behaviour."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from gcn10_b200 import hostlib, lookups, synth
+from oracle import oracle as O
+from tests import fixtures
+
+pytestmark = pytest.mark.gpu
+
+PX = 1.0 / 12000.0
+HSG_PX = 1.0 / 480.0
+
+
+@pytest.fixture(scope="module")
+def world(tmp_path_factory):
+    root = tmp_path_factory.mktemp("gcn10_run")
+    W, H = 3000, 2200
+    esa_t = (-114.0, PX, 0.0, 42.0, 0.0, -PX)
+    esa = synth.esa_tile(W, H, 41, patch=96)
+    hw, hh = 130, 100
+    hsg_t = (-114.0 - 1.3 * HSG_PX, HSG_PX, 0.0, 42.0 + 2.6 * HSG_PX, 0.0, -HSG_PX)
+    hsg = synth.hsg_tile(hw, hh, 42, "coastal", patch=3)
+    hostlib.tiff_write(str(root / "esa.tif"), esa, esa_t)
+    hostlib.tiff_write(str(root / "hsg.tif"), hsg, hsg_t)
+    blocks = [
+        (11, -114.0 + 100 * PX, 42.0 - 1500 * PX, -114.0 + 1400 * PX, 42.0 - 200 * PX),     # inside, 1300 x 1300
+        (12, -114.0 + 1700 * PX, 42.0 - 2500 * PX, -114.0 + 3300 * PX, 42.0 - 900 * PX),    # hangs over the SE corner
+        (13, -120.0, 10.0, -119.0, 11.0),                                                   # outside both rasters
+    ]
+    fixtures.write_block_shapefile(str(root / "blocks.shp"), blocks)
+    lookups.write_default_lookups(str(root / "lookups"))
+    fixtures.write_config(str(root / "config.txt"), str(root / "esa.tif"), str(root / "hsg.tif"),
+                          str(root / "blocks.shp"), str(root / "lookups"), str(root / "logs"))
+    (root / "blocks.txt").write_text("11\n12\n13\n99\n")
+    return dict(root=root, esa=esa, esa_t=esa_t, hsg=hsg, hsg_t=hsg_t, blocks=blocks)
+
+
+def _run(world, *extra):
+    exe = hostlib.EXE_PATH
+    assert os.path.exists(exe), "gcn10 executable not built (make host)"
+    root = world["root"]
+    return subprocess.run([exe, "-c", str(root / "config.txt"), "-l", str(root / "blocks.txt"), "--gpus", "1",
+                           "--io-threads", "4", *extra], cwd=str(root), capture_output=True, text=True, timeout=300)
+
+
+def test_program_matches_reference_process_block(world, ref):
+    r = _run(world, "-o")
+    assert r.returncode == 0, r.stderr
+    root = world["root"]
+    for bid, x0, y0, x1, y1 in world["blocks"][:2]:
+        want = ref.run_block(world["esa"], world["esa_t"], world["hsg"], world["hsg_t"], (x0, y0, x1, y1),
+                             str(root / "lookups"), block_id=bid)
+        assert want["nplanes"] == 18
+        for k, rel in enumerate(want["paths"]):                 # the reference's own file names, save order
+            t = hostlib.Tiff(str(root / rel))
+            assert (t.width, t.height) == (want["w"], want["h"]), rel
+            assert t.gt == want["gt"], rel
+            got = t.read()
+            t.close()
+            assert np.array_equal(got, want["planes"][k]), f"{rel}: {(got != want['planes'][k]).sum()} px differ"
+    # blocks 13 (no overlap) and 99 (not in the shapefile) are skipped with the reference's messages
+    assert "esa load failed for block 13" in r.stderr and "invalid raster bounds" in r.stderr
+    assert "block 99 not found" in r.stderr
+    assert not (root / "cn_rasters_drained" / "cn_p_i_13.tif").exists()
+    log = (root / "logs" / "rank_0.log").read_text()
+    for c in O.CONDS:
+        for h in O.HCS:
+            for a in O.ARCS:
+                assert f"completed condition for 11: {c}/{h}/{a}" in log                # cn.c:366-369
+    assert len(re.findall(r"progress: completed block 12 / total 4", log)) == 18        # log.c:199-207, 18 per block
+    assert "processing block 11" in log and "processed 4 blocks on 1 ranks" in log      # main.c:172,191
+
+
+def test_no_overwrite_appends_underscore(world):
+    root = world["root"]
+    first = root / "cn_rasters_undrained" / "cn_g_iii_11.tif"
+    if not first.exists():
+        assert _run(world, "-o").returncode == 0
+    before = first.read_bytes()
+    r = _run(world)                                             # no -o: existing outputs are kept (cn.c:320-360)
+    assert r.returncode == 0, r.stderr
+    second = root / "cn_rasters_undrained" / "cn_g_iii_11_.tif"
+    assert second.exists() and first.read_bytes() == before
+    a = hostlib.Tiff(str(first)).read()
+    b = hostlib.Tiff(str(second)).read()
+    assert np.array_equal(a, b)
+
+
+def test_block_rows_bands_equal_whole_block(gpu_ctx, port, tables):
+    from tests.cases import make_block
+    b = make_block(w=1300, h=1111, seed=77, shift=(0.0007, 0.0002), margin=1)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    for y0, n in [(0, 256), (256, 512), (768, 343), (1110, 1)]:
+        got = gpu_ctx.block_rows(np.ascontiguousarray(b["esa"][y0:y0 + n]), 1111, y0, b["gt"], b["hsg"], b["soil_gt"])
+        assert np.array_equal(got, want[:, y0:y0 + n]), (y0, n)

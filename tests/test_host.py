@@ -1,0 +1,177 @@
+"""CPU tests of the C host program's CUDA-free parts (gcn10_b200/host/libgcn10host.so): the lookup CSV
+reader, window arithmetic, config file, block list, shapefile extents, GeoTIFF writer/reader and log
+format.  Expected values come from the golden fixtures (reference object code) and the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from gcn10_b200 import hostlib, lookups
+from tests import fixtures, golden_io
+from tests.test_oracle_pinned import _effective_lut
+
+PX = 1.0 / 12000.0
+
+
+def test_lookup_reader_matches_oracle_and_golden(port, lookup_dir, tmp_path):
+    from tests.golden.make_golden import write_hostile
+    g = golden_io.luts()
+    for label, d in (("default", lookup_dir), ("hostile", write_hostile(str(tmp_path / "hostile")))):
+        t = hostlib.load_lookup_tables(d)
+        assert np.array_equal(t, port.load_tables(d)), label
+        assert np.array_equal(_effective_lut(t), g[label]), label
+
+
+def test_lookup_reader_errors(tmp_path):
+    with pytest.raises(hostlib.HostError) as e:
+        hostlib.load_lookup_tables(str(tmp_path))
+    assert e.value.code == -2 and "cannot open lookup table" in e.value.msg       # cn.c:30
+    lookups.write_default_lookups(str(tmp_path))
+    open(tmp_path / "default_lookup_f_ii.csv", "wb").close()
+    with pytest.raises(hostlib.HostError) as e:
+        hostlib.load_lookup_tables(str(tmp_path))
+    assert e.value.code == -3 and "empty lookup table" in e.value.msg             # cn.c:44
+
+
+def test_window_arithmetic_matches_golden():
+    for c in golden_io.window_cases():
+        got = hostlib.raster_window(c["rw"], c["rh"], c["t"], c["bbox"])
+        if c["expect"] is None:
+            assert got is None, c
+        else:
+            e = c["expect"]
+            assert got == (e["xoff"], e["yoff"], e["xsize"], e["ysize"], tuple(e["gt"])), c
+
+
+def test_window_matches_reference_live(ref):
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        rw, rh = int(rng.integers(1, 5000)), int(rng.integers(1, 5000))
+        px = float(rng.choice([PX, 8.3333333333330430e-05, 0.01, 1 / 480]))
+        t = (float(rng.uniform(-180, 180)), px, 0.0, float(rng.uniform(-60, 84)), 0.0, -px)
+        x0, x1 = sorted(rng.uniform(-0.2 * rw, 1.2 * rw, 2))
+        y0, y1 = sorted(rng.uniform(-0.2 * rh, 1.2 * rh, 2))
+        bbox = (t[0] + x0 * px, t[3] - y1 * px, t[0] + x1 * px, t[3] - y0 * px)
+        assert hostlib.raster_window(rw, rh, t, bbox) == ref.window(rw, rh, t, bbox)
+
+
+def test_config_parser(tmp_path):
+    p = fixtures.write_config(str(tmp_path / "config.txt"), "/data/esa.tif", "/data/hsg.tif", "/data/b.shp",
+                              "/data/lookups", "logs/")
+    cfg = hostlib.parse_config(p)
+    assert cfg == {"hysogs_data_path": "/data/hsg.tif", "esa_data_path": "/data/esa.tif",
+                   "blocks_shp_path": "/data/b.shp", "lookup_table_path": "/data/lookups", "log_dir": "logs/"}
+    (tmp_path / "bad.txt").write_text("esa_data_path=x\nnot a pair\n#log_dir=zzz\n")
+    with pytest.raises(hostlib.HostError) as e:
+        hostlib.parse_config(str(tmp_path / "bad.txt"))
+    assert e.value.code == -2 and e.value.msg.startswith("missing one of: hysogs_data_path")   # config.c:108
+    with pytest.raises(hostlib.HostError) as e:
+        hostlib.parse_config(str(tmp_path / "absent.txt"))
+    assert e.value.code == -1 and "cannot open config" in e.value.msg                           # config.c:52
+
+
+def test_block_list(tmp_path):
+    (tmp_path / "blocks.txt").write_text("2234\n2261 2256\n\n 7\nx 9\n")
+    assert hostlib.read_block_list(str(tmp_path / "blocks.txt")) == [2234, 2261, 2256, 7]     # fscanf stops at 'x'
+    with pytest.raises(hostlib.HostError):
+        hostlib.read_block_list(str(tmp_path / "none.txt"))
+
+
+def test_shapefile_reader(tmp_path):
+    blocks = [(3, 168.0, -54.0, 171.0, -51.0), (2234, -114.0, 39.0, -111.0, 42.0), (77, -3.0, 0.0, 0.0, 3.0)]
+    shp = fixtures.write_block_shapefile(str(tmp_path / "blocks.shp"), blocks)
+    b = hostlib.Blocks(shp)
+    assert len(b) == 3 and b.ids() == [3, 2234, 77]
+    assert b.bbox(2234) == (-114.0, 39.0, -111.0, 42.0)                     # minx, miny, maxx, maxy (cn.c:179-182)
+    assert b.bbox(5) is None
+    b.close()
+    with pytest.raises(hostlib.HostError) as e:
+        hostlib.Blocks(str(tmp_path / "missing.shp"))
+    assert "ogr open failed" in e.value.msg                                  # cn.c:157
+
+
+def test_reference_shapefile_if_present():
+    shp = "/root/reference/blocks/esa_extent_blocks.shp"
+    if not os.path.exists(shp):
+        pytest.skip("reference tree not present")
+    b = hostlib.Blocks(shp)
+    ids = b.ids()
+    assert len(ids) == 2651 and min(ids) == 3 and max(ids) == 2653
+    for bid in (2234, 2261, 2256):                                          # src/test/blocks.txt
+        x0, y0, x1, y1 = b.bbox(bid)
+        assert (x1 - x0, y1 - y0) == (3.0, 3.0) and x0 == int(x0) and y0 == int(y0)
+    assert b.bbox(2234) == (-114.0, 39.0, -111.0, 42.0)
+    b.close()
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (255, 257), (256, 256), (700, 1000), (4097, 300)])
+def test_geotiff_roundtrip_and_libtiff_decode(w, h, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(w * 31 + h)
+    a = (rng.integers(0, 4, (h, w)) * 25 + (np.arange(w)[None, :] // 37) % 3).astype(np.uint8)
+    gt = (-114.0, PX, 0.0, 42.0, 0.0, -PX)
+    p = str(tmp_path / "out.tif")
+    hostlib.tiff_write(p, a, gt, threads=3)
+    t = hostlib.Tiff(p)
+    assert (t.width, t.height) == (w, h) and t.georeferenced and t.gt == gt
+    assert np.array_equal(t.read(), a)
+    if w > 10 and h > 10:
+        assert np.array_equal(t.read(3, 5, w - 7, h - 9, threads=1), a[5:h - 4, 3:w - 4])
+    t.close()
+    im = Image.open(p)                                      # independent decoder (libtiff)
+    assert im.size == (w, h) and im.info.get("compression") == "tiff_adobe_deflate"      # raster.c:206
+    assert im.tag_v2[322] == 256 and im.tag_v2[323] == 256                                 # raster.c:207, GDAL default tile
+    assert np.array_equal(np.array(im), a)
+    assert 42113 not in im.tag_v2, "the reference sets no NoData tag"
+
+
+@pytest.mark.parametrize("compression", ["raw", "tiff_lzw", "tiff_adobe_deflate"])
+def test_geotiff_reader_on_libtiff_files(compression, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    a = (rng.integers(0, 6, (333, 517)) * 20).astype(np.uint8)
+    a[100:200, 50:400] = 80
+    p = str(tmp_path / f"{compression}.tif")
+    Image.fromarray(a).save(p, compression=compression)
+    t = hostlib.Tiff(p)
+    assert (t.width, t.height) == (517, 333) and not t.georeferenced
+    assert np.array_equal(t.read(threads=2), a)
+    assert np.array_equal(t.read(17, 99, 200, 101), a[99:200, 17:217])
+    t.close()
+
+
+def test_geotiff_reader_rejects_garbage(tmp_path):
+    (tmp_path / "x.tif").write_bytes(b"not a tiff at all")
+    with pytest.raises(hostlib.HostError) as e:
+        hostlib.Tiff(str(tmp_path / "x.tif"))
+    assert "gdal open failed" in e.value.msg                 # raster.c:121
+
+
+def test_log_format(tmp_path):
+    L = hostlib.load()
+    lg = L.gh_log_open(os.fsencode(str(tmp_path / "logs")), 3)
+    L.gh_log_message(lg, b"INFO", b"completed condition for 2234: drained/p/i", 0)
+    L.gh_log_message(lg, b"ERROR", b"block 9 not found", 0)
+    L.gh_log_close(lg)
+    lines = (tmp_path / "logs" / "rank_3.log").read_text().splitlines()                  # log.c:76
+    ts = r"\[\d{4}-\d\d-\d\dT\d\d:\d\d:\d\d\]"
+    assert re.fullmatch(ts + r" \[rank 3\] logging started", lines[0])                   # log.c:112
+    assert re.fullmatch(ts + r" \[INFO\] \[rank 3\] completed condition for 2234: drained/p/i", lines[1])   # log.c:158
+    assert re.fullmatch(ts + r" \[ERROR\] \[rank 3\] block 9 not found", lines[2])
+    assert re.fullmatch(ts + r" \[rank 3\] logging finished", lines[3])                  # log.c:263
+
+
+def test_cli_meta_flags_and_errors(tmp_path):
+    exe = hostlib.EXE_PATH
+    if not os.path.exists(exe):
+        pytest.skip("gcn10 executable not built")
+    r = subprocess.run([exe, "--version"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == "gcn10 0.1.0\n"                             # main.c:51
+    r = subprocess.run([exe, "-h"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--config, -c <file>" in r.stdout and "--overwrite, -o" in r.stdout
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "missing -c/--config <file>" in r.stderr               # main.c:103-108
+    r = subprocess.run([exe, "-c", str(tmp_path / "nope.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open config" in r.stderr                        # config.c:52
