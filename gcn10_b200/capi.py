@@ -75,6 +75,15 @@ def _d6(a):
     return (C.c_double * 6)(*[float(v) for v in a])
 
 
+def _rows(a):
+    """(array, row pitch in bytes) for a 2-D uint8 array; row-strided views are passed through,
+    anything else is copied to C order."""
+    if a.ndim == 2 and a.shape[1] > 1 and a.strides[1] == 1 and a.strides[0] >= a.shape[1]:
+        return a, a.strides[0]
+    a = np.ascontiguousarray(a)
+    return a, a.shape[1]
+
+
 class PinnedArray:
     """uint8 numpy view over page-locked memory from gcn10_cuda_host_alloc."""
 
@@ -138,7 +147,8 @@ class Context:
         """Host-buffer call.  esa [h,w] uint8, hsg [hsy,hsx] uint8 (numpy, any row stride).
         Returns uint8 [18,h,w]; planes not in the mask are left untouched (zeros if allocated here)."""
         assert esa.dtype == np.uint8 and hsg.dtype == np.uint8
-        assert esa.strides[1] == 1 and hsg.strides[1] == 1
+        esa, esa_pitch = _rows(esa)
+        hsg, hsg_pitch = _rows(hsg)
         h, w = esa.shape
         hsy, hsx = hsg.shape
         if out is None:
@@ -147,12 +157,14 @@ class Context:
         for k in range(NPLANES):
             ptrs[k] = out[k].ctypes.data if plane_mask & (1 << k) else None
         self._check(self.lib.gcn10_cuda_block(
-            self.h, esa.ctypes.data, w, h, esa.strides[0], _d6(gt), hsg.ctypes.data, hsx, hsy,
-            hsg.strides[0], _d6(soil_gt), plane_mask, ptrs, out.strides[1]))
+            self.h, esa.ctypes.data, w, h, esa_pitch, _d6(gt), hsg.ctypes.data, hsx, hsy,
+            hsg_pitch, _d6(soil_gt), plane_mask, ptrs, out.strides[1]))
         return out
 
     def block_rows(self, esa_rows, h, row0, gt, hsg, soil_gt, plane_mask=MASK_ALL):
         """Band call: esa_rows holds rows [row0, row0+len) of a block that is h rows tall."""
+        esa_rows, esa_pitch = _rows(esa_rows)
+        hsg, hsg_pitch = _rows(hsg)
         nrows, w = esa_rows.shape
         hsy, hsx = hsg.shape
         out = np.zeros((NPLANES, nrows, w), dtype=np.uint8)
@@ -160,8 +172,8 @@ class Context:
         for k in range(NPLANES):
             ptrs[k] = out[k].ctypes.data if plane_mask & (1 << k) else None
         self._check(self.lib.gcn10_cuda_block_rows(
-            self.h, esa_rows.ctypes.data, w, h, row0, nrows, esa_rows.strides[0], _d6(gt), hsg.ctypes.data,
-            hsx, hsy, hsg.strides[0], _d6(soil_gt), plane_mask, ptrs, out.strides[1]))
+            self.h, esa_rows.ctypes.data, w, h, row0, nrows, esa_pitch, _d6(gt), hsg.ctypes.data,
+            hsx, hsy, hsg_pitch, _d6(soil_gt), plane_mask, ptrs, out.strides[1]))
         return out
 
     def block_device(self, d_esa, w, h, esa_pitch, gt, d_hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask,
