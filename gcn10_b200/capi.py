@@ -24,7 +24,7 @@ MASK_ALL = 0x3FFFF
 EXPORTS = (
     "gcn10_cuda_version", "gcn10_cuda_last_error", "gcn10_cuda_device_count", "gcn10_cuda_create",
     "gcn10_cuda_destroy", "gcn10_cuda_set_luts", "gcn10_cuda_block", "gcn10_cuda_block_rows",
-    "gcn10_cuda_block_device",
+    "gcn10_cuda_block_deflate", "gcn10_cuda_block_device",
     "gcn10_cuda_index_maps", "gcn10_cuda_synchronize", "gcn10_cuda_last_kernel_ms",
     "gcn10_cuda_launch_count", "gcn10_cuda_set_option", "gcn10_cuda_host_alloc", "gcn10_cuda_host_free",
     "gcn10_cuda_host_register", "gcn10_cuda_host_unregister",
@@ -32,6 +32,16 @@ EXPORTS = (
 
 _vp = C.c_void_p
 _dp = C.POINTER(C.c_double)
+
+
+class TileStrip(C.Structure):
+    """gcn10_tile_strip of include/gcn10_cuda.h."""
+    _fields_ = [("tile_row0", C.c_int), ("n_tile_rows", C.c_int), ("tiles_x", C.c_int), ("n_planes", C.c_int),
+                ("plane_ids", C.POINTER(C.c_int)), ("offsets", C.POINTER(C.c_uint64)),
+                ("sizes", C.POINTER(C.c_uint32)), ("blob", C.POINTER(C.c_uint8)), ("blob_bytes", C.c_size_t)]
+
+
+TILE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(TileStrip))
 
 
 class Gcn10Error(RuntimeError):
@@ -57,6 +67,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     lib.gcn10_cuda_block.argtypes = blk
     lib.gcn10_cuda_block_rows.argtypes = blk[:4] + [C.c_int, C.c_int] + blk[4:]
     lib.gcn10_cuda_block_device.argtypes = blk + [_vp]
+    lib.gcn10_cuda_block_deflate.argtypes = blk[:12] + [TILE_SINK, _vp]
     lib.gcn10_cuda_index_maps.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp, _vp, _vp]
     lib.gcn10_cuda_synchronize.argtypes = [_vp]
     lib.gcn10_cuda_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float)]
@@ -175,6 +186,36 @@ class Context:
             self.h, esa_rows.ctypes.data, w, h, row0, nrows, esa_pitch, _d6(gt), hsg.ctypes.data,
             hsx, hsy, hsg_pitch, _d6(soil_gt), plane_mask, ptrs, out.strides[1]))
         return out
+
+    def block_deflate(self, esa, gt, hsg, soil_gt, plane_mask=MASK_ALL, on_strip=None):
+        """Compressed-tile call.  Returns dict(tiles={plane: {(tile_row, tile_x): bytes}}, bytes=total)
+        unless ``on_strip(strip_struct)`` is given, in which case tiles are not copied."""
+        esa, esa_pitch = _rows(esa)
+        hsg, hsg_pitch = _rows(hsg)
+        h, w = esa.shape
+        hsy, hsx = hsg.shape
+        tiles = {}
+        total = [0]
+
+        def _sink(_user, sp):
+            st = sp.contents
+            total[0] += st.blob_bytes
+            if on_strip is not None:
+                return int(on_strip(st) or 0)
+            blob = C.string_at(st.blob, st.blob_bytes)
+            for k in range(st.n_planes):
+                d = tiles.setdefault(st.plane_ids[k], {})
+                for tr in range(st.n_tile_rows):
+                    for tx in range(st.tiles_x):
+                        i = (k * st.n_tile_rows + tr) * st.tiles_x + tx
+                        d[(st.tile_row0 + tr, tx)] = blob[st.offsets[i]: st.offsets[i] + st.sizes[i]]
+            return 0
+
+        cb = TILE_SINK(_sink)
+        self._check(self.lib.gcn10_cuda_block_deflate(
+            self.h, esa.ctypes.data, w, h, esa_pitch, _d6(gt), hsg.ctypes.data, hsx, hsy, hsg_pitch,
+            _d6(soil_gt), plane_mask, cb, None))
+        return dict(tiles=tiles, bytes=total[0])
 
     def block_device(self, d_esa, w, h, esa_pitch, gt, d_hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask,
                      d_out_ptrs, out_pitch, stream=None):

@@ -8,6 +8,7 @@
 // compute entry point returns an error.
 #include "../../include/gcn10_cuda.h"
 #include "cn_kernels.cuh"
+#include "deflate_tiles.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -47,11 +48,22 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
 struct StripSlot {
     DevBuf esa;
     DevBuf out;                 // nplanes * strip_rows * pitch
     cudaEvent_t k0 = nullptr, k1 = nullptr, done = nullptr;
     bool timed = false;
+    // tile-deflate path
+    DevBuf blob, table;         // compressed tiles; [cursor(16 B) | offsets u64[] | sizes u32[]]
+    HostBuf h_blob, h_table;    // page-locked mirrors
+    cudaEvent_t enc_done = nullptr;
+    int y0 = 0, rows = 0;
+    bool busy = false;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -102,6 +114,27 @@ void release(DevBuf &b)
 {
     if (b.p)
         cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int ensure_host(HostBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes && b.p)
+        return GCN10_OK;
+    if (b.p)
+        cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    CUDA_TRY(cudaHostAlloc(&b.p, bytes, cudaHostAllocPortable));
+    b.cap = bytes;
+    return GCN10_OK;
+}
+
+void release_host(HostBuf &b)
+{
+    if (b.p)
+        cudaFreeHost(b.p);
     b.p = nullptr;
     b.cap = 0;
 }
@@ -410,7 +443,10 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
         CUDA_TRY(cudaEventCreate(&c->slots[i].k0));
         CUDA_TRY(cudaEventCreate(&c->slots[i].k1));
         CUDA_TRY(cudaEventCreateWithFlags(&c->slots[i].done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->slots[i].enc_done, cudaEventDisableTiming));
     }
+    CUDA_TRY(cudaFuncSetAttribute((const void *)deflate_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kEncSmem));
     // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -438,6 +474,11 @@ void gcn10_cuda_destroy(gcn10_ctx *c)
     for (int i = 0; i < kMaxStreams; i++) {
         release(c->slots[i].esa);
         release(c->slots[i].out);
+        release(c->slots[i].blob);
+        release(c->slots[i].table);
+        release_host(c->slots[i].h_blob);
+        release_host(c->slots[i].h_table);
+        if (c->slots[i].enc_done) cudaEventDestroy(c->slots[i].enc_done);
         if (c->slots[i].k0) cudaEventDestroy(c->slots[i].k0);
         if (c->slots[i].k1) cudaEventDestroy(c->slots[i].k1);
         if (c->slots[i].done) cudaEventDestroy(c->slots[i].done);
@@ -655,6 +696,157 @@ int gcn10_cuda_block_rows(gcn10_ctx *c,
         CUDA_TRY(cudaEventElapsedTime(&ms, sl.k0, sl.k1));
         kernel_ms += ms;
         sl.timed = false;
+    }
+    c->last_kernel_ms = kernel_ms;
+    return GCN10_OK;
+}
+
+int gcn10_cuda_block_deflate(gcn10_ctx *c,
+                             const uint8_t *esa, int w, int h, size_t esa_pitch, const double gt[6],
+                             const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                             unsigned plane_mask, gcn10_tile_sink sink, void *user)
+{
+    if (!c)
+        return fail(GCN10_EINVAL, "NULL context");
+    if (!sink)
+        return fail(GCN10_EINVAL, "NULL sink");
+    int rc = check_geometry(esa, w, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask, (const void *)sink,
+                            (size_t)w);
+    if (rc)
+        return rc;
+    if (!c->have_lut)
+        return fail(GCN10_ENOLUT, "gcn10_cuda_set_luts() has not been called");
+    CUDA_TRY(cudaSetDevice(c->device));
+
+    LaunchPlan plans[2];
+    const int nplans = plan_launches(plane_mask, plans);
+    int nplanes = 0, plane_ids[GCN10_NPLANES];
+    for (int k = 0; k < GCN10_NPLANES; k++)
+        if (plane_mask & (1u << k))
+            plane_ids[nplanes++] = k;
+
+    cudaStream_t s0 = c->streams[0];
+    for (int i = 0; i < nplans; i++)
+        if ((rc = upload_lut(c, plans[i].variant_mask, i, s0)))
+            return rc;
+    const size_t hsg_dpitch = round_up((size_t)hsx, 256);
+    if ((rc = ensure(c->hsg, hsg_dpitch * (size_t)hsy)))
+        return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(c->hsg.p, hsg_dpitch, hsg, hsg_pitch, (size_t)hsx, (size_t)hsy,
+                               cudaMemcpyHostToDevice, s0));
+    if ((rc = launch_index_maps(c, w, h, gt, hsx, hsy, soil_gt, s0)))
+        return rc;
+    CUtensorMap map;
+    int tma_ok = 0;
+    make_hsg_map(c, (const uint8_t *)c->hsg.p, hsx, hsy, hsg_dpitch, &map, &tma_ok);
+    CUDA_TRY(cudaStreamSynchronize(s0));
+
+    // strips of whole tile rows
+    const size_t dpitch = round_up((size_t)w, 256);
+    const int ns = c->nstreams;
+    const int strip = std::max(kTile, std::min(c->strip_rows, (int)round_up((size_t)h, kTile)) / kTile * kTile);
+    const int tiles_x = (w + kTile - 1) / kTile;
+    const int strip_tile_rows = strip / kTile;
+    const size_t ntile_slot = (size_t)nplanes * strip_tile_rows * tiles_x;
+    const size_t blob_cap = ntile_slot * (size_t)round_up(kStoredBytes, 16);
+    const size_t table_bytes = 16 + ntile_slot * (sizeof(unsigned long long) + sizeof(uint32_t));
+    for (int i = 0; i < ns; i++) {
+        StripSlot &sl = c->slots[i];
+        if ((rc = ensure(sl.esa, dpitch * (size_t)strip)) || (rc = ensure(sl.out, dpitch * (size_t)strip * nplanes)) ||
+            (rc = ensure(sl.blob, blob_cap)) || (rc = ensure(sl.table, table_bytes)) ||
+            (rc = ensure_host(sl.h_table, table_bytes)))
+            return rc;
+        // the host mirror of the blob only has to hold what a strip really compresses to; start at 1/8 of
+        // the worst case and grow on demand
+        if ((rc = ensure_host(sl.h_blob, std::max<size_t>(blob_cap / 8, 1 << 20))))
+            return rc;
+        sl.busy = false;
+        sl.timed = false;
+    }
+
+    const int nstrips = (h + strip - 1) / strip;
+    float kernel_ms = 0.f;
+
+    auto issue = [&](int s) -> int {
+        StripSlot &sl = c->slots[s % ns];
+        cudaStream_t st = c->streams[s % ns];
+        const int y0 = s * strip, rows = std::min(strip, h - y0);
+        const int tile_rows = (rows + kTile - 1) / kTile;
+        sl.y0 = y0;
+        sl.rows = rows;
+        CUDA_TRY(cudaMemcpy2DAsync(sl.esa.p, dpitch, esa + (size_t)y0 * esa_pitch, esa_pitch, (size_t)w, (size_t)rows,
+                                   cudaMemcpyHostToDevice, st));
+        uint8_t *d_out[GCN10_NPLANES] = { nullptr };
+        for (int k = 0; k < nplanes; k++)
+            d_out[plane_ids[k]] = (uint8_t *)sl.out.p + (size_t)k * dpitch * (size_t)strip;
+        CUDA_TRY(cudaEventRecord(sl.k0, st));
+        for (int i = 0; i < nplans; i++) {
+            int r2 = launch_rows(c, plans[i], i, (const uint8_t *)sl.esa.p, dpitch, w, rows, y0, (const uint8_t *)c->hsg.p,
+                                 hsg_dpitch, hsx, hsy, map, tma_ok, d_out, dpitch, st);
+            if (r2)
+                return r2;
+        }
+        TileEncParams ep;
+        memset(&ep, 0, sizeof(ep));
+        for (int k = 0; k < nplanes; k++)
+            ep.plane[k] = d_out[plane_ids[k]];
+        ep.pitch = dpitch;
+        ep.w = w;
+        ep.rows = rows;
+        ep.tiles_x = tiles_x;
+        ep.tile_rows = tile_rows;
+        ep.blob = (uint8_t *)sl.blob.p;
+        ep.cursor = (unsigned long long *)sl.table.p;
+        ep.offsets = (unsigned long long *)((uint8_t *)sl.table.p + 16);
+        ep.sizes = (uint32_t *)((uint8_t *)sl.table.p + 16 + ntile_slot * sizeof(unsigned long long));
+        CUDA_TRY(cudaMemsetAsync(sl.table.p, 0, 16, st));
+        deflate_tiles_kernel<<<dim3(tiles_x, tile_rows, nplanes), kTile, kEncSmem, st>>>(ep);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(sl.k1, st));
+        CUDA_TRY(cudaMemcpyAsync(sl.h_table.p, sl.table.p, table_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(sl.enc_done, st));
+        sl.busy = true;
+        return GCN10_OK;
+    };
+
+    for (int s = 0; s < std::min(ns, nstrips); s++)
+        if ((rc = issue(s)))
+            return rc;
+    for (int s = 0; s < nstrips; s++) {
+        StripSlot &sl = c->slots[s % ns];
+        cudaStream_t st = c->streams[s % ns];
+        CUDA_TRY(cudaEventSynchronize(sl.enc_done));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, sl.k0, sl.k1));
+        kernel_ms += ms;
+        const size_t used = (size_t) * (const unsigned long long *)sl.h_table.p;
+        if (used > blob_cap)
+            return fail(GCN10_ECUDA, "tile encoder overran its arena (%zu > %zu)", used, blob_cap);
+        if ((rc = ensure_host(sl.h_blob, used ? used : 16)))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(sl.h_blob.p, sl.blob.p, used, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        gcn10_tile_strip ts;
+        ts.tile_row0 = sl.y0 / kTile;
+        ts.n_tile_rows = (sl.rows + kTile - 1) / kTile;
+        ts.tiles_x = tiles_x;
+        ts.n_planes = nplanes;
+        ts.plane_ids = plane_ids;
+        ts.offsets = (const uint64_t *)((const uint8_t *)sl.h_table.p + 16);
+        ts.sizes = (const uint32_t *)((const uint8_t *)sl.h_table.p + 16 + ntile_slot * sizeof(unsigned long long));
+        ts.blob = (const uint8_t *)sl.h_blob.p;
+        ts.blob_bytes = used;
+        // NB: the tables are laid out [plane][strip_tile_rows (capacity)][tiles_x] only when the strip is
+        // full; the kernel indexes with the strip's own tile_rows, which is what n_tile_rows reports
+        const int sink_rc = sink(user, &ts);
+        sl.busy = false;
+        if (sink_rc) {
+            gcn10_cuda_synchronize(c);
+            return fail(GCN10_EINVAL, "tile sink returned %d", sink_rc);
+        }
+        if (s + ns < nstrips && (rc = issue(s + ns)))
+            return rc;
     }
     c->last_kernel_ms = kernel_ms;
     return GCN10_OK;

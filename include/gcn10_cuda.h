@@ -113,6 +113,35 @@ int gcn10_cuda_block_rows(gcn10_ctx *ctx,
                           const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
                           unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch);
 
+/* One block, outputs delivered as DEFLATE-compressed 256 x 256 GeoTIFF tiles instead of raw planes.
+ *
+ * This fuses the reference's save_raster() encode step (raster.c:204-219: GTiff, TILED=YES,
+ * COMPRESS=DEFLATE) into the GPU pipeline: after the Curve Number kernel, every tile of every
+ * selected plane is compressed on the device into a complete zlib stream (exactly what a TIFF
+ * Compression=8 tile holds), and only the compressed tiles cross PCIe.  Tiles on the right / bottom
+ * edge are zero padded to 256 x 256.  The block is processed in strips of whole tile rows; `sink` is
+ * called once per strip, in order, from the calling thread.  The memory behind strip->blob / offsets /
+ * sizes is page-locked, owned by the library and valid only during the call: copy or write it out.
+ * A non-zero return from `sink` aborts the block (returned as GCN10_EINVAL). */
+typedef struct {
+    int tile_row0;              /* first tile row (of the block) in this strip                    */
+    int n_tile_rows;            /* tile rows in this strip                                        */
+    int tiles_x;                /* tiles per tile row = ceil(w / 256)                             */
+    int n_planes;               /* planes selected by the mask                                    */
+    const int *plane_ids;       /* [n_planes] plane numbers, ascending                            */
+    const uint64_t *offsets;    /* [n_planes][n_tile_rows][tiles_x] byte offset of a tile in blob */
+    const uint32_t *sizes;      /* [n_planes][n_tile_rows][tiles_x] bytes of its zlib stream      */
+    const uint8_t *blob;        /* the compressed tiles of the strip                              */
+    size_t blob_bytes;
+} gcn10_tile_strip;
+
+typedef int (*gcn10_tile_sink)(void *user, const gcn10_tile_strip *strip);
+
+int gcn10_cuda_block_deflate(gcn10_ctx *ctx,
+                             const uint8_t *esa, int w, int h, size_t esa_pitch, const double gt[6],
+                             const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                             unsigned plane_mask, gcn10_tile_sink sink, void *user);
+
 /* Same computation with every buffer already in DEVICE memory; asynchronous on `stream`
  * (NULL = the context's own non-blocking stream; to use the legacy default stream pass
  * cudaStreamLegacy, i.e. (void *)1).  Fast path requirements: esa, every selected out[k], and

@@ -1,0 +1,81 @@
+"""GPU tile DEFLATE (gcn10_cuda_block_deflate): every tile must be a valid zlib stream (decoded here with
+CPython's zlib, an independent inflate) whose 256 x 256 bytes equal the oracle's plane, zero padded at
+the right / bottom edge exactly like the CPU GeoTIFF writer pads."""
+import zlib
+
+import numpy as np
+import pytest
+
+from gcn10_b200 import capi
+from tests.cases import make_block
+
+pytestmark = pytest.mark.gpu
+
+T = 256
+
+
+def _assemble(tiles, w, h):
+    tx_n, ty_n = (w + T - 1) // T, (h + T - 1) // T
+    full = np.zeros((ty_n * T, tx_n * T), dtype=np.uint8)
+    assert sorted(tiles) == [(r, c) for r in range(ty_n) for c in range(tx_n)], "tile grid incomplete"
+    for (r, c), z in tiles.items():
+        raw = zlib.decompress(z)
+        assert len(raw) == T * T
+        full[r * T:(r + 1) * T, c * T:(c + 1) * T] = np.frombuffer(raw, dtype=np.uint8).reshape(T, T)
+    return full
+
+
+CASES = [
+    ("one_tile", dict(w=256, h=256)),
+    ("ragged", dict(w=1300, h=777, seed=4)),
+    ("tiny", dict(w=5, h=3)),
+    ("multi_strip", dict(w=700, h=2600, seed=6)),
+    ("coastal", dict(w=1000, h=600, profile="coastal", seed=7)),
+    ("random_incompressible", dict(w=600, h=520, profile="random", seed=8)),
+]
+
+
+@pytest.mark.parametrize("name,kw", CASES, ids=[c[0] for c in CASES])
+def test_deflate_tiles_decode_to_oracle_planes(name, kw, gpu_ctx, port, tables):
+    b = make_block(**kw)
+    h, w = b["esa"].shape
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    gpu_ctx.set_option("strip_rows", 1024)
+    try:
+        res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    finally:
+        gpu_ctx.set_option("strip_rows", 2048)
+    assert sorted(res["tiles"]) == list(range(18))
+    for k in range(18):
+        full = _assemble(res["tiles"][k], w, h)
+        assert np.array_equal(full[:h, :w], want[k]), f"{name}: plane {k}"
+        assert not full[h:, :].any() and not full[:, w:].any(), "edge padding must be zero"
+
+
+def test_deflate_stored_fallback_and_masks(gpu_ctx, port, tables):
+    """Noise through a noisy table cannot be compressed: tiles must fall back to stored blocks and still
+    decode; a mask selects planes."""
+    rng = np.random.default_rng(1)
+    t = rng.integers(0, 255, size=tables.shape).astype(np.int32)
+    b = make_block(w=520, h=300, profile="random", seed=9)
+    b["esa"] = rng.integers(0, 256, size=b["esa"].shape, dtype=np.uint8)
+    b["hsg"] = rng.integers(1, 5, size=b["hsg"].shape, dtype=np.uint8)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], t)
+    mask = capi.MASK_DRAINED
+    try:
+        gpu_ctx.set_luts(t)
+        res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], plane_mask=mask)
+    finally:
+        gpu_ctx.set_luts(tables)
+    assert sorted(res["tiles"]) == list(range(9))
+    sizes = [len(z) for d in res["tiles"].values() for z in d.values()]
+    assert max(sizes) == 2 + 10 + 65536 + 4, "expected at least one stored tile"
+    for k in range(9):
+        assert np.array_equal(_assemble(res["tiles"][k], 520, 300)[:300, :520], want[k])
+
+
+def test_deflate_compresses_cn_rasters(gpu_ctx):
+    b = make_block(w=2048, h=2048, seed=10, esa_patch=192, hsg_patch=9)
+    res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], plane_mask=capi.MASK_DRAINED)
+    ratio = 9 * 2048 * 2048 / res["bytes"]
+    assert ratio > 4.0, f"compression ratio only {ratio:.2f}"
