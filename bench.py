@@ -404,6 +404,40 @@ def run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_o
             step()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        # ---- same call with the reference's save_raster() encode step fused in: DEFLATE tiles come back
+        nbytes = [0, 0]
+
+        def _sink(_user, sp):
+            st = sp.contents
+            nbytes[0] += st.blob_bytes
+            nbytes[1] += st.n_planes * st.n_tile_rows * st.tiles_x * 12 + 16
+            return 0
+
+        cb = capi.TILE_SINK(_sink)
+
+        def step_deflate():
+            rc = lib.gcn10_cuda_block_deflate(ctx.h, esa_pin.array.ctypes.data, w, rows, w, gt6, hsg_np.ctypes.data, hsx,
+                                              hsy, hsx, sgt6, capi.MASK_DRAINED, cb, None)
+            if rc:
+                raise RuntimeError(lib.gcn10_cuda_last_error().decode())
+
+        for _ in range(2):
+            step_deflate()
+        barrier()
+        nbytes[0] = nbytes[1] = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_deflate()
+        barrier()
+        dt_z = max_over_ranks(time.perf_counter() - t0)
+        deflate = {"value": world * float(w) * rows * steps / dt_z / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": int(w * rows + hsg_np.size),
+                   "d2h_bytes_per_step": int((nbytes[0] + nbytes[1]) / steps),
+                   "steps": steps, "ms_per_step": dt_z / steps * 1e3, "kernel_ms_per_step": ctx.last_kernel_ms(),
+                   "compression_ratio": NVAR * float(w) * rows * steps / max(nbytes[0], 1),
+                   "path": "gcn10_cuda_block_deflate: pinned host raster -> H2D / fused CN kernel / GPU tile DEFLATE / "
+                           "D2H of zlib tile streams (the payload of save_raster's GTiff tiles) -> pinned host"}
+
         res = {"value": world * float(w) * rows * steps / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(w * rows + hsg_np.size), "d2h_bytes_per_step": int(NVAR * w * rows),
                "steps": steps, "ms_per_step": dt / steps * 1e3,
@@ -411,6 +445,7 @@ def run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_o
                "path": "gcn10_cuda_block: pinned host rasters -> strip-pipelined H2D / fused kernel / D2H -> pinned host planes"}
         if note:
             res["note"] = note
+        res["deflate_tiles"] = deflate
         return res
     finally:
         esa_pin.free()

@@ -22,7 +22,7 @@
 namespace gcn10 {
 
 constexpr int kTile = 256;                  // GDAL's default block size for TILED=YES
-constexpr int kTileStride = 260;            // smem row stride: 65 words -> row-per-thread access hits distinct banks
+constexpr int kTileStride = 272;            // smem row stride: 17 x 16 B -> one-row-per-thread LDS.128 is conflict free
 constexpr int kTileBytes = kTile * kTile;
 constexpr int kEncCap = 40 * 1024;          // compressed tiles larger than this are emitted as stored blocks
 constexpr int kStoredBytes = 2 + 2 * 5 + kTileBytes + 4;     // zlib header + two stored blocks + Adler-32
@@ -86,43 +86,52 @@ __device__ __forceinline__ void match_code(int len, bool above, uint32_t &bits, 
     n = nb;
 }
 
-// length of the run starting at column x in which row[] equals ref[] (ref = row above) -- word at a time
-__device__ __forceinline__ int run_equal(const uint8_t *row, const uint8_t *ref, int x)
+// Per-row word masks, built once and reused by both parses:
+//   above bit j : word j of the row equals word j of the row above
+//   left  bit j : word j consists of four copies of the last byte of word j-1
+struct RowMasks {
+    unsigned long long above, left;
+};
+
+__device__ __forceinline__ uint32_t bcast_byte(uint32_t v) { return (v & 255u) * 0x01010101u; }
+
+// number of consecutive set bits of m starting at bit j (j < 64)
+__device__ __forceinline__ int ones_from(unsigned long long m, int j)
 {
-    int n = 0;
-    while (x + n < kTile && ((x + n) & 3)) {
-        if (row[x + n] != ref[x + n])
-            return n;
-        n++;
-    }
-    while (x + n < kTile) {
-        uint32_t a = *reinterpret_cast<const uint32_t *>(row + x + n);
-        uint32_t b = *reinterpret_cast<const uint32_t *>(ref + x + n);
-        uint32_t d = a ^ b;
-        if (d)
-            return n + ((__ffs(d) - 1) >> 3);
-        n += 4;
-    }
-    return n;
+    const unsigned long long inv = ~(m >> j);       // bits shifted in from the top are 0 -> 1 after the inversion
+    return __ffsll((long long)inv) - 1;             // inv != 0 whenever j > 0; for j == 0 a full mask gives ffs = 0
 }
 
-// length of the run starting at column x of bytes equal to v
-__device__ __forceinline__ int run_value(const uint8_t *row, uint32_t v, int x)
+// length of the match starting at column x where the row equals `pat` word by word:
+// pat_word(j) is the reference word for word j (row above, or four copies of the run byte)
+template <bool ABOVE>
+__device__ __forceinline__ int run_len(const uint8_t *row, unsigned long long mask, uint32_t runv, int x)
 {
-    const uint32_t vv = v * 0x01010101u;
-    int n = 0;
-    while (x + n < kTile && ((x + n) & 3)) {
-        if (row[x + n] != v)
-            return n;
-        n++;
-    }
-    while (x + n < kTile) {
-        uint32_t d = *reinterpret_cast<const uint32_t *>(row + x + n) ^ vv;
+    const uint32_t *rw = reinterpret_cast<const uint32_t *>(row);
+    const uint32_t *uw = reinterpret_cast<const uint32_t *>(row - kTileStride);
+    int j = x >> 2, len = 0;
+    const int o = x & 3;
+    if (o) {
+        const uint32_t ref = ABOVE ? uw[j] : runv;
+        const uint32_t d = (rw[j] ^ ref) >> (8 * o);
         if (d)
-            return n + ((__ffs(d) - 1) >> 3);
-        n += 4;
+            return (__ffs(d) - 1) >> 3;
+        len = 4 - o;
+        j++;
+        if (j == kTile / 4)
+            return len;
     }
-    return n;
+    int nw = (j == 0 && mask == ~0ull) ? 64 : ones_from(mask, j);
+    if (nw > kTile / 4 - j)
+        nw = kTile / 4 - j;
+    len += 4 * nw;
+    j += nw;
+    if (j < kTile / 4) {
+        const uint32_t ref = ABOVE ? uw[j] : runv;
+        const uint32_t d = rw[j] ^ ref;             // non-zero: the mask bit is clear
+        len += d ? (__ffs(d) - 1) >> 3 : 4;
+    }
+    return len;
 }
 
 __device__ __forceinline__ void put_bits(uint32_t *out, unsigned long long pos, uint32_t v, int n)
@@ -136,14 +145,19 @@ __device__ __forceinline__ void put_bits(uint32_t *out, unsigned long long pos, 
 // Greedy parse of one tile row.  WRITE = false: returns the bit count.  WRITE = true: emits the bits
 // at position pos and returns the end position.
 template <bool WRITE>
-__device__ __forceinline__ unsigned long long parse_row(const uint8_t *tile, int r, uint32_t *out, unsigned long long pos)
+__device__ __forceinline__ unsigned long long parse_row(const uint8_t *tile, int r, const RowMasks &m, uint32_t *out,
+                                                        unsigned long long pos)
 {
     const uint8_t *row = tile + r * kTileStride;
-    const uint8_t *up = row - kTileStride;
     int x = 0;
     while (x < kTile) {
-        const int la = r > 0 ? run_equal(row, up, x) : 0;
-        const int lr = x > 0 ? run_value(row, row[x - 1], x) : 0;
+        const int la = r > 0 ? run_len<true>(row, m.above, 0, x) : 0;
+        int lr = 0;
+        if (x > 0) {
+            // the left mask says "word == copies of the previous word's last byte"; starting inside a run of
+            // row[x-1] that chain is exactly "equals row[x-1]"
+            lr = run_len<false>(row, m.left, bcast_byte(row[x - 1]), x);
+        }
         const int len = la >= lr ? la : lr;
         uint32_t bits;
         int n;
@@ -196,30 +210,45 @@ deflate_tiles_kernel(const __grid_constant__ TileEncParams p)
                 v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
         }
-        uint32_t *d = reinterpret_cast<uint32_t *>(tile + r * kTileStride + c);
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        *reinterpret_cast<uint4 *>(tile + r * kTileStride + c) = v;
     }
     for (int i = tid; i < kEncCap / 4 + 8; i += kTile)
         out[i] = 0;
     __syncthreads();
 
-    // ---- pass 1: bits per row; Adler-32 partial sums of the row (thread r owns tile row r)
-    const unsigned long long row_bits = parse_row<false>(tile, tid, nullptr, 0);
+    // ---- pass 1 (thread r owns tile row r): word masks, Adler-32 partial sums, bits per row
+    RowMasks m;
+    m.above = 0;
+    m.left = 0;
     unsigned long long sa = 0, sb = 0;
     {
-        const uint8_t *row = tile + tid * kTileStride;
-        for (int x = 0; x < kTile; x += 4) {
-            const uint32_t wv = *reinterpret_cast<const uint32_t *>(row + x);
+        const uint4 *rowv = reinterpret_cast<const uint4 *>(tile + tid * kTileStride);
+        const uint4 *upv = rowv - kTileStride / 16;
+        uint32_t s1 = 0, s2 = 0, last = 0;
+#pragma unroll 4
+        for (int i = 0; i < kTile / 16; i++) {
+            const uint4 cv = rowv[i];
+            const uint4 uv = tid > 0 ? upv[i] : make_uint4(~cv.x, ~cv.y, ~cv.z, ~cv.w);
+            const uint32_t cw[4] = { cv.x, cv.y, cv.z, cv.w };
+            const uint32_t uw[4] = { uv.x, uv.y, uv.z, uv.w };
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t b = (wv >> (8 * k)) & 255u;
-                sa += b;
-                sb += (unsigned long long)b * (unsigned)(x + k);
+                const int j = 4 * i + k;
+                if (cw[k] == uw[k])
+                    m.above |= 1ull << j;
+                if (j > 0 && cw[k] == last * 0x01010101u)
+                    m.left |= 1ull << j;
+                last = cw[k] >> 24;
+                const uint32_t s = __dp4a(cw[k], 0x01010101u, 0u);           // sum of the four bytes
+                s1 += s;
+                s2 += 4u * j * s + __dp4a(cw[k], 0x03020100u, 0u);           // sum of x * byte
             }
         }
+        sa = s1;
         // contribution of this row to s2 = N + sum_i (N - i) d_i with i = 256 r + x
-        sb = (unsigned long long)(kTileBytes - kTile * tid) * sa - sb;
+        sb = (unsigned long long)(kTileBytes - kTile * tid) * s1 - s2;
     }
+    const unsigned long long row_bits = parse_row<false>(tile, tid, m, nullptr, 0);
     // inclusive scan of row_bits over the block + block sums of sa / sb
     unsigned long long inc = row_bits;
 #pragma unroll
@@ -276,7 +305,7 @@ deflate_tiles_kernel(const __grid_constant__ TileEncParams p)
             put_bits(out, 0, 0x9C78u, 16);      // CMF = 0x78 (deflate, 32K window), FLG = 0x9C
             put_bits(out, 16, 0x3u, 3);         // BFINAL = 1, BTYPE = 01 (fixed Huffman), LSB first
         }
-        parse_row<true>(tile, tid, out, row_pos);
+        parse_row<true>(tile, tid, m, out, row_pos);
         __syncthreads();
         if (tid == 0) {
             // end-of-block is seven zero bits (already zero); Adler-32 big endian after the padding
