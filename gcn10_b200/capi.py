@@ -24,7 +24,7 @@ MASK_ALL = 0x3FFFF
 EXPORTS = (
     "gcn10_cuda_version", "gcn10_cuda_last_error", "gcn10_cuda_device_count", "gcn10_cuda_create",
     "gcn10_cuda_destroy", "gcn10_cuda_set_luts", "gcn10_cuda_block", "gcn10_cuda_block_rows",
-    "gcn10_cuda_block_deflate", "gcn10_cuda_block_device",
+    "gcn10_cuda_block_deflate", "gcn10_cuda_block_deflate_rows", "gcn10_cuda_block_device",
     "gcn10_cuda_index_maps", "gcn10_cuda_synchronize", "gcn10_cuda_last_kernel_ms",
     "gcn10_cuda_launch_count", "gcn10_cuda_set_option", "gcn10_cuda_host_alloc", "gcn10_cuda_host_free",
     "gcn10_cuda_host_register", "gcn10_cuda_host_unregister",
@@ -68,6 +68,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     lib.gcn10_cuda_block_rows.argtypes = blk[:4] + [C.c_int, C.c_int] + blk[4:]
     lib.gcn10_cuda_block_device.argtypes = blk + [_vp]
     lib.gcn10_cuda_block_deflate.argtypes = blk[:12] + [TILE_SINK, _vp]
+    lib.gcn10_cuda_block_deflate_rows.argtypes = blk[:4] + [C.c_int, C.c_int] + blk[4:12] + [TILE_SINK, _vp]
     lib.gcn10_cuda_index_maps.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp, _vp, _vp]
     lib.gcn10_cuda_synchronize.argtypes = [_vp]
     lib.gcn10_cuda_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float)]

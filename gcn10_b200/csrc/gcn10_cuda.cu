@@ -706,10 +706,23 @@ int gcn10_cuda_block_deflate(gcn10_ctx *c,
                              const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
                              unsigned plane_mask, gcn10_tile_sink sink, void *user)
 {
+    return gcn10_cuda_block_deflate_rows(c, esa, w, h, 0, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt,
+                                         plane_mask, sink, user);
+}
+
+int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
+                                  const uint8_t *esa, int w, int h, int row0, int nrows, size_t esa_pitch,
+                                  const double gt[6],
+                                  const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                                  unsigned plane_mask, gcn10_tile_sink sink, void *user)
+{
     if (!c)
         return fail(GCN10_EINVAL, "NULL context");
     if (!sink)
         return fail(GCN10_EINVAL, "NULL sink");
+    if (row0 < 0 || nrows <= 0 || row0 > h - nrows || row0 % kTile != 0 || (nrows % kTile != 0 && row0 + nrows != h))
+        return fail(GCN10_EINVAL, "row band [%d, +%d) must start on a 256-row tile boundary and end on one or at "
+                                  "the block's last row (%d)", row0, nrows, h);
     int rc = check_geometry(esa, w, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask, (const void *)sink,
                             (size_t)w);
     if (rc)
@@ -744,7 +757,7 @@ int gcn10_cuda_block_deflate(gcn10_ctx *c,
     // strips of whole tile rows
     const size_t dpitch = round_up((size_t)w, 256);
     const int ns = c->nstreams;
-    const int strip = std::max(kTile, std::min(c->strip_rows, (int)round_up((size_t)h, kTile)) / kTile * kTile);
+    const int strip = std::max(kTile, std::min(c->strip_rows, (int)round_up((size_t)nrows, kTile)) / kTile * kTile);
     const int tiles_x = (w + kTile - 1) / kTile;
     const int strip_tile_rows = strip / kTile;
     const size_t ntile_slot = (size_t)nplanes * strip_tile_rows * tiles_x;
@@ -764,13 +777,13 @@ int gcn10_cuda_block_deflate(gcn10_ctx *c,
         sl.timed = false;
     }
 
-    const int nstrips = (h + strip - 1) / strip;
+    const int nstrips = (nrows + strip - 1) / strip;
     float kernel_ms = 0.f;
 
     auto issue = [&](int s) -> int {
         StripSlot &sl = c->slots[s % ns];
         cudaStream_t st = c->streams[s % ns];
-        const int y0 = s * strip, rows = std::min(strip, h - y0);
+        const int y0 = s * strip, rows = std::min(strip, nrows - y0);      // y0 counts rows of the caller's band
         const int tile_rows = (rows + kTile - 1) / kTile;
         sl.y0 = y0;
         sl.rows = rows;
@@ -781,7 +794,7 @@ int gcn10_cuda_block_deflate(gcn10_ctx *c,
             d_out[plane_ids[k]] = (uint8_t *)sl.out.p + (size_t)k * dpitch * (size_t)strip;
         CUDA_TRY(cudaEventRecord(sl.k0, st));
         for (int i = 0; i < nplans; i++) {
-            int r2 = launch_rows(c, plans[i], i, (const uint8_t *)sl.esa.p, dpitch, w, rows, y0, (const uint8_t *)c->hsg.p,
+            int r2 = launch_rows(c, plans[i], i, (const uint8_t *)sl.esa.p, dpitch, w, rows, row0 + y0, (const uint8_t *)c->hsg.p,
                                  hsg_dpitch, hsx, hsy, map, tma_ok, d_out, dpitch, st);
             if (r2)
                 return r2;
@@ -828,7 +841,7 @@ int gcn10_cuda_block_deflate(gcn10_ctx *c,
         CUDA_TRY(cudaMemcpyAsync(sl.h_blob.p, sl.blob.p, used, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         gcn10_tile_strip ts;
-        ts.tile_row0 = sl.y0 / kTile;
+        ts.tile_row0 = (row0 + sl.y0) / kTile;
         ts.n_tile_rows = (sl.rows + kTile - 1) / kTile;
         ts.tiles_x = tiles_x;
         ts.n_planes = nplanes;

@@ -4,9 +4,12 @@
  * inputs (block id -> bbox -> two raster windows), same 18 outputs with the same names, same log
  * lines and the same two-tier error convention (recoverable: log ERROR and skip the block; fatal:
  * exit(1) where the reference calls MPI_Abort).  What changes is the middle: instead of five CPU
- * passes per raster (cn.c:218-290) the block is streamed band by band (1024 rows, a multiple of the
- * 256-row GeoTIFF tiles) through gcn10_cuda_block_rows(), and while the GPU works on band i+1 the
- * DEFLATE threads encode band i.
+ * passes per raster (cn.c:218-290) the block is streamed band by band (2048 rows, a multiple of the
+ * 256-row GeoTIFF tiles).  Default path: a reader thread decodes land-cover band i+1 while the GPU runs
+ * gcn10_cuda_block_deflate_rows() on band i -- Curve Numbers AND the DEFLATE tiles of save_raster()
+ * (raster.c:204-219) are produced on the device -- and the worker only appends the compressed tiles to
+ * the 18 GeoTIFFs.  With GCN10_HOST_DEFLATE=1 the raw planes come back instead
+ * (gcn10_cuda_block_rows) and a zlib thread pool encodes them, overlapped with the next band.
  *
  * gh_run_blocks() replaces the MPI round-robin of main.c:171: one worker thread and one gcn10_ctx
  * per GPU, block ids popped from a shared atomic counter; the join of the workers is the barrier
@@ -27,7 +30,7 @@
 #include <sys/stat.h>
 #include <time.h>
 
-enum { BAND_ROWS = 1024, NPLANES = GCN10_NPLANES };
+enum { BAND_ROWS = 2048, NPLANES = GCN10_NPLANES };
 
 static const char *const k_conds[2] = { "drained", "undrained" };      /* cn.c:145 */
 static const char *const k_hcs[3] = { "p", "f", "g" };                 /* cn.c:146 */
@@ -37,7 +40,7 @@ typedef struct {
     uint8_t *esa;                   /* pinned: BAND_ROWS x pitch */
     uint8_t *planes[NPLANES];       /* pinned: BAND_ROWS x pitch each */
     int y0, rows;
-    int state;                      /* 0 free, 1 filled (waiting for the encoder) */
+    int state;                      /* 0 free, 1 filled (waiting for its consumer), -1 read failed */
 } band_buf;
 
 typedef struct worker {
@@ -53,6 +56,7 @@ typedef struct worker {
     gh_log *log0;                   /* worker 0's log: progress lines go there (log.c:199-207) */
     gcn10_ctx *ctx;
     size_t pitch_cap;
+    int have_planes;
     band_buf bands[2];
     /* encoder hand-off */
     pthread_mutex_t mu;
@@ -77,17 +81,17 @@ static void fatal(worker *wk, const char *msg)
     exit(1);
 }
 
-static int ensure_bands(worker *wk, size_t pitch)
+static int ensure_bands(worker *wk, size_t pitch, int need_planes)
 {
-    if (wk->pitch_cap >= pitch)
+    if (wk->pitch_cap >= pitch && (!need_planes || wk->have_planes))
         return 0;
     for (int b = 0; b < 2; b++) {
         gcn10_cuda_host_free(wk->bands[b].esa);
         wk->bands[b].esa = gcn10_cuda_host_alloc(pitch * BAND_ROWS);
         for (int k = 0; k < NPLANES; k++) {
             gcn10_cuda_host_free(wk->bands[b].planes[k]);
-            wk->bands[b].planes[k] = gcn10_cuda_host_alloc(pitch * BAND_ROWS);
-            if (!wk->bands[b].planes[k])
+            wk->bands[b].planes[k] = need_planes ? gcn10_cuda_host_alloc(pitch * BAND_ROWS) : NULL;
+            if (need_planes && !wk->bands[b].planes[k])
                 return -1;
         }
         if (!wk->bands[b].esa)
@@ -95,6 +99,7 @@ static int ensure_bands(worker *wk, size_t pitch)
         wk->bands[b].state = 0;
     }
     wk->pitch_cap = pitch;
+    wk->have_planes = need_planes;
     return 0;
 }
 
@@ -138,6 +143,165 @@ static void output_path(const worker *wk, int cond, int hi, int ai, int block_id
                      block_id);
         }
     }
+}
+
+/* ---- GPU-deflate path: reader thread -> gcn10_cuda_block_deflate_rows -> append compressed tiles ---- */
+
+typedef struct {
+    worker *wk;
+    gh_tiff *esa_ds;
+    const gh_window *we;
+    int w, h;
+    size_t pitch;
+    double t_read;
+    char err[GH_ERRLEN];
+} reader_job;
+
+static void *reader_main(void *arg)
+{
+    reader_job *rj = arg;
+    worker *wk = rj->wk;
+    int turn = 0;
+    for (int y0 = 0; y0 < rj->h; y0 += BAND_ROWS, turn ^= 1) {
+        band_buf *bb = &wk->bands[turn];
+        pthread_mutex_lock(&wk->mu);
+        while (bb->state != 0 && !wk->encoder_quit)
+            pthread_cond_wait(&wk->cv, &wk->mu);
+        int quit = wk->encoder_quit;
+        pthread_mutex_unlock(&wk->mu);
+        if (quit)
+            return NULL;
+        int rows = rj->h - y0 < BAND_ROWS ? rj->h - y0 : BAND_ROWS;
+        double t0 = now_s();
+        int rc = gh_tiff_read_window(rj->esa_ds, rj->we->xoff, rj->we->yoff + y0, rj->w, rows, bb->esa, rj->pitch,
+                                     wk->opt->io_threads, rj->err, sizeof rj->err);
+        rj->t_read += now_s() - t0;
+        bb->y0 = y0;
+        bb->rows = rows;
+        pthread_mutex_lock(&wk->mu);
+        bb->state = rc ? -1 : 1;
+        pthread_cond_broadcast(&wk->cv);
+        pthread_mutex_unlock(&wk->mu);
+        if (rc)
+            return NULL;
+    }
+    return NULL;
+}
+
+static int tile_sink(void *user, const gcn10_tile_strip *st)
+{
+    worker *wk = user;
+    for (int k = 0; k < st->n_planes; k++) {
+        gh_tiffw *tw = wk->writers[st->plane_ids[k]];
+        for (int tr = 0; tr < st->n_tile_rows; tr++) {
+            size_t base = ((size_t)k * st->n_tile_rows + tr) * (size_t)st->tiles_x;
+            if (gh_tiffw_put_tile_row(tw, st->tile_row0 + tr, st->blob, st->offsets + base, st->sizes + base)) {
+                wk->encode_failed = 1;
+                return 1;
+            }
+        }
+    }
+    return 0;
+}
+
+/* returns 0 ok, 1 = land-cover read failed (recoverable tier) */
+static int bands_gpu_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const gh_window *we, const uint8_t *hsg,
+                             const gh_window *wh, size_t pitch, double *t_read, double *t_gpu)
+{
+    char msg[1024];
+    const int w = we->xcount, h = we->ycount;
+    reader_job rj = { wk, esa_ds, we, w, h, pitch, 0.0, "" };
+    pthread_t rd;
+    wk->encoder_quit = 0;
+    wk->bands[0].state = wk->bands[1].state = 0;
+    if (pthread_create(&rd, NULL, reader_main, &rj) != 0)
+        fatal(wk, "cannot start the reader thread");
+    int turn = 0, failed = 0;
+    for (int y0 = 0; y0 < h; y0 += BAND_ROWS, turn ^= 1) {
+        band_buf *bb = &wk->bands[turn];
+        pthread_mutex_lock(&wk->mu);
+        while (bb->state == 0)
+            pthread_cond_wait(&wk->cv, &wk->mu);
+        int st = bb->state;
+        pthread_mutex_unlock(&wk->mu);
+        if (st < 0) {
+            gh_log_message(wk->log, "ERROR", rj.err, 1);                            /* raster.c:182-186 */
+            failed = 1;
+            break;
+        }
+        double t1 = now_s();
+        int rc = gcn10_cuda_block_deflate_rows(wk->ctx, bb->esa, w, h, bb->y0, bb->rows, pitch, we->gt, hsg, wh->xcount,
+                                               wh->ycount, (size_t)wh->xcount, wh->gt, GCN10_MASK_ALL, tile_sink, wk);
+        if (rc && !wk->encode_failed) {
+            snprintf(msg, sizeof msg, "cuda failure on block %d: %s", block_id, gcn10_cuda_last_error());
+            fatal(wk, msg);                         /* CUDA errors are the fatal tier; there is no CPU path */
+        }
+        *t_gpu += now_s() - t1;
+        pthread_mutex_lock(&wk->mu);
+        bb->state = 0;
+        pthread_cond_broadcast(&wk->cv);
+        pthread_mutex_unlock(&wk->mu);
+        if (wk->encode_failed)
+            break;
+    }
+    pthread_mutex_lock(&wk->mu);
+    wk->encoder_quit = 1;
+    pthread_cond_broadcast(&wk->cv);
+    pthread_mutex_unlock(&wk->mu);
+    pthread_join(rd, NULL);
+    *t_read += rj.t_read;
+    return failed;
+}
+
+/* ---- host-deflate path: raw planes back, zlib thread pool encodes band i while band i+1 is computed ---- */
+
+static int bands_host_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const gh_window *we, const uint8_t *hsg,
+                              const gh_window *wh, size_t pitch, double *t_read, double *t_gpu)
+{
+    char msg[1024], err[GH_ERRLEN] = "";
+    const int w = we->xcount, h = we->ycount;
+    wk->encoder_quit = 0;
+    wk->bands[0].state = wk->bands[1].state = 0;
+    pthread_t enc;
+    if (pthread_create(&enc, NULL, encoder_main, wk) != 0)
+        fatal(wk, "cannot start the encoder thread");
+    int turn = 0, failed = 0;
+    for (int y0 = 0; y0 < h && !failed; y0 += BAND_ROWS, turn ^= 1) {
+        band_buf *bb = &wk->bands[turn];
+        int rows = h - y0 < BAND_ROWS ? h - y0 : BAND_ROWS;
+        pthread_mutex_lock(&wk->mu);
+        while (bb->state != 0)
+            pthread_cond_wait(&wk->cv, &wk->mu);
+        pthread_mutex_unlock(&wk->mu);
+        double t0 = now_s();
+        if (gh_tiff_read_window(esa_ds, we->xoff, we->yoff + y0, w, rows, bb->esa, pitch, wk->opt->io_threads, err,
+                                sizeof err)) {
+            gh_log_message(wk->log, "ERROR", err, 1);                               /* raster.c:182-186 */
+            failed = 1;
+            break;
+        }
+        double t1 = now_s();
+        int rc = gcn10_cuda_block_rows(wk->ctx, bb->esa, w, h, y0, rows, pitch, we->gt, hsg, wh->xcount, wh->ycount,
+                                       (size_t)wh->xcount, wh->gt, GCN10_MASK_ALL, bb->planes, pitch);
+        if (rc) {
+            snprintf(msg, sizeof msg, "cuda failure on block %d: %s", block_id, gcn10_cuda_last_error());
+            fatal(wk, msg);
+        }
+        *t_read += t1 - t0;
+        *t_gpu += now_s() - t1;
+        bb->y0 = y0;
+        bb->rows = rows;
+        pthread_mutex_lock(&wk->mu);
+        bb->state = 1;
+        pthread_cond_broadcast(&wk->cv);
+        pthread_mutex_unlock(&wk->mu);
+    }
+    pthread_mutex_lock(&wk->mu);
+    wk->encoder_quit = 1;
+    pthread_cond_broadcast(&wk->cv);
+    pthread_mutex_unlock(&wk->mu);
+    pthread_join(enc, NULL);
+    return failed;
 }
 
 static int gh_process_block(worker *wk, int block_id, int total_blocks)
@@ -196,7 +360,9 @@ static int gh_process_block(worker *wk, int block_id, int total_blocks)
 
     const int w = we.xcount, h = we.ycount;
     const size_t pitch = ((size_t)w + 255) / 256 * 256;
-    if (ensure_bands(wk, pitch)) {
+    const char *hd = getenv("GCN10_HOST_DEFLATE");
+    const int host_deflate = hd && *hd && *hd != '0';
+    if (ensure_bands(wk, pitch, host_deflate)) {
         snprintf(msg, sizeof msg, "pinned allocation failed for block %d: %s", block_id, gcn10_cuda_last_error());
         fatal(wk, msg);
     }
@@ -230,50 +396,11 @@ static int gh_process_block(worker *wk, int block_id, int total_blocks)
         return -1;
     }
 
-    /* band loop: decode -> GPU -> (encoder thread) DEFLATE + append */
+    /* band loop */
     wk->encode_failed = 0;
-    wk->encoder_quit = 0;
-    wk->bands[0].state = wk->bands[1].state = 0;
-    pthread_t enc;
-    if (pthread_create(&enc, NULL, encoder_main, wk) != 0)
-        fatal(wk, "cannot start the encoder thread");
-    int turn = 0, failed = 0;
     double t_read = 0, t_gpu = 0;
-    for (int y0 = 0; y0 < h && !failed; y0 += BAND_ROWS, turn ^= 1) {
-        band_buf *bb = &wk->bands[turn];
-        int rows = h - y0 < BAND_ROWS ? h - y0 : BAND_ROWS;
-        pthread_mutex_lock(&wk->mu);
-        while (bb->state != 0)
-            pthread_cond_wait(&wk->cv, &wk->mu);
-        pthread_mutex_unlock(&wk->mu);
-        double t0 = now_s();
-        if (gh_tiff_read_window(esa_ds, we.xoff, we.yoff + y0, w, rows, bb->esa, pitch, wk->opt->io_threads, err,
-                                sizeof err)) {
-            gh_log_message(wk->log, "ERROR", err, 1);                               /* raster.c:182-186 */
-            failed = 1;
-            break;
-        }
-        double t1 = now_s();
-        int rc = gcn10_cuda_block_rows(wk->ctx, bb->esa, w, h, y0, rows, pitch, we.gt, hsg, wh.xcount, wh.ycount,
-                                       (size_t)wh.xcount, wh.gt, GCN10_MASK_ALL, bb->planes, pitch);
-        if (rc) {
-            snprintf(msg, sizeof msg, "cuda failure on block %d: %s", block_id, gcn10_cuda_last_error());
-            fatal(wk, msg);                         /* CUDA errors are the fatal tier; there is no CPU path */
-        }
-        t_read += t1 - t0;
-        t_gpu += now_s() - t1;
-        bb->y0 = y0;
-        bb->rows = rows;
-        pthread_mutex_lock(&wk->mu);
-        bb->state = 1;
-        pthread_cond_broadcast(&wk->cv);
-        pthread_mutex_unlock(&wk->mu);
-    }
-    pthread_mutex_lock(&wk->mu);
-    wk->encoder_quit = 1;
-    pthread_cond_broadcast(&wk->cv);
-    pthread_mutex_unlock(&wk->mu);
-    pthread_join(enc, NULL);
+    int failed = host_deflate ? bands_host_deflate(wk, block_id, esa_ds, &we, hsg, &wh, pitch, &t_read, &t_gpu)
+                              : bands_gpu_deflate(wk, block_id, esa_ds, &we, hsg, &wh, pitch, &t_read, &t_gpu);
     free(hsg);
     gh_tiff_close(esa_ds);
 
@@ -301,8 +428,8 @@ static int gh_process_block(worker *wk, int block_id, int total_blocks)
     }
     double dt = now_s() - t_start;
     snprintf(msg, sizeof msg,
-             "block %d: %d x %d px, 18 rasters in %.2f s (%.1f Mpx/s; decode %.2f s, gpu+copies %.2f s)", block_id,
-             w, h, dt, (double)w * h / dt / 1e6, t_read, t_gpu);
+             "block %d: %d x %d px, 18 rasters in %.2f s (%.1f Mpx/s; decode %.2f s, gpu+copies %.2f s; %s deflate)",
+             block_id, w, h, dt, (double)w * h / dt / 1e6, t_read, t_gpu, host_deflate ? "host" : "gpu");
     gh_log_message(wk->log, "INFO", msg, 0);
     return ok ? 0 : -1;
 

@@ -611,6 +611,25 @@ int gh_tiffw_write_rows(gh_tiffw *tw, const uint8_t *data, size_t pitch, int y0,
     return tw->failed ? -1 : 0;
 }
 
+int gh_tiffw_put_tile_row(gh_tiffw *tw, int tile_row, const uint8_t *blob, const uint64_t *offsets,
+                          const uint32_t *sizes)
+{
+    if (tw->failed || tile_row != tw->next_tile_row || tile_row >= tw->tiles_y)
+        return -1;
+    for (int tx = 0; tx < tw->tiles_x; tx++) {
+        size_t ti = (size_t)tile_row * (size_t)tw->tiles_x + (size_t)tx;
+        if (tw->pos + sizes[tx] > 0xFFFFFFF0ull || fwrite(blob + offsets[tx], 1, sizes[tx], tw->fp) != sizes[tx]) {
+            tw->failed = 1;
+            return -1;
+        }
+        tw->offsets[ti] = (uint32_t)tw->pos;
+        tw->counts[ti] = sizes[tx];
+        tw->pos += sizes[tx];
+    }
+    tw->next_tile_row++;
+    return 0;
+}
+
 static void put16(unsigned char **p, uint16_t v) { (*p)[0] = (unsigned char)v; (*p)[1] = (unsigned char)(v >> 8); *p += 2; }
 static void put32(unsigned char **p, uint32_t v) { for (int i = 0; i < 4; i++) (*p)[i] = (unsigned char)(v >> (8 * i)); *p += 4; }
 static void put_f64(unsigned char **p, double d) { uint64_t v; memcpy(&v, &d, 8); for (int i = 0; i < 8; i++) (*p)[i] = (unsigned char)(v >> (8 * i)); *p += 8; }

@@ -16,6 +16,11 @@ int gh_tiffw_open(const char *path, int w, int h, const double gt[6], gh_tiffw *
 /* Appends rows [y0, y0+nrows): y0 must continue where the previous call stopped and be a multiple
  * of 256; nrows must be a multiple of 256 except for the last band of the raster. */
 int gh_tiffw_write_rows(gh_tiffw *tw, const uint8_t *data, size_t pitch, int y0, int nrows, int threads);
+/* Appends tiles that are already compressed (complete zlib streams of 256 x 256 bytes, e.g. from
+ * gcn10_cuda_block_deflate): tile row `tile_row` must be the next one not yet written; sizes / offsets
+ * address `blob` for the tiles_x tiles of that row. */
+int gh_tiffw_put_tile_row(gh_tiffw *tw, int tile_row, const uint8_t *blob, const uint64_t *offsets,
+                          const uint32_t *sizes);
 /* Writes the tile tables, georeferencing and IFD; 0 ok. */
 int gh_tiffw_close(gh_tiffw *tw);
 void gh_tiffw_abort(gh_tiffw *tw);

@@ -142,6 +142,14 @@ int gcn10_cuda_block_deflate(gcn10_ctx *ctx,
                              const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
                              unsigned plane_mask, gcn10_tile_sink sink, void *user);
 
+/* Band form of gcn10_cuda_block_deflate (see gcn10_cuda_block_rows): esa points at block row `row0`,
+ * which must be a multiple of 256; nrows must be a multiple of 256 unless the band ends the block. */
+int gcn10_cuda_block_deflate_rows(gcn10_ctx *ctx,
+                                  const uint8_t *esa, int w, int h, int row0, int nrows, size_t esa_pitch,
+                                  const double gt[6],
+                                  const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                                  unsigned plane_mask, gcn10_tile_sink sink, void *user);
+
 /* Same computation with every buffer already in DEVICE memory; asynchronous on `stream`
  * (NULL = the context's own non-blocking stream; to use the legacy default stream pass
  * cudaStreamLegacy, i.e. (void *)1).  Fast path requirements: esa, every selected out[k], and

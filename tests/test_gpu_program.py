@@ -42,16 +42,22 @@ def world(tmp_path_factory):
     return dict(root=root, esa=esa, esa_t=esa_t, hsg=hsg, hsg_t=hsg_t, blocks=blocks)
 
 
-def _run(world, *extra):
+def _run(world, *extra, host_deflate=False):
     exe = hostlib.EXE_PATH
     assert os.path.exists(exe), "gcn10 executable not built (make host)"
     root = world["root"]
+    env = dict(os.environ, GCN10_HOST_DEFLATE="1" if host_deflate else "0")
     return subprocess.run([exe, "-c", str(root / "config.txt"), "-l", str(root / "blocks.txt"), "--gpus", "1",
-                           "--io-threads", "4", *extra], cwd=str(root), capture_output=True, text=True, timeout=300)
+                           "--io-threads", "4", *extra], cwd=str(root), capture_output=True, text=True, timeout=300,
+                          env=env)
 
 
-def test_program_matches_reference_process_block(world, ref):
-    r = _run(world, "-o")
+@pytest.mark.parametrize("host_deflate", [False, True], ids=["gpu_deflate", "host_deflate"])
+def test_program_matches_reference_process_block(world, ref, host_deflate):
+    from PIL import Image
+    import shutil
+    shutil.rmtree(world["root"] / "logs", ignore_errors=True)      # log files are opened for append (log.c:79)
+    r = _run(world, "-o", host_deflate=host_deflate)
     assert r.returncode == 0, r.stderr
     root = world["root"]
     for bid, x0, y0, x1, y1 in world["blocks"][:2]:
@@ -65,6 +71,8 @@ def test_program_matches_reference_process_block(world, ref):
             got = t.read()
             t.close()
             assert np.array_equal(got, want["planes"][k]), f"{rel}: {(got != want['planes'][k]).sum()} px differ"
+            if k in (0, 17):                                    # independent decoder (libtiff) on the same file
+                assert np.array_equal(np.array(Image.open(str(root / rel))), want["planes"][k]), rel
     # blocks 13 (no overlap) and 99 (not in the shapefile) are skipped with the reference's messages
     assert "esa load failed for block 13" in r.stderr and "invalid raster bounds" in r.stderr
     assert "block 99 not found" in r.stderr

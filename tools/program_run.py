@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--size", type=int, default=9000, help="block edge in pixels")
     ap.add_argument("--io-threads", type=int, default=0)
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--host-deflate", action="store_true", help="raw planes over PCIe + zlib on the host")
     a = ap.parse_args()
     px = 1.0 / 12000.0
     hpx = 1.0 / 480.0
@@ -50,14 +51,15 @@ def main():
     if a.io_threads:
         cmd += ["--io-threads", str(a.io_threads)]
     t0 = time.time()
-    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True)
+    env = dict(os.environ, GCN10_HOST_DEFLATE="1" if a.host_deflate else "0")
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, env=env)
     dt = time.time() - t0
     print(f"gcn10 rc={r.returncode} wall {dt:.2f} s -> {n * s * s / dt / 1e6:.1f} Mpx/s end to end "
           f"({18 * n} GeoTIFFs, {sum(os.path.getsize(p) for p in glob.glob(root + '/cn_rasters_*/*.tif')) / 1e6:.1f} MB)")
     for lp in sorted(glob.glob(os.path.join(root, "logs", "rank_*.log"))):
         txt = open(lp).read()
         ids = re.findall(r"processing block (\d+)", txt)
-        per = re.findall(r"block (\d+): .* in ([\d.]+) s \(([\d.]+) Mpx/s; decode ([\d.]+) s, gpu\+copies ([\d.]+) s\)", txt)
+        per = re.findall(r"block (\d+): .* in ([\d.]+) s \(([\d.]+) Mpx/s; decode ([\d.]+) s, gpu\+copies ([\d.]+) s; (\w+) deflate\)", txt)
         print(os.path.basename(lp), "blocks", ids, per[:3])
     if r.returncode != 0:
         print(r.stderr[-2000:])
