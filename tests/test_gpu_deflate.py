@@ -79,3 +79,42 @@ def test_deflate_compresses_cn_rasters(gpu_ctx):
     res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], plane_mask=capi.MASK_DRAINED)
     ratio = 9 * 2048 * 2048 / res["bytes"]
     assert ratio > 4.0, f"compression ratio only {ratio:.2f}"
+
+
+def test_deflate_rows_bands_equal_whole_block(gpu_ctx, port, tables):
+    """Band form: tiles of rows [row0, row0+n) carry the block's tile-row numbers and decode to the same
+    bytes as the whole-block call."""
+    import ctypes as C
+    b = make_block(w=900, h=1400, seed=21, shift=(0.0005, 0.0003), margin=1)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    lib = gpu_ctx.lib
+    h, w = b["esa"].shape
+    hsy, hsx = b["hsg"].shape
+    got = {}
+
+    def _sink(_u, sp):
+        st = sp.contents
+        blob = C.string_at(st.blob, st.blob_bytes)
+        for k in range(st.n_planes):
+            for tr in range(st.n_tile_rows):
+                for tx in range(st.tiles_x):
+                    i = (k * st.n_tile_rows + tr) * st.tiles_x + tx
+                    got[(st.plane_ids[k], st.tile_row0 + tr, tx)] = blob[st.offsets[i]: st.offsets[i] + st.sizes[i]]
+        return 0
+
+    cb = capi.TILE_SINK(_sink)
+    gt6 = (C.c_double * 6)(*b["gt"])
+    sgt6 = (C.c_double * 6)(*b["soil_gt"])
+    for row0, n in [(0, 512), (512, 768), (1280, 120)]:
+        band = np.ascontiguousarray(b["esa"][row0:row0 + n])
+        rc = lib.gcn10_cuda_block_deflate_rows(gpu_ctx.h, band.ctypes.data, w, h, row0, n, w, gt6, b["hsg"].ctypes.data,
+                                               hsx, hsy, hsx, sgt6, capi.MASK_UNDRAINED, cb, None)
+        assert rc == 0, lib.gcn10_cuda_last_error()
+    # a band that does not start on a tile boundary is refused
+    band = np.ascontiguousarray(b["esa"][100:356])
+    assert lib.gcn10_cuda_block_deflate_rows(gpu_ctx.h, band.ctypes.data, w, h, 100, 256, w, gt6, b["hsg"].ctypes.data,
+                                             hsx, hsy, hsx, sgt6, capi.MASK_UNDRAINED, cb, None) == -1
+    for k in range(9, 18):
+        tiles = {(r, c): z for (p, r, c), z in got.items() if p == k}
+        full = _assemble(tiles, w, h)
+        assert np.array_equal(full[:h, :w], want[k]), k
