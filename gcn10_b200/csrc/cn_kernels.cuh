@@ -184,6 +184,14 @@ __device__ __forceinline__ uint32_t soil_slot(uint32_t hv, int drained)
 constexpr int kSmemHsgOff = kLutBytes;
 constexpr int kSmemBarOff = kSmemHsgOff + kBoxRows * kBoxCols;
 constexpr int kSmemBytes = kSmemBarOff + 16;
+// store path: with GCN10_BULK_STORE=1 (default) results are staged per row in shared memory and written with
+// cp.async.bulk (TMA engine, SASS UBLKCP: +3 % over per-thread STG.128, profiles/r01_kernel_sweeps.md);
+// GCN10_BULK_STORE=0 keeps the direct-store kernel
+#ifndef GCN10_BULK_STORE
+#define GCN10_BULK_STORE 1
+#endif
+constexpr int kSmemStageOff = kSmemBarOff + 128;
+constexpr int smem_bytes_for(int planes) { return GCN10_BULK_STORE ? kSmemStageOff + 2 * planes * kStripPx : kSmemBytes; }
 
 template <int NP>
 __device__ __forceinline__ void transpose_store_word(const uint4 (&r)[4], uint32_t (&ow)[NP][4], int j)
@@ -221,8 +229,14 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
 
     const int tid = threadIdx.x;
     const int x_first = blockIdx.x * kStripPx;
-    const int x0 = x_first + tid * kVecPx;
     const int w16 = p.w & ~(kVecPx - 1);            // the right edge (< 16 px) is cn_bytes_kernel's
+#if GCN10_BULK_STORE
+    // every thread stays for the per-row barrier; threads right of the raster recompute column group 0
+    const bool active = x_first + tid * kVecPx < w16;
+    const int x0 = active ? x_first + tid * kVecPx : x_first;
+#else
+    const int x0 = x_first + tid * kVecPx;
+#endif
     const int y_begin = blockIdx.y * p.rows_per_cta;
     const int y_end = min(p.h, y_begin + p.rows_per_cta);
 
@@ -236,25 +250,47 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
     const int ci_min = min(ca, cb) & ~15, cj_min = min(ra, rb);
     const bool staged = p.use_tma && (max(ca, cb) - ci_min < kBoxCols) && (max(ra, rb) - cj_min < kBoxRows);
 
-    if (staged && tid == 0) {
+    // One thread arms the mbarrier and launches the two asynchronous fills of shared memory: the 32 KB of
+    // LUT records (1-D bulk copy, L2 resident after the first CTA) and the HSG box (2-D tensor load).
+    if (tid == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(s_bar, kBoxRows * kBoxCols);
-        tma_load_2d(s_hsg, &hsg_map, ci_min, cj_min, s_bar);
+        mbar_expect_tx(s_bar, kLutBytes + (staged ? kBoxRows * kBoxCols : 0));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(smem)), "l"(p.lut), "r"(kLutBytes), "r"(s_bar) : "memory");
+        if (staged)
+            tma_load_2d(s_hsg, &hsg_map, ci_min, cj_min, s_bar);
     }
-    // LUT records -> shared memory (32 KB, L2 resident after the first CTA)
-    {
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-#pragma unroll
-        for (int i = 0; i < kLutRecords / kThreads; i++)
-            dst[tid + i * kThreads] = __ldg(p.lut + tid + i * kThreads);
-    }
-    __syncthreads();
-    if (staged)
-        mbar_wait(s_bar, 0);
 
-    if (x0 >= w16)
+#if !GCN10_BULK_STORE
+    const bool active = x0 < w16;
+#else
+    const uint32_t row_bytes = (uint32_t)(min(w16, x_first + kStripPx) - x_first);      // multiple of 16
+    size_t row_off = (size_t)y_begin * p.out_pitch + x_first;
+#endif
+
+    // software pipeline: the land-cover vectors (and HSG row indices) of the next kPrefetch rows are in
+    // flight while the current row is looked up and stored; the first ones are issued before the wait
+    // on the shared-memory fills
+    const uint8_t *esa_ptr = p.esa + (size_t)y_begin * p.esa_pitch + x0;
+    size_t out_off = (size_t)y_begin * p.out_pitch + x0;
+    const int32_t *rowp = p.row_idx + p.y_base + y_begin;
+    uint4 eq[kPrefetch];
+    int cq[kPrefetch];
+#pragma unroll
+    for (int s = 0; s < kPrefetch; s++) {
+        const bool in = y_begin + s < y_end && (GCN10_BULK_STORE || active);
+        eq[s] = in ? ldg_stream16(esa_ptr + (size_t)s * p.esa_pitch) : make_uint4(0, 0, 0, 0);
+        cq[s] = in ? __ldg(rowp + s) : 0;
+    }
+
+    __syncthreads();            // the mbarrier is initialised
+    mbar_wait(s_bar, 0);
+
+#if !GCN10_BULK_STORE
+    if (!active)
         return;
+#endif
 
     const uint32_t swz_mask = 0x07070707u;
     uint32_t slot[G][4];            // per pixel: (slot << 4) in one byte, 4 pixels per word
@@ -264,20 +300,6 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 4; j++)
             slot[g][j] = 0;
-
-    const uint8_t *esa_ptr = p.esa + (size_t)y_begin * p.esa_pitch + x0;
-    size_t out_off = (size_t)y_begin * p.out_pitch + x0;
-    // software pipeline: the land-cover vectors (and HSG row indices) of the next kPrefetch rows
-    // are in flight while the current row is looked up and stored
-    const int32_t *rowp = p.row_idx + p.y_base + y_begin;
-    uint4 eq[kPrefetch];
-    int cq[kPrefetch];
-#pragma unroll
-    for (int s = 0; s < kPrefetch; s++) {
-        const bool in = y_begin + s < y_end;
-        eq[s] = in ? ldg_stream16(esa_ptr + (size_t)s * p.esa_pitch) : make_uint4(0, 0, 0, 0);
-        cq[s] = in ? __ldg(rowp + s) : 0;
-    }
 
     for (int y = y_begin; y < y_end; y++) {
         const uint4 e = eq[0];
@@ -344,14 +366,44 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
                 }
                 transpose_store_word<NP>(r, ow, j);
             }
+#if GCN10_BULK_STORE
+            {
+                uint8_t *stage = smem + kSmemStageOff + ((y - y_begin) & 1) * (NP * G * kStripPx) + g * NP * kStripPx;
+#pragma unroll
+                for (int k = 0; k < NP; k++)
+                    *reinterpret_cast<uint4 *>(stage + k * kStripPx + tid * kVecPx) =
+                        make_uint4(ow[k][0], ow[k][1], ow[k][2], ow[k][3]);
+            }
+#else
 #pragma unroll
             for (int k = 0; k < NP; k++)
                 stg_stream16(p.out[g * NP + k] + out_off, ow[k][0], ow[k][1], ow[k][2], ow[k][3]);
+#endif
         }
 
+#if GCN10_BULK_STORE
+        // generic-proxy writes -> visible to the async proxy; the row before last has left its stage
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tid == 0)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t stage = smem_u32(smem + kSmemStageOff + ((y - y_begin) & 1) * (NP * G * kStripPx));
+#pragma unroll
+            for (int k = 0; k < NP * G; k++)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(p.out[k] + row_off), "r"(stage + k * kStripPx), "r"(row_bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        row_off += p.out_pitch;
+#endif
         esa_ptr += p.esa_pitch;
         out_off += p.out_pitch;
     }
+#if GCN10_BULK_STORE
+    if (tid == 0)
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all bulk stores of this CTA have completed
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

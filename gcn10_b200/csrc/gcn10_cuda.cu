@@ -197,9 +197,10 @@ void pack_lut_records(const int tables[GCN10_NVARIANTS][256][5], unsigned varian
 }
 
 // Rows each CTA walks.  Measured on B200 (profiles/r01_kernel_sweeps.md): short chunks keep the
-// co-resident CTAs inside a narrow band of rows and leave no tail wave; 12 rows is best for <= 9
-// planes, 16 for 18 planes; below 8 the per-CTA prologue (LUT copy, HSG box) starts to show.
-int auto_rows_per_cta(int planes) { return planes > 9 ? 16 : 12; }
+// co-resident CTAs inside a narrow band of rows and leave no tail wave, long ones amortise the per-CTA
+// prologue (LUT + HSG box fills).  Bulk-store kernel: 12 rows is best for <= 9 planes (2 CTAs/SM), 32 for
+// 10..18 planes (1 CTA/SM); direct-store kernel: 12 / 16.
+int auto_rows_per_cta(int planes) { return planes > 9 ? (GCN10_BULK_STORE ? 32 : 16) : 12; }
 
 int popcount9(unsigned m) { return __builtin_popcount(m & 0x1FFu); }
 
@@ -366,7 +367,7 @@ int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t 
         int w16 = w & ~(kVecPx - 1);
         dim3 grid((w16 + kStripPx - 1) / kStripPx, (rows + p.rows_per_cta - 1) / p.rows_per_cta);
         BlockKernel k = pick_kernel(lp.np, lp.groups);
-        k<<<grid, kThreads, kSmemBytes, st>>>(p, map);
+        k<<<grid, kThreads, smem_bytes_for(lp.np * lp.groups), st>>>(p, map);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         x_bytes = w16;
@@ -456,7 +457,7 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
     for (int np = 1; np <= 9; np++)
         for (int g = 1; g <= 2; g++)
             CUDA_TRY(cudaFuncSetAttribute((const void *)pick_kernel(np, g),
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(np * g)));
     *out = c;
     return GCN10_OK;
 }
