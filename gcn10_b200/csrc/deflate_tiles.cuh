@@ -177,7 +177,7 @@ __device__ __forceinline__ unsigned long long parse_row(const uint8_t *tile, int
 }
 
 // One CTA = one tile of one plane.  grid = (tiles_x, tile_rows, planes), 256 threads.
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kTile, 2)
 deflate_tiles_kernel(const __grid_constant__ TileEncParams p)
 {
     extern __shared__ __align__(16) uint8_t smem_enc[];
@@ -194,23 +194,38 @@ deflate_tiles_kernel(const __grid_constant__ TileEncParams p)
     const int x0 = tx * kTile, y0 = ty * kTile;
 
     // ---- tile -> shared memory, zero padded at the right / bottom edge (like the CPU writer)
-    for (int i = tid; i < kTile * (kTile / 16); i += kTile) {
-        const int r = i >> 4, c = (i & 15) * 16;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        const int gy = y0 + r, gx = x0 + c;
-        if (gy < p.rows && gx < p.w) {
-            const uint8_t *g = src + (size_t)gy * p.pitch + gx;
-            if (gx + 16 <= p.w && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
-                v = *reinterpret_cast<const uint4 *>(g);
+    const bool interior = x0 + kTile <= p.w && y0 + kTile <= p.rows &&
+                          ((reinterpret_cast<uintptr_t>(src) | p.pitch) & 15) == 0;
+    if (interior) {
+        // all 16 independent 16-byte loads of a thread are in flight before the first store
+        const uint8_t *g = src + (size_t)(y0 + (tid >> 4)) * p.pitch + x0 + (tid & 15) * 16;
+        uint4 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            v[k] = __ldcs(reinterpret_cast<const uint4 *>(g + (size_t)k * 16 * p.pitch));
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            *reinterpret_cast<uint4 *>(tile + ((tid >> 4) + 16 * k) * kTileStride + (tid & 15) * 16) = v[k];
+    }
+    else {
+        for (int i = tid; i < kTile * (kTile / 16); i += kTile) {
+            const int r = i >> 4, c = (i & 15) * 16;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            const int gy = y0 + r, gx = x0 + c;
+            if (gy < p.rows && gx < p.w) {
+                const uint8_t *g = src + (size_t)gy * p.pitch + gx;
+                if (gx + 16 <= p.w && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+                    v = *reinterpret_cast<const uint4 *>(g);
+                }
+                else {
+                    uint32_t w4[4] = { 0, 0, 0, 0 };
+                    for (int k = 0; k < 16 && gx + k < p.w; k++)
+                        w4[k >> 2] |= (uint32_t)g[k] << (8 * (k & 3));
+                    v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
             }
-            else {
-                uint32_t w4[4] = { 0, 0, 0, 0 };
-                for (int k = 0; k < 16 && gx + k < p.w; k++)
-                    w4[k >> 2] |= (uint32_t)g[k] << (8 * (k & 3));
-                v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-            }
+            *reinterpret_cast<uint4 *>(tile + r * kTileStride + c) = v;
         }
-        *reinterpret_cast<uint4 *>(tile + r * kTileStride + c) = v;
     }
     for (int i = tid; i < kEncCap / 4 + 8; i += kTile)
         out[i] = 0;
