@@ -131,18 +131,20 @@ def test_block_device_api(w, h, pitch_extra, gpu_ctx, port, tables):
     b = make_block(w=w, h=h, seed=31)
     want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
     pitch = (w + 15) // 16 * 16 + pitch_extra
+    guard = 3                                                   # sentinel rows above and below every plane
     d_esa = torch.zeros((h, pitch), dtype=torch.uint8, device="cuda")
     d_esa[:, :w] = torch.from_numpy(b["esa"]).cuda()
     hsy, hsx = b["hsg"].shape
     d_hsg = torch.from_numpy(b["hsg"]).cuda().contiguous()
-    d_out = torch.full((18, h, pitch), 3, dtype=torch.uint8, device="cuda")
+    d_out = torch.full((18, h + 2 * guard, pitch), 3, dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream or 1      # 0 would mean "the context's stream"; 1 = cudaStreamLegacy
     gpu_ctx.block_device(d_esa.data_ptr(), w, h, pitch, b["gt"], d_hsg.data_ptr(), hsx, hsy, hsx, b["soil_gt"],
-                         capi.MASK_ALL, [d_out[k].data_ptr() for k in range(18)], pitch, stream=st)
+                         capi.MASK_ALL, [d_out[k, guard].data_ptr() for k in range(18)], pitch, stream=st)
     torch.cuda.synchronize()
     got = d_out.cpu().numpy()
-    assert np.array_equal(got[:, :, :w], want)
-    assert (got[:, :, w:] == 3).all(), "padding columns were written"
+    assert np.array_equal(got[:, guard:guard + h, :w], want)
+    assert (got[:, guard:guard + h, w:] == 3).all(), "padding columns were written"
+    assert (got[:, :guard] == 3).all() and (got[:, guard + h:] == 3).all(), "rows outside the block were written"
 
 
 def test_full_tile_sampled_rows(gpu_ctx, port, tables):
