@@ -272,6 +272,8 @@ def run_ours(args):
 
     ctx = capi.Context(local_rank)
     ctx.set_luts(tables)
+    # host thread -> NUMA node of this GPU, before any pinned allocation (matters at N > 1: see DESIGN.md 6)
+    numa_node = ctx.lib.gcn10_cuda_bind_host_thread(local_rank)
 
     w = h = args.tile
     # every rank (GPU worker) takes its own block of the id list, round-robin like main.c:171
@@ -356,7 +358,7 @@ def run_ours(args):
             "config": workload_config(args),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu,
-            "output_gpixel_per_s": value * NVAR,
+            "output_gpixel_per_s": value * NVAR, "numa_node_rank0": numa_node,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

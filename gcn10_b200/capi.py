@@ -27,7 +27,7 @@ EXPORTS = (
     "gcn10_cuda_block_deflate", "gcn10_cuda_block_deflate_rows", "gcn10_cuda_block_device",
     "gcn10_cuda_index_maps", "gcn10_cuda_synchronize", "gcn10_cuda_last_kernel_ms",
     "gcn10_cuda_launch_count", "gcn10_cuda_set_option", "gcn10_cuda_host_alloc", "gcn10_cuda_host_free",
-    "gcn10_cuda_host_register", "gcn10_cuda_host_unregister",
+    "gcn10_cuda_host_register", "gcn10_cuda_host_unregister", "gcn10_cuda_bind_host_thread",
 )
 
 _vp = C.c_void_p
@@ -80,6 +80,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     lib.gcn10_cuda_host_free.restype = None
     lib.gcn10_cuda_host_register.argtypes = [_vp, C.c_size_t]
     lib.gcn10_cuda_host_unregister.argtypes = [_vp]
+    lib.gcn10_cuda_bind_host_thread.argtypes = [C.c_int]
     return lib
 
 

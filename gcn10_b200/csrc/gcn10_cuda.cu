@@ -11,6 +11,8 @@
 #include "deflate_tiles.cuh"
 
 #include <algorithm>
+#include <cctype>
+#include <sched.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -81,6 +83,8 @@ struct gcn10_ctx {
     int strip_rows = 2048;
     int rows_per_cta = 0;       // 0 = auto (see auto_rows_per_cta)
     int use_tma = 1;
+    int persistent = 0;         // 1 = persistent-CTA form of the streaming kernel (measured slower, see profiles/)
+    int persistent_ctas[10][3] = {};         // resident CTAs per SM by [np][groups], from the occupancy API
     EncodeTiledFn encode_tiled = nullptr;
 
     bool have_lut = false;
@@ -230,6 +234,28 @@ BlockKernel pick_kernel(int np, int groups)
     return nullptr;
 }
 
+template <int NP>
+BlockKernel pick_pg(int groups)
+{
+    return groups == 2 ? (BlockKernel)cn_block_persistent<NP, 2> : (BlockKernel)cn_block_persistent<NP, 1>;
+}
+
+BlockKernel pick_persistent(int np, int groups)
+{
+    switch (np) {
+    case 1: return pick_pg<1>(groups);
+    case 2: return pick_pg<2>(groups);
+    case 3: return pick_pg<3>(groups);
+    case 4: return pick_pg<4>(groups);
+    case 5: return pick_pg<5>(groups);
+    case 6: return pick_pg<6>(groups);
+    case 7: return pick_pg<7>(groups);
+    case 8: return pick_pg<8>(groups);
+    case 9: return pick_pg<9>(groups);
+    }
+    return nullptr;
+}
+
 struct LaunchPlan {
     int np = 0, groups = 0;     // planes per group, number of groups in this launch
     int drained[2] = { 1, 0 };
@@ -366,8 +392,18 @@ int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t 
     if (aligned && (w & ~(kVecPx - 1)) > 0) {
         int w16 = w & ~(kVecPx - 1);
         dim3 grid((w16 + kStripPx - 1) / kStripPx, (rows + p.rows_per_cta - 1) / p.rows_per_cta);
-        BlockKernel k = pick_kernel(lp.np, lp.groups);
-        k<<<grid, kThreads, smem_bytes_for(lp.np * lp.groups), st>>>(p, map);
+        const int resident = c->persistent_ctas[lp.np][lp.groups];
+        if (c->persistent && GCN10_BULK_STORE && resident > 0) {
+            if (c->rows_per_cta <= 0)
+                p.rows_per_cta = 8;         // no per-unit prologue left to amortise: short units balance best
+            const long long units = (long long)grid.x * ((rows + p.rows_per_cta - 1) / p.rows_per_cta);
+            const int ctas = (int)std::min<long long>(units, (long long)resident * c->sm_count);
+            pick_persistent(lp.np, lp.groups)<<<ctas, kThreads, persistent_smem_bytes(lp.np * lp.groups), st>>>(p, map);
+        }
+        else {
+            BlockKernel k = pick_kernel(lp.np, lp.groups);
+            k<<<grid, kThreads, smem_bytes_for(lp.np * lp.groups), st>>>(p, map);
+        }
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         x_bytes = w16;
@@ -458,6 +494,17 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
         for (int g = 1; g <= 2; g++)
             CUDA_TRY(cudaFuncSetAttribute((const void *)pick_kernel(np, g),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(np * g)));
+    for (int np = 1; np <= 9; np++)
+        for (int g = 1; g <= 2; g++) {
+            const void *k = (const void *)pick_persistent(np, g);
+            const int bytes = persistent_smem_bytes(np * g);
+            int n = 0;
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kThreads, bytes) == cudaSuccess)
+                c->persistent_ctas[np][g] = n;
+            else
+                cudaGetLastError();         // this shape falls back to the one-CTA-per-chunk kernel
+        }
     *out = c;
     return GCN10_OK;
 }
@@ -508,6 +555,7 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
     else if (!strcmp(key, "streams") && value >= 1 && value <= kMaxStreams) c->nstreams = (int)value;
     else if (!strcmp(key, "rows_per_cta") && value >= 0) c->rows_per_cta = (int)value;
     else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
+    else if (!strcmp(key, "persistent") && (value == 0 || value == 1)) c->persistent = (int)value;
     else return fail(GCN10_EINVAL, "unknown option or bad value: %s=%ld", key, value);
     return GCN10_OK;
 }
@@ -864,6 +912,52 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
     }
     c->last_kernel_ms = kernel_ms;
     return GCN10_OK;
+}
+
+int gcn10_cuda_bind_host_thread(int device)
+{
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char *q = bus; *q; q++)
+        *q = (char)tolower((unsigned char)*q);
+    char path[256];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    int node = -1;
+    if (!f || fscanf(f, "%d", &node) != 1)
+        node = -1;
+    if (f)
+        fclose(f);
+    if (node < 0)
+        return -2;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f)
+        return -3;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int a, b, n = 0;
+    // cpulist: comma separated ranges "0-15,32-47"
+    while (fscanf(f, "%d", &a) == 1) {
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') {
+            if (fscanf(f, "%d", &b) != 1)
+                break;
+            ch = fgetc(f);
+        }
+        for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; cpu++, n++)
+            CPU_SET(cpu, &set);
+        if (ch != ',')
+            break;
+    }
+    fclose(f);
+    if (n == 0 || sched_setaffinity(0, sizeof(set), &set) != 0)
+        return -4;
+    return node;
 }
 
 void *gcn10_cuda_host_alloc(size_t bytes)

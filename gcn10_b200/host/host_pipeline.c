@@ -450,6 +450,11 @@ static void *worker_main(void *arg)
 {
     worker *wk = arg;
     char msg[256];
+    /* keep this worker (and the reader / encoder threads it spawns, which inherit the mask) on the
+     * NUMA node of its GPU so that the pinned band buffers are node-local */
+    int node = gcn10_cuda_bind_host_thread(wk->index);
+    snprintf(msg, sizeof msg, "gpu worker %d on numa node %d", wk->index, node);
+    gh_log_message(wk->log, "INFO", msg, 0);
     if (gcn10_cuda_create(wk->index, &wk->ctx) || gcn10_cuda_set_luts(wk->ctx, wk->tables)) {
         snprintf(msg, sizeof msg, "cannot initialise GPU %d: %s", wk->index, gcn10_cuda_last_error());
         fatal(wk, msg);

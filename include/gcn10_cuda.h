@@ -180,8 +180,16 @@ int gcn10_cuda_launch_count(gcn10_ctx *ctx, uint64_t *launches);
 
 /* Tunables: "strip_rows" (rows per pipelined strip in gcn10_cuda_block), "streams"
  * (1..8), "rows_per_cta" (0 = automatic), "tma" (0 = always use the gather fallback for HSG
- * staging). */
+ * staging), "persistent" (0 = one CTA per row chunk instead of the persistent-CTA kernel). */
 int gcn10_cuda_set_option(gcn10_ctx *ctx, const char *key, long value);
+
+/* Pins the calling host thread to the CPUs of the NUMA node the GPU hangs off (from
+ * /sys/bus/pci/devices/<bus id>/numa_node and .../node<N>/cpulist), so that page-locked buffers
+ * allocated afterwards are node-local and the staging copies do not cross the socket interconnect.
+ * On an 8-GPU box this is what keeps eight concurrent H2D/D2H streams from sharing one memory
+ * controller.  Returns the node number, or a negative value when the topology cannot be read (no
+ * error is raised: the call is an optimisation). */
+int gcn10_cuda_bind_host_thread(int device);
 
 /* Page-locked host memory for rasters, so that the strip copies run asynchronously
  * (replaces malloc at raster.c:169 / cn.c:278 in a host program built on this library). */

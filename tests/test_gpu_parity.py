@@ -21,18 +21,35 @@ def test_block_host_api_all_planes(name, kw, gpu_ctx, port, tables):
         assert np.array_equal(got[k], want[k]), f"{name}: plane {k} differs in {(got[k] != want[k]).sum()} px"
 
 
+@pytest.mark.parametrize("persistent", [0, 1])
 @pytest.mark.parametrize("tma", [0, 1])
-@pytest.mark.parametrize("rows_per_cta", [7, 128, 1000])
-def test_tma_and_gather_staging_agree(tma, rows_per_cta, gpu_ctx, port, tables):
+@pytest.mark.parametrize("rows_per_cta", [1, 7, 128, 1000])
+def test_kernel_forms_agree(persistent, tma, rows_per_cta, gpu_ctx, port, tables):
+    """Persistent vs one-CTA-per-chunk kernel, TMA-staged vs gathered HSG box, several unit heights."""
     b = make_block(w=4500, h=700, seed=21, shift=(0.0003, 0.0007), margin=1)
     want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
     gpu_ctx.set_option("tma", tma)
     gpu_ctx.set_option("rows_per_cta", rows_per_cta)
+    gpu_ctx.set_option("persistent", persistent)
     try:
         got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
     finally:
         gpu_ctx.set_option("tma", 1)
         gpu_ctx.set_option("rows_per_cta", 0)
+        gpu_ctx.set_option("persistent", 0)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("persistent", [0, 1])
+def test_wide_hsg_span_falls_back_to_gather(persistent, gpu_ctx, port, tables):
+    """Ratio 3: a 4096-pixel strip spans > 256 HSG columns, so no unit fits the TMA box."""
+    b = make_block(w=9000, h=150, hsg_px=1.0 / 12000.0 * 3, seed=23)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    gpu_ctx.set_option("persistent", persistent)
+    try:
+        got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    finally:
+        gpu_ctx.set_option("persistent", 0)
     assert np.array_equal(got, want)
 
 
