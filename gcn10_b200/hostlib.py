@@ -65,6 +65,12 @@ def load() -> C.CDLL:
     L.gh_tiff_close.argtypes = [_vp]
     L.gh_tiff_close.restype = None
     L.gh_tiff_write.argtypes = [C.c_char_p, _vp, C.c_int, C.c_int, C.c_size_t, _dp, C.c_int, C.c_char_p, C.c_size_t]
+    L.gh_tiffw_open.argtypes = [C.c_char_p, C.c_int, C.c_int, _dp, C.POINTER(_vp), C.c_char_p, C.c_size_t]
+    L.gh_tiffw_put_tile_row.argtypes = [_vp, C.c_int, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    L.gh_tiffw_write_rows.argtypes = [_vp, _vp, C.c_size_t, C.c_int, C.c_int, C.c_int]
+    L.gh_tiffw_close.argtypes = [_vp]
+    L.gh_tiffw_abort.argtypes = [_vp]
+    L.gh_tiffw_abort.restype = None
     L.gh_log_open.argtypes = [C.c_char_p, C.c_int]
     L.gh_log_open.restype = _vp
     L.gh_log_message.argtypes = [_vp, C.c_char_p, C.c_char_p, C.c_int]
@@ -191,3 +197,39 @@ class Tiff:
         if self.h:
             self.L.gh_tiff_close(self.h)
             self.h = None
+
+
+class TiffWriter:
+    """Incremental tiled-DEFLATE GeoTIFF writer (gh_tiffw_*): raw row bands or pre-compressed tile rows."""
+
+    def __init__(self, path: str, w: int, h: int, gt):
+        self.L = load()
+        h_ = _vp()
+        e = _err()
+        rc = self.L.gh_tiffw_open(os.fsencode(path), w, h, (C.c_double * 6)(*gt), C.byref(h_), e, ERRLEN)
+        if rc:
+            raise HostError(rc, e.value.decode())
+        self.h = h_
+        self.tiles_x = (w + 255) // 256
+
+    def put_tile_row(self, tile_row: int, streams):
+        """streams: tiles_x zlib streams (bytes) of one tile row."""
+        assert len(streams) == self.tiles_x
+        blob = b"".join(streams)
+        offs = (C.c_uint64 * len(streams))()
+        sizes = (C.c_uint32 * len(streams))()
+        pos = 0
+        for i, z in enumerate(streams):
+            offs[i], sizes[i] = pos, len(z)
+            pos += len(z)
+        buf = C.create_string_buffer(blob, len(blob))
+        return self.L.gh_tiffw_put_tile_row(self.h, tile_row, buf, offs, sizes)
+
+    def write_rows(self, data: np.ndarray, y0: int, threads: int = 2):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        return self.L.gh_tiffw_write_rows(self.h, data.ctypes.data, data.shape[1], y0, data.shape[0], threads)
+
+    def close(self):
+        rc = self.L.gh_tiffw_close(self.h)
+        self.h = None
+        return rc

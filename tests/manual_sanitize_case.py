@@ -9,7 +9,7 @@ import zlib
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT)
 
 from gcn10_b200 import capi, lookups, synth  # noqa: E402

@@ -175,3 +175,40 @@ def test_cli_meta_flags_and_errors(tmp_path):
     assert r.returncode == 1 and "missing -c/--config <file>" in r.stderr               # main.c:103-108
     r = subprocess.run([exe, "-c", str(tmp_path / "nope.txt")], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open config" in r.stderr                        # config.c:52
+
+
+def test_geotiff_writer_accepts_precompressed_tile_rows(tmp_path):
+    """The path the GPU encoder feeds: complete zlib streams per 256 x 256 tile, appended tile row by tile row
+    (here produced with CPython's zlib at two different levels, to show any valid stream is accepted)."""
+    import zlib
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    w, h = 700, 600
+    a = (rng.integers(0, 5, (h, w)) * 20).astype(np.uint8)
+    a[:, 300:] = 77
+    p = str(tmp_path / "tiles.tif")
+    gt = (10.0, PX, 0.0, 5.0, 0.0, -PX)
+    tw = hostlib.TiffWriter(p, w, h, gt)
+    pad = np.zeros((768, 768), dtype=np.uint8)
+    pad[:h, :w] = a
+    for tr in range(3):
+        streams = [zlib.compress(pad[tr * 256:(tr + 1) * 256, tx * 256:(tx + 1) * 256].tobytes(), 1 + 4 * (tx % 2))
+                   for tx in range(3)]
+        assert tw.put_tile_row(tr, streams) == 0
+    assert tw.close() == 0
+    t = hostlib.Tiff(p)
+    assert (t.width, t.height) == (w, h) and t.gt == gt
+    assert np.array_equal(t.read(), a)
+    t.close()
+    assert np.array_equal(np.array(Image.open(p)), a)
+
+
+def test_geotiff_writer_rejects_out_of_order_and_incomplete(tmp_path):
+    import zlib
+    z = zlib.compress(bytes(65536))
+    tw = hostlib.TiffWriter(str(tmp_path / "a.tif"), 256, 512, (0, 1, 0, 0, 0, -1))
+    assert tw.put_tile_row(1, [z]) != 0                         # must start at tile row 0
+    assert tw.close() != 0                                      # nothing valid was written
+    tw = hostlib.TiffWriter(str(tmp_path / "b.tif"), 256, 512, (0, 1, 0, 0, 0, -1))
+    assert tw.put_tile_row(0, [z]) == 0
+    assert tw.close() != 0                                      # second tile row missing
