@@ -188,7 +188,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print_json(line)
     return 0
 
 
@@ -360,7 +360,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "output_gpixel_per_s": value * NVAR, "numa_node_rank0": numa_node,
         }
-        print(json.dumps(line), flush=True)
+        print_json(line)
     ctx.close()
     group.close()
     return 0
@@ -503,8 +503,21 @@ def profiled_traffic():
         return None
 
 
+print_json = None
+
+
 def main():
     args = parse_args()
+    # stdout must carry exactly one JSON line: libraries (NCCL prints its version banner to stdout on the
+    # first collective) are diverted to stderr for the whole run and the line is written to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    global print_json
+    def print_json(obj):
+        out.write(json.dumps(obj) + "\n")
+        out.flush()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)
