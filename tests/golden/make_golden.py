@@ -181,7 +181,21 @@ def main():
         assert r["nplanes"] == 18 and (r["w"], r["h"]) == (256, len(codes)), (label, r["w"], r["h"], r["log"])
         luts[label] = r["planes"]            # [18, len(codes), 256]: plane, hsg code, land cover
     np.savez_compressed(os.path.join(HERE, "luts.npz"), **luts)
-    for fn in ("blocks.npz", "windows.json", "luts.npz"):
+    # every block extent of the shipped shapefile (all are integer-degree 3 x 3 squares)
+    shp = "/root/reference/blocks/esa_extent_blocks.shp"
+    if os.path.exists(shp):
+        from gcn10_b200 import hostlib
+        b = hostlib.Blocks(shp)
+        rows = []
+        for i in b.ids():
+            x0, y0, x1, y1 = b.bbox(i)
+            assert (x1 - x0, y1 - y0) == (3.0, 3.0) and x0 == int(x0) and y0 == int(y0)
+            rows.append([i, int(x0), int(y1)])
+        with open(os.path.join(HERE, "block_extents.json"), "w") as f:
+            json.dump({"comment": "id, west edge (deg), north edge (deg) of every 3x3 degree block of "
+                                  "/root/reference/blocks/esa_extent_blocks.shp (read with gcn10_b200/hostlib.Blocks); "
+                                  "generated by tests/golden/make_golden.py", "blocks": rows}, f, separators=(",", ":"))
+    for fn in ("blocks.npz", "windows.json", "luts.npz", "block_extents.json"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
 
 

@@ -22,3 +22,9 @@ def window_cases():
 def luts():
     z = np.load(os.path.join(GOLDEN, "luts.npz"))
     return {k: z[k] for k in z.files}
+
+
+def block_extents():
+    """[(id, west, north)] of the 2651 blocks of the reference's shapefile."""
+    with open(os.path.join(GOLDEN, "block_extents.json")) as f:
+        return [tuple(r) for r in json.load(f)["blocks"]]
