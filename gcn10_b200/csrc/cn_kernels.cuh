@@ -195,6 +195,9 @@ constexpr int kSmemBytes = kSmemBarOff + 16;
 #ifndef GCN10_BULK_STORE
 #define GCN10_BULK_STORE 1
 #endif
+#ifndef GCN10_STORE_HINT
+#define GCN10_STORE_HINT 1      // L2 evict-first cache hint on the bulk stores (+0.5 %: the planes are never re-read)
+#endif
 constexpr int kSmemStageOff = kSmemBarOff + 128;
 constexpr int smem_bytes_for(int planes) { return GCN10_BULK_STORE ? kSmemStageOff + 2 * planes * kStripPx : kSmemBytes; }
 
@@ -394,10 +397,19 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
         __syncthreads();
         if (tid == 0) {
             const uint32_t stage = smem_u32(smem + kSmemStageOff + ((y - y_begin) & 1) * (NP * G * kStripPx));
+#if GCN10_STORE_HINT
+            uint64_t pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#pragma unroll
+            for (int k = 0; k < NP * G; k++)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                             :: "l"(p.out[k] + row_off), "r"(stage + k * kStripPx), "r"(row_bytes), "l"(pol) : "memory");
+#else
 #pragma unroll
             for (int k = 0; k < NP * G; k++)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(p.out[k] + row_off), "r"(stage + k * kStripPx), "r"(row_bytes) : "memory");
+#endif
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         row_off += p.out_pitch;

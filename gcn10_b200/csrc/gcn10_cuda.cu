@@ -391,6 +391,8 @@ int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t 
     int x_bytes = 0;
     if (aligned && (w & ~(kVecPx - 1)) > 0) {
         int w16 = w & ~(kVecPx - 1);
+        while ((rows + p.rows_per_cta - 1) / p.rows_per_cta > 65535)     // gridDim.y limit, only for absurdly tall rasters
+            p.rows_per_cta *= 2;
         dim3 grid((w16 + kStripPx - 1) / kStripPx, (rows + p.rows_per_cta - 1) / p.rows_per_cta);
         const int resident = c->persistent_ctas[lp.np][lp.groups];
         if (c->persistent && GCN10_BULK_STORE && resident > 0) {

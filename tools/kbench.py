@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--profile", default="worldcover")
     ap.add_argument("--planes", default="9")
     ap.add_argument("--tma", default="1")
-    ap.add_argument("--persistent", default="1")
+    ap.add_argument("--persistent", default="0")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--once", action="store_true", help="one launch per config, no timing loop (for ncu)")
     a = ap.parse_args()
