@@ -28,6 +28,7 @@ EXPORTS = (
     "gcn10_cuda_index_maps", "gcn10_cuda_synchronize", "gcn10_cuda_last_kernel_ms",
     "gcn10_cuda_launch_count", "gcn10_cuda_set_option", "gcn10_cuda_host_alloc", "gcn10_cuda_host_free",
     "gcn10_cuda_host_register", "gcn10_cuda_host_unregister", "gcn10_cuda_bind_host_thread",
+    "gcn10_cuda_inflate_tiles", "gcn10_cuda_block_tiles_deflate", "gcn10_cuda_last_inflate_ms",
 )
 
 _vp = C.c_void_p
@@ -42,6 +43,67 @@ class TileStrip(C.Structure):
 
 
 TILE_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(TileStrip))
+
+
+class TileSourceStruct(C.Structure):
+    """gcn10_tile_source of include/gcn10_cuda.h."""
+    _fields_ = [("tile_w", C.c_int), ("tile_h", C.c_int), ("tiles_x", C.c_int), ("tiles_y", C.c_int),
+                ("x_off", C.c_int), ("y_off", C.c_int), ("blob", C.c_void_p), ("blob_bytes", C.c_size_t),
+                ("offsets", C.c_void_p), ("sizes", C.c_void_p)]
+
+
+class TileSource:
+    """Compressed tiles of a raster window as a tiled DEFLATE GeoTIFF holds them (one zlib stream per tile).
+
+    ``blob`` uint8 [n], ``offsets`` uint64 [tiles_y*tiles_x], ``sizes`` uint32 [tiles_y*tiles_x] (0 = sparse
+    tile).  ``from_raster`` builds one from a decoded raster with zlib on the host: a test / benchmark
+    convenience standing in for "read the tile bytes from the file"."""
+
+    def __init__(self, tile_w, tile_h, tiles_x, tiles_y, x_off, y_off, blob, offsets, sizes):
+        self.tile_w, self.tile_h, self.tiles_x, self.tiles_y = tile_w, tile_h, tiles_x, tiles_y
+        self.x_off, self.y_off = x_off, y_off
+        self.blob = blob
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+
+    @classmethod
+    def from_raster(cls, raster, tile_w=1024, tile_h=1024, level=6, x_off=0, y_off=0, sparse=(), gap=0,
+                    pad_value=0, blob_alloc=None):
+        """Tile ``raster`` (the window occupies raster[y_off:, x_off:] of the grid's pixel space only in the
+        sense that the CALLER passes x_off / y_off to say where its window starts)."""
+        import zlib
+        h, w = raster.shape
+        tiles_x, tiles_y = (w + tile_w - 1) // tile_w, (h + tile_h - 1) // tile_h
+        streams, offsets, sizes = [], [], []
+        pos = 0
+        for ty in range(tiles_y):
+            for tx in range(tiles_x):
+                if (ty, tx) in sparse:
+                    offsets.append(0)
+                    sizes.append(0)
+                    continue
+                t = np.full((tile_h, tile_w), pad_value, dtype=np.uint8)
+                part = raster[ty * tile_h:(ty + 1) * tile_h, tx * tile_w:(tx + 1) * tile_w]
+                t[:part.shape[0], :part.shape[1]] = part
+                z = zlib.compress(t.tobytes(), level) if level >= 0 else t.tobytes()
+                pos += gap
+                streams.append(b"\x00" * gap + z)
+                offsets.append(pos)
+                sizes.append(len(z))
+                pos += len(z)
+        data = b"".join(streams)
+        if blob_alloc is not None:
+            blob = blob_alloc(max(len(data), 1))
+            blob[:len(data)] = np.frombuffer(data, dtype=np.uint8)
+            blob = blob[:len(data)]
+        else:
+            blob = np.frombuffer(data, dtype=np.uint8).copy()
+        return cls(tile_w, tile_h, tiles_x, tiles_y, x_off, y_off, blob, offsets, sizes)
+
+    def struct(self):
+        return TileSourceStruct(self.tile_w, self.tile_h, self.tiles_x, self.tiles_y, self.x_off, self.y_off,
+                                self.blob.ctypes.data, self.blob.size, self.offsets.ctypes.data,
+                                self.sizes.ctypes.data)
 
 
 class Gcn10Error(RuntimeError):
@@ -81,6 +143,10 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     lib.gcn10_cuda_host_register.argtypes = [_vp, C.c_size_t]
     lib.gcn10_cuda_host_unregister.argtypes = [_vp]
     lib.gcn10_cuda_bind_host_thread.argtypes = [C.c_int]
+    lib.gcn10_cuda_inflate_tiles.argtypes = [_vp, C.POINTER(TileSourceStruct), C.c_int, C.c_int, _vp, C.c_size_t, _vp]
+    lib.gcn10_cuda_block_tiles_deflate.argtypes = [_vp, C.POINTER(TileSourceStruct), C.c_int, C.c_int, _dp,
+                                                   _vp, C.c_int, C.c_int, C.c_size_t, _dp, C.c_uint, TILE_SINK, _vp]
+    lib.gcn10_cuda_last_inflate_ms.argtypes = [_vp, C.POINTER(C.c_float)]
     return lib
 
 
@@ -218,6 +284,53 @@ class Context:
             self.h, esa.ctypes.data, w, h, esa_pitch, _d6(gt), hsg.ctypes.data, hsx, hsy, hsg_pitch,
             _d6(soil_gt), plane_mask, cb, None))
         return dict(tiles=tiles, bytes=total[0])
+
+    def inflate_tiles(self, src: "TileSource", w, h, out=None, want_status=False):
+        """GPU inflate of a tile source into a host raster uint8 [h, w]."""
+        if out is None:
+            out = np.zeros((h, w), dtype=np.uint8)
+        status = np.full(src.tiles_x * src.tiles_y, -1, dtype=np.int32)
+        st = src.struct()
+        rc = self.lib.gcn10_cuda_inflate_tiles(self.h, C.byref(st), w, h, out.ctypes.data, out.strides[0],
+                                               status.ctypes.data)
+        if want_status:
+            return rc, out, status
+        self._check(rc)
+        return out
+
+    def block_tiles_deflate(self, src: "TileSource", w, h, gt, hsg, soil_gt, plane_mask=MASK_ALL, on_strip=None):
+        """Compressed land-cover tiles in, compressed Curve Number tiles out (same result layout as
+        block_deflate)."""
+        hsg, hsg_pitch = _rows(hsg)
+        hsy, hsx = hsg.shape
+        tiles = {}
+        total = [0]
+
+        def _sink(_user, sp):
+            st = sp.contents
+            total[0] += st.blob_bytes
+            if on_strip is not None:
+                return int(on_strip(st) or 0)
+            blob = C.string_at(st.blob, st.blob_bytes)
+            for k in range(st.n_planes):
+                d = tiles.setdefault(st.plane_ids[k], {})
+                for tr in range(st.n_tile_rows):
+                    for tx in range(st.tiles_x):
+                        i = (k * st.n_tile_rows + tr) * st.tiles_x + tx
+                        d[(st.tile_row0 + tr, tx)] = blob[st.offsets[i]: st.offsets[i] + st.sizes[i]]
+            return 0
+
+        cb = TILE_SINK(_sink)
+        st = src.struct()
+        self._check(self.lib.gcn10_cuda_block_tiles_deflate(
+            self.h, C.byref(st), w, h, _d6(gt), hsg.ctypes.data, hsx, hsy, hsg_pitch, _d6(soil_gt), plane_mask,
+            cb, None))
+        return dict(tiles=tiles, bytes=total[0])
+
+    def last_inflate_ms(self) -> float:
+        v = C.c_float()
+        self._check(self.lib.gcn10_cuda_last_inflate_ms(self.h, C.byref(v)))
+        return v.value
 
     def block_device(self, d_esa, w, h, esa_pitch, gt, d_hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask,
                      d_out_ptrs, out_pitch, stream=None):

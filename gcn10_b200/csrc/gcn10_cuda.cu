@@ -9,6 +9,7 @@
 #include "../../include/gcn10_cuda.h"
 #include "cn_kernels.cuh"
 #include "deflate_tiles.cuh"
+#include "inflate_tiles.cuh"
 
 #include <algorithm>
 #include <cctype>
@@ -95,6 +96,11 @@ struct gcn10_ctx {
 
     DevBuf col_idx, row_idx, hsg;
     StripSlot slots[kMaxStreams];
+    // compressed-input path: the tiles' bytes, their tables and the inflated land-cover plane of a block
+    DevBuf in_blob, in_table, esa_full;
+    HostBuf h_in_status;
+    cudaEvent_t inf0 = nullptr, inf1 = nullptr;
+    float last_inflate_ms = 0.f;
     float last_kernel_ms = 0.f;
     uint64_t launches = 0;
 };
@@ -486,6 +492,10 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
     }
     CUDA_TRY(cudaFuncSetAttribute((const void *)deflate_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kEncSmem));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)inflate_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kInflateSmem));
+    CUDA_TRY(cudaEventCreate(&c->inf0));
+    CUDA_TRY(cudaEventCreate(&c->inf1));
     // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -521,6 +531,12 @@ void gcn10_cuda_destroy(gcn10_ctx *c)
     release(c->col_idx);
     release(c->row_idx);
     release(c->hsg);
+    release(c->in_blob);
+    release(c->in_table);
+    release(c->esa_full);
+    release_host(c->h_in_status);
+    if (c->inf0) cudaEventDestroy(c->inf0);
+    if (c->inf1) cudaEventDestroy(c->inf1);
     for (int i = 0; i < kMaxStreams; i++) {
         release(c->slots[i].esa);
         release(c->slots[i].out);
@@ -761,11 +777,15 @@ int gcn10_cuda_block_deflate(gcn10_ctx *c,
                                          plane_mask, sink, user);
 }
 
-int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
-                                  const uint8_t *esa, int w, int h, int row0, int nrows, size_t esa_pitch,
-                                  const double gt[6],
-                                  const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
-                                  unsigned plane_mask, gcn10_tile_sink sink, void *user)
+// Strips of whole tile rows: [H2D of the land-cover rows ->] Curve Number kernel -> tile DEFLATE -> D2H of
+// the compressed tiles -> sink.  The land cover comes either from the caller's host raster (esa) or from a
+// device-resident plane (d_esa, valid once `esa_ready` has fired: the compressed-input path).
+static int deflate_rows_impl(gcn10_ctx *c,
+                             const uint8_t *esa, size_t esa_pitch, const uint8_t *d_esa, size_t d_esa_pitch,
+                             cudaEvent_t esa_ready, int w, int h, int row0, int nrows,
+                             const double gt[6],
+                             const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                             unsigned plane_mask, gcn10_tile_sink sink, void *user)
 {
     if (!c)
         return fail(GCN10_EINVAL, "NULL context");
@@ -774,8 +794,8 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
     if (row0 < 0 || nrows <= 0 || row0 > h - nrows || row0 % kTile != 0 || (nrows % kTile != 0 && row0 + nrows != h))
         return fail(GCN10_EINVAL, "row band [%d, +%d) must start on a 256-row tile boundary and end on one or at "
                                   "the block's last row (%d)", row0, nrows, h);
-    int rc = check_geometry(esa, w, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask, (const void *)sink,
-                            (size_t)w);
+    int rc = check_geometry(esa ? esa : d_esa, w, h, esa ? esa_pitch : d_esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt,
+                            plane_mask, (const void *)sink, (size_t)w);
     if (rc)
         return rc;
     if (!c->have_lut)
@@ -816,7 +836,7 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
     const size_t table_bytes = 16 + ntile_slot * (sizeof(unsigned long long) + sizeof(uint32_t));
     for (int i = 0; i < ns; i++) {
         StripSlot &sl = c->slots[i];
-        if ((rc = ensure(sl.esa, dpitch * (size_t)strip)) || (rc = ensure(sl.out, dpitch * (size_t)strip * nplanes)) ||
+        if ((esa && (rc = ensure(sl.esa, dpitch * (size_t)strip))) || (rc = ensure(sl.out, dpitch * (size_t)strip * nplanes)) ||
             (rc = ensure(sl.blob, blob_cap)) || (rc = ensure(sl.table, table_bytes)) ||
             (rc = ensure_host(sl.h_table, table_bytes)))
             return rc;
@@ -826,6 +846,8 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
             return rc;
         sl.busy = false;
         sl.timed = false;
+        if (esa_ready)
+            CUDA_TRY(cudaStreamWaitEvent(c->streams[i], esa_ready, 0));
     }
 
     const int nstrips = (nrows + strip - 1) / strip;
@@ -838,14 +860,17 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
         const int tile_rows = (rows + kTile - 1) / kTile;
         sl.y0 = y0;
         sl.rows = rows;
-        CUDA_TRY(cudaMemcpy2DAsync(sl.esa.p, dpitch, esa + (size_t)y0 * esa_pitch, esa_pitch, (size_t)w, (size_t)rows,
-                                   cudaMemcpyHostToDevice, st));
+        const uint8_t *strip_esa = d_esa ? d_esa + (size_t)y0 * d_esa_pitch : (const uint8_t *)sl.esa.p;
+        const size_t strip_esa_pitch = d_esa ? d_esa_pitch : dpitch;
+        if (!d_esa)
+            CUDA_TRY(cudaMemcpy2DAsync(sl.esa.p, dpitch, esa + (size_t)y0 * esa_pitch, esa_pitch, (size_t)w, (size_t)rows,
+                                       cudaMemcpyHostToDevice, st));
         uint8_t *d_out[GCN10_NPLANES] = { nullptr };
         for (int k = 0; k < nplanes; k++)
             d_out[plane_ids[k]] = (uint8_t *)sl.out.p + (size_t)k * dpitch * (size_t)strip;
         CUDA_TRY(cudaEventRecord(sl.k0, st));
         for (int i = 0; i < nplans; i++) {
-            int r2 = launch_rows(c, plans[i], i, (const uint8_t *)sl.esa.p, dpitch, w, rows, row0 + y0, (const uint8_t *)c->hsg.p,
+            int r2 = launch_rows(c, plans[i], i, strip_esa, strip_esa_pitch, w, rows, row0 + y0, (const uint8_t *)c->hsg.p,
                                  hsg_dpitch, hsx, hsy, map, tma_ok, d_out, dpitch, st);
             if (r2)
                 return r2;
@@ -913,6 +938,145 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
             return rc;
     }
     c->last_kernel_ms = kernel_ms;
+    return GCN10_OK;
+}
+
+int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
+                                  const uint8_t *esa, int w, int h, int row0, int nrows, size_t esa_pitch,
+                                  const double gt[6],
+                                  const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                                  unsigned plane_mask, gcn10_tile_sink sink, void *user)
+{
+    if (!esa)
+        return fail(GCN10_EINVAL, "NULL argument");
+    return deflate_rows_impl(c, esa, esa_pitch, nullptr, 0, nullptr, w, h, row0, nrows, gt, hsg, hsx, hsy, hsg_pitch,
+                             soil_gt, plane_mask, sink, user);
+}
+
+// Upload the compressed tiles of `src` and inflate them into c->esa_full (pitch *dpitch) on stream 0.
+// Leaves the per-tile status codes in c->h_in_status after the stream has been synchronised by the caller;
+// records c->inf1 behind the kernel.
+static int inflate_to_device(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h, size_t *dpitch_out)
+{
+    if (!src || !src->blob || !src->offsets || !src->sizes)
+        return fail(GCN10_EINVAL, "NULL argument");
+    if (w <= 0 || h <= 0 || src->tile_w <= 0 || src->tile_h <= 0 || src->tiles_x <= 0 || src->tiles_y <= 0)
+        return fail(GCN10_EINVAL, "non-positive size");
+    if ((long long)src->tile_w * src->tile_h > (1ll << 28))
+        return fail(GCN10_EINVAL, "tile of %d x %d pixels is too large", src->tile_w, src->tile_h);
+    if (src->x_off < 0 || src->y_off < 0 || (long long)src->x_off + w > (long long)src->tiles_x * src->tile_w ||
+        (long long)src->y_off + h > (long long)src->tiles_y * src->tile_h)
+        return fail(GCN10_EINVAL, "the %d x %d tile grid does not cover the %d x %d window at (%d, %d)", src->tiles_x,
+                    src->tiles_y, w, h, src->x_off, src->y_off);
+    const size_t ntiles = (size_t)src->tiles_x * src->tiles_y;
+    for (size_t i = 0; i < ntiles; i++)
+        if (src->sizes[i] && (src->offsets[i] > src->blob_bytes || src->sizes[i] > src->blob_bytes - src->offsets[i]))
+            return fail(GCN10_EINVAL, "tile %zu lies outside the blob", i);
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->streams[0];
+    const size_t dpitch = round_up((size_t)w, 256);
+    int rc;
+    // the kernel's 512-byte input refills may run ~2 KB past a stream: keep that readable
+    if ((rc = ensure(c->in_blob, round_up(src->blob_bytes, 256) + 4096)) ||
+        (rc = ensure(c->in_table, ntiles * 16)) || (rc = ensure_host(c->h_in_status, ntiles * sizeof(int))) ||
+        (rc = ensure(c->esa_full, dpitch * (size_t)h)))
+        return rc;
+    unsigned long long *d_off = (unsigned long long *)c->in_table.p;
+    uint32_t *d_size = (uint32_t *)((uint8_t *)c->in_table.p + ntiles * 8);
+    int *d_status = (int *)((uint8_t *)c->in_table.p + ntiles * 12);
+    if (src->blob_bytes)
+        CUDA_TRY(cudaMemcpyAsync(c->in_blob.p, src->blob, src->blob_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_off, src->offsets, ntiles * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_size, src->sizes, ntiles * 4, cudaMemcpyHostToDevice, st));
+    InflateParams ip;
+    memset(&ip, 0, sizeof(ip));
+    ip.blob = (const uint8_t *)c->in_blob.p;
+    ip.offsets = d_off;
+    ip.sizes = d_size;
+    ip.tiles_x = src->tiles_x;
+    ip.tiles_y = src->tiles_y;
+    ip.tile_w = src->tile_w;
+    ip.tile_h = src->tile_h;
+    ip.tw_shift = (src->tile_w & (src->tile_w - 1)) == 0 ? __builtin_ctz((unsigned)src->tile_w) : -1;
+    ip.x_off = src->x_off;
+    ip.y_off = src->y_off;
+    ip.dst = (uint8_t *)c->esa_full.p;
+    ip.pitch = dpitch;
+    ip.w = w;
+    ip.h = h;
+    ip.status = d_status;
+    CUDA_TRY(cudaEventRecord(c->inf0, st));
+    inflate_tiles_kernel<<<(unsigned)ntiles, 32, kInflateSmem, st>>>(ip);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->inf1, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_in_status.p, d_status, ntiles * sizeof(int), cudaMemcpyDeviceToHost, st));
+    *dpitch_out = dpitch;
+    return GCN10_OK;
+}
+
+static int check_tile_status(gcn10_ctx *c, size_t ntiles, int *tile_status)
+{
+    const int *hs = (const int *)c->h_in_status.p;
+    size_t bad = 0, first_bad = 0;
+    for (size_t i = 0; i < ntiles; i++) {
+        if (tile_status)
+            tile_status[i] = hs[i];
+        if (hs[i] && !bad++)
+            first_bad = i;
+    }
+    cudaEventElapsedTime(&c->last_inflate_ms, c->inf0, c->inf1);
+    if (bad)
+        return fail(GCN10_EDATA, "%zu of %zu compressed tiles could not be decoded (first: tile %zu, inflate error %d)",
+                    bad, ntiles, first_bad, hs[first_bad]);
+    return GCN10_OK;
+}
+
+int gcn10_cuda_inflate_tiles(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h, uint8_t *out, size_t out_pitch,
+                             int *tile_status)
+{
+    if (!c || !out)
+        return fail(GCN10_EINVAL, "NULL argument");
+    if (w > 0 && out_pitch < (size_t)w)
+        return fail(GCN10_EINVAL, "pitch smaller than row width");
+    size_t dpitch = 0;
+    int rc = inflate_to_device(c, src, w, h, &dpitch);
+    if (rc)
+        return rc;
+    cudaStream_t st = c->streams[0];
+    CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, c->esa_full.p, dpitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return check_tile_status(c, (size_t)src->tiles_x * src->tiles_y, tile_status);
+}
+
+int gcn10_cuda_block_tiles_deflate(gcn10_ctx *c, const gcn10_tile_source *esa_tiles, int w, int h, const double gt[6],
+                                   const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                                   unsigned plane_mask, gcn10_tile_sink sink, void *user)
+{
+    if (!c)
+        return fail(GCN10_EINVAL, "NULL context");
+    if (!sink || !hsg || !gt || !soil_gt)
+        return fail(GCN10_EINVAL, "NULL argument");
+    if (!c->have_lut)
+        return fail(GCN10_ENOLUT, "gcn10_cuda_set_luts() has not been called");
+    size_t dpitch = 0;
+    int rc = inflate_to_device(c, esa_tiles, w, h, &dpitch);
+    if (rc)
+        return rc;
+    // a damaged tile must stop the block before any output tile reaches the sink (the reference skips a
+    // block whose land cover cannot be read, cn.c:188-192)
+    CUDA_TRY(cudaStreamSynchronize(c->streams[0]));
+    if ((rc = check_tile_status(c, (size_t)esa_tiles->tiles_x * esa_tiles->tiles_y, nullptr)))
+        return rc;
+    return deflate_rows_impl(c, nullptr, 0, (const uint8_t *)c->esa_full.p, dpitch, nullptr, w, h, 0, h, gt, hsg, hsx,
+                             hsy, hsg_pitch, soil_gt, plane_mask, sink, user);
+}
+
+int gcn10_cuda_last_inflate_ms(gcn10_ctx *c, float *ms)
+{
+    if (!c || !ms)
+        return fail(GCN10_EINVAL, "NULL argument");
+    *ms = c->last_inflate_ms;
     return GCN10_OK;
 }
 

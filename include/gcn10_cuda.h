@@ -57,7 +57,9 @@ enum {
     GCN10_ECUDA   = -2,     /* a CUDA runtime/driver call failed                          */
     GCN10_ENOMEM  = -3,     /* host or device allocation failed                           */
     GCN10_ENOLUT  = -4,     /* gcn10_cuda_set_luts() has not been called                  */
-    GCN10_ENODEV  = -5      /* no CUDA device / device index out of range                 */
+    GCN10_ENODEV  = -5,     /* no CUDA device / device index out of range                 */
+    GCN10_EDATA   = -6      /* a compressed input tile is not a valid zlib stream of the tile's size
+                               (the recoverable tier: GDALRasterIO failing at raster.c:177-186)  */
 };
 
 typedef struct gcn10_ctx gcn10_ctx;
@@ -149,6 +151,53 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *ctx,
                                   const double gt[6],
                                   const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
                                   unsigned plane_mask, gcn10_tile_sink sink, void *user);
+
+/* Land cover handed over as the COMPRESSED tiles of a tiled GeoTIFF instead of a decoded raster.
+ *
+ * The reference obtains its land-cover window from load_raster() (raster.c:106-189), where GDAL inflates
+ * the TIFF tiles on the CPU (GDALRasterIO, raster.c:177-179; the ESA WorldCover files are 1024 x 1024
+ * DEFLATE tiles, landcover/esa_worldcover_2021.vrt).  With a gcn10_tile_source the caller passes the
+ * tiles that intersect the window exactly as they lie in the file (TIFF Compression 8 or 32946: one zlib
+ * stream per tile, no predictor) and the library inflates them on the GPU, one warp per tile, directly
+ * into the device-resident land-cover plane.  Only compressed bytes cross PCIe.
+ *
+ *   tile_w, tile_h     TIFF TileWidth / TileLength (any positive size)
+ *   tiles_x, tiles_y   the tile grid handed over (row-major in offsets / sizes)
+ *   x_off, y_off       position of the window's pixel (0, 0) inside that grid, i.e. window pixel (x, y)
+ *                      is pixel (x_off + x, y_off + y) of the grid; the grid must cover the w x h window
+ *   blob, blob_bytes   the tiles' bytes (host memory; page-locked memory makes the copy asynchronous)
+ *   offsets, sizes     per tile: start of its zlib stream in blob and its length; size 0 = a sparse tile,
+ *                      read as zeros (what GDAL returns for a tile that was never written)
+ */
+typedef struct {
+    int tile_w, tile_h;
+    int tiles_x, tiles_y;
+    int x_off, y_off;
+    const uint8_t *blob;
+    size_t blob_bytes;
+    const uint64_t *offsets;
+    const uint32_t *sizes;
+} gcn10_tile_source;
+
+/* Inflate the tiles of `src` on the GPU and return the w x h window as a raster in HOST memory
+ * (the load_raster() half alone).  tile_status, if not NULL, receives tiles_x * tiles_y codes: 0 = ok,
+ * 1..9 = the reason a tile could not be decoded (see inflate_core.h).  Returns GCN10_EDATA if any tile
+ * failed (the window is then incomplete).  The Adler-32 trailer of the streams is not verified. */
+int gcn10_cuda_inflate_tiles(gcn10_ctx *ctx, const gcn10_tile_source *src, int w, int h,
+                             uint8_t *out, size_t out_pitch, int *tile_status);
+
+/* gcn10_cuda_block_deflate with the land cover given as compressed tiles: inflate on the GPU, Curve
+ * Number kernel, tile DEFLATE on the GPU, compressed tiles back.  The whole load_raster -> cn.c ->
+ * save_raster chain of process_block() (cn.c:187-363) with compressed bytes on PCIe in both directions.
+ * Returns GCN10_EDATA (and calls the sink for no strip) if a land-cover tile cannot be decoded. */
+int gcn10_cuda_block_tiles_deflate(gcn10_ctx *ctx, const gcn10_tile_source *esa_tiles, int w, int h,
+                                   const double gt[6],
+                                   const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                                   unsigned plane_mask, gcn10_tile_sink sink, void *user);
+
+/* Device time of the inflate kernel of the most recent gcn10_cuda_inflate_tiles /
+ * gcn10_cuda_block_tiles_deflate call (CUDA events on the launching stream). */
+int gcn10_cuda_last_inflate_ms(gcn10_ctx *ctx, float *ms);
 
 /* Same computation with every buffer already in DEVICE memory; asynchronous on `stream`
  * (NULL = the context's own non-blocking stream; to use the legacy default stream pass

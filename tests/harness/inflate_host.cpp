@@ -1,0 +1,121 @@
+// tests/harness/inflate_host.cpp -- TEST HARNESS, not product code.
+//
+// Compiles gcn10_b200/csrc/inflate_core.h (the decode-lane half of the GPU tile inflater) for the host
+// and drives it with a scalar emulation of the warp loop of inflate_tiles.cuh: same 2 KB input ring and
+// refill rule, same batch order (all literals of a batch first, then the matches one after the other in
+// 32-byte read-then-write steps against a 32 KB history ring).  tests/test_inflate_core.py compares the
+// result with zlib on the CPU, so the bit reader, the Huffman table builder, the symbol decoder and the
+// batch-hazard rule are checked without a GPU.  Built by the test itself (g++ -shared); nothing under
+// gcn10_b200/ links or loads it.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../gcn10_b200/csrc/inflate_core.h"
+
+using namespace gcn10::inflate;
+
+extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t misalign, uint8_t *out,
+                                  uint32_t out_len, uint64_t *stats /* [symbols, matches, steps, blocks] */)
+{
+    // the device reads 16-byte aligned chunks and may run up to ~2 KB past the stream: give it that room
+    std::vector<uint8_t> padded((size_t)misalign + size + 4096 + 64, 0xA5);
+    const uint32_t first = misalign & 15u;
+    memcpy(padded.data() + first, stream, size);
+    const uint8_t *base = padded.data();
+
+    static Tables t;
+    uint32_t ring[kRingWords];
+    uint32_t queue[kQueue];
+    std::vector<uint8_t> window(kWindow, 0);
+    uint32_t filled = 0;
+    auto top_up = [&](uint32_t cons) {
+        while (filled < cons + 1024u) {
+            for (uint32_t k = 0; k < 512; k++)
+                ((uint8_t *)ring)[(filled + k) & 2047u] = base[filled + k];
+            filled += 512u;
+        }
+    };
+    auto emit = [&](uint32_t pos, uint8_t b) {
+        window[pos & (kWindow - 1)] = b;
+        if (pos < out_len)
+            out[pos] = b;
+    };
+
+    DecodeLane s;
+    lane_init(s, first, first + size, out_len);
+    top_up(first & ~3u);
+    s.err = read_zlib_header(s, ring, first);
+    int ev = s.err ? kEvError : kEvMore;
+    uint32_t out_base = 0;
+    uint64_t nsym = 0, nmatch = 0, nsteps = 0, nblocks = 0;
+    while (ev != kEvError && ev != kEvEnd) {
+        top_up(s.cons);
+        const int was_in_block = s.in_block;
+        const int n = decode_step(s, ring, t, queue, &ev);
+        nsteps++;
+        if (!was_in_block && ev != kEvError)
+            nblocks++;
+        uint32_t start[kQueue], pos = out_base;
+        for (int k = 0; k < n; k++) {
+            start[k] = pos;
+            pos += (queue[k] >> 31) ? (queue[k] & 0x1FFu) : 1u;
+        }
+        for (int k = 0; k < n; k++)
+            if (!(queue[k] >> 31))
+                emit(start[k], (uint8_t)(queue[k] & 255u));
+        for (int k = 0; k < n; k++) {
+            if (!(queue[k] >> 31))
+                continue;
+            nmatch++;
+            const uint32_t len = queue[k] & 0x1FFu, dist = ((queue[k] >> 16) & 0x7FFFu) + 1u, mp = start[k];
+            if (dist >= 32u) {
+                for (uint32_t b = 0; b < len; b += 32u) {
+                    uint8_t tmp[32];
+                    const uint32_t m = len - b < 32u ? len - b : 32u;
+                    for (uint32_t j = 0; j < m; j++)
+                        tmp[j] = window[(mp - dist + b + j) & (kWindow - 1)];
+                    for (uint32_t j = 0; j < m; j++)
+                        emit(mp + b + j, tmp[j]);
+                }
+            }
+            else {
+                uint8_t pat[32];
+                for (uint32_t j = 0; j < dist; j++)
+                    pat[j] = window[(mp - dist + j) & (kWindow - 1)];
+                for (uint32_t i = 0; i < len; i++)
+                    emit(mp + i, pat[i % dist]);
+            }
+        }
+        nsym += (uint64_t)n;
+        out_base = pos;
+        if (ev == kEvStored) {
+            const uint32_t so = s.stored_src, sl = s.stored_len;
+            for (uint32_t i = 0; i < sl; i++)
+                emit(out_base + i, base[so + i]);
+            out_base += sl;
+            const uint32_t q = so + sl;
+            filled = q & ~511u;
+            top_up(q & ~3u);
+            s.out_pos += sl;
+            seek(s, ring, q);
+            int done = 0;
+            if (s.bfinal) {
+                done = 1;
+                if (s.out_pos != s.out_end)
+                    s.err = kErrShort;
+            }
+            else if (q > s.in_end)
+                s.err = kErrInput;
+            ev = s.err ? kEvError : (done ? kEvEnd : kEvMore);
+        }
+    }
+    if (stats) {
+        stats[0] = nsym;
+        stats[1] = nmatch;
+        stats[2] = nsteps;
+        stats[3] = nblocks;
+    }
+    return s.err;
+}

@@ -1,0 +1,203 @@
+"""GPU tile inflate (gcn10_cuda_inflate_tiles / gcn10_cuda_block_tiles_deflate) against zlib and the oracle.
+
+The reference's load_raster() lets GDAL/zlib decode the land-cover tiles on the CPU
+(/root/reference/src/raster.c:177-179); the checker is therefore zlib itself: every tile handed to the GPU
+was produced by zlib.compress from a known raster, and the inflated window must equal that raster
+byte for byte.  The chained call (compressed tiles in -> Curve Numbers -> compressed tiles out) is checked
+against the oracle planes after decoding the output tiles with zlib."""
+import zlib
+
+import numpy as np
+import pytest
+
+from gcn10_b200 import capi, synth
+from tests.cases import make_block
+
+pytestmark = pytest.mark.gpu
+
+
+def _raster(w, h, seed, profile="worldcover", patch=48):
+    return synth.esa_tile(w, h, seed, profile=profile, patch=patch)
+
+
+GEOMS = [
+    # name, grid w, grid h, tile w, tile h, window (x_off, y_off, w, h) or None, level
+    ("tiles256", 1300, 777, 256, 256, None, 6),
+    ("tiles1024", 2500, 2100, 1024, 1024, None, 6),
+    ("tiles512_level9", 1500, 1100, 512, 512, None, 9),
+    ("tiles_not_pow2", 1000, 500, 240, 112, None, 6),
+    ("window_inside", 3000, 2200, 1024, 1024, (700, 300, 1500, 1300), 6),
+    ("window_inside_small_tiles", 1200, 900, 256, 256, (255, 257, 600, 500), 1),
+    ("stored_only", 700, 600, 256, 256, None, 0),
+    ("one_pixel_window", 600, 600, 256, 256, (300, 299, 1, 1), 6),
+]
+
+
+@pytest.mark.parametrize("name,gw,gh,tw,th,win,level", GEOMS, ids=[g[0] for g in GEOMS])
+@pytest.mark.parametrize("profile", ["worldcover", "random"])
+def test_inflate_equals_zlib_source(name, gw, gh, tw, th, win, level, profile, gpu_ctx):
+    grid = _raster(gw, gh, seed=len(name) * 7 + gw, profile=profile)
+    x_off, y_off, w, h = win if win else (0, 0, gw, gh)
+    src = capi.TileSource.from_raster(grid, tw, th, level=level, x_off=x_off, y_off=y_off, gap=3)
+    # guard band: a destination wider than the window must keep its padding
+    out = np.full((h + 2, w + 37), 0xEE, dtype=np.uint8)
+    view = out[1:h + 1, :w]
+    rc, _, status = gpu_ctx.inflate_tiles(src, w, h, out=view, want_status=True)
+    assert rc == 0, gpu_ctx.lib.gcn10_cuda_last_error().decode()
+    assert not status.any()
+    assert np.array_equal(view, grid[y_off:y_off + h, x_off:x_off + w])
+    assert (out[0] == 0xEE).all() and (out[-1] == 0xEE).all() and (out[:, w:] == 0xEE).all()
+    assert gpu_ctx.last_inflate_ms() > 0
+
+
+def test_every_stream_alignment_and_strategy(gpu_ctx):
+    """Streams at all 16 byte alignments inside the blob; fixed-Huffman, RLE, Huffman-only and filtered
+    strategies; tiny windows (wbits 9) and short blocks (memLevel 1)."""
+    tw = th = 256
+    variants = [(6, zlib.Z_DEFAULT_STRATEGY, 15, 8), (6, zlib.Z_FIXED, 15, 8), (6, zlib.Z_RLE, 15, 8),
+                (6, zlib.Z_HUFFMAN_ONLY, 15, 8), (6, zlib.Z_FILTERED, 15, 8), (6, zlib.Z_DEFAULT_STRATEGY, 9, 1),
+                (9, zlib.Z_DEFAULT_STRATEGY, 12, 9), (1, zlib.Z_DEFAULT_STRATEGY, 15, 1)]
+    n = 32
+    grid = _raster(tw * n, th, seed=5, patch=20)
+    grid[:, tw * 8:tw * 12] = _raster(tw * 4, th, seed=6, profile="random")
+    blob, offsets, sizes = bytearray(), [], []
+    for i in range(n):
+        level, strat, wbits, mem = variants[i % len(variants)]
+        c = zlib.compressobj(level, zlib.DEFLATED, wbits, mem, strat)
+        z = c.compress(np.ascontiguousarray(grid[:, i * tw:(i + 1) * tw]).tobytes()) + c.flush()
+        while len(blob) % 16 != (i * 5 + 1) % 16:
+            blob.append(0x5A)
+        offsets.append(len(blob))
+        sizes.append(len(z))
+        blob += z
+    src = capi.TileSource(tw, th, n, 1, 0, 0, np.frombuffer(bytes(blob), dtype=np.uint8).copy(), offsets, sizes)
+    assert len({o % 16 for o in offsets}) == 16
+    out = gpu_ctx.inflate_tiles(src, tw * n, th)
+    assert np.array_equal(out, grid)
+
+
+def test_long_codes_far_matches_and_block_mixes(gpu_ctx):
+    """Skewed byte statistics (Huffman codes longer than the 10-bit lookup), matches at distance ~30000
+    (the batch-closing rule of the decode lane), and stored/fixed/dynamic blocks mixed by flushes."""
+    rng = np.random.default_rng(3)
+    tw, th = 1024, 512
+    skew = rng.choice(np.arange(256, dtype=np.uint8), size=tw * th, p=np.r_[[0.6], np.full(255, 0.4 / 255)])
+    period = rng.integers(0, 256, 30011, dtype=np.uint8)
+    far = np.resize(period, tw * th)
+    mixed_raw, parts = [], []
+    c = zlib.compressobj(6)
+    left = tw * th
+    k = 0
+    while left:
+        m = min(left, 20000 + 1000 * k)
+        chunk = (rng.integers(0, 256, m, dtype=np.uint8) if k % 3 == 0
+                 else np.resize(_raster(300, 40, k, patch=16).ravel(), m))
+        mixed_raw.append(chunk)
+        parts.append(c.compress(chunk.tobytes()))
+        parts.append(c.flush(zlib.Z_FULL_FLUSH if k % 2 else zlib.Z_SYNC_FLUSH))
+        left -= m
+        k += 1
+    parts.append(c.flush())
+    tiles = [skew, far, np.concatenate(mixed_raw)]
+    streams = [zlib.compress(skew.tobytes(), 6), zlib.compress(far.tobytes(), 9), b"".join(parts)]
+    offsets, pos = [], 0
+    for z in streams:
+        offsets.append(pos)
+        pos += len(z)
+    src = capi.TileSource(tw, th, 3, 1, 0, 0, np.frombuffer(b"".join(streams), dtype=np.uint8).copy(), offsets,
+                          [len(z) for z in streams])
+    out = gpu_ctx.inflate_tiles(src, 3 * tw, th)
+    for i, t in enumerate(tiles):
+        assert np.array_equal(out[:, i * tw:(i + 1) * tw], t.reshape(th, tw)), f"tile {i}"
+
+
+def test_sparse_tiles_read_as_zero(gpu_ctx):
+    grid = _raster(1024, 768, seed=12)
+    src = capi.TileSource.from_raster(grid, 256, 256, sparse={(0, 1), (2, 3)})
+    out = np.full(grid.shape, 7, dtype=np.uint8)
+    gpu_ctx.inflate_tiles(src, 1024, 768, out=out)
+    want = grid.copy()
+    want[0:256, 256:512] = 0
+    want[512:768, 768:1024] = 0
+    assert np.array_equal(out, want)
+
+
+def test_damaged_tiles_are_reported_not_fatal(gpu_ctx):
+    grid = _raster(1024, 512, seed=13)
+    src = capi.TileSource.from_raster(grid, 256, 256)
+    blob = src.blob.copy()
+    blob[int(src.offsets[2])] = 0x79                             # tile 2: bad zlib method
+    o5, s5 = int(src.offsets[5]), int(src.sizes[5])
+    blob[o5 + 2:o5 + s5] = 0xFF                                   # tile 5: garbage body
+    bad = capi.TileSource(256, 256, src.tiles_x, src.tiles_y, 0, 0, blob, src.offsets, src.sizes)
+    rc, out, status = gpu_ctx.inflate_tiles(bad, 1024, 512, want_status=True)
+    assert rc == -6, "GCN10_EDATA expected"
+    assert status[2] == 1 and status[5] != 0
+    good = [i for i in range(8) if i not in (2, 5)]
+    assert not status[good].any()
+    for i in good:
+        r, c = divmod(i, 4)
+        assert np.array_equal(out[r * 256:(r + 1) * 256, c * 256:(c + 1) * 256],
+                              grid[r * 256:(r + 1) * 256, c * 256:(c + 1) * 256])
+    # truncated tile: the size table says fewer bytes than the stream needs
+    sizes = src.sizes.copy()
+    sizes[1] = sizes[1] // 2
+    cut = capi.TileSource(256, 256, src.tiles_x, src.tiles_y, 0, 0, src.blob, src.offsets, sizes)
+    rc, _, status = gpu_ctx.inflate_tiles(cut, 1024, 512, want_status=True)
+    assert rc == -6 and status[1] != 0
+    # the context stays usable
+    assert np.array_equal(gpu_ctx.inflate_tiles(src, 1024, 512), grid)
+
+
+def test_bad_arguments(gpu_ctx):
+    grid = _raster(512, 512, seed=1)
+    src = capi.TileSource.from_raster(grid, 256, 256)
+    rc, _, _ = gpu_ctx.inflate_tiles(src, 513, 512, want_status=True)            # grid does not cover the window
+    assert rc == -1
+    sizes = src.sizes.copy()
+    sizes[3] = 1 << 30
+    rc, _, _ = gpu_ctx.inflate_tiles(capi.TileSource(256, 256, 2, 2, 0, 0, src.blob, src.offsets, sizes), 512, 512,
+                                     want_status=True)
+    assert rc == -1
+
+
+def _assemble(tiles, w, h, T=256):
+    tx_n, ty_n = (w + T - 1) // T, (h + T - 1) // T
+    full = np.zeros((ty_n * T, tx_n * T), dtype=np.uint8)
+    for (r, c), z in tiles.items():
+        full[r * T:(r + 1) * T, c * T:(c + 1) * T] = np.frombuffer(zlib.decompress(z), dtype=np.uint8).reshape(T, T)
+    return full[:h, :w]
+
+
+@pytest.mark.parametrize("kw,tile,off", [
+    (dict(w=1300, h=777, seed=4), 256, (0, 0)),
+    (dict(w=2300, h=2600, seed=6), 1024, (100, 900)),
+    (dict(w=1000, h=600, profile="coastal", seed=7), 512, (511, 1)),
+], ids=["t256", "t1024_window", "coastal_t512"])
+def test_compressed_in_compressed_out_matches_oracle(kw, tile, off, gpu_ctx, port, tables):
+    b = make_block(**kw)
+    h, w = b["esa"].shape
+    x_off, y_off = off
+    grid = _raster(w + x_off + 50, h + y_off + 70, seed=99, profile="random")
+    grid[y_off:y_off + h, x_off:x_off + w] = b["esa"]
+    src = capi.TileSource.from_raster(grid, tile, tile, x_off=x_off, y_off=y_off)
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    res = gpu_ctx.block_tiles_deflate(src, w, h, b["gt"], b["hsg"], b["soil_gt"])
+    assert sorted(res["tiles"]) == list(range(18))
+    for k in range(18):
+        assert np.array_equal(_assemble(res["tiles"][k], w, h), want[k]), f"plane {k}"
+    # identical to the raw-raster entry point, tile for tile
+    ref = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    assert ref["tiles"] == res["tiles"]
+
+
+def test_damaged_land_cover_stops_the_block(gpu_ctx):
+    b = make_block(w=600, h=520, seed=3)
+    src = capi.TileSource.from_raster(b["esa"], 256, 256)
+    blob = src.blob.copy()
+    blob[int(src.offsets[4]) + 1] ^= 0x01
+    bad = capi.TileSource(256, 256, src.tiles_x, src.tiles_y, 0, 0, blob, src.offsets, src.sizes)
+    calls = []
+    with pytest.raises(capi.Gcn10Error) as ei:
+        gpu_ctx.block_tiles_deflate(bad, 600, 520, b["gt"], b["hsg"], b["soil_gt"], on_strip=lambda s: calls.append(1))
+    assert ei.value.code == -6 and not calls
