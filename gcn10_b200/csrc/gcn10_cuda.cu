@@ -494,6 +494,8 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
                                   kEncSmem));
     CUDA_TRY(cudaFuncSetAttribute((const void *)inflate_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kInflateSmem));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)inflate_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaEventCreate(&c->inf0));
     CUDA_TRY(cudaEventCreate(&c->inf1));
     // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -978,12 +980,20 @@ static int inflate_to_device(gcn10_ctx *c, const gcn10_tile_source *src, int w, 
     int rc;
     // the kernel's 512-byte input refills may run ~2 KB past a stream: keep that readable
     if ((rc = ensure(c->in_blob, round_up(src->blob_bytes, 256) + 4096)) ||
-        (rc = ensure(c->in_table, ntiles * 16)) || (rc = ensure_host(c->h_in_status, ntiles * sizeof(int))) ||
+        (rc = ensure(c->in_table, ntiles * 20)) || (rc = ensure_host(c->h_in_status, 2 * ntiles * sizeof(int))) ||
         (rc = ensure(c->esa_full, dpitch * (size_t)h)))
         return rc;
     unsigned long long *d_off = (unsigned long long *)c->in_table.p;
     uint32_t *d_size = (uint32_t *)((uint8_t *)c->in_table.p + ntiles * 8);
     int *d_status = (int *)((uint8_t *)c->in_table.p + ntiles * 12);
+    int *d_order = (int *)((uint8_t *)c->in_table.p + ntiles * 16);
+    // longest streams first: a tile's decode time grows with its compressed size, and a block has only a
+    // few tiles per resident CTA slot (1296 tiles of 1024 x 1024 on 740 slots), so the order sets the tail
+    int *h_order = (int *)c->h_in_status.p + ntiles;
+    for (size_t i = 0; i < ntiles; i++)
+        h_order[i] = (int)i;
+    std::stable_sort(h_order, h_order + ntiles, [&](int a, int b) { return src->sizes[a] > src->sizes[b]; });
+    CUDA_TRY(cudaMemcpyAsync(d_order, h_order, ntiles * 4, cudaMemcpyHostToDevice, st));
     if (src->blob_bytes)
         CUDA_TRY(cudaMemcpyAsync(c->in_blob.p, src->blob, src->blob_bytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_off, src->offsets, ntiles * 8, cudaMemcpyHostToDevice, st));
@@ -1005,8 +1015,9 @@ static int inflate_to_device(gcn10_ctx *c, const gcn10_tile_source *src, int w, 
     ip.w = w;
     ip.h = h;
     ip.status = d_status;
+    ip.order = d_order;
     CUDA_TRY(cudaEventRecord(c->inf0, st));
-    inflate_tiles_kernel<<<(unsigned)ntiles, 32, kInflateSmem, st>>>(ip);
+    inflate_tiles_kernel<<<(unsigned)ntiles, kInflateThreads, kInflateSmem, st>>>(ip);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->inf1, st));

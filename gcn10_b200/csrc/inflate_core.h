@@ -54,6 +54,7 @@ struct Tables {
     uint32_t ll_lut[1 << kLlBits];
     uint32_t d_lut[1 << kDBits];
     uint16_t sorted[288 + 32];      // symbols ordered by (code length, symbol): literal/length, then distance
+    uint16_t codes[288 + 32];       // bit-reversed code word of every symbol
     uint16_t ll_count[16], d_count[16];
     uint8_t lens[288 + 32];
 };
@@ -63,8 +64,6 @@ struct DecodeLane {
     int cnt;                // valid bits in buf
     uint32_t cons;          // byte offset (from the 16-byte aligned stream base) of the next ring word to load
     uint32_t in_end;        // byte offset one past the compressed tile
-    uint32_t out_pos;       // bytes produced so far
-    uint32_t out_end;       // tile_w * tile_h
     int in_block;           // inside a Huffman block
     int bfinal;
     int fixed_ready;        // tables currently hold the fixed code
@@ -151,10 +150,11 @@ GCN10_HD uint32_t d_entry(int sym, int nbits)
     return (uint32_t)nbits | ((uint32_t)eb << 4) | ((uint32_t)base << 16);
 }
 
-// Canonical Huffman tables from code lengths (RFC 1951 3.2.2).  Returns 0, or kErrCodeLengths for an
-// over-subscribed set.  Incomplete sets are accepted (unused bit patterns decode to kErrBadCode).
-GCN10_HD int build_table(const uint8_t *lens, int nsyms, int max_valid, bool dist, uint32_t *lut, int tbits,
-                         uint16_t *sorted, uint16_t *count)
+// Canonical Huffman code assignment from code lengths (RFC 1951 3.2.2), sequential part: per-length
+// counts, the symbols ordered by (length, symbol) for the canonical walk, and every symbol's code word
+// (bit-reversed, ready to index a lookup table).  Returns 0, or kErrCodeLengths for an over-subscribed
+// set.  Incomplete sets are accepted (unused bit patterns decode to kErrBadCode).
+GCN10_HD int assign_codes(const uint8_t *lens, int nsyms, uint16_t *sorted, uint16_t *count, uint16_t *codes)
 {
     uint16_t offs[16], next[16];
     for (int l = 0; l < 16; l++)
@@ -178,22 +178,36 @@ GCN10_HD int build_table(const uint8_t *lens, int nsyms, int max_valid, bool dis
         code = (code + count[l - 1]) << 1;
         next[l] = (uint16_t)code;
     }
-    const uint32_t slow = (uint32_t)(kSlow << 8);
-    for (int i = 0; i < (1 << tbits); i++)
-        lut[i] = slow;
     for (int s = 0; s < nsyms; s++) {
         const int l = lens[s];
         if (!l)
             continue;
         sorted[offs[l]++] = (uint16_t)s;
-        const uint32_t c = next[l]++;
-        if (l <= tbits && s < max_valid) {
-            const uint32_t e = dist ? d_entry(s, l) : ll_entry(s, l);
-            for (uint32_t k = bit_reverse(c, l); k < (1u << tbits); k += 1u << l)
-                lut[k] = e;
-        }
+        codes[s] = (uint16_t)bit_reverse(next[l]++, l);
     }
     return 0;
+}
+
+// Lookup-table fill, written so that `nlanes` workers can share it: worker `lane` clears and fills a
+// strided part.  The caller separates clear_lut and fill_lut by a barrier (a warp barrier on the device).
+GCN10_HD void clear_lut(uint32_t *lut, int tbits, int lane, int nlanes)
+{
+    const uint32_t slow = (uint32_t)(kSlow << 8);
+    for (int i = lane; i < (1 << tbits); i += nlanes)
+        lut[i] = slow;
+}
+
+GCN10_HD void fill_lut(const uint8_t *lens, const uint16_t *codes, int nsyms, int max_valid, bool dist, uint32_t *lut,
+                       int tbits, int lane, int nlanes)
+{
+    for (int s = lane; s < nsyms && s < max_valid; s += nlanes) {
+        const int l = lens[s];
+        if (!l || l > tbits)
+            continue;
+        const uint32_t e = dist ? d_entry(s, l) : ll_entry(s, l);
+        for (uint32_t k = codes[s]; k < (1u << tbits); k += 1u << l)
+            lut[k] = e;
+    }
 }
 
 // Bit-by-bit canonical decode for code words longer than the lookup width (or invalid patterns).
@@ -326,22 +340,33 @@ GCN10_HD int read_dynamic_header(DecodeLane &s, const uint32_t *ring, Tables &t)
     return 0;
 }
 
-GCN10_HD int build_block_tables(Tables &t)
+// code assignment for both alphabets of a block (sequential; the lookup fill follows, see fill_block_luts)
+GCN10_HD int assign_block_codes(Tables &t)
 {
-    int rc = build_table(t.lens, 288, 286, false, t.ll_lut, kLlBits, t.sorted, t.ll_count);
+    const int rc = assign_codes(t.lens, 288, t.sorted, t.ll_count, t.codes);
     if (rc)
         return rc;
-    return build_table(t.lens + 288, 32, 30, true, t.d_lut, kDBits, t.sorted + 288, t.d_count);
+    return assign_codes(t.lens + 288, 32, t.sorted + 288, t.d_count, t.codes + 288);
 }
 
-GCN10_HD void lane_init(DecodeLane &s, uint32_t first_byte, uint32_t in_end, uint32_t out_end)
+GCN10_HD void clear_block_luts(Tables &t, int lane, int nlanes)
+{
+    clear_lut(t.ll_lut, kLlBits, lane, nlanes);
+    clear_lut(t.d_lut, kDBits, lane, nlanes);
+}
+
+GCN10_HD void fill_block_luts(Tables &t, int lane, int nlanes)
+{
+    fill_lut(t.lens, t.codes, 288, 286, false, t.ll_lut, kLlBits, lane, nlanes);
+    fill_lut(t.lens + 288, t.codes + 288, 32, 30, true, t.d_lut, kDBits, lane, nlanes);
+}
+
+GCN10_HD void lane_init(DecodeLane &s, uint32_t first_byte, uint32_t in_end)
 {
     s.buf = 0;
     s.cnt = 0;
     s.cons = first_byte & ~3u;
     s.in_end = in_end;
-    s.out_pos = 0;
-    s.out_end = out_end;
     s.in_block = 0;
     s.bfinal = 0;
     s.fixed_ready = 0;
@@ -360,10 +385,65 @@ GCN10_HD int read_zlib_header(DecodeLane &s, const uint32_t *ring, uint32_t firs
     return 0;
 }
 
-// One step of the decode lane: either a block header or up to kQueue symbols.
+// what read_block_header() asks its caller to do
+enum { kHdrError = 0, kHdrStored = 1, kHdrReady = 2, kHdrBuild = 3 };
+
+// Block header (RFC 1951 3.2.3).  kHdrStored: s.stored_src / s.stored_len describe the raw bytes, the caller
+// copies them and re-seeks the reader behind them.  kHdrBuild: t.lens holds the block's code lengths and
+// t.codes / t.sorted / counts are assigned; the caller runs clear_block_luts + fill_block_luts.  kHdrReady:
+// the tables already hold this (fixed) code.
+GCN10_HD int read_block_header(DecodeLane &s, const uint32_t *ring, Tables &t)
+{
+    if (byte_pos(s) > s.in_end + 8u) {
+        s.err = kErrInput;
+        return kHdrError;
+    }
+    s.bfinal = (int)get_bits(s, ring, 1);
+    const int btype = (int)get_bits(s, ring, 2);
+    if (btype == 0) {
+        const int drop = s.cnt & 7;
+        s.buf >>= drop;
+        s.cnt -= drop;
+        const uint32_t len = get_bits(s, ring, 16), nlen = get_bits(s, ring, 16);
+        if ((len ^ nlen) != 0xFFFFu) {
+            s.err = kErrStoredLen;
+            return kHdrError;
+        }
+        s.stored_src = byte_pos(s);
+        s.stored_len = len;
+        if (s.stored_src + len > s.in_end) {
+            s.err = kErrInput;
+            return kHdrError;
+        }
+        return kHdrStored;
+    }
+    if (btype == 3) {
+        s.err = kErrBlockType;
+        return kHdrError;
+    }
+    s.in_block = 1;
+    if (btype == 1) {
+        if (s.fixed_ready)
+            return kHdrReady;
+        fixed_lengths(t.lens);
+        s.fixed_ready = 1;
+    }
+    else {
+        s.fixed_ready = 0;
+        s.err = read_dynamic_header(s, ring, t);
+        if (s.err)
+            return kHdrError;
+    }
+    s.err = assign_block_codes(t);
+    return s.err ? kHdrError : kHdrBuild;
+}
+
+// Up to kQueue symbols of the current Huffman block.
 //   queue entry: literal = byte; match = 1<<31 | (dist-1) << 16 | len
-// Returns the number of symbols queued; *event says what the warp has to do next.
-GCN10_HD int decode_step(DecodeLane &s, const uint32_t *ring, Tables &t, uint32_t *queue, int *event)
+// The decode lane does not know output positions: range checks (distance before the start of the tile,
+// more bytes than the tile holds) are made by whoever executes the queue (check_batch below / the writer
+// warp).  Returns the number of symbols queued; *event = kEvMore, kEvEnd (final block closed) or kEvError.
+GCN10_HD int decode_symbols(DecodeLane &s, const uint32_t *ring, const Tables &t, uint32_t *queue, int *event)
 {
     *event = kEvMore;
     if (byte_pos(s) > s.in_end + 8u) {
@@ -371,68 +451,11 @@ GCN10_HD int decode_step(DecodeLane &s, const uint32_t *ring, Tables &t, uint32_
         *event = kEvError;
         return 0;
     }
-    if (!s.in_block) {
-        s.bfinal = (int)get_bits(s, ring, 1);
-        const int btype = (int)get_bits(s, ring, 2);
-        if (btype == 0) {
-            const int drop = s.cnt & 7;
-            s.buf >>= drop;
-            s.cnt -= drop;
-            const uint32_t len = get_bits(s, ring, 16), nlen = get_bits(s, ring, 16);
-            if ((len ^ nlen) != 0xFFFFu) {
-                s.err = kErrStoredLen;
-                *event = kEvError;
-                return 0;
-            }
-            if (s.out_pos + len > s.out_end) {
-                s.err = kErrOverflow;
-                *event = kEvError;
-                return 0;
-            }
-            s.stored_src = byte_pos(s);
-            s.stored_len = len;
-            if (s.stored_src + len > s.in_end) {
-                s.err = kErrInput;
-                *event = kEvError;
-                return 0;
-            }
-            *event = kEvStored;        // the warp copies, advances out_pos, re-seeks the reader
-            return 0;
-        }
-        if (btype == 3) {
-            s.err = kErrBlockType;
-            *event = kEvError;
-            return 0;
-        }
-        int rc = 0;
-        if (btype == 1) {
-            if (!s.fixed_ready) {
-                fixed_lengths(t.lens);
-                rc = build_block_tables(t);
-                s.fixed_ready = 1;
-            }
-        }
-        else {
-            s.fixed_ready = 0;
-            rc = read_dynamic_header(s, ring, t);
-            if (!rc)
-                rc = build_block_tables(t);
-        }
-        if (rc) {
-            s.err = rc;
-            *event = kEvError;
-            return 0;
-        }
-        s.in_block = 1;
-        return 0;
-    }
-
     int n = 0;
-    uint32_t pos = s.out_pos;
     while (n < kQueue) {
         need32(s, ring);
         uint32_t e = t.ll_lut[(uint32_t)s.buf & ((1u << kLlBits) - 1u)];
-        if (((e >> 8) & 3u) == kSlow) {
+        if ((e & 15u) == 0u) {
             int used = 0;
             const int sym = slow_symbol(s.buf, t.sorted, t.ll_count, &used);
             if (sym < 0 || sym > 285) {
@@ -446,12 +469,7 @@ GCN10_HD int decode_step(DecodeLane &s, const uint32_t *ring, Tables &t, uint32_
         s.cnt -= nb;
         const uint32_t kind = (e >> 8) & 3u;
         if (kind == kLit) {
-            if (pos >= s.out_end) {
-                s.err = kErrOverflow;
-                break;
-            }
             queue[n++] = e >> 16;
-            pos++;
             continue;
         }
         if (kind == kEob) {
@@ -461,7 +479,7 @@ GCN10_HD int decode_step(DecodeLane &s, const uint32_t *ring, Tables &t, uint32_
             break;
         }
         const int eb = (int)((e >> 4) & 15u);
-        const uint32_t len = (e >> 16) + ((uint32_t)s.buf & ((1u << eb) - 1u));
+        const uint32_t len = (e >> 16) + ((uint32_t)s.buf & ~(~0u << eb));
         s.buf >>= eb;
         s.cnt -= eb;
         need32(s, ring);
@@ -478,36 +496,26 @@ GCN10_HD int decode_step(DecodeLane &s, const uint32_t *ring, Tables &t, uint32_
         const int dn = (int)(d & 15u), deb = (int)((d >> 4) & 15u);
         s.buf >>= dn;
         s.cnt -= dn;
-        const uint32_t dist = (d >> 16) + ((uint32_t)s.buf & ((1u << deb) - 1u));
+        const uint32_t dist = (d >> 16) + ((uint32_t)s.buf & ~(~0u << deb));
         s.buf >>= deb;
         s.cnt -= deb;
-        if (dist > pos) {
-            s.err = kErrDistance;
-            break;
-        }
-        if (pos + len > s.out_end) {
-            s.err = kErrOverflow;
-            break;
-        }
         queue[n++] = 0x80000000u | ((dist - 1u) << 16) | len;
-        pos += len;
-        // The warp writes every literal of a batch before it copies the matches, and the history ring is
-        // indexed modulo 32768: a literal up to kMaxBatchOut bytes further on lands on the byte 32768
-        // positions behind it.  A match that reaches back into that zone therefore closes its batch.
-        if (dist + (uint32_t)kMaxBatchOut > (uint32_t)kWindow)
-            break;
     }
-    s.out_pos = pos;
     if (s.err) {
         *event = kEvError;
         return 0;
     }
-    if (*event == kEvEnd && pos != s.out_end) {
-        s.err = kErrShort;
-        *event = kEvError;
-    }
     return n;
 }
+
+GCN10_HD uint32_t sym_is_match(uint32_t sym) { return sym >> 31; }
+GCN10_HD uint32_t sym_len(uint32_t sym) { return (sym >> 31) ? (sym & 0x1FFu) : 1u; }
+GCN10_HD uint32_t sym_dist(uint32_t sym) { return ((sym >> 16) & 0x7FFFu) + 1u; }
+
+// The executor hoists all literals of a batch in front of its matches; with the history ring indexed
+// modulo 32768 a literal up to kMaxBatchOut bytes further on lands on the byte 32768 positions behind it,
+// so a batch holding a match that reaches back into that zone is executed strictly in order instead.
+GCN10_HD bool sym_is_far(uint32_t sym) { return sym_is_match(sym) && sym_dist(sym) + (uint32_t)kMaxBatchOut > (uint32_t)kWindow; }
 
 }  // namespace inflate
 }  // namespace gcn10

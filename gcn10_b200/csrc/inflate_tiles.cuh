@@ -5,15 +5,18 @@
 // device as they lie in the file and one warp per tile inflates them straight into the land-cover plane
 // the Curve Number kernel reads (window clipping included), so PCIe carries ~1/20 of the raster.
 //
-// One CTA = one warp = one tile (zlib stream).  Shared memory per warp (41 KB, five warps per SM):
-//   window   32 KB   the DEFLATE history as a ring indexed by output position (every distance <= 32768)
-//   tables    7 KB   10-bit literal/length and 9-bit distance lookup + canonical-walk arrays (inflate_core.h)
-//   ring      2 KB   compressed input, refilled 512 B at a time by all lanes (16-byte loads)
-//   queue   128 B    one batch of LZ77 symbols
-// Loop: the warp tops up the input ring; lane 0 runs one decode step (a block header, or up to 32
-// symbols); a warp scan of the symbol lengths gives every symbol its output position; all literals are
-// written at once; matches are copied one after the other, 32 bytes per step, from the history ring.
-// Every byte goes to the ring and -- if it falls inside the requested window -- to the plane in HBM.
+// One CTA = one tile (zlib stream) = two warps in a producer / consumer pair:
+//   decoder warp  tops up the 2 KB compressed-input ring (16-byte loads by all lanes); lane 0 owns the bit
+//                 reader and turns code words into batches of up to 32 LZ77 symbols (inflate_core.h); block
+//                 headers are parsed by lane 0, the Huffman lookup tables are filled by all 32 lanes.
+//   writer warp   executes the batches against a 32 KB history ring in shared memory: a warp scan of the
+//                 symbol lengths gives every symbol its output position, all literals are written at once,
+//                 matches are copied one after the other (32 or 128 bytes per step); finished 4 KB pieces of
+//                 the ring are flushed to the land-cover plane in HBM with 16-byte stores, clipped to the
+//                 requested window.
+// The two warps hand over through a double-buffered symbol queue guarded by named barriers (bar.sync /
+// bar.arrive), so decoding batch k+1 overlaps executing batch k.  Shared memory per CTA: 43 KB (history 32 KB,
+// tables 7.6 KB, input ring 2 KB, queues 0.5 KB) -> five tiles in flight per SM.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -35,42 +38,131 @@ struct InflateParams {
     size_t pitch;
     int w, h;                           // window size: pixels outside are decoded but not stored
     int *status;                        // [tiles_y][tiles_x] 0 or an inflate::kErr* code
+    const int *order;                   // launch order: CTA i takes tile order[i] (longest streams first), or NULL
 };
 
 struct InflateSmem {
     inflate::Tables t;
     uint32_t ring[inflate::kRingWords];
-    uint32_t queue[inflate::kQueue];
+    uint32_t queue[2][inflate::kQueue];
+    int meta[2][8];                     // n, event, stored_src, stored_len, decoder error, final flag
+    volatile int writer_err;
+    int pad[3];
     uint8_t window[inflate::kWindow];
 };
 
 constexpr int kInflateSmem = (int)sizeof(InflateSmem);
+constexpr int kInflateThreads = 64;
+constexpr uint32_t kFlushChunk = 4096;
 
 struct TileDst {
     uint8_t *dst;
     size_t pitch;
     int dx0, dy0, w, h, tile_w, tw_shift;
+    bool rows16;                        // tile_w % 16 == 0: a 16-byte group never straddles tile rows
 };
 
-__device__ __forceinline__ void inflate_emit(uint8_t *window, const TileDst &d, uint32_t pos, uint32_t byte)
+enum { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4 };
+
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+// history ring piece [p0, p0 + nbytes) -> plane (p0 is a multiple of 16); whole warp
+__device__ __forceinline__ void inflate_flush(const uint8_t *window, const TileDst &d, uint32_t p0, uint32_t nbytes,
+                                              int lane)
 {
-    window[pos & (inflate::kWindow - 1)] = (uint8_t)byte;
-    const uint32_t r = d.tw_shift >= 0 ? pos >> d.tw_shift : pos / (uint32_t)d.tile_w;
-    const uint32_t c = pos - r * (uint32_t)d.tile_w;
-    const int gy = d.dy0 + (int)r, gx = d.dx0 + (int)c;
-    if ((unsigned)gy < (unsigned)d.h && (unsigned)gx < (unsigned)d.w)
-        d.dst[(size_t)gy * d.pitch + gx] = (uint8_t)byte;
+    using inflate::kWindow;
+    if (d.rows16) {
+        for (uint32_t g = lane; g * 16u < nbytes; g += 32u) {
+            const uint32_t p = p0 + 16u * g;
+            const uint32_t r = d.tw_shift >= 0 ? p >> d.tw_shift : p / (uint32_t)d.tile_w;
+            const uint32_t c = p - r * (uint32_t)d.tile_w;
+            const int gy = d.dy0 + (int)r, gx = d.dx0 + (int)c;
+            if ((unsigned)gy >= (unsigned)d.h || gx + 16 <= 0 || gx >= d.w)
+                continue;
+            uint8_t *o = d.dst + (size_t)gy * d.pitch + gx;
+            const uint32_t left = nbytes - 16u * g;
+            if (gx >= 0 && gx + 16 <= d.w && left >= 16u && (reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+                *reinterpret_cast<uint4 *>(o) = *reinterpret_cast<const uint4 *>(window + (p & (kWindow - 1)));
+            }
+            else {
+                const uint32_t m = left < 16u ? left : 16u;
+                for (uint32_t k = 0; k < m; k++)
+                    if ((unsigned)(gx + (int)k) < (unsigned)d.w)
+                        o[k] = window[(p + k) & (kWindow - 1)];
+            }
+        }
+    }
+    else {
+        for (uint32_t i = lane; i < nbytes; i += 32u) {
+            const uint32_t p = p0 + i;
+            const uint32_t r = p / (uint32_t)d.tile_w, c = p - r * (uint32_t)d.tile_w;
+            const int gy = d.dy0 + (int)r, gx = d.dx0 + (int)c;
+            if ((unsigned)gy < (unsigned)d.h && (unsigned)gx < (unsigned)d.w)
+                d.dst[(size_t)gy * d.pitch + gx] = window[p & (kWindow - 1)];
+        }
+    }
 }
 
-__global__ void __launch_bounds__(32)
+// copy of one match by the whole warp: bytes [mp, mp + len) := bytes [mp - dist, ...) of the history ring
+__device__ __forceinline__ void inflate_copy(uint8_t *window, uint32_t mp, uint32_t len, uint32_t dist, int lane)
+{
+    constexpr uint32_t M = inflate::kWindow - 1;
+    if (dist >= 128u) {
+        // a 128-byte step never reads what the same step writes
+        for (uint32_t b = 0; b < len; b += 128u) {
+            uint8_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = b + lane + 32u * k;
+                v[k] = i < len ? window[(mp - dist + i) & M] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = b + lane + 32u * k;
+                if (i < len)
+                    window[(mp + i) & M] = v[k];
+            }
+            __syncwarp();
+        }
+    }
+    else if (dist >= 32u) {
+        for (uint32_t b = 0; b < len; b += 32u) {
+            const uint32_t i = b + lane;
+            if (i < len)
+                window[(mp + i) & M] = window[(mp - dist + i) & M];
+            __syncwarp();
+        }
+    }
+    else if (dist == 1u) {
+        const uint8_t v = window[(mp - 1u) & M];
+        for (uint32_t i = lane; i < len; i += 32u)
+            window[(mp + i) & M] = v;
+        __syncwarp();
+    }
+    else {
+        // overlapping copy: the pattern of the last `dist` bytes repeats; sources all lie before mp
+        uint32_t q = (uint32_t)lane % dist;
+        const uint32_t step = 32u % dist;
+        for (uint32_t i = lane; i < len; i += 32u) {
+            window[(mp + i) & M] = window[(mp - dist + q) & M];
+            q += step;
+            if (q >= dist)
+                q -= dist;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kInflateThreads)
 inflate_tiles_kernel(const __grid_constant__ InflateParams p)
 {
     using namespace inflate;
     extern __shared__ __align__(16) uint8_t smem_inf[];
     InflateSmem &sm = *reinterpret_cast<InflateSmem *>(smem_inf);
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x;
-    const int tile = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
 
     TileDst d;
@@ -82,16 +174,17 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
     d.h = p.h;
     d.tile_w = p.tile_w;
     d.tw_shift = p.tw_shift;
+    d.rows16 = (p.tile_w & 15) == 0;
 
     const uint32_t size = p.sizes[tile];
     if (size == 0) {
         // sparse tile: GDAL returns zeros for a tile without data
         const int x0 = max(d.dx0, 0), x1 = min(d.dx0 + p.tile_w, p.w);
         const int y0 = max(d.dy0, 0), y1 = min(d.dy0 + p.tile_h, p.h);
-        for (int y = y0; y < y1; y++)
+        for (int y = y0 + warp; y < y1; y += 2)
             for (int x = x0 + lane; x < x1; x += 32)
                 p.dst[(size_t)y * p.pitch + x] = 0;
-        if (lane == 0)
+        if (threadIdx.x == 0)
             p.status[tile] = 0;
         return;
     }
@@ -99,102 +192,206 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
     const uint8_t *src = p.blob + p.offsets[tile];
     const uint8_t *base = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15);
     const uint32_t first = (uint32_t)(src - base);
-    uint32_t filled = 0;                // [base, base + filled) has been staged; the ring holds its last 2 KB
+    const uint32_t out_end = (uint32_t)p.tile_w * (uint32_t)p.tile_h;
+    if (threadIdx.x == 0)
+        sm.writer_err = 0;
+    __syncthreads();
 
-    auto top_up = [&](uint32_t cons) {
-        while (filled < cons + 1024u) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + filled) + lane);
-            *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(sm.ring) + ((filled + 16u * lane) & 2047u)) = v;
-            filled += 512u;
-        }
-        __syncwarp();
-    };
-
-    DecodeLane s;
-    lane_init(s, first, first + size, (uint32_t)p.tile_w * (uint32_t)p.tile_h);
-    top_up(first & ~3u);
-    if (lane == 0)
-        s.err = read_zlib_header(s, sm.ring, first);
-    int ev = __shfl_sync(full, s.err, 0) ? kEvError : kEvMore;
-    uint32_t out_base = 0;
-
-    while (ev != kEvError && ev != kEvEnd) {
-        top_up(__shfl_sync(full, s.cons, 0));
-        int n = 0;
-        if (lane == 0)
-            n = decode_step(s, sm.ring, sm.t, sm.queue, &ev);
-        n = __shfl_sync(full, n, 0);
-        ev = __shfl_sync(full, ev, 0);
-        __syncwarp();
-
-        if (n > 0) {
-            const uint32_t sym = lane < n ? sm.queue[lane] : 0u;
-            const bool is_match = (sym >> 31) != 0u;
-            const uint32_t l = lane < n ? (is_match ? (sym & 0x1FFu) : 1u) : 0u;
-            uint32_t inc = l;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(full, inc, o);
-                if (lane >= o)
-                    inc += t;
+    if (warp == 0) {
+        // ------------------------------------------------------------------ decoder warp
+        uint32_t filled = 0;            // [base, base + filled) has been staged; the ring holds its last 2 KB
+        auto top_up = [&](uint32_t cons) {
+            while (filled < cons + 1024u) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + filled) + lane);
+                *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(sm.ring) + ((filled + 16u * lane) & 2047u)) = v;
+                filled += 512u;
             }
-            const uint32_t start = out_base + inc - l;
-            out_base += __shfl_sync(full, inc, 31);
-            if (lane < n && !is_match)
-                inflate_emit(sm.window, d, start, sym & 255u);
             __syncwarp();
-            unsigned mm = __ballot_sync(full, is_match);
-            while (mm) {
-                const int owner = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const uint32_t ms = __shfl_sync(full, sym, owner);
-                const uint32_t mp = __shfl_sync(full, start, owner);
-                const uint32_t len = ms & 0x1FFu, dist = ((ms >> 16) & 0x7FFFu) + 1u;
-                if (dist >= 32u) {
-                    // bytes of one 32-byte step never read what the same step writes
-                    for (uint32_t b = 0; b < len; b += 32u) {
-                        const uint32_t i = b + lane;
-                        if (i < len)
-                            inflate_emit(sm.window, d, mp + i, sm.window[(mp - dist + i) & (kWindow - 1)]);
-                        __syncwarp();
+        };
+        DecodeLane s;
+        lane_init(s, first, first + size);
+        top_up(first & ~3u);
+        if (lane == 0)
+            s.err = read_zlib_header(s, sm.ring, first);
+        int b = 0;
+        for (;;) {
+            top_up(__shfl_sync(full, s.cons, 0));
+            if (lane == 0 && !s.err && sm.writer_err)
+                s.err = sm.writer_err;
+            const int err = __shfl_sync(full, s.err, 0);
+            const int in_block = __shfl_sync(full, s.in_block, 0);
+            int n = 0, ev = kEvMore, fin = 0;
+            uint32_t so = 0, sl = 0;
+            bool post = false, acquired = false;
+            if (err) {
+                ev = kEvError;
+                post = true;
+            }
+            else if (!in_block) {
+                int action = 0;
+                if (lane == 0)
+                    action = read_block_header(s, sm.ring, sm.t);
+                action = __shfl_sync(full, action, 0);
+                if (action == kHdrBuild) {
+                    __syncwarp();
+                    clear_block_luts(sm.t, lane, 32);
+                    __syncwarp();
+                    fill_block_luts(sm.t, lane, 32);
+                    __syncwarp();
+                }
+                else if (action == kHdrStored) {
+                    so = __shfl_sync(full, s.stored_src, 0);
+                    sl = __shfl_sync(full, s.stored_len, 0);
+                    fin = __shfl_sync(full, s.bfinal, 0);
+                    const uint32_t q = so + sl;
+                    filled = q & ~511u;
+                    top_up(q & ~3u);
+                    if (lane == 0)
+                        seek(s, sm.ring, q);
+                    ev = kEvStored;
+                    post = true;
+                }
+                else if (action == kHdrError) {
+                    ev = kEvError;
+                    post = true;
+                }
+            }
+            else {
+                bar_sync(kBarEmpty0 + b);
+                acquired = true;
+                if (lane == 0)
+                    n = decode_symbols(s, sm.ring, sm.t, sm.queue[b], &ev);
+                ev = __shfl_sync(full, ev, 0);
+                post = true;
+            }
+            if (post) {
+                if (!acquired)
+                    bar_sync(kBarEmpty0 + b);
+                if (lane == 0) {
+                    sm.meta[b][0] = n;
+                    sm.meta[b][1] = ev;
+                    sm.meta[b][2] = (int)so;
+                    sm.meta[b][3] = (int)sl;
+                    sm.meta[b][4] = s.err;
+                    sm.meta[b][5] = fin;
+                }
+                __syncwarp();
+                bar_arrive(kBarFull0 + b);
+                b ^= 1;
+                if (ev == kEvEnd || ev == kEvError || (ev == kEvStored && fin))
+                    break;
+            }
+        }
+    }
+    else {
+        // ------------------------------------------------------------------ writer warp
+        uint8_t *window = sm.window;
+        constexpr uint32_t M = kWindow - 1;
+        bar_arrive(kBarEmpty0);
+        bar_arrive(kBarEmpty1);
+        uint32_t out_base = 0, flushed = 0;
+        int werr = 0, b = 0;
+        for (;;) {
+            bar_sync(kBarFull0 + b);
+            const int n = sm.meta[b][0], ev = sm.meta[b][1], derr = sm.meta[b][4], fin = sm.meta[b][5];
+            const uint32_t so = (uint32_t)sm.meta[b][2], sl = (uint32_t)sm.meta[b][3];
+            const uint32_t sym = lane < n ? sm.queue[b][lane] : 0u;
+            bar_arrive(kBarEmpty0 + b);
+            b ^= 1;
+
+            if (n > 0 && !werr) {
+                const bool is_match = sym_is_match(sym) != 0u;
+                const uint32_t l = lane < n ? sym_len(sym) : 0u;
+                uint32_t inc = l;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(full, inc, o);
+                    if (lane >= o)
+                        inc += t;
+                }
+                const uint32_t start = out_base + inc - l;
+                const uint32_t total = __shfl_sync(full, inc, 31);
+                const unsigned bad = __ballot_sync(full, is_match && sym_dist(sym) > start);
+                const unsigned far = __ballot_sync(full, sym_is_far(sym));
+                if (out_base + total > out_end)
+                    werr = kErrOverflow;
+                else if (bad)
+                    werr = kErrDistance;
+                else if (!far) {
+                    if (lane < n && !is_match)
+                        window[start & M] = (uint8_t)sym;
+                    __syncwarp();
+                    unsigned mm = __ballot_sync(full, is_match);
+                    while (mm) {
+                        const int owner = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const uint32_t ms = __shfl_sync(full, sym, owner);
+                        const uint32_t mp = __shfl_sync(full, start, owner);
+                        inflate_copy(window, mp, ms & 0x1FFu, sym_dist(ms), lane);
                     }
                 }
                 else {
-                    // overlapping copy: the pattern of the last `dist` bytes repeats
-                    for (uint32_t i = lane; i < len; i += 32u)
-                        inflate_emit(sm.window, d, mp + i, sm.window[(mp - dist + i % dist) & (kWindow - 1)]);
-                    __syncwarp();
+                    // a match reaches far back: no literal hoisting, strictly in stream order
+                    for (int k = 0; k < n; k++) {
+                        const uint32_t ms = __shfl_sync(full, sym, k);
+                        const uint32_t mp = __shfl_sync(full, start, k);
+                        if (sym_is_match(ms))
+                            inflate_copy(window, mp, ms & 0x1FFu, sym_dist(ms), lane);
+                        else {
+                            if (lane == 0)
+                                window[mp & M] = (uint8_t)ms;
+                            __syncwarp();
+                        }
+                    }
+                }
+                if (!werr) {
+                    out_base += total;
+                    while (flushed + kFlushChunk <= out_base) {
+                        inflate_flush(window, d, flushed, kFlushChunk, lane);
+                        flushed += kFlushChunk;
+                    }
                 }
             }
-        }
-
-        if (ev == kEvStored) {
-            // raw bytes: global -> history ring + plane, then restart the bit reader behind them
-            const uint32_t so = __shfl_sync(full, s.stored_src, 0), sl = __shfl_sync(full, s.stored_len, 0);
-            for (uint32_t i = lane; i < sl; i += 32u)
-                inflate_emit(sm.window, d, out_base + i, base[so + i]);
-            out_base += sl;
-            const uint32_t q = so + sl;
-            filled = q & ~511u;
-            top_up(q & ~3u);
-            int done = 0;
-            if (lane == 0) {
-                s.out_pos += sl;
-                seek(s, sm.ring, q);
-                if (s.bfinal) {
-                    done = 1;
-                    if (s.out_pos != s.out_end)
-                        s.err = kErrShort;
+            if (ev == kEvStored && !werr) {
+                if (out_base + sl > out_end)
+                    werr = kErrOverflow;
+                else {
+                    // raw bytes: global -> history ring, flushed piecewise (a stored block can exceed the ring)
+                    uint32_t done = 0;
+                    while (done < sl) {
+                        const uint32_t m = min(sl - done, kFlushChunk);
+                        for (uint32_t i = lane; i < m; i += 32u)
+                            window[(out_base + i) & M] = base[so + done + i];
+                        __syncwarp();
+                        out_base += m;
+                        done += m;
+                        while (flushed + kFlushChunk <= out_base) {
+                            inflate_flush(window, d, flushed, kFlushChunk, lane);
+                            flushed += kFlushChunk;
+                        }
+                    }
                 }
-                else if (q > s.in_end)
-                    s.err = kErrInput;
             }
-            done = __shfl_sync(full, done, 0);
-            ev = __shfl_sync(full, s.err, 0) ? kEvError : (done ? kEvEnd : kEvMore);
+            if (werr && lane == 0)
+                sm.writer_err = werr;
+            if (ev == kEvEnd || (ev == kEvStored && fin)) {
+                if (!werr && out_base != out_end)
+                    werr = kErrShort;
+                break;
+            }
+            if (ev == kEvError) {
+                if (!werr)
+                    werr = derr;
+                break;
+            }
         }
+        if (!werr && flushed < out_end) {
+            __syncwarp();
+            inflate_flush(window, d, flushed, out_end - flushed, lane);
+        }
+        if (lane == 0)
+            p.status[tile] = werr;
     }
-    if (lane == 0)
-        p.status[tile] = s.err;
 }
 
 }  // namespace gcn10

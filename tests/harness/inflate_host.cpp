@@ -44,71 +44,128 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
     };
 
     DecodeLane s;
-    lane_init(s, first, first + size, out_len);
+    lane_init(s, first, first + size);
     top_up(first & ~3u);
     s.err = read_zlib_header(s, ring, first);
-    int ev = s.err ? kEvError : kEvMore;
     uint32_t out_base = 0;
+    int werr = 0;                       // what the writer warp finds (range checks)
     uint64_t nsym = 0, nmatch = 0, nsteps = 0, nblocks = 0;
-    while (ev != kEvError && ev != kEvEnd) {
+    for (;;) {
         top_up(s.cons);
-        const int was_in_block = s.in_block;
-        const int n = decode_step(s, ring, t, queue, &ev);
+        if (!s.err && werr)
+            s.err = werr;
+        int n = 0, ev = kEvMore, fin = 0;
+        uint32_t so = 0, sl = 0;
+        bool post = false;
         nsteps++;
-        if (!was_in_block && ev != kEvError)
-            nblocks++;
-        uint32_t start[kQueue], pos = out_base;
-        for (int k = 0; k < n; k++) {
-            start[k] = pos;
-            pos += (queue[k] >> 31) ? (queue[k] & 0x1FFu) : 1u;
+        if (s.err) {
+            ev = kEvError;
+            post = true;
         }
-        for (int k = 0; k < n; k++)
-            if (!(queue[k] >> 31))
-                emit(start[k], (uint8_t)(queue[k] & 255u));
-        for (int k = 0; k < n; k++) {
-            if (!(queue[k] >> 31))
-                continue;
-            nmatch++;
-            const uint32_t len = queue[k] & 0x1FFu, dist = ((queue[k] >> 16) & 0x7FFFu) + 1u, mp = start[k];
-            if (dist >= 32u) {
-                for (uint32_t b = 0; b < len; b += 32u) {
-                    uint8_t tmp[32];
-                    const uint32_t m = len - b < 32u ? len - b : 32u;
-                    for (uint32_t j = 0; j < m; j++)
-                        tmp[j] = window[(mp - dist + b + j) & (kWindow - 1)];
-                    for (uint32_t j = 0; j < m; j++)
-                        emit(mp + b + j, tmp[j]);
-                }
+        else if (!s.in_block) {
+            const int action = read_block_header(s, ring, t);
+            if (action != kHdrError)
+                nblocks++;
+            if (action == kHdrBuild) {
+                // the device runs these two with 32 lanes; emulate the lanes one after the other
+                for (int lane = 0; lane < 32; lane++)
+                    clear_block_luts(t, lane, 32);
+                for (int lane = 0; lane < 32; lane++)
+                    fill_block_luts(t, lane, 32);
             }
+            else if (action == kHdrStored) {
+                so = s.stored_src;
+                sl = s.stored_len;
+                fin = s.bfinal;
+                const uint32_t q = so + sl;
+                filled = q & ~511u;
+                top_up(q & ~3u);
+                seek(s, ring, q);
+                ev = kEvStored;
+                post = true;
+            }
+            else if (action == kHdrError) {
+                ev = kEvError;
+                post = true;
+            }
+        }
+        else {
+            n = decode_symbols(s, ring, t, queue, &ev);
+            post = true;
+        }
+        if (!post)
+            continue;
+
+        // ---- writer warp
+        if (n > 0 && !werr) {
+            uint32_t start[kQueue], pos = out_base;
+            bool bad = false, far = false;
+            for (int k = 0; k < n; k++) {
+                start[k] = pos;
+                pos += sym_len(queue[k]);
+                if (sym_is_match(queue[k]) && sym_dist(queue[k]) > start[k])
+                    bad = true;
+                if (sym_is_far(queue[k]))
+                    far = true;
+            }
+            if (pos > out_len)
+                werr = kErrOverflow;
+            else if (bad)
+                werr = kErrDistance;
             else {
-                uint8_t pat[32];
-                for (uint32_t j = 0; j < dist; j++)
-                    pat[j] = window[(mp - dist + j) & (kWindow - 1)];
-                for (uint32_t i = 0; i < len; i++)
-                    emit(mp + i, pat[i % dist]);
+                if (!far)
+                    for (int k = 0; k < n; k++)
+                        if (!sym_is_match(queue[k]))
+                            emit(start[k], (uint8_t)(queue[k] & 255u));
+                for (int k = 0; k < n; k++) {
+                    if (!sym_is_match(queue[k])) {
+                        if (far)
+                            emit(start[k], (uint8_t)(queue[k] & 255u));
+                        continue;
+                    }
+                    nmatch++;
+                    const uint32_t len = queue[k] & 0x1FFu, dist = sym_dist(queue[k]), mp = start[k];
+                    const uint32_t stepw = dist >= 128u ? 128u : 32u;
+                    if (dist >= 32u) {
+                        for (uint32_t b = 0; b < len; b += stepw) {
+                            uint8_t tmp[128];
+                            const uint32_t m = len - b < stepw ? len - b : stepw;
+                            for (uint32_t j = 0; j < m; j++)
+                                tmp[j] = window[(mp - dist + b + j) & (kWindow - 1)];
+                            for (uint32_t j = 0; j < m; j++)
+                                emit(mp + b + j, tmp[j]);
+                        }
+                    }
+                    else {
+                        uint8_t pat[32];
+                        for (uint32_t j = 0; j < dist; j++)
+                            pat[j] = window[(mp - dist + j) & (kWindow - 1)];
+                        for (uint32_t i = 0; i < len; i++)
+                            emit(mp + i, pat[i % dist]);
+                    }
+                }
+                nsym += (uint64_t)n;
+                out_base = pos;
             }
         }
-        nsym += (uint64_t)n;
-        out_base = pos;
-        if (ev == kEvStored) {
-            const uint32_t so = s.stored_src, sl = s.stored_len;
-            for (uint32_t i = 0; i < sl; i++)
-                emit(out_base + i, base[so + i]);
-            out_base += sl;
-            const uint32_t q = so + sl;
-            filled = q & ~511u;
-            top_up(q & ~3u);
-            s.out_pos += sl;
-            seek(s, ring, q);
-            int done = 0;
-            if (s.bfinal) {
-                done = 1;
-                if (s.out_pos != s.out_end)
-                    s.err = kErrShort;
+        if (ev == kEvStored && !werr) {
+            if (out_base + sl > out_len)
+                werr = kErrOverflow;
+            else {
+                for (uint32_t i = 0; i < sl; i++)
+                    emit(out_base + i, base[so + i]);
+                out_base += sl;
             }
-            else if (q > s.in_end)
-                s.err = kErrInput;
-            ev = s.err ? kEvError : (done ? kEvEnd : kEvMore);
+        }
+        if (ev == kEvEnd || (ev == kEvStored && fin)) {
+            if (!werr && out_base != out_len)
+                werr = kErrShort;
+            break;
+        }
+        if (ev == kEvError) {
+            if (!werr)
+                werr = s.err;
+            break;
         }
     }
     if (stats) {
@@ -117,5 +174,5 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
         stats[2] = nsteps;
         stats[3] = nblocks;
     }
-    return s.err;
+    return werr;
 }
