@@ -1,0 +1,457 @@
+// gcn10_b200/csrc/cn_deflate_fused.cuh -- Curve Number + tile DEFLATE in one kernel (sm_100a).
+//
+// process_block() of the reference ends every raster with save_raster() (/root/reference/src/cn.c:363 ->
+// raster.c:192-227: tiled DEFLATE GeoTIFF).  When the caller wants the compressed tiles and not the raw
+// planes, writing 9..18 planes to HBM (cn_block_kernel) and reading them back (deflate_tiles_kernel, one CTA
+// per tile per plane, two greedy parses each) is wasted work: all planes of a block are the SAME picture
+// seen through different lookup tables.  A pixel's Curve Numbers in every plane are a function of its
+// (land cover, soil code) pair (cn.c:88-131), so the host numbers the distinct value records (at most 256,
+// 61 with the shipped tables) and this kernel works on the tile of record ids:
+//
+//   1. one CTA per 256 x 256 tile position: land cover (16-byte loads) + nearest-neighbour soil code
+//      (fp64 index maps of cn.c:219-229, precomputed) -> record id per pixel, in shared memory;
+//   2. ONE LZ77 parse of the id tile (distances 256 = pixel above and 1 = run, as deflate_tiles.cuh): equal
+//      ids are equal bytes in every plane, so the token structure is valid for all planes at once;
+//   3. per plane only the literal bytes differ (and, through the 8/9-bit fixed-Huffman literal codes, the
+//      bit positions): a block scan of per-row (common bits, per-plane 9-bit-literal counts) places every
+//      row in every plane's stream; the second parse writes all planes' streams in one go;
+//   4. Adler-32 of every plane from per-id pixel counts and position-weight sums (run based).
+//
+// HBM traffic per pixel: 1 byte read + the compressed bytes (~0.2) instead of 1 + 2 * 9.  The planes are
+// never materialised; zlib streams are byte-identical to those of cn_block_kernel + deflate_tiles_kernel
+// whenever distinct records differ in the plane at hand (the id parse cannot see matches between different
+// records that happen to share a value in one plane, so streams can be a few bytes longer).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "deflate_tiles.cuh"
+
+namespace gcn10 {
+
+constexpr int kFusedOutCap = 32 * 1024;         // shared-memory staging for the streams of one round of planes
+constexpr int kFusedIds = 256;
+constexpr int kFusedPad = 255;                  // record id of the zero padding right / below the raster
+constexpr int kFusedSmem = kTile * kTileStride + kFusedOutCap + 64 + kFusedIds * 32;
+
+struct FusedParams {
+    const uint8_t *esa;             // device land cover, row 0 = block row y_base
+    size_t esa_pitch;
+    int w, rows;                    // raster width, rows in this launch
+    int y_base;
+    const int32_t *col_idx;         // [roundup16(w)]
+    const int32_t *row_idx;         // [block rows]
+    const uint8_t *hsg;
+    size_t hsg_pitch;
+    const uint8_t *idmap;           // [256][16]: (land cover, soil class) -> record id
+    const uint8_t *val;             // [256][32]: record id -> value in the j-th selected plane
+    const unsigned long long *lit9; // [256][6]: per selected plane, 21-bit fields, 1 where the value needs a 9-bit literal
+    int nsel;                       // selected planes (1..18)
+    int tiles_x, tile_rows;
+    uint8_t *blob;
+    unsigned long long *cursor;
+    unsigned long long *offsets;    // [nsel][tile_rows][tiles_x]
+    uint32_t *sizes;
+};
+
+// soil class of a raw HYSOGs byte: 0 = code 0, 1..4 = A..D, 5..8 = A/D..D/D (11..14), 9 = anything else
+__device__ __forceinline__ uint32_t soil_class(uint32_t code)
+{
+    if (code <= 4u)
+        return code;
+    const uint32_t d = code - 11u;
+    return d <= 3u ? 5u + d : 9u;
+}
+
+__device__ __forceinline__ uint32_t field21(const unsigned long long *c, int k)
+{
+    return (uint32_t)(c[k / 3] >> (21 * (k % 3))) & 0x1FFFFFu;
+}
+
+// Greedy parse of one row of the id tile.
+//   WRITE = false: bits common to all planes -> return value; 9-bit-literal counts per plane -> lit (+=)
+//   WRITE = true : emits planes [lo, hi) at their positions; `pos` = common bits before this row,
+//                  lit = per-plane 9-bit-literal counts before this row, obase[k] = byte offset of plane k's
+//                  stream in `out` (16-byte aligned), +19 header bits are added here.
+template <bool WRITE>
+__device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, const RowMasks &m, const uint8_t *val,
+                                                    const unsigned long long *lit9, unsigned long long lit[6],
+                                                    uint32_t pos, uint32_t *out, const uint32_t *obase, int lo, int hi)
+{
+    const uint8_t *row = tile + r * kTileStride;
+    int x = 0;
+    while (x < kTile) {
+        const int la = r > 0 ? run_len<true>(row, m.above, 0, x) : 0;
+        int lr = 0;
+        if (x > 0)
+            lr = run_len<false>(row, m.left, bcast_byte(row[x - 1]), x);
+        const int len = la >= lr ? la : lr;
+        if (len >= 3) {
+            uint32_t bits;
+            int n;
+            match_code(len, la >= lr, bits, n);
+            if (WRITE) {
+#pragma unroll
+                for (int k = 0; k < 18; k++)
+                    if (k >= lo && k < hi)
+                        put_bits(out + (obase[k] >> 2), 19u + pos + field21(lit, k), bits, n);
+            }
+            pos += n;
+            x += len;
+        }
+        else {
+            const uint32_t id = row[x];
+            const ulonglong2 *lp = reinterpret_cast<const ulonglong2 *>(lit9 + 6 * id);
+            const ulonglong2 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
+            if (WRITE) {
+                const uint4 v0 = *reinterpret_cast<const uint4 *>(val + 32 * id);
+                const uint4 v1 = *reinterpret_cast<const uint4 *>(val + 32 * id + 16);
+                const uint32_t vw[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+#pragma unroll
+                for (int k = 0; k < 18; k++)
+                    if (k >= lo && k < hi) {
+                        uint32_t bits;
+                        int n;
+                        lit_code((vw[k >> 2] >> (8 * (k & 3))) & 255u, bits, n);
+                        put_bits(out + (obase[k] >> 2), 19u + pos + field21(lit, k), bits, n);
+                    }
+            }
+            lit[0] += l0.x;
+            lit[1] += l0.y;
+            lit[2] += l1.x;
+            lit[3] += l1.y;
+            lit[4] += l2.x;
+            lit[5] += l2.y;
+            pos += 8;
+            x += 1;
+        }
+    }
+    return pos;
+}
+
+__device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, int o)
+{
+    return __shfl_up_sync(0xffffffffu, v, o);
+}
+
+// grid = (tiles_x, tile_rows), 256 threads, kFusedSmem bytes of dynamic shared memory
+__global__ void __launch_bounds__(kTile, 2)
+cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem_fz[];
+    uint8_t *tile = smem_fz;                                            // record ids, row stride 272
+    uint8_t *outb = smem_fz + kTile * kTileStride;                      // stream staging / early scratch
+    uint32_t *out = reinterpret_cast<uint32_t *>(outb);
+    uint8_t *s_val = outb + kFusedOutCap + 64;                          // [256][32]
+    // early scratch inside the staging area (dead before the first stream bit is written)
+    uint8_t *s_idmap = outb;                                            // 4 KB
+    int32_t *s_col = reinterpret_cast<int32_t *>(outb + 4096);          // 1 KB
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(outb + 5120);        // 1 KB   pixels per id
+    unsigned long long *s_w = reinterpret_cast<unsigned long long *>(outb + 6144);   // 2 KB   sum of (N - i) per id
+
+    __shared__ unsigned long long s_scan[kTile / 32][7];
+    __shared__ uint32_t s_adler[18], s_nbytes[18], s_obase[18], s_stored[18];
+    __shared__ unsigned long long s_goff[18];
+    __shared__ int s_round_hi[19], s_nrounds;
+    __shared__ uint32_t s_total_common;
+    __shared__ unsigned long long s_total_lit[6];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int x0 = tx * kTile, y0 = ty * kTile;
+    const int nsel = p.nsel;
+
+    // ---- tables -> shared memory
+    for (int i = tid; i < 4096 / 16; i += kTile)
+        reinterpret_cast<uint4 *>(s_idmap)[i] = __ldg(reinterpret_cast<const uint4 *>(p.idmap) + i);
+    for (int i = tid; i < kFusedIds * 32 / 16; i += kTile)
+        reinterpret_cast<uint4 *>(s_val)[i] = __ldg(reinterpret_cast<const uint4 *>(p.val) + i);
+    {
+        const int gx = min(x0 + tid, p.w - 1);
+        s_col[tid] = __ldg(p.col_idx + gx);
+        s_cnt[tid] = 0;
+        s_w[tid] = 0;
+    }
+    __syncthreads();
+
+    // ---- 1. record ids of the tile (zero padding beyond the raster = id kFusedPad)
+    {
+        const int g = tid & 15;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.esa) | p.esa_pitch) & 15) == 0;
+#pragma unroll 4
+        for (int j = 0; j < 16; j++) {
+            const int r = (tid >> 4) + 16 * j;
+            const int gy = y0 + r, gx = x0 + 16 * g;
+            uint32_t idw[4] = { 0x01010101u * kFusedPad, 0x01010101u * kFusedPad, 0x01010101u * kFusedPad,
+                                0x01010101u * kFusedPad };
+            if (gy < p.rows && gx < p.w) {
+                const uint8_t *e = p.esa + (size_t)gy * p.esa_pitch + gx;
+                uint32_t ew[4] = { 0, 0, 0, 0 };
+                const int nvalid = min(16, p.w - gx);
+                if (nvalid == 16 && vec_ok) {
+                    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(e));
+                    ew[0] = v.x; ew[1] = v.y; ew[2] = v.z; ew[3] = v.w;
+                }
+                else {
+                    for (int k = 0; k < nvalid; k++)
+                        ew[k >> 2] |= (uint32_t)e[k] << (8 * (k & 3));
+                }
+                const uint8_t *hrow = p.hsg + (size_t)__ldg(p.row_idx + p.y_base + gy) * p.hsg_pitch;
+                int prev = -1;
+                uint32_t sc = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const int ci = s_col[16 * g + k];
+                    if (ci != prev) {
+                        sc = soil_class(__ldg(hrow + ci));
+                        prev = ci;
+                    }
+                    const uint32_t lc = (ew[k >> 2] >> (8 * (k & 3))) & 255u;
+                    const uint32_t id = k < nvalid ? s_idmap[lc * 16u + sc] : (uint32_t)kFusedPad;
+                    idw[k >> 2] = (idw[k >> 2] & ~(255u << (8 * (k & 3)))) | (id << (8 * (k & 3)));
+                }
+            }
+            *reinterpret_cast<uint4 *>(tile + r * kTileStride + 16 * g) = make_uint4(idw[0], idw[1], idw[2], idw[3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. pass 1 (thread r owns tile row r): word masks, per-id pixel counts / weight sums, row bit counts
+    RowMasks m;
+    m.above = 0;
+    m.left = 0;
+    {
+        const uint4 *rowv = reinterpret_cast<const uint4 *>(tile + tid * kTileStride);
+        const uint4 *upv = rowv - kTileStride / 16;
+        uint32_t last = 0;
+        uint32_t cur = tile[tid * kTileStride], n = 0, xs = 0;
+        const uint32_t rowbase = (uint32_t)(kTileBytes - kTile * tid);      // N - i at x = 0
+#pragma unroll 2
+        for (int i = 0; i < kTile / 16; i++) {
+            const uint4 cv = rowv[i];
+            const uint4 uv = tid > 0 ? upv[i] : make_uint4(~cv.x, ~cv.y, ~cv.z, ~cv.w);
+            const uint32_t cw[4] = { cv.x, cv.y, cv.z, cv.w };
+            const uint32_t uw[4] = { uv.x, uv.y, uv.z, uv.w };
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int j = 4 * i + k;
+                if (cw[k] == uw[k])
+                    m.above |= 1ull << j;
+                if (j > 0 && cw[k] == last * 0x01010101u)
+                    m.left |= 1ull << j;
+                last = cw[k] >> 24;
+                if (cw[k] == cur * 0x01010101u) {
+                    n += 4;
+                    xs += 16u * j + 6u;
+                }
+                else {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t v = (cw[k] >> (8 * b)) & 255u;
+                        if (v != cur) {
+                            if (n) {
+                                atomicAdd(&s_cnt[cur], n);
+                                atomicAdd(&s_w[cur], (unsigned long long)n * rowbase - xs);
+                            }
+                            cur = v;
+                            n = 0;
+                            xs = 0;
+                        }
+                        n += 1;
+                        xs += 4u * j + b;
+                    }
+                }
+            }
+        }
+        atomicAdd(&s_cnt[cur], n);
+        atomicAdd(&s_w[cur], (unsigned long long)n * rowbase - xs);
+    }
+    unsigned long long lit[6] = { 0, 0, 0, 0, 0, 0 };
+    const uint32_t row_bits = fused_parse_row<false>(tile, tid, m, s_val, p.lit9, lit, 0u, nullptr, nullptr, 0, 0);
+
+    // ---- 3. inclusive scan over the rows of (common bits, per-plane 9-bit-literal counts)
+    unsigned long long inc[7] = { row_bits, lit[0], lit[1], lit[2], lit[3], lit[4], lit[5] };
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int q = 0; q < 7; q++) {
+            const unsigned long long t = shfl_up_u64(inc[q], o);
+            if (lane >= o)
+                inc[q] += t;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int q = 0; q < 7; q++)
+            s_scan[warp][q] = inc[q];
+    }
+    __syncthreads();                // also: every row's counts / weights are in s_cnt / s_w
+    unsigned long long base[7] = { 0, 0, 0, 0, 0, 0, 0 };
+    for (int wv = 0; wv < warp; wv++) {
+#pragma unroll
+        for (int q = 0; q < 7; q++)
+            base[q] += s_scan[wv][q];
+    }
+    const uint32_t row_pos = (uint32_t)(base[0] + inc[0]) - row_bits;
+    unsigned long long lit_before[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+        lit_before[q] = base[q + 1] + inc[q + 1] - lit[q];
+    if (tid == kTile - 1) {
+        s_total_common = (uint32_t)(base[0] + inc[0]);
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            s_total_lit[q] = base[q + 1] + inc[q + 1];
+    }
+
+    // ---- 4. Adler-32 per plane: s1 = 1 + sum cnt[id] val[id], s2 = N + sum w[id] val[id]  (mod 65521)
+    for (int k = warp; k < nsel; k += kTile / 32) {
+        unsigned long long a = 0, b = 0;
+        for (int id = lane; id < kFusedIds; id += 32) {
+            const unsigned long long v = s_val[32 * id + k];
+            a += (unsigned long long)s_cnt[id] * v;
+            b += (s_w[id] % 65521ull) * v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+            const uint32_t s1 = (uint32_t)((1ull + a) % 65521ull);
+            const uint32_t s2 = (uint32_t)(((unsigned long long)kTileBytes + b) % 65521ull);
+            s_adler[k] = (s2 << 16) | s1;
+        }
+    }
+    __syncthreads();
+
+    // ---- 5. sizes, stored fallbacks, arena allocation, rounds
+    if (tid == 0) {
+        unsigned long long need = 0;
+        uint32_t deflate_end[18];
+        for (int k = 0; k < nsel; k++) {
+            const uint32_t bits = 19u + s_total_common + field21(s_total_lit, k) + 7u;
+            deflate_end[k] = (bits + 7u) >> 3;
+            s_stored[k] = deflate_end[k] + 4u > (uint32_t)kFusedOutCap - 64u;
+            s_nbytes[k] = s_stored[k] ? (uint32_t)kStoredBytes : deflate_end[k] + 4u;
+        }
+        // compressed planes first (contiguous per round, in the arena as in the staging area), stored ones behind
+        int nr = 0;
+        uint32_t used = 0;
+        for (int k = 0; k < nsel; k++) {
+            if (s_stored[k])
+                continue;
+            const uint32_t a16 = (s_nbytes[k] + 15u) & ~15u;
+            if (used + a16 > (uint32_t)kFusedOutCap) {
+                s_round_hi[nr++] = k;
+                used = 0;
+            }
+            s_obase[k] = used;
+            s_goff[k] = need;
+            used += a16;
+            need += a16;
+        }
+        s_round_hi[nr++] = nsel;
+        s_nrounds = nr;
+        for (int k = 0; k < nsel; k++)
+            if (s_stored[k]) {
+                s_goff[k] = need;
+                need += ((unsigned long long)kStoredBytes + 15ull) & ~15ull;
+            }
+        const unsigned long long off = atomicAdd(p.cursor, need);
+        for (int k = 0; k < nsel; k++) {
+            s_goff[k] += off;
+            const size_t ti = ((size_t)k * p.tile_rows + ty) * p.tiles_x + tx;
+            p.offsets[ti] = s_goff[k];
+            p.sizes[ti] = s_nbytes[k];
+        }
+    }
+    __syncthreads();
+
+    // ---- 6. rounds of planes: zero the staging area, second parse writes the streams, copy out
+    const int nrounds = s_nrounds;
+    int lo = 0;
+    for (int rd = 0; rd < nrounds; rd++) {
+        const int hi = s_round_hi[rd];
+        // planes of this round that are compressed: [lo, hi) minus the stored ones
+        uint32_t span = 0;
+        int first = -1;
+        for (int k = lo; k < hi; k++)
+            if (!s_stored[k]) {
+                if (first < 0)
+                    first = k;
+                span = s_obase[k] + ((s_nbytes[k] + 15u) & ~15u);
+            }
+        if (first >= 0) {
+            for (uint32_t i = tid; i < span / 16 + 4; i += kTile)
+                reinterpret_cast<uint4 *>(outb)[i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+            // stored planes of the range must not be written: give the parse a range of compressed planes only
+            // (stored planes are rare; split the range around them)
+            int a = lo;
+            while (a < hi) {
+                while (a < hi && s_stored[a])
+                    a++;
+                int b = a;
+                while (b < hi && !s_stored[b])
+                    b++;
+                if (a < b) {
+                    unsigned long long lw[6];
+#pragma unroll
+                    for (int q = 0; q < 6; q++)
+                        lw[q] = lit_before[q];
+                    fused_parse_row<true>(tile, tid, m, s_val, p.lit9, lw, row_pos, out, s_obase, a, b);
+                }
+                a = b;
+            }
+            if (tid < hi - lo && !s_stored[lo + tid]) {
+                const int k = lo + tid;
+                put_bits(out + (s_obase[k] >> 2), 0, 0x9C78u, 16);      // CMF = 0x78, FLG = 0x9C
+                put_bits(out + (s_obase[k] >> 2), 16, 0x3u, 3);         // BFINAL = 1, BTYPE = 01 (fixed Huffman)
+            }
+            __syncthreads();
+            if (tid < hi - lo && !s_stored[lo + tid]) {
+                // end-of-block = seven zero bits (already there); Adler-32 big endian after the padding
+                const int k = lo + tid;
+                uint8_t *ob = outb + s_obase[k] + s_nbytes[k] - 4;
+                const uint32_t ad = s_adler[k];
+                ob[0] = (uint8_t)(ad >> 24);
+                ob[1] = (uint8_t)(ad >> 16);
+                ob[2] = (uint8_t)(ad >> 8);
+                ob[3] = (uint8_t)ad;
+            }
+            __syncthreads();
+            uint4 *dst = reinterpret_cast<uint4 *>(p.blob + s_goff[first]);
+            const uint4 *so = reinterpret_cast<const uint4 *>(outb + s_obase[first]);
+            const uint32_t n16 = (span - s_obase[first]) / 16;
+            for (uint32_t i = tid; i < n16; i += kTile)
+                dst[i] = so[i];
+            __syncthreads();
+        }
+        lo = hi;
+    }
+
+    // ---- 7. incompressible planes: zlib header, two stored blocks of 32768 bytes, Adler-32
+    for (int k = 0; k < nsel; k++) {
+        if (!s_stored[k])
+            continue;
+        uint8_t *dst = p.blob + s_goff[k];
+        if (tid == 0) {
+            dst[0] = 0x78; dst[1] = 0x9C;
+            dst[2] = 0x00; dst[3] = 0x00; dst[4] = 0x80; dst[5] = 0xFF; dst[6] = 0x7F;
+            uint8_t *b2 = dst + 7 + 32768;
+            b2[0] = 0x01; b2[1] = 0x00; b2[2] = 0x80; b2[3] = 0xFF; b2[4] = 0x7F;
+            const uint32_t ad = s_adler[k];
+            uint8_t *t4 = dst + kStoredBytes - 4;
+            t4[0] = (uint8_t)(ad >> 24); t4[1] = (uint8_t)(ad >> 16); t4[2] = (uint8_t)(ad >> 8); t4[3] = (uint8_t)ad;
+        }
+        for (int i = tid; i < kTileBytes; i += kTile) {
+            const int r = i >> 8, c = i & 255;
+            const int o = i < 32768 ? 7 + i : 7 + 5 + i;
+            dst[o] = s_val[32 * tile[r * kTileStride + c] + k];
+        }
+    }
+}
+
+}  // namespace gcn10

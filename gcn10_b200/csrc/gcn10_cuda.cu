@@ -10,6 +10,7 @@
 #include "cn_kernels.cuh"
 #include "deflate_tiles.cuh"
 #include "inflate_tiles.cuh"
+#include "cn_deflate_fused.cuh"
 
 #include <algorithm>
 #include <cctype>
@@ -86,6 +87,10 @@ struct gcn10_ctx {
     int use_tma = 1;
     int persistent = 0;         // 1 = persistent-CTA form of the streaming kernel (measured slower, see profiles/)
     int persistent_ctas[10][3] = {};         // resident CTAs per SM by [np][groups], from the occupancy API
+    int fused = 1;              // compressed-tile calls use cn_deflate_fused_kernel (0 = CN kernel + tile encoder)
+    DevBuf fused_tab;           // idmap [256][16] | val [256][32] | lit9 [256][6] u64
+    unsigned fused_mask = 0;    // plane mask the tables were built for (0 = none)
+    int fused_ok = 0;           // the mask's value records fit the id space
     EncodeTiledFn encode_tiled = nullptr;
 
     bool have_lut = false;
@@ -426,6 +431,66 @@ int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t 
     return GCN10_OK;
 }
 
+// The value record of a (land cover, soil class) pair = its Curve Number in every selected plane
+// (cn.c:88-131: dual-group remap per drainage condition, table lookup, 255 for anything else).  Distinct
+// records get ids 0..254; id 255 is the all-zero record of the tile padding.  Fails (fused_ok = 0) when
+// the tables hold more than 255 distinct records; the two-kernel path is used then.
+int build_fused_tables(gcn10_ctx *c, unsigned plane_mask, cudaStream_t st)
+{
+    if (c->fused_mask == plane_mask)
+        return GCN10_OK;
+    int plane_ids[GCN10_NPLANES], nsel = 0;
+    for (int k = 0; k < GCN10_NPLANES; k++)
+        if (plane_mask & (1u << k))
+            plane_ids[nsel++] = k;
+    std::vector<uint8_t> host(4096 + kFusedIds * 32 + kFusedIds * 48, 0);
+    uint8_t *idmap = host.data(), *val = host.data() + 4096;
+    unsigned long long *lit9 = (unsigned long long *)(host.data() + 4096 + kFusedIds * 32);
+    std::vector<std::vector<uint8_t>> records;
+    c->fused_ok = 1;
+    for (int lc = 0; lc < 256 && c->fused_ok; lc++) {
+        for (int sc = 0; sc < 16; sc++) {
+            std::vector<uint8_t> rec((size_t)nsel, (uint8_t)GCN10_NODATA);
+            // soil class -> raw code: 0, 1..4, 11..14, anything else
+            const int code = sc <= 4 ? sc : (sc <= 8 ? 11 + (sc - 5) : 255);
+            for (int j = 0; j < nsel && sc <= 9; j++) {
+                const int cond = plane_ids[j] / 9, t = plane_ids[j] % 9;
+                int sg = code;
+                if (code >= 11 && code <= 14)
+                    sg = cond == 0 ? 4 : code - 10;         // drained: 11..14 -> 4; undrained: 11->1 .. 14->4 (cn.c:92-109)
+                if (sg < 5)
+                    rec[j] = cn_byte(c->host_tables[t][lc][sg]);
+            }
+            size_t id = 0;
+            while (id < records.size() && records[id] != rec)
+                id++;
+            if (id == records.size()) {
+                if (records.size() >= (size_t)kFusedPad) {
+                    c->fused_ok = 0;
+                    break;
+                }
+                records.push_back(rec);
+            }
+            idmap[lc * 16 + sc] = (uint8_t)id;
+        }
+    }
+    if (c->fused_ok) {
+        for (size_t id = 0; id < records.size(); id++)
+            for (int j = 0; j < nsel; j++) {
+                val[id * 32 + j] = records[id][j];
+                if (records[id][j] >= 144)
+                    lit9[id * 6 + j / 3] |= 1ull << (21 * (j % 3));
+            }
+        int rc = ensure(c->fused_tab, host.size());
+        if (rc)
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->fused_tab.p, host.data(), host.size(), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    c->fused_mask = plane_mask;
+    return GCN10_OK;
+}
+
 int check_geometry(const void *esa, int w, int h, size_t esa_pitch, const double *gt, const void *hsg, int hsx,
                    int hsy, size_t hsg_pitch, const double *sgt, unsigned mask, const void *out, size_t out_pitch)
 {
@@ -492,6 +557,10 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
     }
     CUDA_TRY(cudaFuncSetAttribute((const void *)deflate_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kEncSmem));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)cn_deflate_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kFusedSmem));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)cn_deflate_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute((const void *)inflate_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kInflateSmem));
     CUDA_TRY(cudaFuncSetAttribute((const void *)inflate_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -535,6 +604,7 @@ void gcn10_cuda_destroy(gcn10_ctx *c)
     release(c->hsg);
     release(c->in_blob);
     release(c->in_table);
+    release(c->fused_tab);
     release(c->esa_full);
     release_host(c->h_in_status);
     if (c->inf0) cudaEventDestroy(c->inf0);
@@ -563,6 +633,7 @@ int gcn10_cuda_set_luts(gcn10_ctx *c, const int tables[GCN10_NVARIANTS][256][5])
     memcpy(c->host_tables, tables, sizeof(c->host_tables));
     c->swz_shift = choose_swizzle(c->host_tables);
     c->lut_mask[0] = c->lut_mask[1] = 0xFFFFFFFFu;
+    c->fused_mask = 0;
     c->have_lut = true;
     return GCN10_OK;
 }
@@ -576,6 +647,7 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
     else if (!strcmp(key, "rows_per_cta") && value >= 0) c->rows_per_cta = (int)value;
     else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
     else if (!strcmp(key, "persistent") && (value == 0 || value == 1)) c->persistent = (int)value;
+    else if (!strcmp(key, "fused") && (value == 0 || value == 1)) c->fused = (int)value;
     else return fail(GCN10_EINVAL, "unknown option or bad value: %s=%ld", key, value);
     return GCN10_OK;
 }
@@ -827,6 +899,8 @@ static int deflate_rows_impl(gcn10_ctx *c,
     make_hsg_map(c, (const uint8_t *)c->hsg.p, hsx, hsy, hsg_dpitch, &map, &tma_ok);
     CUDA_TRY(cudaStreamSynchronize(s0));
 
+    const bool fused = c->fused && !build_fused_tables(c, plane_mask & GCN10_MASK_ALL, s0) && c->fused_ok;
+
     // strips of whole tile rows
     const size_t dpitch = round_up((size_t)w, 256);
     const int ns = c->nstreams;
@@ -838,7 +912,8 @@ static int deflate_rows_impl(gcn10_ctx *c,
     const size_t table_bytes = 16 + ntile_slot * (sizeof(unsigned long long) + sizeof(uint32_t));
     for (int i = 0; i < ns; i++) {
         StripSlot &sl = c->slots[i];
-        if ((esa && (rc = ensure(sl.esa, dpitch * (size_t)strip))) || (rc = ensure(sl.out, dpitch * (size_t)strip * nplanes)) ||
+        if ((esa && (rc = ensure(sl.esa, dpitch * (size_t)strip))) ||
+            (!fused && (rc = ensure(sl.out, dpitch * (size_t)strip * nplanes))) ||
             (rc = ensure(sl.blob, blob_cap)) || (rc = ensure(sl.table, table_bytes)) ||
             (rc = ensure_host(sl.h_table, table_bytes)))
             return rc;
@@ -867,10 +942,42 @@ static int deflate_rows_impl(gcn10_ctx *c,
         if (!d_esa)
             CUDA_TRY(cudaMemcpy2DAsync(sl.esa.p, dpitch, esa + (size_t)y0 * esa_pitch, esa_pitch, (size_t)w, (size_t)rows,
                                        cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(sl.k0, st));
+        if (fused) {
+            FusedParams fp;
+            memset(&fp, 0, sizeof(fp));
+            fp.esa = strip_esa;
+            fp.esa_pitch = strip_esa_pitch;
+            fp.w = w;
+            fp.rows = rows;
+            fp.y_base = row0 + y0;
+            fp.col_idx = (const int32_t *)c->col_idx.p;
+            fp.row_idx = (const int32_t *)c->row_idx.p;
+            fp.hsg = (const uint8_t *)c->hsg.p;
+            fp.hsg_pitch = hsg_dpitch;
+            fp.idmap = (const uint8_t *)c->fused_tab.p;
+            fp.val = (const uint8_t *)c->fused_tab.p + 4096;
+            fp.lit9 = (const unsigned long long *)((const uint8_t *)c->fused_tab.p + 4096 + kFusedIds * 32);
+            fp.nsel = nplanes;
+            fp.tiles_x = tiles_x;
+            fp.tile_rows = tile_rows;
+            fp.blob = (uint8_t *)sl.blob.p;
+            fp.cursor = (unsigned long long *)sl.table.p;
+            fp.offsets = (unsigned long long *)((uint8_t *)sl.table.p + 16);
+            fp.sizes = (uint32_t *)((uint8_t *)sl.table.p + 16 + ntile_slot * sizeof(unsigned long long));
+            CUDA_TRY(cudaMemsetAsync(sl.table.p, 0, 16, st));
+            cn_deflate_fused_kernel<<<dim3(tiles_x, tile_rows), kTile, kFusedSmem, st>>>(fp);
+            c->launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(sl.k1, st));
+            CUDA_TRY(cudaMemcpyAsync(sl.h_table.p, sl.table.p, table_bytes, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaEventRecord(sl.enc_done, st));
+            sl.busy = true;
+            return GCN10_OK;
+        }
         uint8_t *d_out[GCN10_NPLANES] = { nullptr };
         for (int k = 0; k < nplanes; k++)
             d_out[plane_ids[k]] = (uint8_t *)sl.out.p + (size_t)k * dpitch * (size_t)strip;
-        CUDA_TRY(cudaEventRecord(sl.k0, st));
         for (int i = 0; i < nplans; i++) {
             int r2 = launch_rows(c, plans[i], i, strip_esa, strip_esa_pitch, w, rows, row0 + y0, (const uint8_t *)c->hsg.p,
                                  hsg_dpitch, hsx, hsy, map, tma_ok, d_out, dpitch, st);

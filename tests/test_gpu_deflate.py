@@ -14,6 +14,16 @@ pytestmark = pytest.mark.gpu
 T = 256
 
 
+@pytest.fixture(autouse=True, params=["fused", "two_kernel"])
+def encoder_path(request, gpu_ctx):
+    """Every test runs through both compressed-tile paths: cn_deflate_fused_kernel (Curve Numbers and all
+    planes' zlib streams from one parse of the record-id tile) and cn_block_kernel + deflate_tiles_kernel."""
+    gpu_ctx.set_option("fused", 1 if request.param == "fused" else 0)
+    yield request.param
+    gpu_ctx.set_option("fused", 1)
+
+
+
 def _assemble(tiles, w, h):
     tx_n, ty_n = (w + T - 1) // T, (h + T - 1) // T
     full = np.zeros((ty_n * T, tx_n * T), dtype=np.uint8)
@@ -32,6 +42,11 @@ CASES = [
     ("multi_strip", dict(w=700, h=2600, seed=6)),
     ("coastal", dict(w=1000, h=600, profile="coastal", seed=7)),
     ("random_incompressible", dict(w=600, h=520, profile="random", seed=8)),
+    ("busy_multi_round", dict(w=600, h=520, seed=9, esa_patch=5, hsg_patch=1)),
+    ("busy_ragged_vrt", dict(w=1031, h=300, seed=10, esa_patch=9, hsg_patch=2, px=8.3333333333330430e-05, lon0=-3.0,
+                             lat0=3.0, shift=(0.0011, 0.0004), margin=2)),
+    ("ratio3", dict(w=700, h=300, seed=11, hsg_px=3.0 / 12000.0)),
+    ("hsg_too_small_clamp", dict(w=800, h=400, hsx=20, hsy=5)),
 ]
 
 
