@@ -30,10 +30,18 @@
 
 namespace gcn10 {
 
-constexpr int kFusedOutCap = 32 * 1024;         // shared-memory staging for the streams of one round of planes
+constexpr int kFusedOutCap = 31 * 1024;         // shared-memory staging for the streams of one round of planes
 constexpr int kFusedIds = 256;
 constexpr int kFusedPad = 255;                  // record id of the zero padding right / below the raster
-constexpr int kFusedSmem = kTile * kTileStride + kFusedOutCap + 64 + kFusedIds * 32;
+constexpr int kFusedClasses = 3;                // distinct "which records need a 9-bit literal" patterns over the planes
+constexpr int kFusedRowMeta = kTile;            // byte offset of a row's 16 spare bytes inside its 272-byte tile row
+
+template <int MAXP>
+constexpr int fused_smem_bytes()
+{
+    // id tile | stream staging (+64) | value table (16 or 32 bytes per id) | row masks
+    return kTile * kTileStride + kFusedOutCap + 64 + kFusedIds * (MAXP <= 9 ? 16 : 32) + kTile * 16;
+}
 
 struct FusedParams {
     const uint8_t *esa;             // device land cover, row 0 = block row y_base
@@ -44,9 +52,10 @@ struct FusedParams {
     const int32_t *row_idx;         // [block rows]
     const uint8_t *hsg;
     size_t hsg_pitch;
-    const uint8_t *idmap;           // [256][16]: (land cover, soil class) -> record id
-    const uint8_t *val;             // [256][32]: record id -> value in the j-th selected plane
-    const unsigned long long *lit9; // [256][6]: per selected plane, 21-bit fields, 1 where the value needs a 9-bit literal
+    const uint8_t *idmap;           // [16][256]: (soil class, land cover) -> record id
+    const uint8_t *val;             // [256][16 or 32]: record id -> value in the j-th selected plane
+    const unsigned long long *lit9; // [256]: 21-bit field c = 1 when the record needs a 9-bit literal in planes of class c
+    uint8_t cls[18];                // 9-bit-literal class of the j-th selected plane
     int nsel;                       // selected planes (1..18)
     int tiles_x, tile_rows;
     uint8_t *blob;
@@ -64,21 +73,20 @@ __device__ __forceinline__ uint32_t soil_class(uint32_t code)
     return d <= 3u ? 5u + d : 9u;
 }
 
-__device__ __forceinline__ uint32_t field21(const unsigned long long *c, int k)
-{
-    return (uint32_t)(c[k / 3] >> (21 * (k % 3))) & 0x1FFFFFu;
-}
+__device__ __forceinline__ uint32_t field21(unsigned long long c, uint32_t f) { return (uint32_t)(c >> (21u * f)) & 0x1FFFFFu; }
 
 // Greedy parse of one row of the id tile.
-//   WRITE = false: bits common to all planes -> return value; 9-bit-literal counts per plane -> lit (+=)
-//   WRITE = true : emits planes [lo, hi) at their positions; `pos` = common bits before this row,
-//                  lit = per-plane 9-bit-literal counts before this row, obase[k] = byte offset of plane k's
-//                  stream in `out` (16-byte aligned), +19 header bits are added here.
-template <bool WRITE>
+//   WRITE = false: returns the bits common to all planes; lit += 9-bit-literal counts per class
+//   WRITE = true : emits planes [lo, hi) ; `pos` = common bits before this row, lit = class counts before this
+//                  row, obase[k] = byte offset of plane k's stream in `out` (16-byte aligned); the 19 header
+//                  bits are added here.
+template <bool WRITE, int MAXP>
 __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, const RowMasks &m, const uint8_t *val,
-                                                    const unsigned long long *lit9, unsigned long long lit[6],
-                                                    uint32_t pos, uint32_t *out, const uint32_t *obase, int lo, int hi)
+                                                    const unsigned long long *lit9, unsigned long long clsbits,
+                                                    unsigned long long &lit, uint32_t pos, uint32_t *out,
+                                                    const uint32_t *obase, int lo, int hi)
 {
+    constexpr int VALB = MAXP <= 9 ? 16 : 32;
     const uint8_t *row = tile + r * kTileStride;
     int x = 0;
     while (x < kTile) {
@@ -92,37 +100,39 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
             int n;
             match_code(len, la >= lr, bits, n);
             if (WRITE) {
+                const uint32_t pc[3] = { 19u + pos + field21(lit, 0), 19u + pos + field21(lit, 1), 19u + pos + field21(lit, 2) };
 #pragma unroll
-                for (int k = 0; k < 18; k++)
-                    if (k >= lo && k < hi)
-                        put_bits(out + (obase[k] >> 2), 19u + pos + field21(lit, k), bits, n);
+                for (int k = 0; k < MAXP; k++)
+                    if (k >= lo && k < hi) {
+                        const uint32_t c = (uint32_t)(clsbits >> (2 * k)) & 3u;
+                        put_bits(out + (obase[k] >> 2), c == 0u ? pc[0] : (c == 1u ? pc[1] : pc[2]), bits, n);
+                    }
             }
             pos += n;
             x += len;
         }
         else {
             const uint32_t id = row[x];
-            const ulonglong2 *lp = reinterpret_cast<const ulonglong2 *>(lit9 + 6 * id);
-            const ulonglong2 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
             if (WRITE) {
-                const uint4 v0 = *reinterpret_cast<const uint4 *>(val + 32 * id);
-                const uint4 v1 = *reinterpret_cast<const uint4 *>(val + 32 * id + 16);
-                const uint32_t vw[8] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w };
+                uint32_t vw[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+                const uint4 v0 = *reinterpret_cast<const uint4 *>(val + VALB * id);
+                vw[0] = v0.x; vw[1] = v0.y; vw[2] = v0.z; vw[3] = v0.w;
+                if constexpr (VALB == 32) {
+                    const uint4 v1 = *reinterpret_cast<const uint4 *>(val + VALB * id + 16);
+                    vw[4] = v1.x; vw[5] = v1.y; vw[6] = v1.z; vw[7] = v1.w;
+                }
+                const uint32_t pc[3] = { 19u + pos + field21(lit, 0), 19u + pos + field21(lit, 1), 19u + pos + field21(lit, 2) };
 #pragma unroll
-                for (int k = 0; k < 18; k++)
+                for (int k = 0; k < MAXP; k++)
                     if (k >= lo && k < hi) {
                         uint32_t bits;
                         int n;
                         lit_code((vw[k >> 2] >> (8 * (k & 3))) & 255u, bits, n);
-                        put_bits(out + (obase[k] >> 2), 19u + pos + field21(lit, k), bits, n);
+                        const uint32_t c = (uint32_t)(clsbits >> (2 * k)) & 3u;
+                        put_bits(out + (obase[k] >> 2), c == 0u ? pc[0] : (c == 1u ? pc[1] : pc[2]), bits, n);
                     }
             }
-            lit[0] += l0.x;
-            lit[1] += l0.y;
-            lit[2] += l1.x;
-            lit[3] += l1.y;
-            lit[4] += l2.x;
-            lit[5] += l2.y;
+            lit += __ldg(lit9 + id);
             pos += 8;
             x += 1;
         }
@@ -130,32 +140,36 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
     return pos;
 }
 
-__device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, int o)
-{
-    return __shfl_up_sync(0xffffffffu, v, o);
-}
-
-// grid = (tiles_x, tile_rows), 256 threads, kFusedSmem bytes of dynamic shared memory
+// grid = (tiles_x, tile_rows), 256 threads, fused_smem_bytes<MAXP>() of dynamic shared memory
+template <int MAXP>
 __global__ void __launch_bounds__(kTile, 2)
 cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
 {
+    constexpr int VALB = MAXP <= 9 ? 16 : 32;
     extern __shared__ __align__(16) uint8_t smem_fz[];
-    uint8_t *tile = smem_fz;                                            // record ids, row stride 272
+    uint8_t *tile = smem_fz;                                            // record ids, row stride 272 (16 spare bytes per row)
     uint8_t *outb = smem_fz + kTile * kTileStride;                      // stream staging / early scratch
     uint32_t *out = reinterpret_cast<uint32_t *>(outb);
-    uint8_t *s_val = outb + kFusedOutCap + 64;                          // [256][32]
+    uint8_t *s_val = outb + kFusedOutCap + 64;                          // [256][VALB]
+    RowMasks *s_masks = reinterpret_cast<RowMasks *>(s_val + kFusedIds * VALB);     // [256]
     // early scratch inside the staging area (dead before the first stream bit is written)
-    uint8_t *s_idmap = outb;                                            // 4 KB
+    uint8_t *s_idmap = outb;                                            // 4 KB  [16][256]
     int32_t *s_col = reinterpret_cast<int32_t *>(outb + 4096);          // 1 KB
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(outb + 5120);        // 1 KB   pixels per id
-    unsigned long long *s_w = reinterpret_cast<unsigned long long *>(outb + 6144);   // 2 KB   sum of (N - i) per id
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(outb + 5120);        // 1 KB  pixels per id
+    uint32_t *s_w = reinterpret_cast<uint32_t *>(outb + 6144);          // 1 KB  sum of (N - i) per id (< 2^32 over a tile)
 
-    __shared__ unsigned long long s_scan[kTile / 32][7];
+    __shared__ unsigned long long s_scan[kTile / 32][2];
     __shared__ uint32_t s_adler[18], s_nbytes[18], s_obase[18], s_stored[18];
     __shared__ unsigned long long s_goff[18];
     __shared__ int s_round_hi[19], s_nrounds;
     __shared__ uint32_t s_total_common;
-    __shared__ unsigned long long s_total_lit[6];
+    __shared__ unsigned long long s_total_lit;
+    __shared__ uint32_t s_hist[66];
+    __shared__ uint8_t s_perm[kTile], s_cls[18];
+    unsigned long long clsbits = 0;
+#pragma unroll
+    for (int k = 0; k < 18; k++)
+        clsbits |= (unsigned long long)(p.cls[k] & 3u) << (2 * k);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = blockIdx.x, ty = blockIdx.y;
@@ -165,13 +179,17 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     // ---- tables -> shared memory
     for (int i = tid; i < 4096 / 16; i += kTile)
         reinterpret_cast<uint4 *>(s_idmap)[i] = __ldg(reinterpret_cast<const uint4 *>(p.idmap) + i);
-    for (int i = tid; i < kFusedIds * 32 / 16; i += kTile)
+    for (int i = tid; i < kFusedIds * VALB / 16; i += kTile)
         reinterpret_cast<uint4 *>(s_val)[i] = __ldg(reinterpret_cast<const uint4 *>(p.val) + i);
     {
         const int gx = min(x0 + tid, p.w - 1);
         s_col[tid] = __ldg(p.col_idx + gx);
         s_cnt[tid] = 0;
         s_w[tid] = 0;
+        if (tid < 66)
+            s_hist[tid] = 0;
+        if (tid < 18)
+            s_cls[tid] = p.cls[tid];
     }
     __syncthreads();
 
@@ -179,16 +197,18 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     {
         const int g = tid & 15;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.esa) | p.esa_pitch) & 15) == 0;
-#pragma unroll 4
+        const int c_first = s_col[16 * g], c_last = s_col[16 * g + 15];
+        const int gx = x0 + 16 * g;
+        const int nvalid = min(16, p.w - gx);
+#pragma unroll 2
         for (int j = 0; j < 16; j++) {
             const int r = (tid >> 4) + 16 * j;
-            const int gy = y0 + r, gx = x0 + 16 * g;
+            const int gy = y0 + r;
             uint32_t idw[4] = { 0x01010101u * kFusedPad, 0x01010101u * kFusedPad, 0x01010101u * kFusedPad,
                                 0x01010101u * kFusedPad };
-            if (gy < p.rows && gx < p.w) {
+            if (gy < p.rows && nvalid > 0) {
                 const uint8_t *e = p.esa + (size_t)gy * p.esa_pitch + gx;
                 uint32_t ew[4] = { 0, 0, 0, 0 };
-                const int nvalid = min(16, p.w - gx);
                 if (nvalid == 16 && vec_ok) {
                     const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(e));
                     ew[0] = v.x; ew[1] = v.y; ew[2] = v.z; ew[3] = v.w;
@@ -198,18 +218,28 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                         ew[k >> 2] |= (uint32_t)e[k] << (8 * (k & 3));
                 }
                 const uint8_t *hrow = p.hsg + (size_t)__ldg(p.row_idx + p.y_base + gy) * p.hsg_pitch;
-                int prev = -1;
-                uint32_t sc = 0;
+                if (c_first == c_last && nvalid == 16) {
+                    // one soil cell under all 16 pixels (the rule at 25 pixels per cell): one row of the id map
+                    const uint8_t *mrow = s_idmap + 256u * soil_class(__ldg(hrow + c_first));
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const int ci = s_col[16 * g + k];
-                    if (ci != prev) {
-                        sc = soil_class(__ldg(hrow + ci));
-                        prev = ci;
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t wv = ew[q];
+                        idw[q] = (uint32_t)mrow[wv & 255u] | ((uint32_t)mrow[(wv >> 8) & 255u] << 8) |
+                                 ((uint32_t)mrow[(wv >> 16) & 255u] << 16) | ((uint32_t)mrow[wv >> 24] << 24);
                     }
-                    const uint32_t lc = (ew[k >> 2] >> (8 * (k & 3))) & 255u;
-                    const uint32_t id = k < nvalid ? s_idmap[lc * 16u + sc] : (uint32_t)kFusedPad;
-                    idw[k >> 2] = (idw[k >> 2] & ~(255u << (8 * (k & 3)))) | (id << (8 * (k & 3)));
+                }
+                else {
+                    int prev = -1;
+                    const uint8_t *mrow = s_idmap;
+                    for (int k = 0; k < nvalid; k++) {
+                        const int ci = s_col[16 * g + k];
+                        if (ci != prev) {
+                            mrow = s_idmap + 256u * soil_class(__ldg(hrow + ci));
+                            prev = ci;
+                        }
+                        const uint32_t lc = (ew[k >> 2] >> (8 * (k & 3))) & 255u;
+                        idw[k >> 2] = (idw[k >> 2] & ~(255u << (8 * (k & 3)))) | ((uint32_t)mrow[lc] << (8 * (k & 3)));
+                    }
                 }
             }
             *reinterpret_cast<uint4 *>(tile + r * kTileStride + 16 * g) = make_uint4(idw[0], idw[1], idw[2], idw[3]);
@@ -217,11 +247,11 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     }
     __syncthreads();
 
-    // ---- 2. pass 1 (thread r owns tile row r): word masks, per-id pixel counts / weight sums, row bit counts
-    RowMasks m;
-    m.above = 0;
-    m.left = 0;
+    // ---- 2. (thread r owns tile row r) word masks, per-id pixel counts / position-weight sums, work estimate
     {
+        RowMasks m;
+        m.above = 0;
+        m.left = 0;
         const uint4 *rowv = reinterpret_cast<const uint4 *>(tile + tid * kTileStride);
         const uint4 *upv = rowv - kTileStride / 16;
         uint32_t last = 0;
@@ -252,7 +282,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                         if (v != cur) {
                             if (n) {
                                 atomicAdd(&s_cnt[cur], n);
-                                atomicAdd(&s_w[cur], (unsigned long long)n * rowbase - xs);
+                                atomicAdd(&s_w[cur], n * rowbase - xs);
                             }
                             cur = v;
                             n = 0;
@@ -265,53 +295,85 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
             }
         }
         atomicAdd(&s_cnt[cur], n);
-        atomicAdd(&s_w[cur], (unsigned long long)n * rowbase - xs);
+        atomicAdd(&s_w[cur], n * rowbase - xs);
+        s_masks[tid] = m;
+        // rows sorted by expected token count (words that neither repeat the row above nor continue a run), so
+        // that the 32 rows a warp parses in lockstep are of similar length
+        const uint32_t est = (uint32_t)__popcll(~(m.above | m.left));
+        atomicAdd(&s_hist[64u - est], 1u);
+        __syncthreads();
+        if (warp == 0) {
+            // exclusive prefix of the 65 buckets (longest rows first)
+            const uint32_t a = s_hist[lane], b = s_hist[32 + lane];
+            uint32_t ia = a, ib = b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+                if (lane >= o) {
+                    ia += ta;
+                    ib += tb;
+                }
+            }
+            const uint32_t tot_a = __shfl_sync(0xffffffffu, ia, 31), tot_b = __shfl_sync(0xffffffffu, ib, 31);
+            s_hist[lane] = ia - a;
+            s_hist[32 + lane] = tot_a + ib - b;
+            if (lane == 0)
+                s_hist[64] = tot_a + tot_b;
+        }
+        __syncthreads();
+        s_perm[atomicAdd(&s_hist[64u - est], 1u)] = (uint8_t)tid;
     }
-    unsigned long long lit[6] = { 0, 0, 0, 0, 0, 0 };
-    const uint32_t row_bits = fused_parse_row<false>(tile, tid, m, s_val, p.lit9, lit, 0u, nullptr, nullptr, 0, 0);
+    __syncthreads();
 
-    // ---- 3. inclusive scan over the rows of (common bits, per-plane 9-bit-literal counts)
-    unsigned long long inc[7] = { row_bits, lit[0], lit[1], lit[2], lit[3], lit[4], lit[5] };
+    // ---- 3. pass 1: thread t parses row perm[t]; per-row (common bits, 9-bit-literal counts) -> the row's spare bytes
+    const int prow = s_perm[tid];
+    const RowMasks pm = s_masks[prow];
+    {
+        unsigned long long lit = 0;
+        const uint32_t bits = fused_parse_row<false, MAXP>(tile, prow, pm, s_val, p.lit9, clsbits, lit, 0u, nullptr, nullptr, 0, 0);
+        *reinterpret_cast<uint32_t *>(tile + prow * kTileStride + kFusedRowMeta) = bits;
+        *reinterpret_cast<unsigned long long *>(tile + prow * kTileStride + kFusedRowMeta + 8) = lit;
+    }
+    __syncthreads();
+
+    // ---- 4. exclusive scan over the rows (thread r = row r) -> back into the spare bytes
+    {
+        const uint32_t row_bits = *reinterpret_cast<const uint32_t *>(tile + tid * kTileStride + kFusedRowMeta);
+        const unsigned long long row_lit = *reinterpret_cast<const unsigned long long *>(tile + tid * kTileStride + kFusedRowMeta + 8);
+        unsigned long long inc0 = row_bits, inc1 = row_lit;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-        for (int q = 0; q < 7; q++) {
-            const unsigned long long t = shfl_up_u64(inc[q], o);
-            if (lane >= o)
-                inc[q] += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t0 = __shfl_up_sync(0xffffffffu, inc0, o), t1 = __shfl_up_sync(0xffffffffu, inc1, o);
+            if (lane >= o) {
+                inc0 += t0;
+                inc1 += t1;
+            }
+        }
+        if (lane == 31) {
+            s_scan[warp][0] = inc0;
+            s_scan[warp][1] = inc1;
+        }
+        __syncthreads();
+        unsigned long long b0 = 0, b1 = 0;
+        for (int wv = 0; wv < warp; wv++) {
+            b0 += s_scan[wv][0];
+            b1 += s_scan[wv][1];
+        }
+        *reinterpret_cast<uint32_t *>(tile + tid * kTileStride + kFusedRowMeta) = (uint32_t)(b0 + inc0) - row_bits;
+        *reinterpret_cast<unsigned long long *>(tile + tid * kTileStride + kFusedRowMeta + 8) = b1 + inc1 - row_lit;
+        if (tid == kTile - 1) {
+            s_total_common = (uint32_t)(b0 + inc0);
+            s_total_lit = b1 + inc1;
         }
     }
-    if (lane == 31) {
-#pragma unroll
-        for (int q = 0; q < 7; q++)
-            s_scan[warp][q] = inc[q];
-    }
-    __syncthreads();                // also: every row's counts / weights are in s_cnt / s_w
-    unsigned long long base[7] = { 0, 0, 0, 0, 0, 0, 0 };
-    for (int wv = 0; wv < warp; wv++) {
-#pragma unroll
-        for (int q = 0; q < 7; q++)
-            base[q] += s_scan[wv][q];
-    }
-    const uint32_t row_pos = (uint32_t)(base[0] + inc[0]) - row_bits;
-    unsigned long long lit_before[6];
-#pragma unroll
-    for (int q = 0; q < 6; q++)
-        lit_before[q] = base[q + 1] + inc[q + 1] - lit[q];
-    if (tid == kTile - 1) {
-        s_total_common = (uint32_t)(base[0] + inc[0]);
-#pragma unroll
-        for (int q = 0; q < 6; q++)
-            s_total_lit[q] = base[q + 1] + inc[q + 1];
-    }
 
-    // ---- 4. Adler-32 per plane: s1 = 1 + sum cnt[id] val[id], s2 = N + sum w[id] val[id]  (mod 65521)
+    // ---- 5. Adler-32 per plane: s1 = 1 + sum cnt[id] val[id], s2 = N + sum w[id] val[id]  (mod 65521)
     for (int k = warp; k < nsel; k += kTile / 32) {
         unsigned long long a = 0, b = 0;
         for (int id = lane; id < kFusedIds; id += 32) {
-            const unsigned long long v = s_val[32 * id + k];
+            const unsigned long long v = s_val[VALB * id + k];
             a += (unsigned long long)s_cnt[id] * v;
-            b += (s_w[id] % 65521ull) * v;
+            b += (unsigned long long)(s_w[id] % 65521u) * v;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -326,15 +388,14 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     }
     __syncthreads();
 
-    // ---- 5. sizes, stored fallbacks, arena allocation, rounds
+    // ---- 6. sizes, stored fallbacks, arena allocation, rounds
     if (tid == 0) {
         unsigned long long need = 0;
-        uint32_t deflate_end[18];
         for (int k = 0; k < nsel; k++) {
-            const uint32_t bits = 19u + s_total_common + field21(s_total_lit, k) + 7u;
-            deflate_end[k] = (bits + 7u) >> 3;
-            s_stored[k] = deflate_end[k] + 4u > (uint32_t)kFusedOutCap - 64u;
-            s_nbytes[k] = s_stored[k] ? (uint32_t)kStoredBytes : deflate_end[k] + 4u;
+            const uint32_t bits = 19u + s_total_common + field21(s_total_lit, s_cls[k]) + 7u;
+            const uint32_t deflate_end = (bits + 7u) >> 3;
+            s_stored[k] = deflate_end + 4u > (uint32_t)kFusedOutCap - 64u;
+            s_nbytes[k] = s_stored[k] ? (uint32_t)kStoredBytes : deflate_end + 4u;
         }
         // compressed planes first (contiguous per round, in the arena as in the staging area), stored ones behind
         int nr = 0;
@@ -369,7 +430,9 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     }
     __syncthreads();
 
-    // ---- 6. rounds of planes: zero the staging area, second parse writes the streams, copy out
+    // ---- 7. rounds of planes: zero the staging area, second parse writes the streams, copy out
+    const uint32_t row_pos = *reinterpret_cast<const uint32_t *>(tile + prow * kTileStride + kFusedRowMeta);
+    const unsigned long long lit_before = *reinterpret_cast<const unsigned long long *>(tile + prow * kTileStride + kFusedRowMeta + 8);
     const int nrounds = s_nrounds;
     int lo = 0;
     for (int rd = 0; rd < nrounds; rd++) {
@@ -387,8 +450,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
             for (uint32_t i = tid; i < span / 16 + 4; i += kTile)
                 reinterpret_cast<uint4 *>(outb)[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
-            // stored planes of the range must not be written: give the parse a range of compressed planes only
-            // (stored planes are rare; split the range around them)
+            // stored planes must not be written: hand the parse ranges of compressed planes only
             int a = lo;
             while (a < hi) {
                 while (a < hi && s_stored[a])
@@ -397,11 +459,8 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                 while (b < hi && !s_stored[b])
                     b++;
                 if (a < b) {
-                    unsigned long long lw[6];
-#pragma unroll
-                    for (int q = 0; q < 6; q++)
-                        lw[q] = lit_before[q];
-                    fused_parse_row<true>(tile, tid, m, s_val, p.lit9, lw, row_pos, out, s_obase, a, b);
+                    unsigned long long lw = lit_before;
+                    fused_parse_row<true, MAXP>(tile, prow, pm, s_val, p.lit9, clsbits, lw, row_pos, out, s_obase, a, b);
                 }
                 a = b;
             }
@@ -432,7 +491,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         lo = hi;
     }
 
-    // ---- 7. incompressible planes: zlib header, two stored blocks of 32768 bytes, Adler-32
+    // ---- 8. incompressible planes: zlib header, two stored blocks of 32768 bytes, Adler-32
     for (int k = 0; k < nsel; k++) {
         if (!s_stored[k])
             continue;
@@ -449,7 +508,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         for (int i = tid; i < kTileBytes; i += kTile) {
             const int r = i >> 8, c = i & 255;
             const int o = i < 32768 ? 7 + i : 7 + 5 + i;
-            dst[o] = s_val[32 * tile[r * kTileStride + c] + k];
+            dst[o] = s_val[VALB * tile[r * kTileStride + c] + k];
         }
     }
 }

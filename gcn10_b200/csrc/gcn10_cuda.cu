@@ -91,6 +91,7 @@ struct gcn10_ctx {
     DevBuf fused_tab;           // idmap [256][16] | val [256][32] | lit9 [256][6] u64
     unsigned fused_mask = 0;    // plane mask the tables were built for (0 = none)
     int fused_ok = 0;           // the mask's value records fit the id space
+    uint8_t fused_cls[18] = {}; // 9-bit-literal class of the j-th selected plane
     EncodeTiledFn encode_tiled = nullptr;
 
     bool have_lut = false;
@@ -443,7 +444,8 @@ int build_fused_tables(gcn10_ctx *c, unsigned plane_mask, cudaStream_t st)
     for (int k = 0; k < GCN10_NPLANES; k++)
         if (plane_mask & (1u << k))
             plane_ids[nsel++] = k;
-    std::vector<uint8_t> host(4096 + kFusedIds * 32 + kFusedIds * 48, 0);
+    const int valb = nsel <= 9 ? 16 : 32;
+    std::vector<uint8_t> host(4096 + kFusedIds * 32 + kFusedIds * 8, 0);
     uint8_t *idmap = host.data(), *val = host.data() + 4096;
     unsigned long long *lit9 = (unsigned long long *)(host.data() + 4096 + kFusedIds * 32);
     std::vector<std::vector<uint8_t>> records;
@@ -471,16 +473,37 @@ int build_fused_tables(gcn10_ctx *c, unsigned plane_mask, cudaStream_t st)
                 }
                 records.push_back(rec);
             }
-            idmap[lc * 16 + sc] = (uint8_t)id;
+            idmap[sc * 256 + lc] = (uint8_t)id;
         }
     }
-    if (c->fused_ok) {
+    // planes whose records need 9-bit literals (values >= 144, in practice nodata 255) at the same ids share
+    // one bit-position counter in the kernel; at most kFusedClasses distinct patterns are supported
+    std::vector<std::vector<uint8_t>> patterns;
+    memset(c->fused_cls, 0, sizeof(c->fused_cls));
+    for (int j = 0; j < nsel && c->fused_ok; j++) {
+        std::vector<uint8_t> pat(records.size());
         for (size_t id = 0; id < records.size(); id++)
-            for (int j = 0; j < nsel; j++) {
-                val[id * 32 + j] = records[id][j];
-                if (records[id][j] >= 144)
-                    lit9[id * 6 + j / 3] |= 1ull << (21 * (j % 3));
+            pat[id] = records[id][j] >= 144;
+        size_t q = 0;
+        while (q < patterns.size() && patterns[q] != pat)
+            q++;
+        if (q == patterns.size()) {
+            if (patterns.size() >= (size_t)kFusedClasses) {
+                c->fused_ok = 0;
+                break;
             }
+            patterns.push_back(pat);
+        }
+        c->fused_cls[j] = (uint8_t)q;
+    }
+    if (c->fused_ok) {
+        for (size_t id = 0; id < records.size(); id++) {
+            for (int j = 0; j < nsel; j++)
+                val[id * valb + j] = records[id][j];
+            for (size_t q = 0; q < patterns.size(); q++)
+                if (patterns[q][id])
+                    lit9[id] |= 1ull << (21 * q);
+        }
         int rc = ensure(c->fused_tab, host.size());
         if (rc)
             return rc;
@@ -557,9 +580,13 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
     }
     CUDA_TRY(cudaFuncSetAttribute((const void *)deflate_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kEncSmem));
-    CUDA_TRY(cudaFuncSetAttribute((const void *)cn_deflate_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kFusedSmem));
-    CUDA_TRY(cudaFuncSetAttribute((const void *)cn_deflate_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+    CUDA_TRY(cudaFuncSetAttribute((const void *)cn_deflate_fused_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  fused_smem_bytes<9>()));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)cn_deflate_fused_kernel<18>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  fused_smem_bytes<18>()));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)cn_deflate_fused_kernel<9>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
+    CUDA_TRY(cudaFuncSetAttribute((const void *)cn_deflate_fused_kernel<18>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute((const void *)inflate_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kInflateSmem));
@@ -958,6 +985,7 @@ static int deflate_rows_impl(gcn10_ctx *c,
             fp.idmap = (const uint8_t *)c->fused_tab.p;
             fp.val = (const uint8_t *)c->fused_tab.p + 4096;
             fp.lit9 = (const unsigned long long *)((const uint8_t *)c->fused_tab.p + 4096 + kFusedIds * 32);
+            memcpy(fp.cls, c->fused_cls, sizeof(fp.cls));
             fp.nsel = nplanes;
             fp.tiles_x = tiles_x;
             fp.tile_rows = tile_rows;
@@ -966,7 +994,10 @@ static int deflate_rows_impl(gcn10_ctx *c,
             fp.offsets = (unsigned long long *)((uint8_t *)sl.table.p + 16);
             fp.sizes = (uint32_t *)((uint8_t *)sl.table.p + 16 + ntile_slot * sizeof(unsigned long long));
             CUDA_TRY(cudaMemsetAsync(sl.table.p, 0, 16, st));
-            cn_deflate_fused_kernel<<<dim3(tiles_x, tile_rows), kTile, kFusedSmem, st>>>(fp);
+            if (nplanes <= 9)
+                cn_deflate_fused_kernel<9><<<dim3(tiles_x, tile_rows), kTile, fused_smem_bytes<9>(), st>>>(fp);
+            else
+                cn_deflate_fused_kernel<18><<<dim3(tiles_x, tile_rows), kTile, fused_smem_bytes<18>(), st>>>(fp);
             c->launches++;
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaEventRecord(sl.k1, st));

@@ -89,6 +89,30 @@ def test_deflate_stored_fallback_and_masks(gpu_ctx, port, tables):
         assert np.array_equal(_assemble(res["tiles"][k], 520, 300)[:300, :520], want[k])
 
 
+@pytest.mark.parametrize("holes", [1, 2, 5], ids=["2_literal_classes", "3_literal_classes", "too_many_classes"])
+def test_tables_with_missing_rows_per_variant(holes, gpu_ctx, port, tables):
+    """Variants whose lookup CSV lacks rows for some land-cover classes put nodata (255, a 9-bit literal)
+    where the other planes hold a value: the fused kernel keeps one bit-position counter per such pattern
+    (up to 3) and the library falls back to the two-kernel path beyond that.  Negative, >= 255 and column-0
+    entries ride along."""
+    t = tables.copy()
+    for q in range(holes):
+        t[1 + q, 10 * (q + 1), :] = 255                    # variant 1+q has no rows for class 10 (q+1)
+    t[0, 30, 2] = -3                                       # (uint8_t)(-3) = 253, a 9-bit literal in plane 0 only ...
+    t[0, 30, 2] = t[0, 30, 2] if holes < 2 else tables[0, 30, 2]
+    t[7, 50, 0] = 77                                       # column 0: reached by soil code 0
+    b = make_block(w=700, h=540, seed=31, esa_patch=30, hsg_patch=2)
+    b["hsg"][::7, ::5] = 0
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], t)
+    try:
+        gpu_ctx.set_luts(t)
+        res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    finally:
+        gpu_ctx.set_luts(tables)
+    for k in range(18):
+        assert np.array_equal(_assemble(res["tiles"][k], 700, 540)[:540, :700], want[k]), f"plane {k}"
+
+
 def test_deflate_compresses_cn_rasters(gpu_ctx):
     b = make_block(w=2048, h=2048, seed=10, esa_patch=192, hsg_patch=9)
     res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], plane_mask=capi.MASK_DRAINED)

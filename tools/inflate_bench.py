@@ -63,6 +63,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--patch", type=int, default=192)
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--strip-rows", default="2048")
+    ap.add_argument("--streams", default="4")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     tables = B.load_tables_host(lookups.write_default_lookups(tempfile.mkdtemp()))
@@ -104,18 +106,24 @@ def main():
                 def sink(st):
                     nbytes[0] += st.blob_bytes
                     return 0
-                for name, fn in (("tiles_in", lambda: ctx.block_tiles_deflate(src, w, h, gt, hsg, sgt, capi.MASK_DRAINED, on_strip=sink)),
-                                 ("raster_in", lambda: ctx.block_deflate(esa, gt, hsg, sgt, capi.MASK_DRAINED, on_strip=sink))):
-                    fn()
-                    ts = []
-                    for _ in range(a.reps):
-                        nbytes[0] = 0
-                        t0 = time.perf_counter()
-                        fn()
-                        ts.append((time.perf_counter() - t0) * 1e3)
-                    rec[f"e2e_{name}_ms"] = round(float(np.median(ts)), 2)
-                    rec[f"e2e_{name}_gpx_s"] = round(w * h / 1e6 / float(np.median(ts)), 2)
-                    rec[f"e2e_{name}_d2h_mb"] = round(nbytes[0] / 1e6, 1)
+                for sr in [int(x) for x in a.strip_rows.split(",")]:
+                    for ns in [int(x) for x in a.streams.split(",")]:
+                        ctx.set_option("strip_rows", sr)
+                        ctx.set_option("streams", ns)
+                        for name, fn in (("tiles_in", lambda: ctx.block_tiles_deflate(src, w, h, gt, hsg, sgt, capi.MASK_DRAINED, on_strip=sink)),
+                                         ("raster_in", lambda: ctx.block_deflate(esa, gt, hsg, sgt, capi.MASK_DRAINED, on_strip=sink))):
+                            fn()
+                            ts = []
+                            for _ in range(a.reps):
+                                nbytes[0] = 0
+                                t0 = time.perf_counter()
+                                fn()
+                                ts.append((time.perf_counter() - t0) * 1e3)
+                            tag = f"{name}_s{sr}_n{ns}"
+                            rec[f"e2e_{tag}_ms"] = round(float(np.median(ts)), 2)
+                            rec[f"e2e_{tag}_gpx_s"] = round(w * h / 1e6 / float(np.median(ts)), 2)
+                            rec[f"e2e_{tag}_kernels_ms"] = round(ctx.last_kernel_ms(), 2)
+                            rec[f"e2e_{tag}_d2h_mb"] = round(nbytes[0] / 1e6, 1)
             print(json.dumps(rec), flush=True)
     for p in pins:
         p.free()
