@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t field21(unsigned long long c, uint32_t f) { 
 //   WRITE = true : emits planes [lo, hi) ; `pos` = common bits before this row, lit = class counts before this
 //                  row, obase[k] = byte offset of plane k's stream in `out` (16-byte aligned); the 19 header
 //                  bits are added here.
-template <bool WRITE, int MAXP>
+template <bool WRITE, int MAXP, bool ONE = false>
 __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, const RowMasks &m, const uint8_t *val,
                                                     const unsigned long long *lit9, unsigned long long clsbits,
                                                     unsigned long long &lit, uint32_t pos, uint32_t *out,
@@ -99,7 +99,21 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
             uint32_t bits;
             int n;
             match_code(len, la >= lr, bits, n);
-            if (WRITE) {
+            if (WRITE && ONE) {
+                // every plane has the same 9-bit-literal pattern: one bit position for all streams
+                const uint32_t pp = 19u + pos + (uint32_t)lit;
+                const uint32_t sh = pp & 31u, w0 = bits << sh, w1 = sh ? bits >> (32u - sh) : 0u;
+                const bool cross = sh + (uint32_t)n > 32u;
+#pragma unroll
+                for (int k = 0; k < MAXP; k++)
+                    if (k >= lo && k < hi) {
+                        uint32_t *o = out + (obase[k] >> 2) + (pp >> 5);
+                        atomicOr(o, w0);
+                        if (cross)
+                            atomicOr(o + 1, w1);
+                    }
+            }
+            else if (WRITE) {
                 const uint32_t pc[3] = { 19u + pos + field21(lit, 0), 19u + pos + field21(lit, 1), 19u + pos + field21(lit, 2) };
 #pragma unroll
                 for (int k = 0; k < MAXP; k++)
@@ -122,14 +136,23 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
                     vw[4] = v1.x; vw[5] = v1.y; vw[6] = v1.z; vw[7] = v1.w;
                 }
                 const uint32_t pc[3] = { 19u + pos + field21(lit, 0), 19u + pos + field21(lit, 1), 19u + pos + field21(lit, 2) };
+                const uint32_t sh = pc[0] & 31u;
 #pragma unroll
                 for (int k = 0; k < MAXP; k++)
                     if (k >= lo && k < hi) {
                         uint32_t bits;
                         int n;
                         lit_code((vw[k >> 2] >> (8 * (k & 3))) & 255u, bits, n);
-                        const uint32_t c = (uint32_t)(clsbits >> (2 * k)) & 3u;
-                        put_bits(out + (obase[k] >> 2), c == 0u ? pc[0] : (c == 1u ? pc[1] : pc[2]), bits, n);
+                        if (ONE) {
+                            uint32_t *o = out + (obase[k] >> 2) + (pc[0] >> 5);
+                            atomicOr(o, bits << sh);
+                            if (sh + (uint32_t)n > 32u)
+                                atomicOr(o + 1, bits >> (32u - sh));
+                        }
+                        else {
+                            const uint32_t c = (uint32_t)(clsbits >> (2 * k)) & 3u;
+                            put_bits(out + (obase[k] >> 2), c == 0u ? pc[0] : (c == 1u ? pc[1] : pc[2]), bits, n);
+                        }
                     }
             }
             lit += __ldg(lit9 + id);
@@ -197,52 +220,83 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     {
         const int g = tid & 15;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.esa) | p.esa_pitch) & 15) == 0;
-        const int c_first = s_col[16 * g], c_last = s_col[16 * g + 15];
         const int gx = x0 + 16 * g;
-        const int nvalid = min(16, p.w - gx);
-#pragma unroll 2
-        for (int j = 0; j < 16; j++) {
-            const int r = (tid >> 4) + 16 * j;
-            const int gy = y0 + r;
-            uint32_t idw[4] = { 0x01010101u * kFusedPad, 0x01010101u * kFusedPad, 0x01010101u * kFusedPad,
-                                0x01010101u * kFusedPad };
-            if (gy < p.rows && nvalid > 0) {
-                const uint8_t *e = p.esa + (size_t)gy * p.esa_pitch + gx;
-                uint32_t ew[4] = { 0, 0, 0, 0 };
-                if (nvalid == 16 && vec_ok) {
-                    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(e));
-                    ew[0] = v.x; ew[1] = v.y; ew[2] = v.z; ew[3] = v.w;
-                }
-                else {
-                    for (int k = 0; k < nvalid; k++)
-                        ew[k >> 2] |= (uint32_t)e[k] << (8 * (k & 3));
-                }
-                const uint8_t *hrow = p.hsg + (size_t)__ldg(p.row_idx + p.y_base + gy) * p.hsg_pitch;
-                if (c_first == c_last && nvalid == 16) {
-                    // one soil cell under all 16 pixels (the rule at 25 pixels per cell): one row of the id map
-                    const uint8_t *mrow = s_idmap + 256u * soil_class(__ldg(hrow + c_first));
+        const int nvalid = max(0, min(16, p.w - gx));
+        // the soil cells under this thread's 16 pixel columns (the same for all its rows): at 25 pixels per cell
+        // there are one or two; ksw = pixels that lie in the first one
+        const int c0 = s_col[16 * g], c1 = s_col[16 * g + 15];
+        int ksw = 0;
+        while (ksw < 16 && s_col[16 * g + ksw] == c0)
+            ksw++;
+        bool two = true;
+        for (int k = ksw; k < 16; k++)
+            two = two && s_col[16 * g + k] == c1;
+        const uint32_t pad4 = 0x01010101u * kFusedPad;
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            // all loads of eight rows are in flight before the first dependent use
+            int hr[8];
+            uint32_t code0[8], code1[8];
+            uint4 ev[8];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint32_t wv = ew[q];
-                        idw[q] = (uint32_t)mrow[wv & 255u] | ((uint32_t)mrow[(wv >> 8) & 255u] << 8) |
-                                 ((uint32_t)mrow[(wv >> 16) & 255u] << 16) | ((uint32_t)mrow[wv >> 24] << 24);
-                    }
-                }
-                else {
-                    int prev = -1;
-                    const uint8_t *mrow = s_idmap;
-                    for (int k = 0; k < nvalid; k++) {
-                        const int ci = s_col[16 * g + k];
-                        if (ci != prev) {
-                            mrow = s_idmap + 256u * soil_class(__ldg(hrow + ci));
-                            prev = ci;
-                        }
-                        const uint32_t lc = (ew[k >> 2] >> (8 * (k & 3))) & 255u;
-                        idw[k >> 2] = (idw[k >> 2] & ~(255u << (8 * (k & 3)))) | ((uint32_t)mrow[lc] << (8 * (k & 3)));
-                    }
-                }
+            for (int j = 0; j < 8; j++) {
+                const int gy = y0 + (tid >> 4) + 16 * (8 * half + j);
+                hr[j] = gy < p.rows ? __ldg(p.row_idx + p.y_base + gy) : 0;
             }
-            *reinterpret_cast<uint4 *>(tile + r * kTileStride + 16 * g) = make_uint4(idw[0], idw[1], idw[2], idw[3]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int gy = y0 + (tid >> 4) + 16 * (8 * half + j);
+                const uint8_t *hrow = p.hsg + (size_t)hr[j] * p.hsg_pitch;
+                code0[j] = __ldg(hrow + c0);
+                code1[j] = __ldg(hrow + c1);
+                ev[j] = make_uint4(0, 0, 0, 0);
+                if (gy < p.rows && nvalid == 16 && vec_ok)
+                    ev[j] = __ldcs(reinterpret_cast<const uint4 *>(p.esa + (size_t)gy * p.esa_pitch + gx));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int r = (tid >> 4) + 16 * (8 * half + j);
+                const int gy = y0 + r;
+                uint32_t idw[4] = { pad4, pad4, pad4, pad4 };
+                if (gy < p.rows && nvalid > 0) {
+                    uint32_t ew[4] = { ev[j].x, ev[j].y, ev[j].z, ev[j].w };
+                    if (!(nvalid == 16 && vec_ok)) {
+                        const uint8_t *e = p.esa + (size_t)gy * p.esa_pitch + gx;
+#pragma unroll
+                        for (int k = 0; k < 16; k++)
+                            if (k < nvalid)
+                                ew[k >> 2] |= (uint32_t)e[k] << (8 * (k & 3));
+                    }
+                    if (two) {
+                        const uint8_t *m0 = s_idmap + 256u * soil_class(code0[j]);
+                        const uint8_t *m1 = s_idmap + 256u * soil_class(code1[j]);
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const uint32_t lc = (ew[k >> 2] >> (8 * (k & 3))) & 255u;
+                            const uint32_t id = k < nvalid ? (uint32_t)(k < ksw ? m0 : m1)[lc] : (uint32_t)kFusedPad;
+                            idw[k >> 2] = (k & 3) == 0 ? id : (idw[k >> 2] | (id << (8 * (k & 3))));
+                        }
+                    }
+                    else {
+                        // more than two soil cells under 16 pixels (soil grid finer than 16 pixels): cell by cell
+                        const uint8_t *hrow = p.hsg + (size_t)hr[j] * p.hsg_pitch;
+                        int prev = -1;
+                        const uint8_t *mrow = s_idmap;
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const int ci = s_col[16 * g + k];
+                            if (ci != prev) {
+                                mrow = s_idmap + 256u * soil_class(__ldg(hrow + ci));
+                                prev = ci;
+                            }
+                            const uint32_t lc = (ew[k >> 2] >> (8 * (k & 3))) & 255u;
+                            const uint32_t id = k < nvalid ? (uint32_t)mrow[lc] : (uint32_t)kFusedPad;
+                            idw[k >> 2] = (k & 3) == 0 ? id : (idw[k >> 2] | (id << (8 * (k & 3))));
+                        }
+                    }
+                }
+                *reinterpret_cast<uint4 *>(tile + r * kTileStride + 16 * g) = make_uint4(idw[0], idw[1], idw[2], idw[3]);
+            }
         }
     }
     __syncthreads();
@@ -460,7 +514,10 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                     b++;
                 if (a < b) {
                     unsigned long long lw = lit_before;
-                    fused_parse_row<true, MAXP>(tile, prow, pm, s_val, p.lit9, clsbits, lw, row_pos, out, s_obase, a, b);
+                    if (clsbits == 0ull)
+                        fused_parse_row<true, MAXP, true>(tile, prow, pm, s_val, p.lit9, clsbits, lw, row_pos, out, s_obase, a, b);
+                    else
+                        fused_parse_row<true, MAXP, false>(tile, prow, pm, s_val, p.lit9, clsbits, lw, row_pos, out, s_obase, a, b);
                 }
                 a = b;
             }
