@@ -34,6 +34,9 @@ constexpr int kFusedOutCap = 31 * 1024;         // shared-memory staging for the
 constexpr int kFusedIds = 256;
 constexpr int kFusedPad = 255;                  // record id of the zero padding right / below the raster
 constexpr int kFusedClasses = 3;                // distinct "which records need a 9-bit literal" patterns over the planes
+constexpr int kFusedSplitEst = 6;               // rows with at least this many "new" words are cut into four 64-pixel items
+constexpr int kFusedMaxItems = 512;             // two items per thread at most
+constexpr int kFusedMaxSplitRows = (kFusedMaxItems - kTile) / 3;
 constexpr int kFusedRowMeta = kTile;            // byte offset of a row's 16 spare bytes inside its 272-byte tile row
 
 template <int MAXP>
@@ -75,26 +78,27 @@ __device__ __forceinline__ uint32_t soil_class(uint32_t code)
 
 __device__ __forceinline__ uint32_t field21(unsigned long long c, uint32_t f) { return (uint32_t)(c >> (21u * f)) & 0x1FFFFFu; }
 
-// Greedy parse of one row of the id tile.
+// Greedy parse of pixels [xa, xb) of one row of the id tile (a whole row, or one 64-pixel item of a long row).
 //   WRITE = false: returns the bits common to all planes; lit += 9-bit-literal counts per class
-//   WRITE = true : emits planes [lo, hi) ; `pos` = common bits before this row, lit = class counts before this
-//                  row, obase[k] = byte offset of plane k's stream in `out` (16-byte aligned); the 19 header
+//   WRITE = true : emits planes [lo, hi) ; `pos` = common bits before this item, lit = class counts before
+//                  it, obase[k] = byte offset of plane k's stream in `out` (16-byte aligned); the 19 header
 //                  bits are added here.
 template <bool WRITE, int MAXP, bool ONE = false>
 __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, const RowMasks &m, const uint8_t *val,
                                                     const unsigned long long *lit9, unsigned long long clsbits,
                                                     unsigned long long &lit, uint32_t pos, uint32_t *out,
-                                                    const uint32_t *obase, int lo, int hi)
+                                                    const uint32_t *obase, int lo, int hi, int xa, int xb)
 {
     constexpr int VALB = MAXP <= 9 ? 16 : 32;
     const uint8_t *row = tile + r * kTileStride;
-    int x = 0;
-    while (x < kTile) {
+    int x = xa;
+    while (x < xb) {
         const int la = r > 0 ? run_len<true>(row, m.above, 0, x) : 0;
         int lr = 0;
         if (x > 0)
             lr = run_len<false>(row, m.left, bcast_byte(row[x - 1]), x);
-        const int len = la >= lr ? la : lr;
+        int len = la >= lr ? la : lr;
+        len = min(len, xb - x);                 // tokens do not cross the end of the item
         if (len >= 3) {
             uint32_t bits;
             int n;
@@ -180,6 +184,9 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     int32_t *s_col = reinterpret_cast<int32_t *>(outb + 4096);          // 1 KB
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(outb + 5120);        // 1 KB  pixels per id
     uint32_t *s_w = reinterpret_cast<uint32_t *>(outb + 6144);          // 1 KB  sum of (N - i) per id (< 2^32 over a tile)
+    uint16_t *s_perm = reinterpret_cast<uint16_t *>(outb + 8192);       // 1 KB  items in processing order: row | piece << 8
+    uint32_t *s_ibits = reinterpret_cast<uint32_t *>(outb + 10240);     // 2 KB  per item slot (stream order): common bits
+    unsigned long long *s_ilit = reinterpret_cast<unsigned long long *>(outb + 12288);   // 4 KB  ... 9-bit-literal counts
 
     __shared__ unsigned long long s_scan[kTile / 32][2];
     __shared__ uint32_t s_adler[18], s_nbytes[18], s_obase[18], s_stored[18];
@@ -188,7 +195,8 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     __shared__ uint32_t s_total_common;
     __shared__ unsigned long long s_total_lit;
     __shared__ uint32_t s_hist[66];
-    __shared__ uint8_t s_perm[kTile], s_cls[18];
+    __shared__ uint8_t s_cls[18];
+    __shared__ uint32_t s_nitems;
     unsigned long long clsbits = 0;
 #pragma unroll
     for (int k = 0; k < 18; k++)
@@ -351,13 +359,36 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         atomicAdd(&s_cnt[cur], n);
         atomicAdd(&s_w[cur], n * rowbase - xs);
         s_masks[tid] = m;
-        // rows sorted by expected token count (words that neither repeat the row above nor continue a run), so
-        // that the 32 rows a warp parses in lockstep are of similar length
+        // Work items.  A row's parse is serial, so the longest row sets the latency of the whole CTA: rows with
+        // many "new" words (neither a repeat of the row above nor the continuation of a run -- typically the first
+        // row of a soil cell) are cut into four 64-pixel items whose tokens stop at the item border (a few bits
+        // per cut).  Items are sorted by expected work so that the 32 items a warp parses in lockstep are alike.
         const uint32_t est = (uint32_t)__popcll(~(m.above | m.left));
-        atomicAdd(&s_hist[64u - est], 1u);
+        // (the first kFusedMaxSplitRows such rows in row order, so that the streams do not depend on thread timing)
+        const bool cand = est >= (uint32_t)kFusedSplitEst;
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (lane == 0)
+            s_scan[warp][1] = (unsigned long long)__popc(bal);
+        __syncthreads();
+        uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
+        for (int wv = 0; wv < warp; wv++)
+            rank += (uint32_t)s_scan[wv][1];
+        const bool split = cand && rank < (uint32_t)kFusedMaxSplitRows;
+        const uint32_t nseg = split ? 4u : 1u;
+        const uint32_t key = split ? (est + 3u) / 4u : est;
+        atomicAdd(&s_hist[64u - key], nseg);
+        uint32_t inc = nseg;                    // first item slot of every row (stream order)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o)
+                inc += t;
+        }
+        if (lane == 31)
+            s_scan[warp][0] = inc;
         __syncthreads();
         if (warp == 0) {
-            // exclusive prefix of the 65 buckets (longest rows first)
+            // exclusive prefix of the 65 buckets (longest items first)
             const uint32_t a = s_hist[lane], b = s_hist[32 + lane];
             uint32_t ia = a, ib = b;
 #pragma unroll
@@ -374,27 +405,51 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
             if (lane == 0)
                 s_hist[64] = tot_a + tot_b;
         }
+        uint32_t slot0 = inc - nseg;
+        for (int wv = 0; wv < warp; wv++)
+            slot0 += (uint32_t)s_scan[wv][0];
+        *reinterpret_cast<uint16_t *>(tile + tid * kTileStride + kFusedRowMeta) = (uint16_t)slot0;
+        if (tid == kTile - 1)
+            s_nitems = slot0 + nseg;
         __syncthreads();
-        s_perm[atomicAdd(&s_hist[64u - est], 1u)] = (uint8_t)tid;
+        const uint32_t at = atomicAdd(&s_hist[64u - key], nseg);
+        for (uint32_t q = 0; q < nseg; q++)
+            s_perm[at + q] = (uint16_t)(tid | ((split ? q : 4u) << 8));
     }
     __syncthreads();
 
-    // ---- 3. pass 1: thread t parses row perm[t]; per-row (common bits, 9-bit-literal counts) -> the row's spare bytes
-    const int prow = s_perm[tid];
-    const RowMasks pm = s_masks[prow];
-    {
+    // ---- 3. pass 1: thread t parses items perm[t] and perm[t + 256]; (common bits, 9-bit-literal counts) -> item slot
+    const uint32_t n_items = s_nitems;
+    uint32_t item0 = tid < (int)n_items ? s_perm[tid] : 0xFFFFu;
+    uint32_t item1 = tid + kTile < (int)n_items ? s_perm[tid + kTile] : 0xFFFFu;
+    uint32_t slot_a = 0, slot_b = 0;
+#pragma unroll 1
+    for (int q = 0; q < 2; q++) {
+        const uint32_t item = q ? item1 : item0;
+        if (item == 0xFFFFu)
+            break;
+        const int r = item & 255u, piece = item >> 8;
+        const int xa = piece == 4 ? 0 : 64 * piece, xb = piece == 4 ? kTile : xa + 64;
+        const RowMasks pm = s_masks[r];
         unsigned long long lit = 0;
-        const uint32_t bits = fused_parse_row<false, MAXP>(tile, prow, pm, s_val, p.lit9, clsbits, lit, 0u, nullptr, nullptr, 0, 0);
-        *reinterpret_cast<uint32_t *>(tile + prow * kTileStride + kFusedRowMeta) = bits;
-        *reinterpret_cast<unsigned long long *>(tile + prow * kTileStride + kFusedRowMeta + 8) = lit;
+        const uint32_t bits = fused_parse_row<false, MAXP>(tile, r, pm, s_val, p.lit9, clsbits, lit, 0u, nullptr, nullptr, 0,
+                                                           0, xa, xb);
+        const uint32_t slot = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta) + (piece & 3);
+        s_ibits[slot] = bits;
+        s_ilit[slot] = lit;
+        if (q)
+            slot_b = slot;
+        else
+            slot_a = slot;
     }
     __syncthreads();
 
-    // ---- 4. exclusive scan over the rows (thread r = row r) -> back into the spare bytes
+    // ---- 4. exclusive scan over the item slots (thread t: slots 2t, 2t+1), in place
     {
-        const uint32_t row_bits = *reinterpret_cast<const uint32_t *>(tile + tid * kTileStride + kFusedRowMeta);
-        const unsigned long long row_lit = *reinterpret_cast<const unsigned long long *>(tile + tid * kTileStride + kFusedRowMeta + 8);
-        unsigned long long inc0 = row_bits, inc1 = row_lit;
+        const uint32_t i0 = 2u * tid, i1 = 2u * tid + 1u;
+        const uint32_t b0 = i0 < n_items ? s_ibits[i0] : 0u, b1 = i1 < n_items ? s_ibits[i1] : 0u;
+        const unsigned long long l0 = i0 < n_items ? s_ilit[i0] : 0ull, l1 = i1 < n_items ? s_ilit[i1] : 0ull;
+        unsigned long long inc0 = (unsigned long long)b0 + b1, inc1 = l0 + l1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned long long t0 = __shfl_up_sync(0xffffffffu, inc0, o), t1 = __shfl_up_sync(0xffffffffu, inc1, o);
@@ -408,18 +463,28 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
             s_scan[warp][1] = inc1;
         }
         __syncthreads();
-        unsigned long long b0 = 0, b1 = 0;
+        unsigned long long e0 = inc0 - b0 - b1, e1 = inc1 - l0 - l1;
         for (int wv = 0; wv < warp; wv++) {
-            b0 += s_scan[wv][0];
-            b1 += s_scan[wv][1];
+            e0 += s_scan[wv][0];
+            e1 += s_scan[wv][1];
         }
-        *reinterpret_cast<uint32_t *>(tile + tid * kTileStride + kFusedRowMeta) = (uint32_t)(b0 + inc0) - row_bits;
-        *reinterpret_cast<unsigned long long *>(tile + tid * kTileStride + kFusedRowMeta + 8) = b1 + inc1 - row_lit;
+        if (i0 < n_items) {
+            s_ibits[i0] = (uint32_t)e0;
+            s_ilit[i0] = e1;
+        }
+        if (i1 < n_items) {
+            s_ibits[i1] = (uint32_t)e0 + b0;
+            s_ilit[i1] = e1 + l0;
+        }
         if (tid == kTile - 1) {
-            s_total_common = (uint32_t)(b0 + inc0);
-            s_total_lit = b1 + inc1;
+            s_total_common = (uint32_t)e0 + b0 + b1;
+            s_total_lit = e1 + l0 + l1;
         }
     }
+    __syncthreads();
+    // the items' stream positions move into registers: the staging area is about to be reused
+    const uint32_t pos_a = s_ibits[slot_a], pos_b = s_ibits[slot_b];
+    const unsigned long long lit_a = s_ilit[slot_a], lit_b = s_ilit[slot_b];
 
     // ---- 5. Adler-32 per plane: s1 = 1 + sum cnt[id] val[id], s2 = N + sum w[id] val[id]  (mod 65521)
     for (int k = warp; k < nsel; k += kTile / 32) {
@@ -485,8 +550,6 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     __syncthreads();
 
     // ---- 7. rounds of planes: zero the staging area, second parse writes the streams, copy out
-    const uint32_t row_pos = *reinterpret_cast<const uint32_t *>(tile + prow * kTileStride + kFusedRowMeta);
-    const unsigned long long lit_before = *reinterpret_cast<const unsigned long long *>(tile + prow * kTileStride + kFusedRowMeta + 8);
     const int nrounds = s_nrounds;
     int lo = 0;
     for (int rd = 0; rd < nrounds; rd++) {
@@ -513,11 +576,21 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                 while (b < hi && !s_stored[b])
                     b++;
                 if (a < b) {
-                    unsigned long long lw = lit_before;
-                    if (clsbits == 0ull)
-                        fused_parse_row<true, MAXP, true>(tile, prow, pm, s_val, p.lit9, clsbits, lw, row_pos, out, s_obase, a, b);
-                    else
-                        fused_parse_row<true, MAXP, false>(tile, prow, pm, s_val, p.lit9, clsbits, lw, row_pos, out, s_obase, a, b);
+#pragma unroll 1
+                    for (int q = 0; q < 2; q++) {
+                        const uint32_t item = q ? item1 : item0;
+                        if (item == 0xFFFFu)
+                            break;
+                        const int r = item & 255u, piece = item >> 8;
+                        const int xa = piece == 4 ? 0 : 64 * piece, xb = piece == 4 ? kTile : xa + 64;
+                        const RowMasks pm = s_masks[r];
+                        unsigned long long lw = q ? lit_b : lit_a;
+                        const uint32_t pw = q ? pos_b : pos_a;
+                        if (clsbits == 0ull)
+                            fused_parse_row<true, MAXP, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, pw, out, s_obase, a, b, xa, xb);
+                        else
+                            fused_parse_row<true, MAXP, false>(tile, r, pm, s_val, p.lit9, clsbits, lw, pw, out, s_obase, a, b, xa, xb);
+                    }
                 }
                 a = b;
             }
