@@ -90,6 +90,21 @@ int gh_tiff_geotransform(const gh_tiff *t, double gt[6]);
 /* Reads a pixel window into dst (row pitch in bytes); threads > 1 decodes tiles in parallel. */
 int gh_tiff_read_window(gh_tiff *t, int xoff, int yoff, int xcount, int ycount, uint8_t *dst, size_t pitch,
                         int threads, char *err, size_t errlen);
+/* The compressed tiles of a pixel window, as they lie in the file, for gcn10_cuda_block_tiles_deflate (GPU-side
+ * inflate).  gh_tiff_window_tiles_plan returns 0 and fills the plan when the dataset can be handed over that
+ * way (tiled, DEFLATE, no predictor), 1 when it cannot (the caller then decodes on the host with
+ * gh_tiff_read_window).  gh_tiff_window_tiles_read copies the tiles' bytes into blob (plan->blob_bytes, tiles
+ * adjacent in the file are read with one pread) and fills offsets / sizes [tiles_y * tiles_x] (size 0 = sparse). */
+typedef struct {
+    int tile_w, tile_h;
+    int tx0, ty0;               /* first tile column / row of the dataset that the window touches */
+    int tiles_x, tiles_y;       /* tile grid covering the window */
+    int x_in, y_in;             /* window pixel (0,0) inside that grid */
+    size_t blob_bytes;
+} gh_tile_plan;
+int gh_tiff_window_tiles_plan(const gh_tiff *t, int xoff, int yoff, int xcount, int ycount, gh_tile_plan *plan);
+int gh_tiff_window_tiles_read(gh_tiff *t, const gh_tile_plan *plan, uint8_t *blob, uint64_t *offsets, uint32_t *sizes,
+                              int threads, char *err, size_t errlen);
 void gh_tiff_close(gh_tiff *t);
 
 /* What save_raster() produces (raster.c:204-219): 1 band Byte, TILED=YES (256x256),

@@ -58,6 +58,12 @@ typedef struct worker {
     size_t pitch_cap;
     int have_planes;
     band_buf bands[2];
+    /* compressed land-cover tiles of a block (GPU-inflate path) */
+    uint8_t *tile_blob;             /* pinned */
+    size_t tile_blob_cap;
+    uint64_t *tile_off;
+    uint32_t *tile_size;
+    size_t tile_cap;
     /* encoder hand-off */
     pthread_mutex_t mu;
     pthread_cond_t cv;
@@ -188,20 +194,33 @@ static void *reader_main(void *arg)
     return NULL;
 }
 
+typedef struct {
+    worker *wk;
+    const gcn10_tile_strip *st;
+} sink_job;
+
+/* one plane of a strip: append its tile rows to that plane's GeoTIFF */
+static void sink_plane(void *arg, int k)
+{
+    sink_job *j = arg;
+    const gcn10_tile_strip *st = j->st;
+    gh_tiffw *tw = j->wk->writers[st->plane_ids[k]];
+    for (int tr = 0; tr < st->n_tile_rows; tr++) {
+        size_t base = ((size_t)k * st->n_tile_rows + tr) * (size_t)st->tiles_x;
+        if (gh_tiffw_put_tile_row(tw, st->tile_row0 + tr, st->blob, st->offsets + base, st->sizes + base)) {
+            j->wk->encode_failed = 1;
+            return;
+        }
+    }
+}
+
+/* the 18 files are independent: their appends run on the I/O threads while the GPU works on the next strips */
 static int tile_sink(void *user, const gcn10_tile_strip *st)
 {
     worker *wk = user;
-    for (int k = 0; k < st->n_planes; k++) {
-        gh_tiffw *tw = wk->writers[st->plane_ids[k]];
-        for (int tr = 0; tr < st->n_tile_rows; tr++) {
-            size_t base = ((size_t)k * st->n_tile_rows + tr) * (size_t)st->tiles_x;
-            if (gh_tiffw_put_tile_row(tw, st->tile_row0 + tr, st->blob, st->offsets + base, st->sizes + base)) {
-                wk->encode_failed = 1;
-                return 1;
-            }
-        }
-    }
-    return 0;
+    sink_job j = { wk, st };
+    gh_parallel_for(st->n_planes, wk->opt->io_threads > 0 ? wk->opt->io_threads : 1, sink_plane, &j);
+    return wk->encode_failed ? 1 : 0;
 }
 
 /* returns 0 ok, 1 = land-cover read failed (recoverable tier) */
@@ -251,6 +270,67 @@ static int bands_gpu_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const gh
     pthread_join(rd, NULL);
     *t_read += rj.t_read;
     return failed;
+}
+
+/* ---- GPU-inflate path: the land-cover window goes to the device as the DEFLATE tiles of the file
+ * (gcn10_cuda_block_tiles_deflate): no decode on the host at all.  Returns 0 ok, 1 = land-cover read or tile
+ * decode failed (recoverable tier, raster.c:182-186) */
+static int block_gpu_tiles(worker *wk, int block_id, gh_tiff *esa_ds, const gh_window *we, const gh_tile_plan *plan,
+                           const uint8_t *hsg, const gh_window *wh, double *t_read, double *t_gpu)
+{
+    char msg[1024], err[GH_ERRLEN] = "";
+    const size_t ntiles = (size_t)plan->tiles_x * (size_t)plan->tiles_y;
+    if (wk->tile_blob_cap < plan->blob_bytes + 16) {
+        gcn10_cuda_host_free(wk->tile_blob);
+        wk->tile_blob_cap = plan->blob_bytes + plan->blob_bytes / 4 + (1u << 20);
+        wk->tile_blob = gcn10_cuda_host_alloc(wk->tile_blob_cap);
+        if (!wk->tile_blob) {
+            wk->tile_blob_cap = 0;
+            snprintf(msg, sizeof msg, "pinned allocation failed for block %d: %s", block_id, gcn10_cuda_last_error());
+            fatal(wk, msg);
+        }
+    }
+    if (wk->tile_cap < ntiles) {
+        free(wk->tile_off);
+        free(wk->tile_size);
+        wk->tile_off = malloc(ntiles * sizeof *wk->tile_off);
+        wk->tile_size = malloc(ntiles * sizeof *wk->tile_size);
+        if (!wk->tile_off || !wk->tile_size)
+            fatal(wk, "out of memory for raster");
+        wk->tile_cap = ntiles;
+    }
+    double t0 = now_s();
+    if (gh_tiff_window_tiles_read(esa_ds, plan, wk->tile_blob, wk->tile_off, wk->tile_size, wk->opt->io_threads, err,
+                                  sizeof err)) {
+        gh_log_message(wk->log, "ERROR", err, 1);
+        return 1;
+    }
+    double t1 = now_s();
+    *t_read += t1 - t0;
+    gcn10_tile_source src;
+    src.tile_w = plan->tile_w;
+    src.tile_h = plan->tile_h;
+    src.tiles_x = plan->tiles_x;
+    src.tiles_y = plan->tiles_y;
+    src.x_off = plan->x_in;
+    src.y_off = plan->y_in;
+    src.blob = wk->tile_blob;
+    src.blob_bytes = plan->blob_bytes;
+    src.offsets = wk->tile_off;
+    src.sizes = wk->tile_size;
+    int rc = gcn10_cuda_block_tiles_deflate(wk->ctx, &src, we->xcount, we->ycount, we->gt, hsg, wh->xcount, wh->ycount,
+                                            (size_t)wh->xcount, wh->gt, GCN10_MASK_ALL, tile_sink, wk);
+    *t_gpu += now_s() - t1;
+    if (rc == GCN10_EDATA) {
+        snprintf(msg, sizeof msg, "gdalrasterio error 3 (%s)", gcn10_cuda_last_error());
+        gh_log_message(wk->log, "ERROR", msg, 1);
+        return 1;
+    }
+    if (rc && !wk->encode_failed) {
+        snprintf(msg, sizeof msg, "cuda failure on block %d: %s", block_id, gcn10_cuda_last_error());
+        fatal(wk, msg);
+    }
+    return 0;
 }
 
 /* ---- host-deflate path: raw planes back, zlib thread pool encodes band i while band i+1 is computed ---- */
@@ -362,7 +442,14 @@ static int gh_process_block(worker *wk, int block_id, int total_blocks)
     const size_t pitch = ((size_t)w + 255) / 256 * 256;
     const char *hd = getenv("GCN10_HOST_DEFLATE");
     const int host_deflate = hd && *hd && *hd != '0';
-    if (ensure_bands(wk, pitch, host_deflate)) {
+    const char *hi = getenv("GCN10_HOST_INFLATE");
+    const int host_inflate = hi && *hi && *hi != '0';
+    /* a tiled DEFLATE land-cover file (what GDAL writes for COMPRESS=DEFLATE TILED=YES, and what the ESA WorldCover
+     * files are) is handed to the GPU compressed; anything else is decoded here, band by band */
+    gh_tile_plan plan;
+    const int gpu_inflate = !host_deflate && !host_inflate &&
+                            gh_tiff_window_tiles_plan(esa_ds, we.xoff, we.yoff, w, h, &plan) == 0;
+    if (!gpu_inflate && ensure_bands(wk, pitch, host_deflate)) {
         snprintf(msg, sizeof msg, "pinned allocation failed for block %d: %s", block_id, gcn10_cuda_last_error());
         fatal(wk, msg);
     }
@@ -399,8 +486,9 @@ static int gh_process_block(worker *wk, int block_id, int total_blocks)
     /* band loop */
     wk->encode_failed = 0;
     double t_read = 0, t_gpu = 0;
-    int failed = host_deflate ? bands_host_deflate(wk, block_id, esa_ds, &we, hsg, &wh, pitch, &t_read, &t_gpu)
-                              : bands_gpu_deflate(wk, block_id, esa_ds, &we, hsg, &wh, pitch, &t_read, &t_gpu);
+    int failed = gpu_inflate ? block_gpu_tiles(wk, block_id, esa_ds, &we, &plan, hsg, &wh, &t_read, &t_gpu)
+                 : host_deflate ? bands_host_deflate(wk, block_id, esa_ds, &we, hsg, &wh, pitch, &t_read, &t_gpu)
+                                : bands_gpu_deflate(wk, block_id, esa_ds, &we, hsg, &wh, pitch, &t_read, &t_gpu);
     free(hsg);
     gh_tiff_close(esa_ds);
 
@@ -428,8 +516,9 @@ static int gh_process_block(worker *wk, int block_id, int total_blocks)
     }
     double dt = now_s() - t_start;
     snprintf(msg, sizeof msg,
-             "block %d: %d x %d px, 18 rasters in %.2f s (%.1f Mpx/s; decode %.2f s, gpu+copies %.2f s; %s deflate)",
-             block_id, w, h, dt, (double)w * h / dt / 1e6, t_read, t_gpu, host_deflate ? "host" : "gpu");
+             "block %d: %d x %d px, 18 rasters in %.2f s (%.1f Mpx/s; decode %.2f s, gpu+copies %.2f s; %s deflate)%s",
+             block_id, w, h, dt, (double)w * h / dt / 1e6, t_read, t_gpu, host_deflate ? "host" : "gpu",
+             gpu_inflate ? " [land cover inflated on the gpu]" : "");
     gh_log_message(wk->log, "INFO", msg, 0);
     return ok ? 0 : -1;
 
@@ -475,6 +564,9 @@ static void *worker_main(void *arg)
         for (int k = 0; k < NPLANES; k++)
             gcn10_cuda_host_free(wk->bands[b].planes[k]);
     }
+    gcn10_cuda_host_free(wk->tile_blob);
+    free(wk->tile_off);
+    free(wk->tile_size);
     gcn10_cuda_destroy(wk->ctx);
     pthread_cond_destroy(&wk->cv);
     pthread_mutex_destroy(&wk->mu);

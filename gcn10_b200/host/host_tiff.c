@@ -82,6 +82,11 @@ static void parallel_for(int n, int threads, job_fn fn, void *arg)
     free(th);
 }
 
+void gh_parallel_for(int n, int threads, void (*fn)(void *arg, int index), void *arg)
+{
+    parallel_for(n, threads, fn, arg);
+}
+
 /* ------------------------------------------------------------------------------------- reader */
 
 struct gh_tiff {
@@ -489,6 +494,83 @@ int gh_tiff_read_window(gh_tiff *t, int xoff, int yoff, int xcount, int ycount, 
     return 0;
 }
 
+/* ---- compressed tiles of a window, untouched (the GPU inflates them) */
+
+int gh_tiff_window_tiles_plan(const gh_tiff *t, int xoff, int yoff, int xcount, int ycount, gh_tile_plan *plan)
+{
+    if (!t->tiled || (t->compression != 8 && t->compression != 32946) || t->predictor != 1)
+        return 1;
+    if (xoff < 0 || yoff < 0 || xcount <= 0 || ycount <= 0 || xoff + xcount > t->w || yoff + ycount > t->h)
+        return 1;
+    plan->tile_w = t->tw;
+    plan->tile_h = t->th;
+    plan->tx0 = xoff / t->tw;
+    plan->ty0 = yoff / t->th;
+    plan->tiles_x = (xoff + xcount - 1) / t->tw - plan->tx0 + 1;
+    plan->tiles_y = (yoff + ycount - 1) / t->th - plan->ty0 + 1;
+    plan->x_in = xoff - plan->tx0 * t->tw;
+    plan->y_in = yoff - plan->ty0 * t->th;
+    size_t total = 0;
+    for (int ty = 0; ty < plan->tiles_y; ty++)
+        for (int tx = 0; tx < plan->tiles_x; tx++) {
+            uint64_t n = t->counts[(uint64_t)(plan->ty0 + ty) * (uint64_t)t->tiles_x + (uint64_t)(plan->tx0 + tx)];
+            if (n > 0xFFFFFFFFull)
+                return 1;
+            total += (size_t)n;
+        }
+    plan->blob_bytes = total;
+    return 0;
+}
+
+typedef struct {
+    gh_tiff *t;
+    const gh_tile_plan *plan;
+    uint8_t *blob;
+    const uint64_t *offsets;
+    int failed;
+} tiles_job;
+
+/* one job = one tile row of the window: runs of tiles that are adjacent in the file become one pread */
+static void read_tile_row(void *arg, int ty)
+{
+    tiles_job *j = arg;
+    const gh_tile_plan *p = j->plan;
+    const gh_tiff *t = j->t;
+    int tx = 0;
+    while (tx < p->tiles_x) {
+        uint64_t ci = (uint64_t)(p->ty0 + ty) * (uint64_t)t->tiles_x + (uint64_t)(p->tx0 + tx);
+        uint64_t start = t->offsets[ci], len = t->counts[ci];
+        int run = 1;
+        while (tx + run < p->tiles_x && t->counts[ci + run] > 0 && t->offsets[ci + run] == start + len) {
+            len += t->counts[ci + run];
+            run++;
+        }
+        if (len && pread_all(t->fd, j->blob + j->offsets[(size_t)ty * p->tiles_x + tx], (size_t)len, start))
+            j->failed = 1;
+        tx += run;
+    }
+}
+
+int gh_tiff_window_tiles_read(gh_tiff *t, const gh_tile_plan *plan, uint8_t *blob, uint64_t *offsets, uint32_t *sizes,
+                              int threads, char *err, size_t errlen)
+{
+    uint64_t pos = 0;
+    for (int ty = 0; ty < plan->tiles_y; ty++)
+        for (int tx = 0; tx < plan->tiles_x; tx++) {
+            uint64_t n = t->counts[(uint64_t)(plan->ty0 + ty) * (uint64_t)t->tiles_x + (uint64_t)(plan->tx0 + tx)];
+            offsets[(size_t)ty * plan->tiles_x + tx] = pos;
+            sizes[(size_t)ty * plan->tiles_x + tx] = (uint32_t)n;
+            pos += n;
+        }
+    tiles_job j = { t, plan, blob, offsets, 0 };
+    parallel_for(plan->tiles_y, threads, read_tile_row, &j);
+    if (j.failed) {
+        set_err(err, errlen, "gdalrasterio error 3 (tile read failed)");
+        return -1;
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------- writer */
 
 enum { TILE = 256 };
@@ -551,6 +633,8 @@ int gh_tiffw_open(const char *path, int w, int h, const double gt[6], gh_tiffw *
     if (!tw)
         return -1;
     tw->fp = fopen(path, "wb");
+    if (tw->fp)
+        setvbuf(tw->fp, NULL, _IOFBF, 1 << 20);     /* tiles arrive as ~1.5 KB pieces: one write(2) per MB, not per tile */
     if (!tw->fp) {
         set_err(err, errlen, "write error 3 on %s (%s)", path, strerror(errno));     /* raster.c:221 */
         free(tw);

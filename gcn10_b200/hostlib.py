@@ -64,6 +64,8 @@ def load() -> C.CDLL:
                                       C.c_char_p, C.c_size_t]
     L.gh_tiff_close.argtypes = [_vp]
     L.gh_tiff_close.restype = None
+    L.gh_tiff_window_tiles_plan.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
+    L.gh_tiff_window_tiles_read.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_char_p, C.c_size_t]
     L.gh_tiff_write.argtypes = [C.c_char_p, _vp, C.c_int, C.c_int, C.c_size_t, _dp, C.c_int, C.c_char_p, C.c_size_t]
     L.gh_tiffw_open.argtypes = [C.c_char_p, C.c_int, C.c_int, _dp, C.POINTER(_vp), C.c_char_p, C.c_size_t]
     L.gh_tiffw_put_tile_row.argtypes = [_vp, C.c_int, _vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
@@ -193,10 +195,37 @@ class Tiff:
             raise HostError(rc, e.value.decode())
         return out
 
+    def window_tiles(self, xoff=0, yoff=0, xcount=None, ycount=None, threads=4):
+        """The compressed tiles of a window as they lie in the file (gh_tiff_window_tiles_plan / _read), or None when
+        the dataset cannot be handed to the GPU inflater (not tiled, not DEFLATE, predictor 2).
+        Returns dict(tile_w, tile_h, tiles_x, tiles_y, x_in, y_in, blob, offsets, sizes)."""
+        xcount = self.width - xoff if xcount is None else xcount
+        ycount = self.height - yoff if ycount is None else ycount
+        plan = TilePlan()
+        if self.L.gh_tiff_window_tiles_plan(self.h, xoff, yoff, xcount, ycount, C.byref(plan)) != 0:
+            return None
+        n = plan.tiles_x * plan.tiles_y
+        blob = np.zeros(max(plan.blob_bytes, 1), dtype=np.uint8)
+        offsets = np.zeros(n, dtype=np.uint64)
+        sizes = np.zeros(n, dtype=np.uint32)
+        e = _err()
+        rc = self.L.gh_tiff_window_tiles_read(self.h, C.byref(plan), blob.ctypes.data, offsets.ctypes.data,
+                                              sizes.ctypes.data, threads, e, ERRLEN)
+        if rc:
+            raise HostError(rc, e.value.decode())
+        return dict(tile_w=plan.tile_w, tile_h=plan.tile_h, tiles_x=plan.tiles_x, tiles_y=plan.tiles_y, x_in=plan.x_in,
+                    y_in=plan.y_in, blob=blob[:plan.blob_bytes], offsets=offsets, sizes=sizes)
+
     def close(self):
         if self.h:
             self.L.gh_tiff_close(self.h)
             self.h = None
+
+
+class TilePlan(C.Structure):
+    """gh_tile_plan of gcn10_host.h."""
+    _fields_ = [("tile_w", C.c_int), ("tile_h", C.c_int), ("tx0", C.c_int), ("ty0", C.c_int), ("tiles_x", C.c_int),
+                ("tiles_y", C.c_int), ("x_in", C.c_int), ("y_in", C.c_int), ("blob_bytes", C.c_size_t)]
 
 
 class TiffWriter:

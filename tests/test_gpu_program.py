@@ -42,23 +42,27 @@ def world(tmp_path_factory):
     return dict(root=root, esa=esa, esa_t=esa_t, hsg=hsg, hsg_t=hsg_t, blocks=blocks)
 
 
-def _run(world, *extra, host_deflate=False):
+def _run(world, *extra, host_deflate=False, host_inflate=False):
     exe = hostlib.EXE_PATH
     assert os.path.exists(exe), "gcn10 executable not built (make host)"
     root = world["root"]
-    env = dict(os.environ, GCN10_HOST_DEFLATE="1" if host_deflate else "0")
+    env = dict(os.environ, GCN10_HOST_DEFLATE="1" if host_deflate else "0",
+               GCN10_HOST_INFLATE="1" if host_inflate else "0")
     return subprocess.run([exe, "-c", str(root / "config.txt"), "-l", str(root / "blocks.txt"), "--gpus", "1",
                            "--io-threads", "4", *extra], cwd=str(root), capture_output=True, text=True, timeout=300,
                           env=env)
 
 
-@pytest.mark.parametrize("host_deflate", [False, True], ids=["gpu_deflate", "host_deflate"])
-def test_program_matches_reference_process_block(world, ref, host_deflate):
+@pytest.mark.parametrize("host_deflate,host_inflate", [(False, False), (False, True), (True, True)],
+                         ids=["gpu_inflate_gpu_deflate", "host_inflate_gpu_deflate", "host_inflate_host_deflate"])
+def test_program_matches_reference_process_block(world, ref, host_deflate, host_inflate):
     from PIL import Image
     import shutil
     shutil.rmtree(world["root"] / "logs", ignore_errors=True)      # log files are opened for append (log.c:79)
-    r = _run(world, "-o", host_deflate=host_deflate)
+    r = _run(world, "-o", host_deflate=host_deflate, host_inflate=host_inflate)
     assert r.returncode == 0, r.stderr
+    log_all = (world["root"] / "logs" / "rank_0.log").read_text()
+    assert ("land cover inflated on the gpu" in log_all) == (not host_deflate and not host_inflate)
     root = world["root"]
     for bid, x0, y0, x1, y1 in world["blocks"][:2]:
         want = ref.run_block(world["esa"], world["esa_t"], world["hsg"], world["hsg_t"], (x0, y0, x1, y1),
@@ -84,6 +88,31 @@ def test_program_matches_reference_process_block(world, ref, host_deflate):
                 assert f"completed condition for 11: {c}/{h}/{a}" in log                # cn.c:366-369
     assert len(re.findall(r"progress: completed block 12 / total 4", log)) == 18        # log.c:199-207, 18 per block
     assert "processing block 11" in log and "processed 4 blocks on 1 ranks" in log      # main.c:172,191
+
+
+def test_damaged_land_cover_tile_skips_the_block(world, tmp_path):
+    """A land-cover tile that is not a valid zlib stream: the GPU inflater reports it, the block is skipped with
+    the reference's recoverable-error messages (raster.c:182-186 -> cn.c:188-192), the other block is written."""
+    import shutil
+    root = world["root"]
+    data = bytearray((root / "esa.tif").read_bytes())
+    t = hostlib.Tiff(str(root / "esa.tif"))
+    tl = t.window_tiles(0, 0, 256, 256)             # first tile of the file = inside block 11 only
+    t.close()
+    first = bytes(tl["blob"][:int(tl["sizes"][0])].tobytes())
+    at = bytes(data).find(first)
+    assert at > 0
+    data[at + 2:at + 40] = b"\xff" * 38
+    shutil.copy(str(root / "esa.tif"), str(tmp_path / "esa_good.tif"))
+    try:
+        (root / "esa.tif").write_bytes(bytes(data))
+        r = _run(world, "-o")
+    finally:
+        shutil.copy(str(tmp_path / "esa_good.tif"), str(root / "esa.tif"))
+    assert r.returncode == 0, r.stderr
+    assert "gdalrasterio error 3" in r.stderr and "esa load failed for block 11" in r.stderr
+    assert "esa load failed for block 12" not in r.stderr
+    _run(world, "-o")                               # leave intact outputs behind for the following tests
 
 
 def test_no_overwrite_appends_underscore(world):

@@ -212,3 +212,38 @@ def test_geotiff_writer_rejects_out_of_order_and_incomplete(tmp_path):
     tw = hostlib.TiffWriter(str(tmp_path / "b.tif"), 256, 512, (0, 1, 0, 0, 0, -1))
     assert tw.put_tile_row(0, [z]) == 0
     assert tw.close() != 0                                      # second tile row missing
+
+
+def test_window_tiles_are_the_files_zlib_streams(tmp_path):
+    """gh_tiff_window_tiles_plan / _read (the GPU-inflate input path): the tiles of a window come back as the
+    zlib streams the file holds, in window order, with the window's position inside the tile grid; inflating
+    them with zlib reproduces the raster.  Datasets that are not tiled DEFLATE without predictor are refused."""
+    import zlib
+    from gcn10_b200 import synth
+    w, h = 1100, 700
+    esa = synth.esa_tile(w, h, 5, patch=40)
+    path = str(tmp_path / "lc.tif")
+    hostlib.tiff_write(path, esa, (-114.0, 1 / 12000, 0, 42.0, 0, -1 / 12000))
+    t = hostlib.Tiff(path)
+    for (xo, yo, xc, yc) in [(0, 0, w, h), (300, 257, 500, 300), (1099, 699, 1, 1), (255, 0, 2, 700)]:
+        tl = t.window_tiles(xo, yo, xc, yc, threads=3)
+        assert tl is not None and (tl["tile_w"], tl["tile_h"]) == (256, 256)
+        assert tl["x_in"] == xo % 256 and tl["y_in"] == yo % 256
+        grid = np.zeros((tl["tiles_y"] * 256, tl["tiles_x"] * 256), dtype=np.uint8)
+        for i in range(tl["tiles_y"] * tl["tiles_x"]):
+            o, n = int(tl["offsets"][i]), int(tl["sizes"][i])
+            raw = zlib.decompress(tl["blob"][o:o + n].tobytes())
+            r, c = divmod(i, tl["tiles_x"])
+            grid[r * 256:(r + 1) * 256, c * 256:(c + 1) * 256] = np.frombuffer(raw, dtype=np.uint8).reshape(256, 256)
+        got = grid[tl["y_in"]:tl["y_in"] + yc, tl["x_in"]:tl["x_in"] + xc]
+        assert np.array_equal(got, esa[yo:yo + yc, xo:xo + xc])
+    assert t.window_tiles(0, 0, w + 1, h) is None              # outside the raster
+    t.close()
+    # a stripped, uncompressed TIFF (Pillow's default) cannot be handed over compressed
+    from PIL import Image
+    p2 = str(tmp_path / "plain.tif")
+    Image.fromarray(esa[:64, :64]).save(p2)
+    t2 = hostlib.Tiff(p2)
+    assert t2.window_tiles() is None
+    assert np.array_equal(t2.read(), esa[:64, :64])
+    t2.close()

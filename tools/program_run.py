@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--io-threads", type=int, default=0)
     ap.add_argument("--keep", action="store_true")
     ap.add_argument("--host-deflate", action="store_true", help="raw planes over PCIe + zlib on the host")
+    ap.add_argument("--host-inflate", action="store_true", help="decode the land cover on the host (zlib threads)")
     a = ap.parse_args()
     px = 1.0 / 12000.0
     hpx = 1.0 / 480.0
@@ -33,7 +34,12 @@ def main():
     root = tempfile.mkdtemp(prefix="gcn10_world_")
     W, H = s * n, s                                     # blocks side by side in one row
     t0 = time.time()
-    esa = synth.esa_tile(W, H, 2234)
+    try:                                                # full-size tiles take minutes in numpy: use the GPU when there is one
+        import torch
+        esa = synth.esa_tile(W, H, 2234, device=torch.device("cuda:0")).cpu().numpy() if torch.cuda.is_available() \
+            else synth.esa_tile(W, H, 2234)
+    except ImportError:
+        esa = synth.esa_tile(W, H, 2234)
     hsg = synth.hsg_tile(W // 25 + 2, H // 25 + 2, 3234)
     hostlib.tiff_write(os.path.join(root, "esa.tif"), esa, (-114.0, px, 0, 42.0, 0, -px), threads=16)
     hostlib.tiff_write(os.path.join(root, "hsg.tif"), hsg, (-114.0, hpx, 0, 42.0, 0, -hpx))
@@ -51,7 +57,8 @@ def main():
     if a.io_threads:
         cmd += ["--io-threads", str(a.io_threads)]
     t0 = time.time()
-    env = dict(os.environ, GCN10_HOST_DEFLATE="1" if a.host_deflate else "0")
+    env = dict(os.environ, GCN10_HOST_DEFLATE="1" if a.host_deflate else "0",
+               GCN10_HOST_INFLATE="1" if a.host_inflate else "0")
     r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, env=env)
     dt = time.time() - t0
     print(f"gcn10 rc={r.returncode} wall {dt:.2f} s -> {n * s * s / dt / 1e6:.1f} Mpx/s end to end "
