@@ -87,6 +87,7 @@ struct gcn10_ctx {
     int use_tma = 1;
     int persistent = 0;         // 1 = persistent-CTA form of the streaming kernel (measured slower, see profiles/)
     int persistent_ctas[10][3] = {};         // resident CTAs per SM by [np][groups], from the occupancy API
+    int inflate_probe = 0;      // measurement aid for tools/inflate_bench.py (see InflateParams::probe)
     int fused = 1;              // compressed-tile calls use cn_deflate_fused_kernel (0 = CN kernel + tile encoder)
     DevBuf fused_tab;           // idmap [256][16] | val [256][32] | lit9 [256][6] u64
     unsigned fused_mask = 0;    // plane mask the tables were built for (0 = none)
@@ -675,6 +676,7 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
     else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
     else if (!strcmp(key, "persistent") && (value == 0 || value == 1)) c->persistent = (int)value;
     else if (!strcmp(key, "fused") && (value == 0 || value == 1)) c->fused = (int)value;
+    else if (!strcmp(key, "inflate_probe") && (value == 0 || value == 1)) c->inflate_probe = (int)value;
     else return fail(GCN10_EINVAL, "unknown option or bad value: %s=%ld", key, value);
     return GCN10_OK;
 }
@@ -1154,6 +1156,7 @@ static int inflate_to_device(gcn10_ctx *c, const gcn10_tile_source *src, int w, 
     ip.h = h;
     ip.status = d_status;
     ip.order = d_order;
+    ip.probe = c->inflate_probe;
     CUDA_TRY(cudaEventRecord(c->inf0, st));
     inflate_tiles_kernel<<<(unsigned)ntiles, kInflateThreads, kInflateSmem, st>>>(ip);
     c->launches++;

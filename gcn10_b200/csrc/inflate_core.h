@@ -453,8 +453,35 @@ GCN10_HD int decode_symbols(DecodeLane &s, const uint32_t *ring, const Tables &t
     }
     int n = 0;
     while (n < kQueue) {
-        need32(s, ring);
-        uint32_t e = t.ll_lut[(uint32_t)s.buf & ((1u << kLlBits) - 1u)];
+        need32(s, ring);                                    // 33..64 valid bits
+        const uint32_t lo = (uint32_t)s.buf;
+        uint32_t e = t.ll_lut[lo & ((1u << kLlBits) - 1u)];
+        // ---- fast paths: code words inside the lookup tables, all bits of the symbol inside the buffer.  One
+        // branch for a literal; a match is decoded from the low word with a single 64-bit shift at the end.
+        if ((e & 0x300u) == 0u) {                           // kLit
+            const int nb = (int)(e & 15u);
+            s.buf >>= nb;
+            s.cnt -= nb;
+            queue[n++] = e >> 16;
+            continue;
+        }
+        if ((e & 0x300u) == (uint32_t)(kLen << 8)) {
+            const uint32_t nb = e & 15u, eb = (e >> 4) & 15u;           // nb <= 10, eb <= 5
+            uint32_t w = lo >> nb;
+            const uint32_t len = (e >> 16) + (w & ~(~0u << eb));
+            w >>= eb;                                                    // >= 17 valid bits left in w
+            const uint32_t d = t.d_lut[w & ((1u << kDBits) - 1u)];
+            const uint32_t dn = d & 15u, deb = (d >> 4) & 15u;
+            const uint32_t used = nb + eb + dn, need = used + deb;      // <= 24, <= 37
+            if (dn != 0u && (int)need <= s.cnt) {
+                const uint32_t dist = (d >> 16) + ((uint32_t)(s.buf >> used) & ~(~0u << deb));
+                s.buf >>= need;
+                s.cnt -= (int)need;
+                queue[n++] = 0x80000000u | ((dist - 1u) << 16) | len;
+                continue;
+            }
+        }
+        // ---- general path: long code words (canonical walk), end of block, a symbol that straddles the refill
         if ((e & 15u) == 0u) {
             int used = 0;
             const int sym = slow_symbol(s.buf, t.sorted, t.ll_count, &used);

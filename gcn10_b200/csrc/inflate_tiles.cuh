@@ -39,6 +39,7 @@ struct InflateParams {
     int w, h;                           // window size: pixels outside are decoded but not stored
     int *status;                        // [tiles_y][tiles_x] 0 or an inflate::kErr* code
     const int *order;                   // launch order: CTA i takes tile order[i] (longest streams first), or NULL
+    int probe;                          // measurement aid: 1 = the writer warp drops the batches (decoder speed alone)
 };
 
 struct InflateSmem {
@@ -64,8 +65,14 @@ struct TileDst {
 
 enum { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4 };
 
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+// literal barrier numbers: with a register operand ptxas reserves all 16 named barriers for the CTA, which caps
+// the SM at four CTAs (64 barriers); five fit by shared memory
+template <int ID> __device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <int ID> __device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
+__device__ __forceinline__ void bar_sync_full(int b) { if (b) bar_sync_id<kBarFull1>(); else bar_sync_id<kBarFull0>(); }
+__device__ __forceinline__ void bar_arrive_full(int b) { if (b) bar_arrive_id<kBarFull1>(); else bar_arrive_id<kBarFull0>(); }
+__device__ __forceinline__ void bar_sync_empty(int b) { if (b) bar_sync_id<kBarEmpty1>(); else bar_sync_id<kBarEmpty0>(); }
+__device__ __forceinline__ void bar_arrive_empty(int b) { if (b) bar_arrive_id<kBarEmpty1>(); else bar_arrive_id<kBarEmpty0>(); }
 
 // history ring piece [p0, p0 + nbytes) -> plane (p0 is a multiple of 16); whole warp
 __device__ __forceinline__ void inflate_flush(const uint8_t *window, const TileDst &d, uint32_t p0, uint32_t nbytes,
@@ -257,7 +264,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                 }
             }
             else {
-                bar_sync(kBarEmpty0 + b);
+                bar_sync_empty(b);
                 acquired = true;
                 if (lane == 0)
                     n = decode_symbols(s, sm.ring, sm.t, sm.queue[b], &ev);
@@ -266,7 +273,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
             }
             if (post) {
                 if (!acquired)
-                    bar_sync(kBarEmpty0 + b);
+                    bar_sync_empty(b);
                 if (lane == 0) {
                     sm.meta[b][0] = n;
                     sm.meta[b][1] = ev;
@@ -276,7 +283,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                     sm.meta[b][5] = fin;
                 }
                 __syncwarp();
-                bar_arrive(kBarFull0 + b);
+                bar_arrive_full(b);
                 b ^= 1;
                 if (ev == kEvEnd || ev == kEvError || (ev == kEvStored && fin))
                     break;
@@ -287,19 +294,22 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
         // ------------------------------------------------------------------ writer warp
         uint8_t *window = sm.window;
         constexpr uint32_t M = kWindow - 1;
-        bar_arrive(kBarEmpty0);
-        bar_arrive(kBarEmpty1);
+        bar_arrive_empty(0);
+        bar_arrive_empty(1);
         uint32_t out_base = 0, flushed = 0;
         int werr = 0, b = 0;
         for (;;) {
-            bar_sync(kBarFull0 + b);
+            bar_sync_full(b);
             const int n = sm.meta[b][0], ev = sm.meta[b][1], derr = sm.meta[b][4], fin = sm.meta[b][5];
             const uint32_t so = (uint32_t)sm.meta[b][2], sl = (uint32_t)sm.meta[b][3];
             const uint32_t sym = lane < n ? sm.queue[b][lane] : 0u;
-            bar_arrive(kBarEmpty0 + b);
+            bar_arrive_empty(b);
             b ^= 1;
 
-            if (n > 0 && !werr) {
+            if (n > 0 && !werr && p.probe == 1) {
+                out_base = out_end;             // pretend the tile is complete; nothing is written
+            }
+            else if (n > 0 && !werr) {
                 const bool is_match = sym_is_match(sym) != 0u;
                 const uint32_t l = lane < n ? sym_len(sym) : 0u;
                 uint32_t inc = l;
