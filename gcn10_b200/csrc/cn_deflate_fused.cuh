@@ -46,6 +46,22 @@ constexpr int fused_smem_bytes()
     return kTile * kTileStride + kFusedOutCap + 64 + kFusedIds * (MAXP <= 9 ? 16 : 32) + kTile * 16;
 }
 
+// The Huffman code of the streams: the tuned code of tile_code.h (one dynamic block per tile, every literal
+// lit_bits long), or RFC 1951's fixed code when header_bits == 0.
+struct FusedCode {
+    int header_bits;                // bits in front of the first token: zlib header + block header
+    int lit_bits;
+    uint32_t lit_first;             // literal v has the code word lit_first + lit_rank[v] (MSB first)
+    uint16_t len_code[29];          // length symbols 257..285, bit-reversed
+    uint8_t len_bits[29];
+    uint16_t eob_code;
+    uint8_t eob_bits;
+    uint16_t dist_code[2];          // distance 1 / distance 256 (symbol 15, followed by 6 extra bits = 63)
+    uint8_t dist_bits[2];
+    const uint32_t *header_words;   // device: the header_bits bits, LSB first
+    const uint8_t *lit_rank;        // device [256]
+};
+
 struct FusedParams {
     const uint8_t *esa;             // device land cover, row 0 = block row y_base
     size_t esa_pitch;
@@ -58,7 +74,8 @@ struct FusedParams {
     const uint8_t *idmap;           // [16][256]: (soil class, land cover) -> record id
     const uint8_t *val;             // [256][16 or 32]: record id -> value in the j-th selected plane
     const unsigned long long *lit9; // [256]: 21-bit field c = 1 when the record needs a 9-bit literal in planes of class c
-    uint8_t cls[18];                // 9-bit-literal class of the j-th selected plane
+    uint8_t cls[18];                // 9-bit-literal class of the j-th selected plane (fixed code only)
+    FusedCode code;
     int nsel;                       // selected planes (1..18)
     int tiles_x, tile_rows;
     uint8_t *blob;
@@ -76,6 +93,33 @@ __device__ __forceinline__ uint32_t soil_class(uint32_t code)
     return d <= 3u ? 5u + d : 9u;
 }
 
+// all bits of a match token in the tuned code (<= 27 bits), LSB first
+__device__ __forceinline__ void tuned_match_code(const FusedCode &c, int len, bool above, uint32_t &bits, int &n)
+{
+    int idx, e = 0, extra = 0;
+    const int l = len - 3;                      // len <= 256 here (tokens stay inside a tile row)
+    if (l < 8)
+        idx = l;
+    else {
+        e = 29 - __clz(l);
+        idx = 4 + 4 * e + ((l - (4 << e)) >> e);
+        extra = (l - (4 << e)) & ((1 << e) - 1);
+    }
+    int nb = c.len_bits[idx];
+    uint32_t v = (uint32_t)c.len_code[idx] | ((uint32_t)extra << nb);
+    nb += e;
+    if (above) {
+        v |= ((uint32_t)c.dist_code[1] | (63u << c.dist_bits[1])) << nb;
+        nb += c.dist_bits[1] + 6;
+    }
+    else {
+        v |= (uint32_t)c.dist_code[0] << nb;
+        nb += c.dist_bits[0];
+    }
+    bits = v;
+    n = nb;
+}
+
 __device__ __forceinline__ uint32_t field21(unsigned long long c, uint32_t f) { return (uint32_t)(c >> (21u * f)) & 0x1FFFFFu; }
 
 // Greedy parse of pixels [xa, xb) of one row of the id tile (a whole row, or one 64-pixel item of a long row).
@@ -87,9 +131,12 @@ template <bool WRITE, int MAXP, bool ONE = false>
 __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, const RowMasks &m, const uint8_t *val,
                                                     const unsigned long long *lit9, unsigned long long clsbits,
                                                     unsigned long long &lit, uint32_t pos, uint32_t *out,
-                                                    const uint32_t *obase, int lo, int hi, int xa, int xb)
+                                                    const uint32_t *obase, int lo, int hi, int xa, int xb,
+                                                    const FusedCode &code, const uint8_t *rank)
 {
     constexpr int VALB = MAXP <= 9 ? 16 : 32;
+    const bool tuned = code.header_bits != 0;
+    const uint32_t hdr = tuned ? (uint32_t)code.header_bits : 19u;
     const uint8_t *row = tile + r * kTileStride;
     int x = xa;
     while (x < xb) {
@@ -102,10 +149,13 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
         if (len >= 3) {
             uint32_t bits;
             int n;
-            match_code(len, la >= lr, bits, n);
+            if (tuned)
+                tuned_match_code(code, len, la >= lr, bits, n);
+            else
+                match_code(len, la >= lr, bits, n);
             if (WRITE && ONE) {
                 // every plane has the same 9-bit-literal pattern: one bit position for all streams
-                const uint32_t pp = 19u + pos + (uint32_t)lit;
+                const uint32_t pp = hdr + pos + (uint32_t)lit;
                 const uint32_t sh = pp & 31u, w0 = bits << sh, w1 = sh ? bits >> (32u - sh) : 0u;
                 const bool cross = sh + (uint32_t)n > 32u;
 #pragma unroll
@@ -118,7 +168,7 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
                     }
             }
             else if (WRITE) {
-                const uint32_t pc[3] = { 19u + pos + field21(lit, 0), 19u + pos + field21(lit, 1), 19u + pos + field21(lit, 2) };
+                const uint32_t pc[3] = { hdr + pos + field21(lit, 0), hdr + pos + field21(lit, 1), hdr + pos + field21(lit, 2) };
 #pragma unroll
                 for (int k = 0; k < MAXP; k++)
                     if (k >= lo && k < hi) {
@@ -139,14 +189,20 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
                     const uint4 v1 = *reinterpret_cast<const uint4 *>(val + VALB * id + 16);
                     vw[4] = v1.x; vw[5] = v1.y; vw[6] = v1.z; vw[7] = v1.w;
                 }
-                const uint32_t pc[3] = { 19u + pos + field21(lit, 0), 19u + pos + field21(lit, 1), 19u + pos + field21(lit, 2) };
+                const uint32_t pc[3] = { hdr + pos + field21(lit, 0), hdr + pos + field21(lit, 1), hdr + pos + field21(lit, 2) };
                 const uint32_t sh = pc[0] & 31u;
 #pragma unroll
                 for (int k = 0; k < MAXP; k++)
                     if (k >= lo && k < hi) {
                         uint32_t bits;
                         int n;
-                        lit_code((vw[k >> 2] >> (8 * (k & 3))) & 255u, bits, n);
+                        const uint32_t v = (vw[k >> 2] >> (8 * (k & 3))) & 255u;
+                        if (tuned) {
+                            n = code.lit_bits;
+                            bits = __brev(code.lit_first + rank[v]) >> (32 - n);
+                        }
+                        else
+                            lit_code(v, bits, n);
                         if (ONE) {
                             uint32_t *o = out + (obase[k] >> 2) + (pc[0] >> 5);
                             atomicOr(o, bits << sh);
@@ -160,7 +216,7 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
                     }
             }
             lit += __ldg(lit9 + id);
-            pos += 8;
+            pos += tuned ? (uint32_t)code.lit_bits : 8u;
             x += 1;
         }
     }
@@ -196,6 +252,8 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     __shared__ unsigned long long s_total_lit;
     __shared__ uint32_t s_hist[66];
     __shared__ uint8_t s_cls[18];
+    __shared__ uint8_t s_rank[256];                                     // literal value -> code word offset (tuned code)
+    const bool tuned = p.code.header_bits != 0;
     __shared__ uint32_t s_nitems;
     unsigned long long clsbits = 0;
 #pragma unroll
@@ -221,6 +279,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
             s_hist[tid] = 0;
         if (tid < 18)
             s_cls[tid] = p.cls[tid];
+        s_rank[tid] = tuned ? __ldg(p.code.lit_rank + tid) : (uint8_t)0;
     }
     __syncthreads();
 
@@ -433,7 +492,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         const RowMasks pm = s_masks[r];
         unsigned long long lit = 0;
         const uint32_t bits = fused_parse_row<false, MAXP>(tile, r, pm, s_val, p.lit9, clsbits, lit, 0u, nullptr, nullptr, 0,
-                                                           0, xa, xb);
+                                                           0, xa, xb, p.code, s_rank);
         const uint32_t slot = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta) + (piece & 3);
         s_ibits[slot] = bits;
         s_ilit[slot] = lit;
@@ -511,7 +570,8 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     if (tid == 0) {
         unsigned long long need = 0;
         for (int k = 0; k < nsel; k++) {
-            const uint32_t bits = 19u + s_total_common + field21(s_total_lit, s_cls[k]) + 7u;
+            const uint32_t bits = tuned ? (uint32_t)p.code.header_bits + s_total_common + p.code.eob_bits
+                                        : 19u + s_total_common + field21(s_total_lit, s_cls[k]) + 7u;
             const uint32_t deflate_end = (bits + 7u) >> 3;
             s_stored[k] = deflate_end + 4u > (uint32_t)kFusedOutCap - 64u;
             s_nbytes[k] = s_stored[k] ? (uint32_t)kStoredBytes : deflate_end + 4u;
@@ -587,21 +647,33 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                         unsigned long long lw = q ? lit_b : lit_a;
                         const uint32_t pw = q ? pos_b : pos_a;
                         if (clsbits == 0ull)
-                            fused_parse_row<true, MAXP, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, pw, out, s_obase, a, b, xa, xb);
+                            fused_parse_row<true, MAXP, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, pw, out, s_obase, a, b, xa, xb, p.code, s_rank);
                         else
-                            fused_parse_row<true, MAXP, false>(tile, r, pm, s_val, p.lit9, clsbits, lw, pw, out, s_obase, a, b, xa, xb);
+                            fused_parse_row<true, MAXP, false>(tile, r, pm, s_val, p.lit9, clsbits, lw, pw, out, s_obase, a, b, xa, xb, p.code, s_rank);
                     }
                 }
                 a = b;
             }
-            if (tid < hi - lo && !s_stored[lo + tid]) {
+            if (tuned) {
+                // zlib header + dynamic block header (the same words for every stream), then the end-of-block code
+                const int hw = (p.code.header_bits + 31) >> 5;
+                for (int i = tid; i < hw * (hi - lo); i += kTile) {
+                    const int k = lo + i / hw;
+                    if (!s_stored[k])
+                        atomicOr(out + (s_obase[k] >> 2) + i % hw, __ldg(p.code.header_words + i % hw));
+                }
+                if (tid < hi - lo && !s_stored[lo + tid])
+                    put_bits(out + (s_obase[lo + tid] >> 2), (uint32_t)p.code.header_bits + s_total_common, p.code.eob_code,
+                             p.code.eob_bits);
+            }
+            else if (tid < hi - lo && !s_stored[lo + tid]) {
                 const int k = lo + tid;
                 put_bits(out + (s_obase[k] >> 2), 0, 0x9C78u, 16);      // CMF = 0x78, FLG = 0x9C
                 put_bits(out + (s_obase[k] >> 2), 16, 0x3u, 3);         // BFINAL = 1, BTYPE = 01 (fixed Huffman)
             }
             __syncthreads();
             if (tid < hi - lo && !s_stored[lo + tid]) {
-                // end-of-block = seven zero bits (already there); Adler-32 big endian after the padding
+                // (fixed code: end-of-block = seven zero bits, already there); Adler-32 big endian after the padding
                 const int k = lo + tid;
                 uint8_t *ob = outb + s_obase[k] + s_nbytes[k] - 4;
                 const uint32_t ad = s_adler[k];

@@ -11,6 +11,7 @@
 #include "deflate_tiles.cuh"
 #include "inflate_tiles.cuh"
 #include "cn_deflate_fused.cuh"
+#include "tile_code.h"
 
 #include <algorithm>
 #include <cctype>
@@ -93,6 +94,8 @@ struct gcn10_ctx {
     unsigned fused_mask = 0;    // plane mask the tables were built for (0 = none)
     int fused_ok = 0;           // the mask's value records fit the id space
     uint8_t fused_cls[18] = {}; // 9-bit-literal class of the j-th selected plane
+    int tuned_code = 1;         // tile streams use the tuned Huffman code of tile_code.h (0 = RFC 1951 fixed code)
+    FusedCode fused_code = {};  // header_bits == 0: fixed code
     EncodeTiledFn encode_tiled = nullptr;
 
     bool have_lut = false;
@@ -446,7 +449,7 @@ int build_fused_tables(gcn10_ctx *c, unsigned plane_mask, cudaStream_t st)
         if (plane_mask & (1u << k))
             plane_ids[nsel++] = k;
     const int valb = nsel <= 9 ? 16 : 32;
-    std::vector<uint8_t> host(4096 + kFusedIds * 32 + kFusedIds * 8, 0);
+    std::vector<uint8_t> host(4096 + kFusedIds * 32 + kFusedIds * 8 + sizeof(TileCode::header_words) + 256, 0);
     uint8_t *idmap = host.data(), *val = host.data() + 4096;
     unsigned long long *lit9 = (unsigned long long *)(host.data() + 4096 + kFusedIds * 32);
     std::vector<std::vector<uint8_t>> records;
@@ -479,9 +482,18 @@ int build_fused_tables(gcn10_ctx *c, unsigned plane_mask, cudaStream_t st)
     }
     // planes whose records need 9-bit literals (values >= 144, in practice nodata 255) at the same ids share
     // one bit-position counter in the kernel; at most kFusedClasses distinct patterns are supported
+    // the tuned Huffman code: every byte value a plane can hold (table values, nodata, the zero padding)
+    bool present[256] = { false };
+    present[0] = true;
+    for (size_t id = 0; id < records.size(); id++)
+        for (int j = 0; j < nsel; j++)
+            present[records[id][j]] = true;
+    TileCode tc;
+    memset(&c->fused_code, 0, sizeof(c->fused_code));
+    const bool tuned = c->fused_ok && c->tuned_code && build_tile_code(present, tc);
     std::vector<std::vector<uint8_t>> patterns;
     memset(c->fused_cls, 0, sizeof(c->fused_cls));
-    for (int j = 0; j < nsel && c->fused_ok; j++) {
+    for (int j = 0; j < nsel && c->fused_ok && !tuned; j++) {
         std::vector<uint8_t> pat(records.size());
         for (size_t id = 0; id < records.size(); id++)
             pat[id] = records[id][j] >= 144;
@@ -501,13 +513,31 @@ int build_fused_tables(gcn10_ctx *c, unsigned plane_mask, cudaStream_t st)
         for (size_t id = 0; id < records.size(); id++) {
             for (int j = 0; j < nsel; j++)
                 val[id * valb + j] = records[id][j];
-            for (size_t q = 0; q < patterns.size(); q++)
+            for (size_t q = 0; q < patterns.size() && !tuned; q++)      // (all literals equally long in the tuned code)
                 if (patterns[q][id])
                     lit9[id] |= 1ull << (21 * q);
         }
         int rc = ensure(c->fused_tab, host.size());
         if (rc)
             return rc;
+        if (tuned) {
+            memset(c->fused_cls, 0, sizeof(c->fused_cls));
+            uint8_t *hw = host.data() + 4096 + kFusedIds * 32 + kFusedIds * 8;
+            memcpy(hw, tc.header_words, sizeof(tc.header_words));
+            memcpy(hw + sizeof(tc.header_words), tc.lit_rank, 256);
+            FusedCode &fc = c->fused_code;
+            fc.header_bits = tc.header_bits;
+            fc.lit_bits = tc.lit_bits;
+            fc.lit_first = tc.lit_first;
+            memcpy(fc.len_code, tc.len_code, sizeof(fc.len_code));
+            memcpy(fc.len_bits, tc.len_bits, sizeof(fc.len_bits));
+            fc.eob_code = tc.eob_code;
+            fc.eob_bits = tc.eob_bits;
+            memcpy(fc.dist_code, tc.dist_code, sizeof(fc.dist_code));
+            memcpy(fc.dist_bits, tc.dist_bits, sizeof(fc.dist_bits));
+            fc.header_words = (const uint32_t *)((const uint8_t *)c->fused_tab.p + 4096 + kFusedIds * 32 + kFusedIds * 8);
+            fc.lit_rank = (const uint8_t *)c->fused_tab.p + 4096 + kFusedIds * 32 + kFusedIds * 8 + sizeof(tc.header_words);
+        }
         CUDA_TRY(cudaMemcpyAsync(c->fused_tab.p, host.data(), host.size(), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
@@ -677,6 +707,10 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
     else if (!strcmp(key, "persistent") && (value == 0 || value == 1)) c->persistent = (int)value;
     else if (!strcmp(key, "fused") && (value == 0 || value == 1)) c->fused = (int)value;
     else if (!strcmp(key, "inflate_probe") && (value == 0 || value == 1)) c->inflate_probe = (int)value;
+    else if (!strcmp(key, "tuned_code") && (value == 0 || value == 1)) {
+        c->tuned_code = (int)value;
+        c->fused_mask = 0;
+    }
     else return fail(GCN10_EINVAL, "unknown option or bad value: %s=%ld", key, value);
     return GCN10_OK;
 }
@@ -988,6 +1022,7 @@ static int deflate_rows_impl(gcn10_ctx *c,
             fp.val = (const uint8_t *)c->fused_tab.p + 4096;
             fp.lit9 = (const unsigned long long *)((const uint8_t *)c->fused_tab.p + 4096 + kFusedIds * 32);
             memcpy(fp.cls, c->fused_cls, sizeof(fp.cls));
+            fp.code = c->fused_code;
             fp.nsel = nplanes;
             fp.tiles_x = tiles_x;
             fp.tile_rows = tile_rows;

@@ -1,0 +1,125 @@
+// tests/harness/tile_code_host.cpp -- TEST HARNESS, not product code.
+//
+// Compiles gcn10_b200/csrc/tile_code.h (the host-side design of the tuned Huffman code that the fused Curve
+// Number + DEFLATE kernel writes its tiles with) and a scalar reference encoder that applies the kernel's token
+// rules (per row: match at distance 256 = pixel above, match at distance 1 = run, literal) with that code.
+// tests/test_tile_code.py inflates the streams with zlib: the header must parse, the code must be complete, and
+// the bytes must come back.  Built by the test itself (g++ -shared); nothing under gcn10_b200/ links it.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../gcn10_b200/csrc/tile_code.h"
+
+using namespace gcn10;
+
+namespace {
+
+struct Out {
+    std::vector<uint8_t> bytes;
+    uint64_t pos = 0;
+    void put(uint32_t v, int n)
+    {
+        for (int i = 0; i < n; i++, pos++) {
+            if ((pos >> 3) >= bytes.size())
+                bytes.push_back(0);
+            if ((v >> i) & 1u)
+                bytes[pos >> 3] |= (uint8_t)(1u << (pos & 7));
+        }
+    }
+};
+
+void put_match(Out &o, const TileCode &tc, int len, bool above)
+{
+    int idx, e = 0, extra = 0;
+    if (len == 258)
+        idx = 28;
+    else {
+        const int l = len - 3;
+        if (l < 8)
+            idx = l;
+        else {
+            e = 29 - __builtin_clz((unsigned)l);
+            idx = 4 + 4 * e + ((l - (4 << e)) >> e);
+            extra = (l - (4 << e)) & ((1 << e) - 1);
+        }
+    }
+    o.put(tc.len_code[idx], tc.len_bits[idx]);
+    o.put((uint32_t)extra, e);
+    if (above) {
+        o.put(tc.dist_code[1], tc.dist_bits[1]);
+        o.put(63u, 6);                  // 193 + 63 = 256
+    }
+    else
+        o.put(tc.dist_code[0], tc.dist_bits[0]);
+}
+
+}  // namespace
+
+extern "C" int gcn10_test_tile_code(const uint8_t *present, int *lit_bits, int *header_bits, int *len284_bits, int *eob_bits)
+{
+    bool p[256];
+    for (int v = 0; v < 256; v++)
+        p[v] = present[v] != 0;
+    TileCode tc;
+    if (!build_tile_code(p, tc))
+        return 1;
+    *lit_bits = tc.lit_bits;
+    *header_bits = tc.header_bits;
+    *len284_bits = tc.len_bits[27];
+    *eob_bits = tc.eob_bits;
+    return 0;
+}
+
+// tile: 256 x 256 bytes whose values are all `present`; returns the stream length (0 = no code / overflow)
+extern "C" uint32_t gcn10_test_tile_encode(const uint8_t *present, const uint8_t *tile, uint8_t *out, uint32_t cap)
+{
+    bool p[256];
+    for (int v = 0; v < 256; v++)
+        p[v] = present[v] != 0;
+    TileCode tc;
+    if (!build_tile_code(p, tc))
+        return 0;
+    Out o;
+    for (int i = 0; i < tc.header_bits; i++)
+        o.put((tc.header_words[i >> 5] >> (i & 31)) & 1u, 1);
+    uint32_t s1 = 1, s2 = 0;
+    for (int r = 0; r < 256; r++) {
+        const uint8_t *row = tile + 256 * r;
+        int x = 0;
+        while (x < 256) {
+            int la = 0, lr = 0;
+            if (r > 0)
+                while (x + la < 256 && row[x + la] == row[x + la - 256])
+                    la++;
+            if (x > 0)
+                while (x + lr < 256 && row[x + lr] == row[x - 1])
+                    lr++;
+            const int len = la >= lr ? la : lr;
+            if (len >= 3) {
+                put_match(o, tc, len, la >= lr);
+                x += len;
+            }
+            else {
+                const uint32_t code = tc.lit_first + tc.lit_rank[row[x]];
+                o.put(tile_code_detail::reverse_bits(code, tc.lit_bits), tc.lit_bits);
+                x += 1;
+            }
+        }
+    }
+    o.put(tc.eob_code, tc.eob_bits);
+    for (int i = 0; i < 65536; i++) {
+        s1 = (s1 + tile[i]) % 65521u;
+        s2 = (s2 + s1) % 65521u;
+    }
+    std::vector<uint8_t> &b = o.bytes;
+    b.push_back((uint8_t)(s2 >> 8));
+    b.push_back((uint8_t)s2);
+    b.push_back((uint8_t)(s1 >> 8));
+    b.push_back((uint8_t)s1);
+    if (b.size() > cap)
+        return 0;
+    memcpy(out, b.data(), b.size());
+    return (uint32_t)b.size();
+}

@@ -14,13 +14,16 @@ pytestmark = pytest.mark.gpu
 T = 256
 
 
-@pytest.fixture(autouse=True, params=["fused", "two_kernel"])
+@pytest.fixture(autouse=True, params=["fused_tuned_code", "fused_fixed_code", "two_kernel"])
 def encoder_path(request, gpu_ctx):
-    """Every test runs through both compressed-tile paths: cn_deflate_fused_kernel (Curve Numbers and all
-    planes' zlib streams from one parse of the record-id tile) and cn_block_kernel + deflate_tiles_kernel."""
-    gpu_ctx.set_option("fused", 1 if request.param == "fused" else 0)
+    """Every test runs through the compressed-tile paths: cn_deflate_fused_kernel (Curve Numbers and all
+    planes' zlib streams from one parse of the record-id tile) with the tuned Huffman code of tile_code.h or
+    with RFC 1951's fixed code, and cn_block_kernel + deflate_tiles_kernel."""
+    gpu_ctx.set_option("fused", 0 if request.param == "two_kernel" else 1)
+    gpu_ctx.set_option("tuned_code", 1 if request.param == "fused_tuned_code" else 0)
     yield request.param
     gpu_ctx.set_option("fused", 1)
+    gpu_ctx.set_option("tuned_code", 1)
 
 
 

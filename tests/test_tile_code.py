@@ -1,0 +1,101 @@
+"""CPU checks of the tuned Huffman code of the GPU tile encoder (gcn10_b200/csrc/tile_code.h).
+
+save_raster() of the reference produces zlib streams (/root/reference/src/raster.c:204-219); whatever our encoder
+writes must be inflatable by zlib, which is strict about dynamic-block headers (complete literal/length code,
+valid code-length code).  tests/harness/tile_code_host.cpp builds the code for a set of byte values and encodes
+tiles with the kernel's token rules in scalar code; zlib must give the tile back.  The GPU kernel itself is
+checked in tests/test_gpu_deflate.py."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from gcn10_b200 import lookups, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "harness", "tile_code_host.cpp")
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("tile_code") / "libtile_code_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wall", "-o", out, SRC])
+    lib = ctypes.CDLL(out)
+    lib.gcn10_test_tile_code.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 4
+    lib.gcn10_test_tile_encode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+    lib.gcn10_test_tile_encode.restype = ctypes.c_uint32
+    return lib
+
+
+def _present(values):
+    p = np.zeros(256, dtype=np.uint8)
+    p[list(values)] = 1
+    return p
+
+
+def _encode(lib, present, tile):
+    out = np.zeros(200000, dtype=np.uint8)
+    n = lib.gcn10_test_tile_encode(present.ctypes.data, np.ascontiguousarray(tile).ctypes.data, out.ctypes.data, out.size)
+    assert n > 0
+    return out[:n].tobytes()
+
+
+def _cn_values():
+    """every byte the shipped lookup tables can put into a plane, plus nodata and the tile padding"""
+    import tempfile
+    from oracle import oracle as O
+    t = O.Port().load_tables(lookups.write_default_lookups(tempfile.mkdtemp()))
+    vals = {int(v) for v in np.unique(t) if 0 <= v < 255}
+    return sorted(vals | {0, 255})
+
+
+def test_code_for_the_shipped_tables(harness):
+    vals = _cn_values()
+    p = _present(vals)
+    lb, hb, l284, eob = (ctypes.c_int() for _ in range(4))
+    assert harness.gcn10_test_tile_code(p.ctypes.data, lb, hb, l284, eob) == 0
+    assert lb.value <= 7, "the few dozen Curve Number values fit 7-bit literals"
+    assert l284.value <= 4, "the repeated-row length bucket must be cheap"
+    assert hb.value < 19 + 8 * 100, "header under 100 bytes"
+
+
+@pytest.mark.parametrize("nvals", [1, 2, 3, 31, 62, 63, 64, 65, 96, 97, 127, 128, 129, 192, 200, 224, 240])
+def test_streams_inflate_with_zlib(harness, nvals):
+    rng = np.random.default_rng(nvals)
+    vals = sorted(rng.choice(256, size=nvals, replace=False).tolist())
+    p = _present(vals)
+    # piecewise constant tile (soil cells x land-cover patches) mapped onto the value set, plus a noisy band
+    base = synth.esa_tile(256, 256, nvals, patch=20).astype(np.int64)
+    tile = np.asarray(vals, dtype=np.uint8)[base % nvals]
+    tile[100:110] = np.asarray(vals, dtype=np.uint8)[rng.integers(0, nvals, size=(10, 256))]
+    z = _encode(harness, p, tile)
+    assert zlib.decompress(z) == tile.tobytes()
+    if nvals <= 64:
+        assert len(z) < len(zlib.compress(tile.tobytes(), 1)) * 2
+
+
+def test_more_than_240_values_is_refused(harness):
+    p = _present(range(241))
+    out = np.zeros(1000, dtype=np.uint8)
+    tile = np.zeros((256, 256), dtype=np.uint8)
+    assert harness.gcn10_test_tile_encode(p.ctypes.data, tile.ctypes.data, out.ctypes.data, out.size) == 0
+
+
+def test_smaller_than_the_fixed_code(harness):
+    """On a Curve-Number-like tile the tuned code beats RFC 1951's fixed code (what the encoder used before)."""
+    vals = _cn_values()
+    p = _present(vals)
+    base = synth.esa_tile(256, 256, 3, patch=48).astype(np.int64)
+    cells = (np.arange(256)[:, None] // 25 * 11 + np.arange(256)[None, :] // 25)
+    tile = np.asarray(vals, dtype=np.uint8)[(base + cells) % len(vals)]
+    z = _encode(harness, p, tile)
+    assert zlib.decompress(z) == tile.tobytes()
+    c = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+    fixed = c.compress(tile.tobytes()) + c.flush()
+    assert len(z) < len(fixed), (len(z), len(fixed))
+    print("tuned", len(z), "zlib fixed", len(fixed), "zlib 6", len(zlib.compress(tile.tobytes(), 6)))
