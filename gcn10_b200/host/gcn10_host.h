@@ -128,6 +128,7 @@ typedef struct {
     int overwrite;              /* -o / --overwrite (main.c:95-97)                                 */
     int n_gpus;                 /* workers; <= 0 means every visible GPU                           */
     int io_threads;             /* DEFLATE / inflate threads per worker                            */
+    int workers_per_gpu;        /* blocks in flight per GPU (each with its own context); <= 0 means 1 */
     const char *out_root;       /* directory that receives cn_rasters_<cond>/ (reference: CWD)     */
 } gh_run_options;
 

@@ -32,6 +32,7 @@ static void usage(FILE *fp)
             "  --overwrite, -o	overwrite existing outputs if present (optional)\n"
             "  --gpus <n>		number of GPU workers (default: every visible GPU)\n"
             "  --io-threads <n>	decode/encode threads per worker (default: cores / workers)\n"
+            "  --workers-per-gpu <n>	blocks in flight per GPU, each with its own context (default: 1)\n"
             "  --outdir <dir>	where cn_rasters_<condition>/ are created (default: .)\n"
             "  --help, -h		show this help and exit\n"
             "  --version, -v	print version and exit\n"
@@ -69,6 +70,8 @@ int main(int argc, char **argv)
             opt.n_gpus = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--io-threads") && i + 1 < argc)
             opt.io_threads = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--workers-per-gpu") && i + 1 < argc)
+            opt.workers_per_gpu = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--outdir") && i + 1 < argc)
             opt.out_root = argv[++i];
     }

@@ -44,7 +44,8 @@ typedef struct {
 } band_buf;
 
 typedef struct worker {
-    int index;                      /* GPU / worker number: the "rank" of the log lines */
+    int index;                      /* worker number: the "rank" of the log lines */
+    int device;                     /* its GPU */
     const gh_run_options *opt;
     gh_blocks *blocks;
     const int (*tables)[256][5];
@@ -541,11 +542,11 @@ static void *worker_main(void *arg)
     char msg[256];
     /* keep this worker (and the reader / encoder threads it spawns, which inherit the mask) on the
      * NUMA node of its GPU so that the pinned band buffers are node-local */
-    int node = gcn10_cuda_bind_host_thread(wk->index);
-    snprintf(msg, sizeof msg, "gpu worker %d on numa node %d", wk->index, node);
+    int node = gcn10_cuda_bind_host_thread(wk->device);
+    snprintf(msg, sizeof msg, "worker %d on gpu %d, numa node %d", wk->index, wk->device, node);
     gh_log_message(wk->log, "INFO", msg, 0);
-    if (gcn10_cuda_create(wk->index, &wk->ctx) || gcn10_cuda_set_luts(wk->ctx, wk->tables)) {
-        snprintf(msg, sizeof msg, "cannot initialise GPU %d: %s", wk->index, gcn10_cuda_last_error());
+    if (gcn10_cuda_create(wk->device, &wk->ctx) || gcn10_cuda_set_luts(wk->ctx, wk->tables)) {
+        snprintf(msg, sizeof msg, "cannot initialise GPU %d: %s", wk->device, gcn10_cuda_last_error());
         fatal(wk, msg);
     }
     pthread_mutex_init(&wk->mu, NULL);
@@ -583,7 +584,10 @@ int gh_run_blocks(const gh_run_options *opt, const int *block_ids, int n_blocks)
         fprintf(stderr, "gcn10: no usable CUDA device (%s); there is no CPU fallback\n", gcn10_cuda_last_error());
         exit(1);
     }
-    int nworkers = opt->n_gpus > 0 && opt->n_gpus < ngpu ? opt->n_gpus : ngpu;
+    /* several workers per GPU keep more than one block in flight on it: the kernels of one block (inflate, then
+     * the fused Curve Number + DEFLATE kernel) are latency bound and overlap with the other block's copies */
+    const int gpus = opt->n_gpus > 0 && opt->n_gpus < ngpu ? opt->n_gpus : ngpu;
+    int nworkers = gpus * (opt->workers_per_gpu > 0 ? opt->workers_per_gpu : 1);
     if (nworkers > n_blocks)
         nworkers = n_blocks > 0 ? n_blocks : 1;
 
@@ -598,7 +602,8 @@ int gh_run_blocks(const gh_run_options *opt, const int *block_ids, int n_blocks)
         gh_log_message(log0, "ERROR", err, 1);
         exit(1);
     }
-    snprintf(msg, sizeof msg, "processing %d blocks on %d gpu workers", n_blocks, nworkers);
+    snprintf(msg, sizeof msg, "processing %d blocks on %d gpu workers (%d gpus)", n_blocks, nworkers,
+             gpus < nworkers ? gpus : nworkers);
     gh_log_message(log0, "INFO", msg, 1);
 
     atomic_int next = 0, done = 0;
@@ -606,6 +611,7 @@ int gh_run_blocks(const gh_run_options *opt, const int *block_ids, int n_blocks)
     pthread_t *th = calloc((size_t)nworkers, sizeof *th);
     for (int i = 0; i < nworkers; i++) {
         wks[i].index = i;
+        wks[i].device = i % gpus;
         wks[i].opt = opt;
         wks[i].blocks = blocks;
         wks[i].tables = tables;

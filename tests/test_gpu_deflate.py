@@ -116,11 +116,40 @@ def test_tables_with_missing_rows_per_variant(holes, gpu_ctx, port, tables):
         assert np.array_equal(_assemble(res["tiles"][k], 700, 540)[:540, :700], want[k]), f"plane {k}"
 
 
+@pytest.mark.parametrize("mask", [1 << 7, (1 << 0) | (1 << 4) | (1 << 9) | (1 << 17), 0x3FFFF & ~(1 << 8), 0x2AAAA])
+def test_arbitrary_plane_masks(mask, gpu_ctx, port, tables):
+    """Any subset of the 18 rasters, across both drainage conditions: only the selected planes come back, in
+    ascending plane order, and each decodes to the oracle's plane."""
+    b = make_block(w=777, h=515, seed=17, esa_patch=40, hsg_patch=2, profile="coastal")
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], plane_mask=mask)
+    sel = [k for k in range(18) if mask & (1 << k)]
+    assert sorted(res["tiles"]) == sel
+    for k in sel:
+        assert np.array_equal(_assemble(res["tiles"][k], 777, 515)[:515, :777], want[k]), f"plane {k}"
+
+
 def test_deflate_compresses_cn_rasters(gpu_ctx):
     b = make_block(w=2048, h=2048, seed=10, esa_patch=192, hsg_patch=9)
     res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], plane_mask=capi.MASK_DRAINED)
     ratio = 9 * 2048 * 2048 / res["bytes"]
     assert ratio > 4.0, f"compression ratio only {ratio:.2f}"
+
+
+def test_tuned_code_is_smaller_than_fixed_and_close_to_zlib(gpu_ctx, encoder_path):
+    """The tuned Huffman code (tile_code.h) against RFC 1951's fixed code on the same tiles, and both against
+    zlib level 6 (what the reference's save_raster() would write)."""
+    if encoder_path != "fused_tuned_code":
+        pytest.skip("size comparison runs once")
+    b = make_block(w=2048, h=2048, seed=10, esa_patch=192, hsg_patch=9)
+    tuned = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], plane_mask=capi.MASK_DRAINED)
+    gpu_ctx.set_option("tuned_code", 0)
+    fixed = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], plane_mask=capi.MASK_DRAINED)
+    gpu_ctx.set_option("tuned_code", 1)
+    zl = sum(len(zlib.compress(zlib.decompress(z), 6)) for d in tuned["tiles"].values() for z in d.values())
+    assert tuned["bytes"] < 0.85 * fixed["bytes"]
+    assert tuned["bytes"] < 1.6 * zl, (tuned["bytes"], zl)
+    print(f"tile streams: tuned {tuned['bytes']}, fixed {fixed['bytes']}, zlib-6 {zl}")
 
 
 def test_deflate_rows_bands_equal_whole_block(gpu_ctx, port, tables):

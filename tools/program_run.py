@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=4)
     ap.add_argument("--size", type=int, default=9000, help="block edge in pixels")
     ap.add_argument("--io-threads", type=int, default=0)
+    ap.add_argument("--workers-per-gpu", type=int, default=1)
     ap.add_argument("--keep", action="store_true")
     ap.add_argument("--host-deflate", action="store_true", help="raw planes over PCIe + zlib on the host")
     ap.add_argument("--host-inflate", action="store_true", help="decode the land cover on the host (zlib threads)")
@@ -56,6 +57,8 @@ def main():
            "--gpus", str(a.gpus)]
     if a.io_threads:
         cmd += ["--io-threads", str(a.io_threads)]
+    if a.workers_per_gpu > 1:
+        cmd += ["--workers-per-gpu", str(a.workers_per_gpu)]
     t0 = time.time()
     env = dict(os.environ, GCN10_HOST_DEFLATE="1" if a.host_deflate else "0",
                GCN10_HOST_INFLATE="1" if a.host_inflate else "0")
