@@ -127,7 +127,7 @@ __device__ __forceinline__ uint32_t field21(unsigned long long c, uint32_t f) { 
 //   WRITE = true : emits planes [lo, hi) ; `pos` = common bits before this item, lit = class counts before
 //                  it, obase[k] = byte offset of plane k's stream in `out` (16-byte aligned); the 19 header
 //                  bits are added here.
-template <bool WRITE, int MAXP, bool ONE = false>
+template <bool WRITE, int MAXP, bool ONE = false, bool TMPL = false>
 __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, const RowMasks &m, const uint8_t *val,
                                                     const unsigned long long *lit9, unsigned long long clsbits,
                                                     unsigned long long &lit, uint32_t pos, uint32_t *out,
@@ -153,7 +153,16 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
                 tuned_match_code(code, len, la >= lr, bits, n);
             else
                 match_code(len, la >= lr, bits, n);
-            if (WRITE && ONE) {
+            if (WRITE && ONE && TMPL) {
+                // one bit position for all streams AND the same bits: a match goes into the template stream once
+                const uint32_t pp = hdr + pos + (uint32_t)lit;
+                const uint32_t sh = pp & 31u;
+                uint32_t *o = out + (pp >> 5);
+                atomicOr(o, bits << sh);
+                if (sh + (uint32_t)n > 32u)
+                    atomicOr(o + 1, bits >> (32u - sh));
+            }
+            else if (WRITE && ONE) {
                 // every plane has the same 9-bit-literal pattern: one bit position for all streams
                 const uint32_t pp = hdr + pos + (uint32_t)lit;
                 const uint32_t sh = pp & 31u, w0 = bits << sh, w1 = sh ? bits >> (32u - sh) : 0u;
@@ -247,7 +256,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     __shared__ unsigned long long s_scan[kTile / 32][2];
     __shared__ uint32_t s_adler[18], s_nbytes[18], s_obase[18], s_stored[18];
     __shared__ unsigned long long s_goff[18];
-    __shared__ int s_round_hi[19], s_nrounds;
+    __shared__ int s_round_hi[19], s_nrounds, s_use_tmpl;
     __shared__ uint32_t s_total_common;
     __shared__ unsigned long long s_total_lit;
     __shared__ uint32_t s_hist[66];
@@ -579,13 +588,21 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         // compressed planes first (contiguous per round, in the arena as in the staging area), stored ones behind
         int nr = 0;
         uint32_t used = 0;
+        // With one bit position for all streams (tuned code, or one literal class) the streams differ only in
+        // their literal bits: the staging area then holds ONE template stream (header, matches, end of block) in
+        // front of per-plane overlays (literals, Adler-32), OR-ed together on the way out.
+        const uint32_t r16 = (s_nbytes[0] + 15u) & ~15u;
+        const int use_tmpl = clsbits == 0ull && !s_stored[0] && 2u * r16 <= (uint32_t)kFusedOutCap;
+        s_use_tmpl = use_tmpl;
+        if (use_tmpl)
+            used = r16;
         for (int k = 0; k < nsel; k++) {
             if (s_stored[k])
                 continue;
             const uint32_t a16 = (s_nbytes[k] + 15u) & ~15u;
             if (used + a16 > (uint32_t)kFusedOutCap) {
                 s_round_hi[nr++] = k;
-                used = 0;
+                used = use_tmpl ? r16 : 0u;
             }
             s_obase[k] = used;
             s_goff[k] = need;
@@ -611,6 +628,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
 
     // ---- 7. rounds of planes: zero the staging area, second parse writes the streams, copy out
     const int nrounds = s_nrounds;
+    const bool use_tmpl = s_use_tmpl != 0;
     int lo = 0;
     for (int rd = 0; rd < nrounds; rd++) {
         const int hi = s_round_hi[rd];
@@ -623,7 +641,55 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                     first = k;
                 span = s_obase[k] + ((s_nbytes[k] + 15u) & ~15u);
             }
-        if (first >= 0) {
+        if (first >= 0 && use_tmpl) {
+            // ---- template + overlays (see step 6); no stored planes in this mode
+            const uint32_t r16 = s_obase[lo];                           // = size of the template = of every overlay
+            for (uint32_t i = tid; i < span / 16 + 4; i += kTile)
+                reinterpret_cast<uint4 *>(outb)[i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+#pragma unroll 1
+            for (int q = 0; q < 2; q++) {
+                const uint32_t item = q ? item1 : item0;
+                if (item == 0xFFFFu)
+                    break;
+                const int r = item & 255u, piece = item >> 8;
+                const int xa = piece == 4 ? 0 : 64 * piece, xb = piece == 4 ? kTile : xa + 64;
+                const RowMasks pm = s_masks[r];
+                unsigned long long lw = q ? lit_b : lit_a;
+                fused_parse_row<true, MAXP, true, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, q ? pos_b : pos_a, out, s_obase,
+                                                        lo, hi, xa, xb, p.code, s_rank);
+            }
+            if (tuned) {
+                for (int i = tid; i < (p.code.header_bits + 31) >> 5; i += kTile)
+                    atomicOr(out + i, __ldg(p.code.header_words + i));
+                if (tid == 0)
+                    put_bits(out, (uint32_t)p.code.header_bits + s_total_common, p.code.eob_code, p.code.eob_bits);
+            }
+            else if (tid == 0) {
+                put_bits(out, 0, 0x9C78u, 16);
+                put_bits(out, 16, 0x3u, 3);
+            }
+            __syncthreads();            // (the Adler bytes may share a word with the last literal bits: atomics first)
+            if (tid < hi - lo) {
+                uint8_t *ob = outb + s_obase[lo + tid] + s_nbytes[lo + tid] - 4;        // bytes behind the stream's last bit
+                const uint32_t ad = s_adler[lo + tid];
+                ob[0] = (uint8_t)(ad >> 24);
+                ob[1] = (uint8_t)(ad >> 16);
+                ob[2] = (uint8_t)(ad >> 8);
+                ob[3] = (uint8_t)ad;
+            }
+            __syncthreads();
+            uint4 *dst = reinterpret_cast<uint4 *>(p.blob + s_goff[lo]);
+            const uint4 *tm = reinterpret_cast<const uint4 *>(outb);
+            const uint4 *ov = reinterpret_cast<const uint4 *>(outb + r16);
+            const uint32_t per = r16 / 16, n16 = per * (uint32_t)(hi - lo);
+            for (uint32_t i = tid; i < n16; i += kTile) {
+                const uint4 a = ov[i], b = tm[i % per];
+                dst[i] = make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
+            }
+            __syncthreads();
+        }
+        else if (first >= 0) {
             for (uint32_t i = tid; i < span / 16 + 4; i += kTile)
                 reinterpret_cast<uint4 *>(outb)[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
