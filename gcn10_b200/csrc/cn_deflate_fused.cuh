@@ -97,8 +97,10 @@ __device__ __forceinline__ uint32_t soil_class(uint32_t code)
 __device__ __forceinline__ void tuned_match_code(const FusedCode &c, int len, bool above, uint32_t &bits, int &n)
 {
     int idx, e = 0, extra = 0;
-    const int l = len - 3;                      // len <= 256 here (tokens stay inside a tile row)
-    if (l < 8)
+    const int l = len - 3;
+    if (len == 258)
+        idx = 28;                               // symbol 285: only the row-run tokens are this long
+    else if (l < 8)
         idx = l;
     else {
         e = 29 - __clz(l);
@@ -121,6 +123,88 @@ __device__ __forceinline__ void tuned_match_code(const FusedCode &c, int len, bo
 }
 
 __device__ __forceinline__ uint32_t field21(unsigned long long c, uint32_t f) { return (uint32_t)(c >> (21u * f)) & 0x1FFFFFu; }
+
+// One match token into the streams of planes [lo, hi).  TMPL: all streams share positions AND bits, the token
+// goes into the template stream once.  ONE: shared positions, one store per plane.  Otherwise every plane has the
+// position of its literal class.  `at` = header bits + bits common to all planes in front of the token.
+template <int MAXP, bool ONE, bool TMPL>
+__device__ __forceinline__ void fused_emit_match(uint32_t *out, const uint32_t *obase, int lo, int hi,
+                                                 unsigned long long clsbits, unsigned long long lit, uint32_t at,
+                                                 uint32_t bits, int n)
+{
+    if (ONE && TMPL) {
+        const uint32_t pp = at + (uint32_t)lit;
+        const uint32_t sh = pp & 31u;
+        uint32_t *o = out + (pp >> 5);
+        atomicOr(o, bits << sh);
+        if (sh + (uint32_t)n > 32u)
+            atomicOr(o + 1, bits >> (32u - sh));
+    }
+    else if (ONE) {
+        const uint32_t pp = at + (uint32_t)lit;
+        const uint32_t sh = pp & 31u, w0 = bits << sh, w1 = sh ? bits >> (32u - sh) : 0u;
+        const bool cross = sh + (uint32_t)n > 32u;
+#pragma unroll
+        for (int k = 0; k < MAXP; k++)
+            if (k >= lo && k < hi) {
+                uint32_t *o = out + (obase[k] >> 2) + (pp >> 5);
+                atomicOr(o, w0);
+                if (cross)
+                    atomicOr(o + 1, w1);
+            }
+    }
+    else {
+        const uint32_t pc[3] = { at + field21(lit, 0), at + field21(lit, 1), at + field21(lit, 2) };
+#pragma unroll
+        for (int k = 0; k < MAXP; k++)
+            if (k >= lo && k < hi) {
+                const uint32_t c = (uint32_t)(clsbits >> (2 * k)) & 3u;
+                put_bits(out + (obase[k] >> 2), c == 0u ? pc[0] : (c == 1u ? pc[1] : pc[2]), bits, n);
+            }
+    }
+}
+
+// A run of `nrows` >= 2 tile rows that all repeat the row above them: 256 * nrows bytes equal to the bytes 256
+// back, coded as matches of length 258 (the longest DEFLATE has; they run across the tile rows) plus the rest.
+template <bool WRITE, int MAXP, bool ONE, bool TMPL>
+__device__ __forceinline__ uint32_t fused_row_run(int nrows, unsigned long long clsbits, unsigned long long lit,
+                                                  uint32_t pos, uint32_t *out, const uint32_t *obase, int lo, int hi,
+                                                  const FusedCode &code)
+{
+    const bool tuned = code.header_bits != 0;
+    const uint32_t hdr = tuned ? (uint32_t)code.header_bits : 19u;
+    const uint32_t span = (uint32_t)kTile * (uint32_t)nrows;
+    uint32_t q = span / 258u, rest = span - 258u * q;
+    int tail[2] = { (int)rest, 0 };
+    if (rest == 1u || rest == 2u) {             // a match is at least 3 long: split 258 + rest in two
+        q -= 1u;
+        tail[0] = 129;
+        tail[1] = 129 + (int)rest;
+    }
+    uint32_t bits;
+    int n;
+    if (tuned)
+        tuned_match_code(code, 258, true, bits, n);
+    else
+        match_code(258, true, bits, n);
+    if (WRITE) {
+        for (uint32_t i = 0; i < q; i++)
+            fused_emit_match<MAXP, ONE, TMPL>(out, obase, lo, hi, clsbits, lit, hdr + pos + i * (uint32_t)n, bits, n);
+    }
+    pos += q * (uint32_t)n;
+#pragma unroll
+    for (int t = 0; t < 2; t++)
+        if (tail[t]) {
+            if (tuned)
+                tuned_match_code(code, tail[t], true, bits, n);
+            else
+                match_code(tail[t], true, bits, n);
+            if (WRITE)
+                fused_emit_match<MAXP, ONE, TMPL>(out, obase, lo, hi, clsbits, lit, hdr + pos, bits, n);
+            pos += (uint32_t)n;
+        }
+    return pos;
+}
 
 // Greedy parse of pixels [xa, xb) of one row of the id tile (a whole row, or one 64-pixel item of a long row).
 //   WRITE = false: returns the bits common to all planes; lit += 9-bit-literal counts per class
@@ -153,38 +237,8 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
                 tuned_match_code(code, len, la >= lr, bits, n);
             else
                 match_code(len, la >= lr, bits, n);
-            if (WRITE && ONE && TMPL) {
-                // one bit position for all streams AND the same bits: a match goes into the template stream once
-                const uint32_t pp = hdr + pos + (uint32_t)lit;
-                const uint32_t sh = pp & 31u;
-                uint32_t *o = out + (pp >> 5);
-                atomicOr(o, bits << sh);
-                if (sh + (uint32_t)n > 32u)
-                    atomicOr(o + 1, bits >> (32u - sh));
-            }
-            else if (WRITE && ONE) {
-                // every plane has the same 9-bit-literal pattern: one bit position for all streams
-                const uint32_t pp = hdr + pos + (uint32_t)lit;
-                const uint32_t sh = pp & 31u, w0 = bits << sh, w1 = sh ? bits >> (32u - sh) : 0u;
-                const bool cross = sh + (uint32_t)n > 32u;
-#pragma unroll
-                for (int k = 0; k < MAXP; k++)
-                    if (k >= lo && k < hi) {
-                        uint32_t *o = out + (obase[k] >> 2) + (pp >> 5);
-                        atomicOr(o, w0);
-                        if (cross)
-                            atomicOr(o + 1, w1);
-                    }
-            }
-            else if (WRITE) {
-                const uint32_t pc[3] = { hdr + pos + field21(lit, 0), hdr + pos + field21(lit, 1), hdr + pos + field21(lit, 2) };
-#pragma unroll
-                for (int k = 0; k < MAXP; k++)
-                    if (k >= lo && k < hi) {
-                        const uint32_t c = (uint32_t)(clsbits >> (2 * k)) & 3u;
-                        put_bits(out + (obase[k] >> 2), c == 0u ? pc[0] : (c == 1u ? pc[1] : pc[2]), bits, n);
-                    }
-            }
+            if (WRITE)
+                fused_emit_match<MAXP, ONE, TMPL>(out, obase, lo, hi, clsbits, lit, hdr + pos, bits, n);
             pos += n;
             x += len;
         }
@@ -263,7 +317,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     __shared__ uint8_t s_cls[18];
     __shared__ uint8_t s_rank[256];                                     // literal value -> code word offset (tuned code)
     const bool tuned = p.code.header_bits != 0;
-    __shared__ uint32_t s_nitems;
+    __shared__ uint32_t s_nitems, s_rep[kTile / 32];
     unsigned long long clsbits = 0;
 #pragma unroll
     for (int k = 0; k < 18; k++)
@@ -431,19 +485,47 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         // many "new" words (neither a repeat of the row above nor the continuation of a run -- typically the first
         // row of a soil cell) are cut into four 64-pixel items whose tokens stop at the item border (a few bits
         // per cut).  Items are sorted by expected work so that the 32 items a warp parses in lockstep are alike.
+        // Runs of rows that all repeat the row above them (the inside of a soil cell) become ONE item: the first row
+        // of the run codes all of them as length-258 matches that run across the tile rows (fused_row_run), the
+        // other rows of the run contribute nothing.
         const uint32_t est = (uint32_t)__popcll(~(m.above | m.left));
-        // (the first kFusedMaxSplitRows such rows in row order, so that the streams do not depend on thread timing)
+        const bool rep = tid > 0 && m.above == ~0ull;
+        const unsigned repbal = __ballot_sync(0xffffffffu, rep);
+        // (the first kFusedMaxSplitRows long rows in row order, so that the streams do not depend on thread timing)
         const bool cand = est >= (uint32_t)kFusedSplitEst;
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
-        if (lane == 0)
+        if (lane == 0) {
             s_scan[warp][1] = (unsigned long long)__popc(bal);
+            s_rep[warp] = repbal;
+        }
         __syncthreads();
+        uint32_t runlen = 0;                    // 0: ordinary row; 0xFFFF: inside a run; else rows in the run it starts
+        if (rep) {
+            const bool prev = lane ? ((repbal >> (lane - 1)) & 1u) != 0u : (s_rep[warp - 1] >> 31) != 0u;
+            if (prev)
+                runlen = 0xFFFFu;
+            else {
+                uint32_t bits = repbal >> lane, avail = 32u - lane, total = 0;
+                int wv = warp;
+                for (;;) {
+                    uint32_t ones = bits == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~bits) - 1u;
+                    ones = min(ones, avail);
+                    total += ones;
+                    if (ones < avail || ++wv == kTile / 32)
+                        break;
+                    bits = s_rep[wv];
+                    avail = 32u;
+                }
+                runlen = total >= 2u ? total : 0u;      // a single repeated row stays an ordinary row (one token)
+            }
+        }
+        *reinterpret_cast<uint16_t *>(tile + tid * kTileStride + kFusedRowMeta + 2) = (uint16_t)runlen;
         uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
         for (int wv = 0; wv < warp; wv++)
             rank += (uint32_t)s_scan[wv][1];
         const bool split = cand && rank < (uint32_t)kFusedMaxSplitRows;
         const uint32_t nseg = split ? 4u : 1u;
-        const uint32_t key = split ? (est + 3u) / 4u : est;
+        const uint32_t key = runlen == 0xFFFFu ? 0u : runlen ? min(64u, 1u + runlen / 8u) : split ? (est + 3u) / 4u : est;
         atomicAdd(&s_hist[64u - key], nseg);
         uint32_t inc = nseg;                    // first item slot of every row (stream order)
 #pragma unroll
@@ -499,9 +581,12 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         const int r = item & 255u, piece = item >> 8;
         const int xa = piece == 4 ? 0 : 64 * piece, xb = piece == 4 ? kTile : xa + 64;
         const RowMasks pm = s_masks[r];
+        const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
         unsigned long long lit = 0;
-        const uint32_t bits = fused_parse_row<false, MAXP>(tile, r, pm, s_val, p.lit9, clsbits, lit, 0u, nullptr, nullptr, 0,
-                                                           0, xa, xb, p.code, s_rank);
+        const uint32_t bits = rl == 0xFFFFu ? 0u
+                              : rl ? fused_row_run<false, MAXP, false, false>((int)rl, clsbits, lit, 0u, nullptr, nullptr, 0, 0, p.code)
+                                   : fused_parse_row<false, MAXP>(tile, r, pm, s_val, p.lit9, clsbits, lit, 0u, nullptr, nullptr, 0,
+                                                                  0, xa, xb, p.code, s_rank);
         const uint32_t slot = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta) + (piece & 3);
         s_ibits[slot] = bits;
         s_ilit[slot] = lit;
@@ -656,8 +741,14 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                 const int xa = piece == 4 ? 0 : 64 * piece, xb = piece == 4 ? kTile : xa + 64;
                 const RowMasks pm = s_masks[r];
                 unsigned long long lw = q ? lit_b : lit_a;
-                fused_parse_row<true, MAXP, true, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, q ? pos_b : pos_a, out, s_obase,
-                                                        lo, hi, xa, xb, p.code, s_rank);
+                const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
+                if (rl == 0xFFFFu)
+                    continue;
+                if (rl)
+                    fused_row_run<true, MAXP, true, true>((int)rl, clsbits, lw, q ? pos_b : pos_a, out, s_obase, lo, hi, p.code);
+                else
+                    fused_parse_row<true, MAXP, true, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, q ? pos_b : pos_a, out,
+                                                            s_obase, lo, hi, xa, xb, p.code, s_rank);
             }
             if (tuned) {
                 for (int i = tid; i < (p.code.header_bits + 31) >> 5; i += kTile)
@@ -712,7 +803,16 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                         const RowMasks pm = s_masks[r];
                         unsigned long long lw = q ? lit_b : lit_a;
                         const uint32_t pw = q ? pos_b : pos_a;
-                        if (clsbits == 0ull)
+                        const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
+                        if (rl == 0xFFFFu)
+                            continue;
+                        if (rl) {
+                            if (clsbits == 0ull)
+                                fused_row_run<true, MAXP, true, false>((int)rl, clsbits, lw, pw, out, s_obase, a, b, p.code);
+                            else
+                                fused_row_run<true, MAXP, false, false>((int)rl, clsbits, lw, pw, out, s_obase, a, b, p.code);
+                        }
+                        else if (clsbits == 0ull)
                             fused_parse_row<true, MAXP, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, pw, out, s_obase, a, b, xa, xb, p.code, s_rank);
                         else
                             fused_parse_row<true, MAXP, false>(tile, r, pm, s_val, p.lit9, clsbits, lw, pw, out, s_obase, a, b, xa, xb, p.code, s_rank);

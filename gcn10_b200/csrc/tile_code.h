@@ -3,8 +3,8 @@
 // save_raster() of the reference writes DEFLATE tiles through zlib level 6 (/root/reference/src/raster.c:
 // 206-207), which fits a Huffman code to every tile.  The GPU encoder cannot afford a code per tile, but it does
 // not need the fixed code of RFC 1951 3.2.6 either: all tiles of a run have the same statistics, known in
-// advance -- the only distances are 1 (run) and 256 (pixel above), one length bucket (227..257: "this row equals
-// the row above") carries a third of the tokens, and the literals are the few dozen Curve Number values the
+// advance -- the only distances are 1 (run) and 256 (pixel above), the longest match (258: runs of rows that repeat the row
+// above, coded across the tile rows) carries a third of the tokens, and the literals are the few dozen Curve Number values the
 // lookup tables can produce.  build_tile_code() designs ONE code for them and serialises it as the header of a
 // dynamic-Huffman block (RFC 1951 3.2.7); every tile stream starts with that header (about 60 bytes) and then
 // spends 15 bits instead of 24 on a repeated row, 1 bit instead of 5 on a distance, 7 instead of 8 on a literal.
@@ -165,8 +165,8 @@ inline bool build_tile_code(const bool present[256], TileCode &tc)
         w[s - 256] = 10;
     for (int s = 269; s <= 283; s++)
         w[s - 256] = 5;
-    w[284 - 256] = 300;                                 // 227..257: the row that repeats the row above
-    w[285 - 256] = 1;
+    w[284 - 256] = 120;                                 // 227..257: a single row that repeats the row above
+    w[285 - 256] = 250;                                 // 258: runs of such rows, coded across the tile rows
     const uint64_t lit_weight = 300;
     uint64_t nonlit_weight = 0;
     for (uint64_t f : w)
