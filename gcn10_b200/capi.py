@@ -29,6 +29,7 @@ EXPORTS = (
     "gcn10_cuda_launch_count", "gcn10_cuda_set_option", "gcn10_cuda_host_alloc", "gcn10_cuda_host_free",
     "gcn10_cuda_host_register", "gcn10_cuda_host_unregister", "gcn10_cuda_bind_host_thread",
     "gcn10_cuda_inflate_tiles", "gcn10_cuda_block_tiles_deflate", "gcn10_cuda_last_inflate_ms",
+    "gcn10_cuda_tiles_prefetch",
 )
 
 _vp = C.c_void_p
@@ -147,6 +148,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     lib.gcn10_cuda_block_tiles_deflate.argtypes = [_vp, C.POINTER(TileSourceStruct), C.c_int, C.c_int, _dp,
                                                    _vp, C.c_int, C.c_int, C.c_size_t, _dp, C.c_uint, TILE_SINK, _vp]
     lib.gcn10_cuda_last_inflate_ms.argtypes = [_vp, C.POINTER(C.c_float)]
+    lib.gcn10_cuda_tiles_prefetch.argtypes = [_vp, C.POINTER(TileSourceStruct), C.c_int, C.c_int]
     return lib
 
 
@@ -326,6 +328,12 @@ class Context:
             self.h, C.byref(st), w, h, _d6(gt), hsg.ctypes.data, hsx, hsy, hsg_pitch, _d6(soil_gt), plane_mask,
             cb, None))
         return dict(tiles=tiles, bytes=total[0])
+
+    def tiles_prefetch(self, src: "TileSource", w, h):
+        """Start upload + GPU inflate of a block's tiles; the next block_tiles_deflate / inflate_tiles call with the
+        same source picks the result up.  Keep ``src`` alive until then."""
+        st = src.struct()
+        self._check(self.lib.gcn10_cuda_tiles_prefetch(self.h, C.byref(st), w, h))
 
     def last_inflate_ms(self) -> float:
         v = C.c_float()

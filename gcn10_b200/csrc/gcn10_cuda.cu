@@ -78,6 +78,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 }  // namespace
 
+// one compressed land-cover window on its way to / resident on the device (two per context, so that the next
+// block's tiles can be uploaded and inflated while the current block's strips run: gcn10_cuda_tiles_prefetch)
+struct TileSlot {
+    DevBuf in_blob, in_table, esa_full;
+    HostBuf h_status;           // [ntiles] status codes | [ntiles] launch order
+    cudaEvent_t inf0 = nullptr, inf1 = nullptr, done = nullptr;     // around the inflate kernel; behind the status copy
+    bool pending = false;       // inflate issued, result not consumed yet
+    uint64_t seq = 0;           // issue order of pending slots
+    const void *key_blob = nullptr;
+    size_t key_bytes = 0, ntiles = 0, dpitch = 0;
+    int key_w = 0, key_h = 0;
+};
+
 struct gcn10_ctx {
     int device = -1;
     int sm_count = 148;
@@ -107,9 +120,9 @@ struct gcn10_ctx {
     DevBuf col_idx, row_idx, hsg;
     StripSlot slots[kMaxStreams];
     // compressed-input path: the tiles' bytes, their tables and the inflated land-cover plane of a block
-    DevBuf in_blob, in_table, esa_full;
-    HostBuf h_in_status;
-    cudaEvent_t inf0 = nullptr, inf1 = nullptr;
+    TileSlot tslot[2];
+    cudaStream_t pre_stream = nullptr;      // uploads + inflate kernels
+    uint64_t tile_seq = 0;
     float last_inflate_ms = 0.f;
     float last_kernel_ms = 0.f;
     uint64_t launches = 0;
@@ -623,8 +636,12 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
                                   kInflateSmem));
     CUDA_TRY(cudaFuncSetAttribute((const void *)inflate_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(cudaEventCreate(&c->inf0));
-    CUDA_TRY(cudaEventCreate(&c->inf1));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->pre_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaEventCreate(&c->tslot[i].inf0));
+        CUDA_TRY(cudaEventCreate(&c->tslot[i].inf1));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->tslot[i].done, cudaEventDisableTiming));
+    }
     // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -660,13 +677,17 @@ void gcn10_cuda_destroy(gcn10_ctx *c)
     release(c->col_idx);
     release(c->row_idx);
     release(c->hsg);
-    release(c->in_blob);
-    release(c->in_table);
     release(c->fused_tab);
-    release(c->esa_full);
-    release_host(c->h_in_status);
-    if (c->inf0) cudaEventDestroy(c->inf0);
-    if (c->inf1) cudaEventDestroy(c->inf1);
+    for (int i = 0; i < 2; i++) {
+        release(c->tslot[i].in_blob);
+        release(c->tslot[i].in_table);
+        release(c->tslot[i].esa_full);
+        release_host(c->tslot[i].h_status);
+        if (c->tslot[i].inf0) cudaEventDestroy(c->tslot[i].inf0);
+        if (c->tslot[i].inf1) cudaEventDestroy(c->tslot[i].inf1);
+        if (c->tslot[i].done) cudaEventDestroy(c->tslot[i].done);
+    }
+    if (c->pre_stream) cudaStreamDestroy(c->pre_stream);
     for (int i = 0; i < kMaxStreams; i++) {
         release(c->slots[i].esa);
         release(c->slots[i].out);
@@ -1130,12 +1151,11 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
                              soil_gt, plane_mask, sink, user);
 }
 
-// Upload the compressed tiles of `src` and inflate them into c->esa_full (pitch *dpitch) on stream 0.
-// Leaves the per-tile status codes in c->h_in_status after the stream has been synchronised by the caller;
-// records c->inf1 behind the kernel.
-static int inflate_to_device(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h, size_t *dpitch_out)
+// Upload the compressed tiles of `src` and inflate them into sl.esa_full (pitch sl.dpitch) on the context's
+// upload stream, without waiting.  The per-tile status codes are in sl.h_status once that stream has drained.
+static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_source *src, int w, int h)
 {
-    if (!src || !src->blob || !src->offsets || !src->sizes)
+    if (!src || !src->offsets || !src->sizes || (!src->blob && src->blob_bytes))
         return fail(GCN10_EINVAL, "NULL argument");
     if (w <= 0 || h <= 0 || src->tile_w <= 0 || src->tile_h <= 0 || src->tiles_x <= 0 || src->tiles_y <= 0)
         return fail(GCN10_EINVAL, "non-positive size");
@@ -1150,32 +1170,32 @@ static int inflate_to_device(gcn10_ctx *c, const gcn10_tile_source *src, int w, 
         if (src->sizes[i] && (src->offsets[i] > src->blob_bytes || src->sizes[i] > src->blob_bytes - src->offsets[i]))
             return fail(GCN10_EINVAL, "tile %zu lies outside the blob", i);
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = c->streams[0];
+    cudaStream_t st = c->pre_stream;
     const size_t dpitch = round_up((size_t)w, 256);
     int rc;
     // the kernel's 512-byte input refills may run ~2 KB past a stream: keep that readable
-    if ((rc = ensure(c->in_blob, round_up(src->blob_bytes, 256) + 4096)) ||
-        (rc = ensure(c->in_table, ntiles * 20)) || (rc = ensure_host(c->h_in_status, 2 * ntiles * sizeof(int))) ||
-        (rc = ensure(c->esa_full, dpitch * (size_t)h)))
+    if ((rc = ensure(sl.in_blob, round_up(src->blob_bytes, 256) + 4096)) ||
+        (rc = ensure(sl.in_table, ntiles * 20)) || (rc = ensure_host(sl.h_status, 2 * ntiles * sizeof(int))) ||
+        (rc = ensure(sl.esa_full, dpitch * (size_t)h)))
         return rc;
-    unsigned long long *d_off = (unsigned long long *)c->in_table.p;
-    uint32_t *d_size = (uint32_t *)((uint8_t *)c->in_table.p + ntiles * 8);
-    int *d_status = (int *)((uint8_t *)c->in_table.p + ntiles * 12);
-    int *d_order = (int *)((uint8_t *)c->in_table.p + ntiles * 16);
+    unsigned long long *d_off = (unsigned long long *)sl.in_table.p;
+    uint32_t *d_size = (uint32_t *)((uint8_t *)sl.in_table.p + ntiles * 8);
+    int *d_status = (int *)((uint8_t *)sl.in_table.p + ntiles * 12);
+    int *d_order = (int *)((uint8_t *)sl.in_table.p + ntiles * 16);
     // longest streams first: a tile's decode time grows with its compressed size, and a block has only a
     // few tiles per resident CTA slot (1296 tiles of 1024 x 1024 on 740 slots), so the order sets the tail
-    int *h_order = (int *)c->h_in_status.p + ntiles;
+    int *h_order = (int *)sl.h_status.p + ntiles;
     for (size_t i = 0; i < ntiles; i++)
         h_order[i] = (int)i;
     std::stable_sort(h_order, h_order + ntiles, [&](int a, int b) { return src->sizes[a] > src->sizes[b]; });
     CUDA_TRY(cudaMemcpyAsync(d_order, h_order, ntiles * 4, cudaMemcpyHostToDevice, st));
     if (src->blob_bytes)
-        CUDA_TRY(cudaMemcpyAsync(c->in_blob.p, src->blob, src->blob_bytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(sl.in_blob.p, src->blob, src->blob_bytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_off, src->offsets, ntiles * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_size, src->sizes, ntiles * 4, cudaMemcpyHostToDevice, st));
     InflateParams ip;
     memset(&ip, 0, sizeof(ip));
-    ip.blob = (const uint8_t *)c->in_blob.p;
+    ip.blob = (const uint8_t *)sl.in_blob.p;
     ip.offsets = d_off;
     ip.sizes = d_size;
     ip.tiles_x = src->tiles_x;
@@ -1185,38 +1205,86 @@ static int inflate_to_device(gcn10_ctx *c, const gcn10_tile_source *src, int w, 
     ip.tw_shift = (src->tile_w & (src->tile_w - 1)) == 0 ? __builtin_ctz((unsigned)src->tile_w) : -1;
     ip.x_off = src->x_off;
     ip.y_off = src->y_off;
-    ip.dst = (uint8_t *)c->esa_full.p;
+    ip.dst = (uint8_t *)sl.esa_full.p;
     ip.pitch = dpitch;
     ip.w = w;
     ip.h = h;
     ip.status = d_status;
     ip.order = d_order;
     ip.probe = c->inflate_probe;
-    CUDA_TRY(cudaEventRecord(c->inf0, st));
+    CUDA_TRY(cudaEventRecord(sl.inf0, st));
     inflate_tiles_kernel<<<(unsigned)ntiles, kInflateThreads, kInflateSmem, st>>>(ip);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(c->inf1, st));
-    CUDA_TRY(cudaMemcpyAsync(c->h_in_status.p, d_status, ntiles * sizeof(int), cudaMemcpyDeviceToHost, st));
-    *dpitch_out = dpitch;
+    CUDA_TRY(cudaEventRecord(sl.inf1, st));
+    CUDA_TRY(cudaMemcpyAsync(sl.h_status.p, d_status, ntiles * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(sl.done, st));
+    sl.pending = true;
+    sl.seq = ++c->tile_seq;
+    sl.key_blob = src->blob;
+    sl.key_bytes = src->blob_bytes;
+    sl.key_w = w;
+    sl.key_h = h;
+    sl.ntiles = ntiles;
+    sl.dpitch = dpitch;
     return GCN10_OK;
 }
 
-static int check_tile_status(gcn10_ctx *c, size_t ntiles, int *tile_status)
+// waits for a slot's inflate, hands out the status codes, consumes the slot
+static int finish_slot(gcn10_ctx *c, TileSlot &sl, int *tile_status)
 {
-    const int *hs = (const int *)c->h_in_status.p;
+    sl.pending = false;
+    CUDA_TRY(cudaEventSynchronize(sl.done));                // this slot only: a later prefetch keeps running
+    const int *hs = (const int *)sl.h_status.p;
     size_t bad = 0, first_bad = 0;
-    for (size_t i = 0; i < ntiles; i++) {
+    for (size_t i = 0; i < sl.ntiles; i++) {
         if (tile_status)
             tile_status[i] = hs[i];
         if (hs[i] && !bad++)
             first_bad = i;
     }
-    cudaEventElapsedTime(&c->last_inflate_ms, c->inf0, c->inf1);
+    cudaEventElapsedTime(&c->last_inflate_ms, sl.inf0, sl.inf1);
     if (bad)
         return fail(GCN10_EDATA, "%zu of %zu compressed tiles could not be decoded (first: tile %zu, inflate error %d)",
-                    bad, ntiles, first_bad, hs[first_bad]);
+                    bad, sl.ntiles, first_bad, hs[first_bad]);
     return GCN10_OK;
+}
+
+// the slot a call works with: the oldest prefetched one that matches, else a free one (inflated now)
+static int acquire_slot(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h, TileSlot **out)
+{
+    TileSlot *hit = nullptr;
+    for (int i = 0; i < 2; i++) {
+        TileSlot &sl = c->tslot[i];
+        if (src && sl.pending && sl.key_blob == src->blob && sl.key_bytes == src->blob_bytes && sl.key_w == w &&
+            sl.key_h == h && sl.ntiles == (size_t)src->tiles_x * (size_t)src->tiles_y && (!hit || sl.seq < hit->seq))
+            hit = &sl;
+    }
+    if (!hit) {
+        // not prefetched: take the slot without pending work (or, both pending, drop the older prefetch)
+        TileSlot *sl = !c->tslot[0].pending ? &c->tslot[0] : !c->tslot[1].pending ? &c->tslot[1]
+                       : c->tslot[0].seq < c->tslot[1].seq ? &c->tslot[0] : &c->tslot[1];
+        if (sl->pending) {
+            CUDA_TRY(cudaEventSynchronize(sl->done));
+            sl->pending = false;
+        }
+        int rc = inflate_to_device(c, *sl, src, w, h);
+        if (rc)
+            return rc;
+        hit = sl;
+    }
+    *out = hit;
+    return GCN10_OK;
+}
+
+int gcn10_cuda_tiles_prefetch(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h)
+{
+    if (!c)
+        return fail(GCN10_EINVAL, "NULL context");
+    TileSlot *sl = !c->tslot[0].pending ? &c->tslot[0] : !c->tslot[1].pending ? &c->tslot[1] : nullptr;
+    if (!sl)
+        return fail(GCN10_EINVAL, "two prefetched blocks are already waiting; consume one first");
+    return inflate_to_device(c, *sl, src, w, h);
 }
 
 int gcn10_cuda_inflate_tiles(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h, uint8_t *out, size_t out_pitch,
@@ -1226,14 +1294,14 @@ int gcn10_cuda_inflate_tiles(gcn10_ctx *c, const gcn10_tile_source *src, int w, 
         return fail(GCN10_EINVAL, "NULL argument");
     if (w > 0 && out_pitch < (size_t)w)
         return fail(GCN10_EINVAL, "pitch smaller than row width");
-    size_t dpitch = 0;
-    int rc = inflate_to_device(c, src, w, h, &dpitch);
+    TileSlot *sl = nullptr;
+    int rc = acquire_slot(c, src, w, h, &sl);
     if (rc)
         return rc;
-    cudaStream_t st = c->streams[0];
-    CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, c->esa_full.p, dpitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, st));
+    cudaStream_t st = c->pre_stream;
+    CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, sl->esa_full.p, sl->dpitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    return check_tile_status(c, (size_t)src->tiles_x * src->tiles_y, tile_status);
+    return finish_slot(c, *sl, tile_status);
 }
 
 int gcn10_cuda_block_tiles_deflate(gcn10_ctx *c, const gcn10_tile_source *esa_tiles, int w, int h, const double gt[6],
@@ -1246,17 +1314,16 @@ int gcn10_cuda_block_tiles_deflate(gcn10_ctx *c, const gcn10_tile_source *esa_ti
         return fail(GCN10_EINVAL, "NULL argument");
     if (!c->have_lut)
         return fail(GCN10_ENOLUT, "gcn10_cuda_set_luts() has not been called");
-    size_t dpitch = 0;
-    int rc = inflate_to_device(c, esa_tiles, w, h, &dpitch);
+    TileSlot *sl = nullptr;
+    int rc = acquire_slot(c, esa_tiles, w, h, &sl);
     if (rc)
         return rc;
     // a damaged tile must stop the block before any output tile reaches the sink (the reference skips a
     // block whose land cover cannot be read, cn.c:188-192)
-    CUDA_TRY(cudaStreamSynchronize(c->streams[0]));
-    if ((rc = check_tile_status(c, (size_t)esa_tiles->tiles_x * esa_tiles->tiles_y, nullptr)))
+    if ((rc = finish_slot(c, *sl, nullptr)))
         return rc;
-    return deflate_rows_impl(c, nullptr, 0, (const uint8_t *)c->esa_full.p, dpitch, nullptr, w, h, 0, h, gt, hsg, hsx,
-                             hsy, hsg_pitch, soil_gt, plane_mask, sink, user);
+    return deflate_rows_impl(c, nullptr, 0, (const uint8_t *)sl->esa_full.p, sl->dpitch, nullptr, w, h, 0, h, gt, hsg,
+                             hsx, hsy, hsg_pitch, soil_gt, plane_mask, sink, user);
 }
 
 int gcn10_cuda_last_inflate_ms(gcn10_ctx *c, float *ms)

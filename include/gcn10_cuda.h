@@ -195,6 +195,19 @@ int gcn10_cuda_block_tiles_deflate(gcn10_ctx *ctx, const gcn10_tile_source *esa_
                                    const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
                                    unsigned plane_mask, gcn10_tile_sink sink, void *user);
 
+/* Starts the upload and the GPU inflate of a block's land-cover tiles and returns without waiting.  The next
+ * gcn10_cuda_block_tiles_deflate / gcn10_cuda_inflate_tiles call on this context with the same tile source (same
+ * blob pointer and size, same w x h) picks the result up instead of starting over, so a caller that knows its next
+ * block overlaps that block's upload + inflate with the current block's Curve Number strips:
+ *
+ *     gcn10_cuda_tiles_prefetch(ctx, &tiles[i + 1], w, h);
+ *     gcn10_cuda_block_tiles_deflate(ctx, &tiles[i], w, h, ...);        -- prefetched in the previous iteration
+ *
+ * The memory behind src->blob / offsets / sizes must stay valid and unchanged until that call has returned.
+ * At most two blocks can be waiting.  (Replaces nothing in the reference: its ranks read one block at a time,
+ * cn.c:187.) */
+int gcn10_cuda_tiles_prefetch(gcn10_ctx *ctx, const gcn10_tile_source *src, int w, int h);
+
 /* Device time of the inflate kernel of the most recent gcn10_cuda_inflate_tiles /
  * gcn10_cuda_block_tiles_deflate call (CUDA events on the launching stream). */
 int gcn10_cuda_last_inflate_ms(gcn10_ctx *ctx, float *ms);

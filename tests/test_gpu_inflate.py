@@ -201,3 +201,34 @@ def test_damaged_land_cover_stops_the_block(gpu_ctx):
     with pytest.raises(capi.Gcn10Error) as ei:
         gpu_ctx.block_tiles_deflate(bad, 600, 520, b["gt"], b["hsg"], b["soil_gt"], on_strip=lambda s: calls.append(1))
     assert ei.value.code == -6 and not calls
+
+
+def test_prefetch_overlaps_the_next_block_and_results_do_not_change(gpu_ctx, port, tables):
+    """gcn10_cuda_tiles_prefetch: block i+1's tiles are uploaded and inflated while block i's strips run; each
+    block_tiles_deflate call picks up its own prefetched land cover (oldest first), a call without a prefetch still
+    works, and a third prefetch is refused while two are waiting."""
+    blocks = [make_block(w=900, h=700, seed=60 + i, esa_patch=30) for i in range(4)]
+    srcs = [capi.TileSource.from_raster(b["esa"], 256, 256) for b in blocks]
+    wants = [port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables) for b in blocks]
+
+    def check(res, want):
+        for k in range(18):
+            assert np.array_equal(_assemble(res["tiles"][k], 900, 700), want[k])
+
+    gpu_ctx.tiles_prefetch(srcs[0], 900, 700)
+    for i in range(4):
+        if i + 1 < 4:
+            gpu_ctx.tiles_prefetch(srcs[i + 1], 900, 700)
+        b = blocks[i]
+        check(gpu_ctx.block_tiles_deflate(srcs[i], 900, 700, b["gt"], b["hsg"], b["soil_gt"]), wants[i])
+    # no prefetch: inflated inside the call
+    check(gpu_ctx.block_tiles_deflate(srcs[2], 900, 700, blocks[2]["gt"], blocks[2]["hsg"], blocks[2]["soil_gt"]), wants[2])
+    # two waiting, a third is refused; a call for another block drops nothing it needs and still works
+    gpu_ctx.tiles_prefetch(srcs[0], 900, 700)
+    gpu_ctx.tiles_prefetch(srcs[1], 900, 700)
+    with pytest.raises(capi.Gcn10Error):
+        gpu_ctx.tiles_prefetch(srcs[2], 900, 700)
+    check(gpu_ctx.block_tiles_deflate(srcs[3], 900, 700, blocks[3]["gt"], blocks[3]["hsg"], blocks[3]["soil_gt"]), wants[3])
+    check(gpu_ctx.block_tiles_deflate(srcs[1], 900, 700, blocks[1]["gt"], blocks[1]["hsg"], blocks[1]["soil_gt"]), wants[1])
+    out = gpu_ctx.inflate_tiles(srcs[0], 900, 700)
+    assert np.array_equal(out, blocks[0]["esa"])

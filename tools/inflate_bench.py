@@ -118,7 +118,12 @@ def main():
                     for ns in [int(x) for x in a.streams.split(",")]:
                         ctx.set_option("strip_rows", sr)
                         ctx.set_option("streams", ns)
-                        for name, fn in (("tiles_in", lambda: ctx.block_tiles_deflate(src, w, h, gt, hsg, sgt, capi.MASK_DRAINED, on_strip=sink)),
+                        def piped():
+                            ctx.tiles_prefetch(src, w, h)           # the next block's tiles, while this block runs
+                            ctx.block_tiles_deflate(src, w, h, gt, hsg, sgt, capi.MASK_DRAINED, on_strip=sink)
+                        ctx.tiles_prefetch(src, w, h)
+                        for name, fn in (("tiles_in_prefetch", piped),
+                                         ("tiles_in", lambda: ctx.block_tiles_deflate(src, w, h, gt, hsg, sgt, capi.MASK_DRAINED, on_strip=sink)),
                                          ("raster_in", lambda: ctx.block_deflate(esa, gt, hsg, sgt, capi.MASK_DRAINED, on_strip=sink))):
                             fn()
                             ts = []
