@@ -542,11 +542,18 @@ def run_e2e_tiles(args, ctx, capi, esa, rows, w, gt6, sgt6, hsg_np, cb, nbytes, 
         hsy, hsx = hsg_np.shape
 
         def step():
+            # the next block's tiles start their way to the GPU (H2D + inflate) beside this block's strips, as a
+            # worker that knows its next block would do; every step still uploads and inflates exactly one block
+            rc = lib.gcn10_cuda_tiles_prefetch(ctx.h, C.byref(st), w, rows)
+            if rc:
+                raise RuntimeError(lib.gcn10_cuda_last_error().decode())
             rc = lib.gcn10_cuda_block_tiles_deflate(ctx.h, C.byref(st), w, rows, gt6, hsg_np.ctypes.data, hsx, hsy, hsx,
                                                     sgt6, capi.MASK_DRAINED, cb, None)
             if rc:
                 raise RuntimeError(lib.gcn10_cuda_last_error().decode())
 
+        if lib.gcn10_cuda_tiles_prefetch(ctx.h, C.byref(st), w, rows):
+            raise RuntimeError(lib.gcn10_cuda_last_error().decode())
         for _ in range(2):
             step()
         barrier()
@@ -586,7 +593,9 @@ def run_e2e_tiles(args, ctx, capi, esa, rows, w, gt6, sgt6, hsg_np, cb, nbytes, 
                 "path": "gcn10_cuda_block_tiles_deflate: pinned host DEFLATE tiles of the land-cover GeoTIFF (zlib "
                         f"level {level}, {in_tile} x {in_tile}) -> H2D / GPU inflate / fused Curve Number + tile DEFLATE "
                         "kernel / D2H of the nine rasters' zlib tile streams -> pinned host (load_raster + cn.c + "
-                        "save_raster of process_block with compressed bytes on PCIe both ways)"}
+                        "save_raster of process_block with compressed bytes on PCIe both ways); each step also issues "
+                        "gcn10_cuda_tiles_prefetch for the following block, so one block's upload + inflate overlaps "
+                        "the previous block's strips"}
     finally:
         blob_pin.free()
 
