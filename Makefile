@@ -11,7 +11,7 @@ NVCCFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall -Xptxas -v
 
 CUDA_SO := gcn10_b200/libgcn10cuda.so
 CUDA_SRC := gcn10_b200/csrc/gcn10_cuda.cu
-CUDA_HDR := $(wildcard gcn10_b200/csrc/*.cuh) include/gcn10_cuda.h
+CUDA_HDR := $(wildcard gcn10_b200/csrc/*.cuh) $(wildcard gcn10_b200/csrc/*.h) include/gcn10_cuda.h
 
 all: cuda host oracle
 

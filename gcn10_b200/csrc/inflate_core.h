@@ -255,11 +255,11 @@ GCN10_HD int read_dynamic_header(DecodeLane &s, const uint32_t *ring, Tables &t)
     for (int i = 0; i < hclen; i++)
         cl[order[i]] = (uint8_t)get_bits(s, ring, 3);
     // the code-length code is decoded through the (not yet needed) distance lookup storage
-    uint16_t cl_sorted[19], cl_count[16];
+    uint16_t cl_count[16];
     uint32_t *cl_lut = t.d_lut;
     {
-        // 7-bit lookup: entry = nbits | sym << 16 (build_table's generic entry helpers do not apply)
-        uint16_t offs[16], next[16];
+        // 7-bit lookup: entry = nbits | sym << 16
+        uint16_t next[16];
         for (int l = 0; l < 16; l++)
             cl_count[l] = 0;
         for (int i = 0; i < 19; i++)
@@ -273,10 +273,7 @@ GCN10_HD int read_dynamic_header(DecodeLane &s, const uint32_t *ring, Tables &t)
                 return kErrCodeLengths;
         }
         uint32_t code = 0;
-        offs[1] = 0;
         for (int l = 1; l < 8; l++) {
-            if (l > 1)
-                offs[l] = (uint16_t)(offs[l - 1] + cl_count[l - 1]);
             code = (code + cl_count[l - 1]) << 1;
             next[l] = (uint16_t)code;
         }
@@ -286,12 +283,10 @@ GCN10_HD int read_dynamic_header(DecodeLane &s, const uint32_t *ring, Tables &t)
             const int l = cl[i];
             if (!l)
                 continue;
-            cl_sorted[offs[l]++] = (uint16_t)i;
             const uint32_t c = next[l]++;
             for (uint32_t k = bit_reverse(c, l); k < 128u; k += 1u << l)
                 cl_lut[k] = (uint32_t)l | ((uint32_t)i << 16);
         }
-        (void)cl_sorted;
     }
     const int total = hlit + hdist;
     int n = 0, prev = 0;
