@@ -727,7 +727,7 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
     else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
     else if (!strcmp(key, "persistent") && (value == 0 || value == 1)) c->persistent = (int)value;
     else if (!strcmp(key, "fused") && (value == 0 || value == 1)) c->fused = (int)value;
-    else if (!strcmp(key, "inflate_probe") && (value == 0 || value == 1)) c->inflate_probe = (int)value;
+    else if (!strcmp(key, "inflate_probe") && value >= 0 && value <= 2) c->inflate_probe = (int)value;
     else if (!strcmp(key, "tuned_code") && (value == 0 || value == 1)) {
         c->tuned_code = (int)value;
         c->fused_mask = 0;

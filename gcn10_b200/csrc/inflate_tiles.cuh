@@ -39,7 +39,8 @@ struct InflateParams {
     int w, h;                           // window size: pixels outside are decoded but not stored
     int *status;                        // [tiles_y][tiles_x] 0 or an inflate::kErr* code
     const int *order;                   // launch order: CTA i takes tile order[i] (longest streams first), or NULL
-    int probe;                          // measurement aid: 1 = the writer warp drops the batches (decoder speed alone)
+    int probe;                          // measurement aid: 1 = the writer warp drops the batches (decoder speed alone),
+                                        // 2 = the writer runs but does not flush the ring to the plane
 };
 
 struct InflateSmem {
@@ -357,7 +358,8 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                 if (!werr) {
                     out_base += total;
                     while (flushed + kFlushChunk <= out_base) {
-                        inflate_flush(window, d, flushed, kFlushChunk, lane);
+                        if (p.probe != 2)
+                            inflate_flush(window, d, flushed, kFlushChunk, lane);
                         flushed += kFlushChunk;
                     }
                 }

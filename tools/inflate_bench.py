@@ -101,11 +101,17 @@ def main():
             for _ in range(3):
                 ctx.inflate_tiles(src, w, h, out=out, want_status=True)
                 ms_p.append(ctx.last_inflate_ms())
+            ctx.set_option("inflate_probe", 2)
+            ms_q = []
+            for _ in range(3):
+                ctx.inflate_tiles(src, w, h, out=out, want_status=True)
+                ms_q.append(ctx.last_inflate_ms())
             ctx.set_option("inflate_probe", 0)
             rec = {"profile": prof, "tile": a.tile, "in_tile": tsz, "ntiles": int(src.sizes.size),
                    "compressed_mb": round(src.blob.size / 1e6, 2), "ratio": round(w * h / max(src.blob.size, 1), 2),
                    "host_compress_s": round(t_comp, 2), "inflate_kernel_ms": round(float(np.median(ms_k)), 3),
                    "decoder_only_ms": round(float(np.median(ms_p)), 3),
+                   "no_flush_ms": round(float(np.median(ms_q)), 3),
                    "inflate_out_gbs": round(w * h / 1e6 / float(np.median(ms_k)), 1),
                    "inflate_to_host_ms": round(float(np.median(ms_e2e)), 2), "matches_source": ok}
             if not a.skip_e2e:
