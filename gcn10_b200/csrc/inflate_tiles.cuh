@@ -5,18 +5,19 @@
 // device as they lie in the file and one warp per tile inflates them straight into the land-cover plane
 // the Curve Number kernel reads (window clipping included), so PCIe carries ~1/20 of the raster.
 //
-// One CTA = one tile (zlib stream) = two warps in a producer / consumer pair:
+// One CTA = one tile (zlib stream) = three warps in a pipeline:
 //   decoder warp  tops up the 2 KB compressed-input ring (16-byte loads by all lanes); lane 0 owns the bit
 //                 reader and turns code words into batches of up to 32 LZ77 symbols (inflate_core.h); block
 //                 headers are parsed by lane 0, the Huffman lookup tables are filled by all 32 lanes.
 //   writer warp   executes the batches against a 32 KB history ring in shared memory: a warp scan of the
 //                 symbol lengths gives every symbol its output position, all literals are written at once,
-//                 matches are copied one after the other (32 or 128 bytes per step); finished 4 KB pieces of
-//                 the ring are flushed to the land-cover plane in HBM with 16-byte stores, clipped to the
-//                 requested window.
-// The two warps hand over through a double-buffered symbol queue guarded by named barriers (bar.sync /
-// bar.arrive), so decoding batch k+1 overlaps executing batch k.  Shared memory per CTA: 43 KB (history 32 KB,
-// tables 7.6 KB, input ring 2 KB, queues 0.5 KB) -> five tiles in flight per SM.
+//                 matches are copied one after the other (32 or 128 bytes per step).
+//   flusher warp  writes finished 4 KB pieces of the ring to the land-cover plane in HBM with 16-byte stores,
+//                 clipped to the requested window, while the writer goes on (at most two pieces in flight).
+// The warps hand over through a double-buffered symbol queue and a two-deep piece queue, both guarded by named
+// barriers (bar.sync / bar.arrive with literal barrier numbers), so decoding batch k+1, executing batch k and
+// storing the bytes of earlier batches overlap.  Shared memory per CTA: 43 KB (history 32 KB, tables 7.6 KB,
+// input ring 2 KB, queues 0.5 KB) -> five tiles in flight per SM.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -49,12 +50,13 @@ struct InflateSmem {
     uint32_t queue[2][inflate::kQueue];
     int meta[2][8];                     // n, event, stored_src, stored_len, decoder error, final flag
     volatile int writer_err;
+    volatile uint32_t fl_pos[2], fl_len[2];     // ring pieces handed to the flusher warp (len 0 = quit)
     int pad[3];
     uint8_t window[inflate::kWindow];
 };
 
 constexpr int kInflateSmem = (int)sizeof(InflateSmem);
-constexpr int kInflateThreads = 64;
+constexpr int kInflateThreads = 96;      // decoder warp, writer warp, flusher warp
 constexpr uint32_t kFlushChunk = 4096;
 
 struct TileDst {
@@ -74,6 +76,11 @@ __device__ __forceinline__ void bar_sync_full(int b) { if (b) bar_sync_id<kBarFu
 __device__ __forceinline__ void bar_arrive_full(int b) { if (b) bar_arrive_id<kBarFull1>(); else bar_arrive_id<kBarFull0>(); }
 __device__ __forceinline__ void bar_sync_empty(int b) { if (b) bar_sync_id<kBarEmpty1>(); else bar_sync_id<kBarEmpty0>(); }
 __device__ __forceinline__ void bar_arrive_empty(int b) { if (b) bar_arrive_id<kBarEmpty1>(); else bar_arrive_id<kBarEmpty0>(); }
+// writer <-> flusher: 5, 6 = "piece k is ready", 7, 8 = "piece k has been written out"
+__device__ __forceinline__ void bar_sync_ready(int k) { if (k) bar_sync_id<6>(); else bar_sync_id<5>(); }
+__device__ __forceinline__ void bar_arrive_ready(int k) { if (k) bar_arrive_id<6>(); else bar_arrive_id<5>(); }
+__device__ __forceinline__ void bar_sync_done(int k) { if (k) bar_sync_id<8>(); else bar_sync_id<7>(); }
+__device__ __forceinline__ void bar_arrive_done(int k) { if (k) bar_arrive_id<8>(); else bar_arrive_id<7>(); }
 
 // history ring piece [p0, p0 + nbytes) -> plane (p0 is a multiple of 16); whole warp
 __device__ __forceinline__ void inflate_flush(const uint8_t *window, const TileDst &d, uint32_t p0, uint32_t nbytes,
@@ -189,7 +196,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
         // sparse tile: GDAL returns zeros for a tile without data
         const int x0 = max(d.dx0, 0), x1 = min(d.dx0 + p.tile_w, p.w);
         const int y0 = max(d.dy0, 0), y1 = min(d.dy0 + p.tile_h, p.h);
-        for (int y = y0 + warp; y < y1; y += 2)
+        for (int y = y0 + warp; y < y1; y += kInflateThreads / 32)
             for (int x = x0 + lane; x < x1; x += 32)
                 p.dst[(size_t)y * p.pitch + x] = 0;
         if (threadIdx.x == 0)
@@ -291,6 +298,19 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
             }
         }
     }
+    else if (warp == 2) {
+        // ------------------------------------------------------------------ flusher warp: ring pieces -> plane
+        bar_arrive_done(0);
+        bar_arrive_done(1);
+        for (int k = 0;; k ^= 1) {
+            bar_sync_ready(k);
+            const uint32_t pos = sm.fl_pos[k], len = sm.fl_len[k];
+            if (len == 0)
+                break;
+            inflate_flush(sm.window, d, pos, len, lane);
+            bar_arrive_done(k);
+        }
+    }
     else {
         // ------------------------------------------------------------------ writer warp
         uint8_t *window = sm.window;
@@ -298,6 +318,19 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
         bar_arrive_empty(0);
         bar_arrive_empty(1);
         uint32_t out_base = 0, flushed = 0;
+        int npost = 0;
+        // hands ring piece [pos, pos + len) to the flusher warp (len 0: no more pieces); at most two are in flight
+        auto post = [&](uint32_t pos, uint32_t len) {
+            const int k = npost & 1;
+            bar_sync_done(k);
+            if (lane == 0) {
+                sm.fl_pos[k] = pos;
+                sm.fl_len[k] = len;
+            }
+            __syncwarp();
+            bar_arrive_ready(k);
+            npost++;
+        };
         int werr = 0, b = 0;
         for (;;) {
             bar_sync_full(b);
@@ -359,7 +392,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                     out_base += total;
                     while (flushed + kFlushChunk <= out_base) {
                         if (p.probe != 2)
-                            inflate_flush(window, d, flushed, kFlushChunk, lane);
+                            post(flushed, kFlushChunk);
                         flushed += kFlushChunk;
                     }
                 }
@@ -378,7 +411,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                         out_base += m;
                         done += m;
                         while (flushed + kFlushChunk <= out_base) {
-                            inflate_flush(window, d, flushed, kFlushChunk, lane);
+                            post(flushed, kFlushChunk);
                             flushed += kFlushChunk;
                         }
                     }
@@ -399,8 +432,9 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
         }
         if (!werr && flushed < out_end) {
             __syncwarp();
-            inflate_flush(window, d, flushed, out_end - flushed, lane);
+            post(flushed, out_end - flushed);
         }
+        post(0, 0);
         if (lane == 0)
             p.status[tile] = werr;
     }
