@@ -82,6 +82,24 @@ __device__ __forceinline__ void bar_arrive_ready(int k) { if (k) bar_arrive_id<6
 __device__ __forceinline__ void bar_sync_done(int k) { if (k) bar_sync_id<8>(); else bar_sync_id<7>(); }
 __device__ __forceinline__ void bar_arrive_done(int k) { if (k) bar_arrive_id<8>(); else bar_arrive_id<7>(); }
 
+// The writer warp addresses the history ring through its 32-bit shared-memory address with explicit ld.shared /
+// st.shared: through a generic pointer the compiler rebuilds the shared window base (S2R SR_CgaCtaId + LEA) at
+// every predicated access of its copy loops.
+struct Ring {
+    uint32_t base;              // shared-space address of window[0]
+    __device__ __forceinline__ uint32_t at(uint32_t pos) const { return base + (pos & (uint32_t)(inflate::kWindow - 1)); }
+    __device__ __forceinline__ uint32_t ld8(uint32_t pos) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(at(pos)) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void st8(uint32_t pos, uint32_t v) const
+    {
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(at(pos)), "r"(v) : "memory");
+    }
+};
+
 // history ring piece [p0, p0 + nbytes) -> plane (p0 is a multiple of 16); whole warp
 __device__ __forceinline__ void inflate_flush(const uint8_t *window, const TileDst &d, uint32_t p0, uint32_t nbytes,
                                               int lane)
@@ -120,47 +138,54 @@ __device__ __forceinline__ void inflate_flush(const uint8_t *window, const TileD
 }
 
 // copy of one match by the whole warp: bytes [mp, mp + len) := bytes [mp - dist, ...) of the history ring
-__device__ __forceinline__ void inflate_copy(uint8_t *window, uint32_t mp, uint32_t len, uint32_t dist, int lane)
+__device__ __forceinline__ void inflate_copy(const Ring window, uint32_t mp, uint32_t len, uint32_t dist, int lane)
 {
-    constexpr uint32_t M = inflate::kWindow - 1;
-    if (dist >= 128u) {
-        // a 128-byte step never reads what the same step writes
+    if (dist >= len) {
+        // source and destination do not overlap (nearly every match): a plain 32-lane loop, one barrier
+        for (uint32_t i = lane; i < len; i += 32u)
+            window.st8(mp + i, window.ld8(mp - dist + i));
+        __syncwarp();
+    }
+    else if (dist >= 128u) {
+        // overlapping (a 258-byte match at distance 256: the row above in a 256-wide tile), but a 128-byte step
+        // never reads what the same step writes
         for (uint32_t b = 0; b < len; b += 128u) {
-            uint8_t v[4];
+            uint32_t v[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t i = b + lane + 32u * k;
-                v[k] = i < len ? window[(mp - dist + i) & M] : (uint8_t)0;
+                v[k] = i < len ? window.ld8(mp - dist + i) : 0u;
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t i = b + lane + 32u * k;
                 if (i < len)
-                    window[(mp + i) & M] = v[k];
+                    window.st8(mp + i, v[k]);
             }
             __syncwarp();
         }
     }
     else if (dist >= 32u) {
+        // overlapping, but a 32-byte step never reads what the same step writes
         for (uint32_t b = 0; b < len; b += 32u) {
             const uint32_t i = b + lane;
             if (i < len)
-                window[(mp + i) & M] = window[(mp - dist + i) & M];
+                window.st8(mp + i, window.ld8(mp - dist + i));
             __syncwarp();
         }
     }
     else if (dist == 1u) {
-        const uint8_t v = window[(mp - 1u) & M];
+        const uint32_t v = window.ld8(mp - 1u);
         for (uint32_t i = lane; i < len; i += 32u)
-            window[(mp + i) & M] = v;
+            window.st8(mp + i, v);
         __syncwarp();
     }
     else {
-        // overlapping copy: the pattern of the last `dist` bytes repeats; sources all lie before mp
+        // the pattern of the last `dist` bytes repeats; sources all lie before mp
         uint32_t q = (uint32_t)lane % dist;
         const uint32_t step = 32u % dist;
         for (uint32_t i = lane; i < len; i += 32u) {
-            window[(mp + i) & M] = window[(mp - dist + q) & M];
+            window.st8(mp + i, window.ld8(mp - dist + q));
             q += step;
             if (q >= dist)
                 q -= dist;
@@ -313,8 +338,8 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
     }
     else {
         // ------------------------------------------------------------------ writer warp
-        uint8_t *window = sm.window;
-        constexpr uint32_t M = kWindow - 1;
+        Ring window;
+        window.base = (uint32_t)__cvta_generic_to_shared(sm.window);
         bar_arrive_empty(0);
         bar_arrive_empty(1);
         uint32_t out_base = 0, flushed = 0;
@@ -363,7 +388,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                     werr = kErrDistance;
                 else if (!far) {
                     if (lane < n && !is_match)
-                        window[start & M] = (uint8_t)sym;
+                        window.st8(start, sym);
                     __syncwarp();
                     unsigned mm = __ballot_sync(full, is_match);
                     while (mm) {
@@ -383,7 +408,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                             inflate_copy(window, mp, ms & 0x1FFu, sym_dist(ms), lane);
                         else {
                             if (lane == 0)
-                                window[mp & M] = (uint8_t)ms;
+                                window.st8(mp, ms);
                             __syncwarp();
                         }
                     }
@@ -406,7 +431,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                     while (done < sl) {
                         const uint32_t m = min(sl - done, kFlushChunk);
                         for (uint32_t i = lane; i < m; i += 32u)
-                            window[(out_base + i) & M] = base[so + done + i];
+                            window.st8(out_base + i, base[so + done + i]);
                         __syncwarp();
                         out_base += m;
                         done += m;
