@@ -400,17 +400,27 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                     }
                 }
                 else {
-                    // a match reaches far back: no literal hoisting, strictly in stream order
-                    for (int k = 0; k < n; k++) {
-                        const uint32_t ms = __shfl_sync(full, sym, k);
-                        const uint32_t mp = __shfl_sync(full, start, k);
-                        if (sym_is_match(ms))
+                    // A match reaches far back: hoisting ALL literals of the batch could overwrite history it still
+                    // reads.  The batch is cut behind every such match; inside a part the literals (all in front of the
+                    // far match that ends it) are hoisted as usual, then its matches run in order.
+                    unsigned rest = n >= 32 ? 0xffffffffu : (1u << n) - 1u;
+                    const unsigned matches = __ballot_sync(full, is_match);
+                    while (rest) {
+                        const unsigned f = far & rest;
+                        const int end = f ? __ffs(f) - 1 : 31 - __clz(rest);
+                        const unsigned part = rest & ((2u << end) - 1u);
+                        if (((part >> lane) & 1u) && !is_match)
+                            window.st8(start, sym);
+                        __syncwarp();
+                        unsigned mm = matches & part;
+                        while (mm) {
+                            const int owner = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const uint32_t ms = __shfl_sync(full, sym, owner);
+                            const uint32_t mp = __shfl_sync(full, start, owner);
                             inflate_copy(window, mp, ms & 0x1FFu, sym_dist(ms), lane);
-                        else {
-                            if (lane == 0)
-                                window.st8(mp, ms);
-                            __syncwarp();
                         }
+                        rest &= ~part;
                     }
                 }
                 if (!werr) {

@@ -3,7 +3,7 @@
 // Compiles gcn10_b200/csrc/inflate_core.h (the decode-lane half of the GPU tile inflater) for the host
 // and drives it with a scalar emulation of the warp loop of inflate_tiles.cuh: same 2 KB input ring and
 // refill rule, same batch order (all literals of a batch first, then the matches one after the other in
-// 32-byte read-then-write steps against a 32 KB history ring).  tests/test_inflate_core.py compares the
+// 32- or 128-byte read-then-write steps against a 32 KB history ring, the batch cut behind every far-reaching match).  tests/test_inflate_core.py compares the
 // result with zlib on the CPU, so the bit reader, the Huffman table builder, the symbol decoder and the
 // batch-hazard rule are checked without a GPU.  Built by the test itself (g++ -shared); nothing under
 // gcn10_b200/ links or loads it.
@@ -99,50 +99,60 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
         // ---- writer warp
         if (n > 0 && !werr) {
             uint32_t start[kQueue], pos = out_base;
-            bool bad = false, far = false;
+            bool bad = false;
             for (int k = 0; k < n; k++) {
                 start[k] = pos;
                 pos += sym_len(queue[k]);
                 if (sym_is_match(queue[k]) && sym_dist(queue[k]) > start[k])
                     bad = true;
-                if (sym_is_far(queue[k]))
-                    far = true;
             }
             if (pos > out_len)
                 werr = kErrOverflow;
             else if (bad)
                 werr = kErrDistance;
             else {
-                if (!far)
-                    for (int k = 0; k < n; k++)
+                // as the writer warp does it: the batch is cut behind every far match; inside a part all literals
+                // are written first, then the part's matches in order (one part = the whole batch without far matches)
+                int lo = 0;
+                while (lo < n) {
+                    int hi = lo;
+                    while (hi < n - 1 && !sym_is_far(queue[hi]))
+                        hi++;
+                    for (int k = lo; k <= hi; k++)
                         if (!sym_is_match(queue[k]))
                             emit(start[k], (uint8_t)(queue[k] & 255u));
-                for (int k = 0; k < n; k++) {
-                    if (!sym_is_match(queue[k])) {
-                        if (far)
-                            emit(start[k], (uint8_t)(queue[k] & 255u));
-                        continue;
-                    }
-                    nmatch++;
-                    const uint32_t len = queue[k] & 0x1FFu, dist = sym_dist(queue[k]), mp = start[k];
-                    const uint32_t stepw = dist >= 128u ? 128u : 32u;
-                    if (dist >= 32u) {
-                        for (uint32_t b = 0; b < len; b += stepw) {
-                            uint8_t tmp[128];
-                            const uint32_t m = len - b < stepw ? len - b : stepw;
-                            for (uint32_t j = 0; j < m; j++)
-                                tmp[j] = window[(mp - dist + b + j) & (kWindow - 1)];
-                            for (uint32_t j = 0; j < m; j++)
-                                emit(mp + b + j, tmp[j]);
+                    for (int k = lo; k <= hi; k++) {
+                        if (!sym_is_match(queue[k]))
+                            continue;
+                        nmatch++;
+                        const uint32_t len = queue[k] & 0x1FFu, dist = sym_dist(queue[k]), mp = start[k];
+                        if (dist >= len) {
+                            std::vector<uint8_t> tmp(len);
+                            for (uint32_t j = 0; j < len; j++)
+                                tmp[j] = window[(mp - dist + j) & (kWindow - 1)];
+                            for (uint32_t j = 0; j < len; j++)
+                                emit(mp + j, tmp[j]);
+                        }
+                        else if (dist >= 32u) {
+                            const uint32_t stepw = dist >= 128u ? 128u : 32u;
+                            for (uint32_t b = 0; b < len; b += stepw) {
+                                uint8_t tmp[128];
+                                const uint32_t m = len - b < stepw ? len - b : stepw;
+                                for (uint32_t j = 0; j < m; j++)
+                                    tmp[j] = window[(mp - dist + b + j) & (kWindow - 1)];
+                                for (uint32_t j = 0; j < m; j++)
+                                    emit(mp + b + j, tmp[j]);
+                            }
+                        }
+                        else {
+                            uint8_t pat[32];
+                            for (uint32_t j = 0; j < dist; j++)
+                                pat[j] = window[(mp - dist + j) & (kWindow - 1)];
+                            for (uint32_t i = 0; i < len; i++)
+                                emit(mp + i, pat[i % dist]);
                         }
                     }
-                    else {
-                        uint8_t pat[32];
-                        for (uint32_t j = 0; j < dist; j++)
-                            pat[j] = window[(mp - dist + j) & (kWindow - 1)];
-                        for (uint32_t i = 0; i < len; i++)
-                            emit(mp + i, pat[i % dist]);
-                    }
+                    lo = hi + 1;
                 }
                 nsym += (uint64_t)n;
                 out_base = pos;
