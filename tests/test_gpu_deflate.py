@@ -189,3 +189,25 @@ def test_deflate_rows_bands_equal_whole_block(gpu_ctx, port, tables):
         tiles = {(r, c): z for (p, r, c), z in got.items() if p == k}
         full = _assemble(tiles, w, h)
         assert np.array_equal(full[:h, :w], want[k]), k
+
+
+@pytest.mark.parametrize("break_row", [None, 129, 2, 255, 130, 3])
+def test_long_row_runs(break_row, gpu_ctx, port, tables, encoder_path):
+    """Uniform rasters: every tile row repeats the row above, so whole tiles are coded as runs of length-258
+    matches across the rows (fused_row_run).  break_row starts a new run there: run lengths 255, 128 (the case whose
+    remainder of 2 bytes has to be merged into the last two matches), 1, 254, 129, 2 ..."""
+    w, h = 700, 600
+    b = make_block(w=w, h=h, seed=3)
+    b["esa"][:] = 20
+    b["hsg"][:] = 2
+    if break_row is not None:
+        b["esa"][break_row:] = 40
+        b["esa"][256 + break_row:] = 10            # the second tile row gets the same structure
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    for k in range(18):
+        assert np.array_equal(_assemble(res["tiles"][k], w, h)[:h, :w], want[k]), f"plane {k}"
+    # a tile of 256 repeated rows: 254 tokens of 10 bits (tuned code), 19 bits (fixed code), or one 24-bit token per
+    # row (two-kernel path), plus a few tokens where the raster changes
+    per_tile = {"fused_tuned_code": 450, "fused_fixed_code": 750, "two_kernel": 900}[encoder_path]
+    assert res["bytes"] < 18 * 9 * per_tile, "uniform tiles must collapse to a few hundred bytes each"
