@@ -240,9 +240,12 @@ int gcn10_cuda_last_kernel_ms(gcn10_ctx *ctx, float *ms);
 /* Number of kernels this context has launched since it was created. */
 int gcn10_cuda_launch_count(gcn10_ctx *ctx, uint64_t *launches);
 
-/* Tunables: "strip_rows" (rows per pipelined strip in gcn10_cuda_block), "streams"
- * (1..8), "rows_per_cta" (0 = automatic), "tma" (0 = always use the gather fallback for HSG
- * staging), "persistent" (0 = one CTA per row chunk instead of the persistent-CTA kernel). */
+/* Tunables: "strip_rows" (rows per pipelined strip in the host-buffer calls), "streams" (1..8), "rows_per_cta"
+ * (0 = automatic), "tma" (0 = always use the gather fallback for HSG staging), "persistent" (1 = the persistent-CTA
+ * form of the streaming kernel), "fused" (0 = compressed-tile calls run the Curve Number kernel and the per-plane
+ * tile encoder instead of the fused kernel), "tuned_code" (0 = tile streams use RFC 1951's fixed Huffman code instead
+ * of the tuned one), "inflate_probe" (measurement aid of tools/inflate_bench.py: 1 / 2 switch parts of the inflate
+ * kernel's writer off; results are then invalid). */
 int gcn10_cuda_set_option(gcn10_ctx *ctx, const char *key, long value);
 
 /* Pins the calling host thread to the CPUs of the NUMA node the GPU hangs off (from
