@@ -147,7 +147,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     import multiprocessing as mp
-    from gcn10_b200 import lookups
+    from tests import lookups
     lookup_dir = lookups.write_default_lookups(tempfile.mkdtemp(prefix="gcn10_lookups_"))
     try:
         cores = len(os.sched_getaffinity(0))
@@ -253,7 +253,8 @@ def run_ours(args):
     import numpy as np
     import torch
 
-    from gcn10_b200 import capi, lookups, synth
+    from gcn10_b200 import capi, synth
+    from tests import lookups
 
     from gcn10_b200 import dist as gdist
     rank, local_rank, world = gdist.env_world()
@@ -609,7 +610,7 @@ def load_tables_host(lookup_dir):
         return hostlib.load_lookup_tables(lookup_dir)
     except Exception:
         pass
-    from gcn10_b200 import lookups
+    from tests import lookups
     t = np.full((9, 256, 5), 255, dtype=np.int32)
     for i, v in enumerate(lookups.VARIANTS):
         with open(os.path.join(lookup_dir, f"default_lookup_{v}.csv"), "rb") as f:

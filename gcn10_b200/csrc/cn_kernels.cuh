@@ -424,226 +424,6 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent form of the streaming kernel (bulk-store build): one launch of (resident CTAs per SM) x
-// (SM count) CTAs; each CTA walks the units (4096-pixel strip x rows_per_cta rows) u = blockIdx.x,
-// blockIdx.x + gridDim.x, ... in row-major order.  The LUT is filled once per CTA, the HSG box of the
-// next unit is requested (TMA, second buffer) while the current one is processed, and the land-cover
-// prefetch queue runs across unit boundaries, so there is no per-unit prologue left.
-// Measured on B200 it is SLOWER than the one-CTA-per-chunk kernel above (2.28 ms vs 2.06 ms for the 9-plane
-// tile, profiles/r01_kernel_sweeps.md): the hardware CTA scheduler's dynamic balancing and the tighter row
-// locality of freshly launched CTAs outweigh the saved prologues.  Kept selectable (option "persistent") and
-// parity-tested; not the default.
-
-constexpr int kP_BoxOff = kLutBytes;                                // two HSG boxes
-constexpr int kP_BarOff = kP_BoxOff + 2 * kBoxRows * kBoxCols;      // LUT barrier + two box barriers
-constexpr int kP_StageOff = kP_BarOff + 128;
-constexpr int persistent_smem_bytes(int planes) { return kP_StageOff + 2 * planes * kStripPx; }
-
-struct UnitGeom {
-    int x_first, y_begin, y_end, ci_min, cj_min;
-    bool staged;
-};
-
-__device__ __forceinline__ UnitGeom unit_geom(const BlockParams &p, int u, int n_strips, int w16)
-{
-    UnitGeom g;
-    const int strip = u % n_strips, chunk = u / n_strips;
-    g.x_first = strip * kStripPx;
-    g.y_begin = chunk * p.rows_per_cta;
-    g.y_end = min(p.h, g.y_begin + p.rows_per_cta);
-    const int x_last = min(w16, g.x_first + kStripPx) - 1;
-    const int ca = __ldg(p.col_idx + g.x_first), cb = __ldg(p.col_idx + x_last);
-    const int ra = __ldg(p.row_idx + p.y_base + g.y_begin), rb = __ldg(p.row_idx + p.y_base + g.y_end - 1);
-    g.ci_min = min(ca, cb) & ~15;
-    g.cj_min = min(ra, rb);
-    g.staged = p.use_tma && (max(ca, cb) - g.ci_min < kBoxCols) && (max(ra, rb) - g.cj_min < kBoxRows);
-    return g;
-}
-
-template <int NP, int G>
-__global__ void __launch_bounds__(kThreads, 2)
-cn_block_persistent(const __grid_constant__ BlockParams p, const __grid_constant__ CUtensorMap hsg_map)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x;
-    const int w16 = p.w & ~(kVecPx - 1);
-    const int n_strips = (w16 + kStripPx - 1) / kStripPx;
-    const int n_chunks = (p.h + p.rows_per_cta - 1) / p.rows_per_cta;
-    const int n_units = n_strips * n_chunks;
-    const int stride = gridDim.x;
-    int u = blockIdx.x;
-    if (u >= n_units)
-        return;
-
-    const uint32_t bar_lut = smem_u32(smem + kP_BarOff);
-    const uint32_t bar_box = bar_lut + 8;           // two barriers, 8 bytes apart
-    const uint32_t s_box = smem_u32(smem + kP_BoxOff);
-
-    UnitGeom g = unit_geom(p, u, n_strips, w16);
-    if (tid == 0) {
-        mbar_init(bar_lut, 1);
-        mbar_init(bar_box, 1);
-        mbar_init(bar_box + 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_lut, kLutBytes);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"(smem_u32(smem)), "l"(p.lut), "r"(kLutBytes), "r"(bar_lut) : "memory");
-        if (g.staged) {
-            mbar_expect_tx(bar_box, kBoxRows * kBoxCols);
-            tma_load_2d(s_box, &hsg_map, g.ci_min, g.cj_min, bar_box);
-        }
-        else {
-            mbar_arrive(bar_box);       // keep the phase sequence of the box barriers uniform
-        }
-    }
-
-    // land-cover prefetch iterator: runs kPrefetch rows ahead of the compute position, across units
-    int pu = u, py = g.y_begin, py_end = g.y_end;
-    int px = (g.x_first + tid * kVecPx < w16) ? g.x_first + tid * kVecPx : g.x_first;
-    uint4 eq[kPrefetch];
-    int cq[kPrefetch];
-    auto fetch = [&](uint4 &e, int &c) {
-        if (pu < n_units) {
-            e = ldg_stream16(p.esa + (size_t)py * p.esa_pitch + px);
-            c = __ldg(p.row_idx + p.y_base + py);
-            if (++py == py_end) {
-                pu += stride;
-                if (pu < n_units) {
-                    const int strip = pu % n_strips, chunk = pu / n_strips;
-                    const int xf = strip * kStripPx;
-                    px = (xf + tid * kVecPx < w16) ? xf + tid * kVecPx : xf;
-                    py = chunk * p.rows_per_cta;
-                    py_end = min(p.h, py + p.rows_per_cta);
-                }
-            }
-        }
-    };
-#pragma unroll
-    for (int s = 0; s < kPrefetch; s++) {
-        eq[s] = make_uint4(0, 0, 0, 0);
-        cq[s] = 0;
-        fetch(eq[s], cq[s]);
-    }
-
-    __syncthreads();            // barriers initialised
-    mbar_wait(bar_lut, 0);
-
-    const uint32_t swz_mask = 0x07070707u;
-    uint32_t rowctr = 0;
-    for (int k = 0; u < n_units; u += stride, k++) {
-        if (k > 0)
-            g = unit_geom(p, u, n_strips, w16);
-        // request the next unit's HSG box into the other buffer (its last readers passed the per-row barrier
-        // of the previous unit's last row)
-        if (tid == 0 && u + stride < n_units) {
-            const UnitGeom gn = unit_geom(p, u + stride, n_strips, w16);
-            const uint32_t b = bar_box + 8 * ((k + 1) & 1);
-            if (gn.staged) {
-                mbar_expect_tx(b, kBoxRows * kBoxCols);
-                tma_load_2d(s_box + ((k + 1) & 1) * (kBoxRows * kBoxCols), &hsg_map, gn.ci_min, gn.cj_min, b);
-            }
-            else {
-                mbar_arrive(b);
-            }
-        }
-        mbar_wait(bar_box + 8 * (k & 1), (k >> 1) & 1);
-
-        const int x0 = (g.x_first + tid * kVecPx < w16) ? g.x_first + tid * kVecPx : g.x_first;
-        const uint32_t row_bytes = (uint32_t)(min(w16, g.x_first + kStripPx) - g.x_first);
-        size_t row_off = (size_t)g.y_begin * p.out_pitch + g.x_first;
-        const int box_off = kP_BoxOff + (k & 1) * (kBoxRows * kBoxCols);
-        uint32_t slot[G][4];
-        int cj_cur = INT_MIN;
-#pragma unroll
-        for (int gi = 0; gi < G; gi++)
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                slot[gi][j] = 0;
-
-        for (int y = g.y_begin; y < g.y_end; y++, rowctr++) {
-            const uint4 e = eq[0];
-            const int cj = cq[0];
-#pragma unroll
-            for (int s = 0; s + 1 < kPrefetch; s++) {
-                eq[s] = eq[s + 1];
-                cq[s] = cq[s + 1];
-            }
-            fetch(eq[kPrefetch - 1], cq[kPrefetch - 1]);
-
-            if (cj != cj_cur) {
-                cj_cur = cj;
-                const int4 *cp = reinterpret_cast<const int4 *>(p.col_idx + x0);
-                const uint8_t *row_g = p.hsg + (size_t)cj * p.hsg_pitch;
-                const int row_s = box_off + (cj - g.cj_min) * kBoxCols - g.ci_min;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int4 c4 = __ldg(cp + j);
-                    const int cc[4] = { c4.x, c4.y, c4.z, c4.w };
-                    uint32_t acc[G];
-#pragma unroll
-                    for (int gi = 0; gi < G; gi++)
-                        acc[gi] = 0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint32_t hv = g.staged ? (uint32_t)smem[row_s + cc[q]] : (uint32_t)__ldg(row_g + cc[q]);
-#pragma unroll
-                        for (int gi = 0; gi < G; gi++)
-                            acc[gi] |= (soil_slot(hv, p.group_drained[gi]) << 4) << (8 * q);
-                    }
-#pragma unroll
-                    for (int gi = 0; gi < G; gi++)
-                        slot[gi][j] = acc[gi];
-                }
-            }
-
-            const uint32_t ew[4] = { e.x, e.y, e.z, e.w };
-            uint32_t fz[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                fz[j] = ((ew[j] >> p.swz_shift) & swz_mask) << 4;
-
-            uint8_t *stage_row = smem + kP_StageOff + (rowctr & 1) * (NP * G * kStripPx);
-#pragma unroll
-            for (int gi = 0; gi < G; gi++) {
-                uint32_t ow[NP][4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t sx = slot[gi][j] ^ fz[j];
-                    uint4 r[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint32_t lc = __byte_perm(ew[j], 0, 0x4440 | q);
-                        const uint32_t sb = __byte_perm(sx, 0, 0x4440 | q);
-                        r[q] = *reinterpret_cast<const uint4 *>(smem + (lc * 128u + sb));
-                    }
-                    transpose_store_word<NP>(r, ow, j);
-                }
-#pragma unroll
-                for (int kk = 0; kk < NP; kk++)
-                    *reinterpret_cast<uint4 *>(stage_row + (gi * NP + kk) * kStripPx + tid * kVecPx) =
-                        make_uint4(ow[kk][0], ow[kk][1], ow[kk][2], ow[kk][3]);
-            }
-
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (tid == 0)
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncthreads();
-            if (tid == 0) {
-                const uint32_t stage = smem_u32(stage_row);
-#pragma unroll
-                for (int kk = 0; kk < NP * G; kk++)
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(p.out[kk] + row_off), "r"(stage + kk * kStripPx), "r"(row_bytes) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            row_off += p.out_pitch;
-        }
-    }
-    if (tid == 0)
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
-// ---------------------------------------------------------------------------------------------
 // Byte-wise kernel for columns [x_begin, w) of every row: the right edge the vector kernel leaves
 // (w % 16 pixels) or, with x_begin = 0, whole blocks whose buffers are not 16-byte aligned.
 // Planes are addressed through the same compacted out[] list; NP and G are runtime values here.

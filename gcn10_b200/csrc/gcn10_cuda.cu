@@ -99,8 +99,6 @@ struct gcn10_ctx {
     int strip_rows = 2048;
     int rows_per_cta = 0;       // 0 = auto (see auto_rows_per_cta)
     int use_tma = 1;
-    int persistent = 0;         // 1 = persistent-CTA form of the streaming kernel (measured slower, see profiles/)
-    int persistent_ctas[10][3] = {};         // resident CTAs per SM by [np][groups], from the occupancy API
     int inflate_probe = 0;      // measurement aid for tools/inflate_bench.py (see InflateParams::probe)
     int fused = 1;              // compressed-tile calls use cn_deflate_fused_kernel (0 = CN kernel + tile encoder)
     DevBuf fused_tab;           // idmap [256][16] | val [256][32] | lit9 [256][6] u64
@@ -263,28 +261,6 @@ BlockKernel pick_kernel(int np, int groups)
     return nullptr;
 }
 
-template <int NP>
-BlockKernel pick_pg(int groups)
-{
-    return groups == 2 ? (BlockKernel)cn_block_persistent<NP, 2> : (BlockKernel)cn_block_persistent<NP, 1>;
-}
-
-BlockKernel pick_persistent(int np, int groups)
-{
-    switch (np) {
-    case 1: return pick_pg<1>(groups);
-    case 2: return pick_pg<2>(groups);
-    case 3: return pick_pg<3>(groups);
-    case 4: return pick_pg<4>(groups);
-    case 5: return pick_pg<5>(groups);
-    case 6: return pick_pg<6>(groups);
-    case 7: return pick_pg<7>(groups);
-    case 8: return pick_pg<8>(groups);
-    case 9: return pick_pg<9>(groups);
-    }
-    return nullptr;
-}
-
 struct LaunchPlan {
     int np = 0, groups = 0;     // planes per group, number of groups in this launch
     int drained[2] = { 1, 0 };
@@ -423,18 +399,8 @@ int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t 
         while ((rows + p.rows_per_cta - 1) / p.rows_per_cta > 65535)     // gridDim.y limit, only for absurdly tall rasters
             p.rows_per_cta *= 2;
         dim3 grid((w16 + kStripPx - 1) / kStripPx, (rows + p.rows_per_cta - 1) / p.rows_per_cta);
-        const int resident = c->persistent_ctas[lp.np][lp.groups];
-        if (c->persistent && GCN10_BULK_STORE && resident > 0) {
-            if (c->rows_per_cta <= 0)
-                p.rows_per_cta = 8;         // no per-unit prologue left to amortise: short units balance best
-            const long long units = (long long)grid.x * ((rows + p.rows_per_cta - 1) / p.rows_per_cta);
-            const int ctas = (int)std::min<long long>(units, (long long)resident * c->sm_count);
-            pick_persistent(lp.np, lp.groups)<<<ctas, kThreads, persistent_smem_bytes(lp.np * lp.groups), st>>>(p, map);
-        }
-        else {
-            BlockKernel k = pick_kernel(lp.np, lp.groups);
-            k<<<grid, kThreads, smem_bytes_for(lp.np * lp.groups), st>>>(p, map);
-        }
+        BlockKernel k = pick_kernel(lp.np, lp.groups);
+        k<<<grid, kThreads, smem_bytes_for(lp.np * lp.groups), st>>>(p, map);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         x_bytes = w16;
@@ -652,17 +618,6 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
         for (int g = 1; g <= 2; g++)
             CUDA_TRY(cudaFuncSetAttribute((const void *)pick_kernel(np, g),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(np * g)));
-    for (int np = 1; np <= 9; np++)
-        for (int g = 1; g <= 2; g++) {
-            const void *k = (const void *)pick_persistent(np, g);
-            const int bytes = persistent_smem_bytes(np * g);
-            int n = 0;
-            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess &&
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kThreads, bytes) == cudaSuccess)
-                c->persistent_ctas[np][g] = n;
-            else
-                cudaGetLastError();         // this shape falls back to the one-CTA-per-chunk kernel
-        }
     *out = c;
     return GCN10_OK;
 }
@@ -725,7 +680,6 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
     else if (!strcmp(key, "streams") && value >= 1 && value <= kMaxStreams) c->nstreams = (int)value;
     else if (!strcmp(key, "rows_per_cta") && value >= 0) c->rows_per_cta = (int)value;
     else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
-    else if (!strcmp(key, "persistent") && (value == 0 || value == 1)) c->persistent = (int)value;
     else if (!strcmp(key, "fused") && (value == 0 || value == 1)) c->fused = (int)value;
     else if (!strcmp(key, "inflate_probe") && value >= 0 && value <= 2) c->inflate_probe = (int)value;
     else if (!strcmp(key, "tuned_code") && (value == 0 || value == 1)) {

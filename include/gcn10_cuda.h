@@ -241,8 +241,7 @@ int gcn10_cuda_last_kernel_ms(gcn10_ctx *ctx, float *ms);
 int gcn10_cuda_launch_count(gcn10_ctx *ctx, uint64_t *launches);
 
 /* Tunables: "strip_rows" (rows per pipelined strip in the host-buffer calls), "streams" (1..8), "rows_per_cta"
- * (0 = automatic), "tma" (0 = always use the gather fallback for HSG staging), "persistent" (1 = the persistent-CTA
- * form of the streaming kernel), "fused" (0 = compressed-tile calls run the Curve Number kernel and the per-plane
+ * (0 = automatic), "tma" (0 = always use the gather fallback for HSG staging), "fused" (0 = compressed-tile calls run the Curve Number kernel and the per-plane
  * tile encoder instead of the fused kernel), "tuned_code" (0 = tile streams use RFC 1951's fixed Huffman code instead
  * of the tuned one), "inflate_probe" (measurement aid of tools/inflate_bench.py: 1 / 2 switch parts of the inflate
  * kernel's writer off; results are then invalid). */

@@ -15,7 +15,7 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def lookup_dir(tmp_path_factory):
     """Directory with the nine default lookup CSVs, byte-identical to the reference's."""
-    from gcn10_b200 import lookups
+    from tests import lookups
     return lookups.write_default_lookups(str(tmp_path_factory.mktemp("lookups")))
 
 

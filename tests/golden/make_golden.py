@@ -28,7 +28,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from gcn10_b200 import lookups, synth  # noqa: E402
+from gcn10_b200 import synth
+from tests import lookups  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -12,7 +12,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT)
 
-from gcn10_b200 import capi, lookups, synth  # noqa: E402
+from gcn10_b200 import capi, synth
+from tests import lookups  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 port = O.Port()

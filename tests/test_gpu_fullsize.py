@@ -1,0 +1,190 @@
+"""Exhaustive bit-exact parity at BASELINE.json's full sizes: EVERY row of every selected plane.
+
+north_star: "bit-exact 9-variant CN output for a 36000 x 36000 tile" (/root/reference/src/cn.c:218-290).
+Each case runs one whole block through BOTH product paths of the C ABI
+
+  * gcn10_cuda_block_device          (device-resident planes, the kernel the roofline is quoted on), and
+  * gcn10_cuda_block_tiles_deflate   (zlib land-cover tiles in -> GPU inflate -> fused Curve Number + DEFLATE
+                                      kernel -> zlib tiles out; every output tile is inflated with CPython's zlib)
+
+and compares every byte with the CPU oracle, which is evaluated with the WHOLE block's geometry over 256-row
+bands in one thread per host core (the C call releases the GIL).  Cases = BASELINE.json configs:
+
+  worldcover_18   configs[1] shape, all 18 planes (both drainage conditions); also compared directly with the
+                  reference's own object code (oracle/_ref, process_block() on the full block) when the box has
+                  the RAM for it -- the one-hop check
+  coastal_18      configs[2]: >= 50 % land cover 0 / 80, >= 30 % dual HSG 11..14, >= 20 % HSG 255
+  g_ii_only       configs[0]: a single plane (drained, good, ARC II)
+  vrt_36001       the real-VRT shape: 36001 x 36001 at pixel 8.3333333333330430e-05, origin (-3, 3) where an
+                  FMA-contracted index map would move 62 tie columns; ragged right edge
+
+Tolerance: none.
+"""
+import os
+import threading
+import time
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from gcn10_b200 import capi, synth
+from tests.cases import PX, PX_VRT
+
+pytestmark = pytest.mark.gpu
+
+G_II = 1 << 7           # plane 7 = drained / g / ii  (cn.c:145-147 order)
+
+CASES = {
+    "worldcover_18": dict(w=36000, h=36000, px=PX, lon0=-114.0, lat0=42.0, profile="worldcover", mask=capi.MASK_ALL,
+                          seed=2234, level=6, ref=True),
+    "coastal_18": dict(w=36000, h=36000, px=PX, lon0=-114.0, lat0=42.0, profile="coastal", mask=capi.MASK_ALL,
+                       seed=2301, level=1, ref=False),
+    "g_ii_only": dict(w=36000, h=36000, px=PX, lon0=-111.0, lat0=39.0, profile="worldcover", mask=G_II,
+                      seed=2235, level=1, ref=False),
+    "vrt_36001": dict(w=36001, h=36001, px=PX_VRT, lon0=-3.0, lat0=3.0, profile="worldcover", mask=capi.MASK_ALL,
+                      seed=1500, level=1, ref=False),
+}
+NTHREADS = max(4, len(os.sched_getaffinity(0)))
+IN_TILE = 1024          # the ESA WorldCover files' tile size (landcover/esa_worldcover_2021.vrt: BlockXSize)
+
+
+def _coastal_fractions(esa, hsg):
+    """SURVEY 8d config 3 mix, checked on the generated rasters so the case really is what it claims."""
+    return (float(np.isin(esa[::37, ::41], (0, 80)).mean()), float(((hsg >= 11) & (hsg <= 14)).mean()),
+            float((hsg == 255).mean()))
+
+
+def _tile_source(esa, level):
+    h, w = esa.shape
+    tx_n, ty_n = (w + IN_TILE - 1) // IN_TILE, (h + IN_TILE - 1) // IN_TILE
+
+    def one(i):
+        ty, tx = divmod(i, tx_n)
+        t = np.zeros((IN_TILE, IN_TILE), dtype=np.uint8)
+        part = esa[ty * IN_TILE:(ty + 1) * IN_TILE, tx * IN_TILE:(tx + 1) * IN_TILE]
+        t[:part.shape[0], :part.shape[1]] = part
+        return zlib.compress(t.tobytes(), level)
+
+    with ThreadPoolExecutor(NTHREADS) as ex:
+        streams = list(ex.map(one, range(tx_n * ty_n)))
+    sizes = np.array([len(z) for z in streams], dtype=np.uint32)
+    offsets = np.concatenate([[0], np.cumsum(sizes[:-1], dtype=np.uint64)]).astype(np.uint64)
+    blob = np.frombuffer(b"".join(streams), dtype=np.uint8).copy()
+    return capi.TileSource(IN_TILE, IN_TILE, tx_n, ty_n, 0, 0, blob, offsets, sizes)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_every_row_of_a_full_block(name, gpu_ctx, port, tables, lookup_dir):
+    import ctypes as C
+
+    import psutil
+    import torch
+    c = CASES[name]
+    w, h, mask = c["w"], c["h"], c["mask"]
+    planes = [k for k in range(18) if mask & (1 << k)]
+    dev = torch.device("cuda:0")
+    gt, sgt, hsx, hsy = synth.block_geometry(c["lon0"], c["lat0"], w, h, px=c["px"])
+    pitch = (w + 15) // 16 * 16
+    d_esa = torch.zeros((h, pitch), dtype=torch.uint8, device=dev)
+    synth.esa_tile(w, h, c["seed"], c["profile"], device=dev, out=d_esa[:, :w])
+    hsg = synth.hsg_tile(hsx, hsy, c["seed"] + 1000, c["profile"])
+    esa = np.ascontiguousarray(d_esa[:, :w].cpu().numpy())
+    if c["profile"] == "coastal":
+        f_esa, f_dual, f_nodata = _coastal_fractions(esa, hsg)
+        assert f_esa >= 0.5 and f_dual >= 0.3 and f_nodata >= 0.2, (f_esa, f_dual, f_nodata)
+
+    # ---- the one-hop check starts first: the reference's process_block() on the whole block, one host thread
+    ref_box = {}
+    ref_thread = None
+    from oracle import oracle as O
+    if c["ref"] and O.Ref.available() and psutil.virtual_memory().available > 56 * 2**30:
+        def run_ref():
+            bbox = (gt[0], gt[3] + (h - 0.25) * gt[5], gt[0] + (w - 0.25) * gt[1], gt[3])
+            t0 = time.time()
+            ref_box["res"] = O.Ref().run_block(esa, gt, hsg, sgt, bbox, lookup_dir, block_id=2234, keep=True)
+            ref_box["s"] = time.time() - t0
+        ref_thread = threading.Thread(target=run_ref)
+        ref_thread.start()
+
+    # ---- path 1: device-resident planes
+    d_hsg = torch.from_numpy(hsg).to(dev)
+    d_out = torch.full((len(planes), h, pitch), 7, dtype=torch.uint8, device=dev)
+    ptrs = [0] * 18
+    for j, k in enumerate(planes):
+        ptrs[k] = d_out[j].data_ptr()
+    gpu_ctx.block_device(d_esa.data_ptr(), w, h, pitch, gt, d_hsg.data_ptr(), hsx, hsy, hsx, sgt, mask, ptrs, pitch,
+                         stream=torch.cuda.current_stream().cuda_stream or 1)
+    torch.cuda.synchronize()
+    if pitch > w:
+        assert bool((d_out[:, :, w:] == 7).all()), "padding columns were written"
+
+    # ---- path 2: compressed tiles in, compressed tiles out; the strips' bytes are kept as they arrive
+    src = _tile_source(esa, c["level"])
+    tiles_x, tile_rows = (w + 255) // 256, (h + 255) // 256
+    strips = []
+
+    def on_strip(st):
+        n = st.n_planes * st.n_tile_rows * st.tiles_x
+        strips.append((st.tile_row0, st.n_tile_rows, [st.plane_ids[j] for j in range(st.n_planes)],
+                       np.ctypeslib.as_array(st.offsets, (n,)).copy(), np.ctypeslib.as_array(st.sizes, (n,)).copy(),
+                       C.string_at(st.blob, st.blob_bytes)))
+        return 0
+
+    gpu_ctx.block_tiles_deflate(src, w, h, gt, hsg, sgt, plane_mask=mask, on_strip=on_strip)
+    by_row = {}
+    for s in strips:
+        assert s[2] == planes
+        for tr in range(s[1]):
+            by_row[s[0] + tr] = (s, tr)
+    assert sorted(by_row) == list(range(tile_rows))
+    total_out = sum(len(s[5]) for s in strips)
+
+    # ---- every band of 256 rows, one thread per host core
+    def check_band(tr):
+        y0, y1 = tr * 256, min(h, tr * 256 + 256)
+        want = port.block_rows(esa[y0:y1], gt, hsg, sgt, tables, y0=y0, y1=y1, h=h)
+        got = d_out[:, y0:y1, :w].cpu().numpy()
+        bad = []
+        s, r = by_row[tr]
+        _, ntr, _, offs, sizes, blob = s
+        for j, k in enumerate(planes):
+            if not np.array_equal(got[j], want[k]):
+                bad.append(("device", k, tr, int((got[j] != want[k]).sum())))
+            i0 = (j * ntr + r) * tiles_x
+            raw = b"".join(zlib.decompress(blob[int(offs[i0 + tx]): int(offs[i0 + tx]) + int(sizes[i0 + tx])])
+                           for tx in range(tiles_x))
+            if len(raw) != tiles_x * 65536:
+                bad.append(("tile size", k, tr, len(raw)))
+                continue
+            band = np.frombuffer(raw, dtype=np.uint8).reshape(tiles_x, 256, 256).transpose(1, 0, 2).reshape(256, -1)
+            if not np.array_equal(band[:y1 - y0, :w], want[k]):
+                bad.append(("tiles", k, tr, int((band[:y1 - y0, :w] != want[k]).sum())))
+            if band[y1 - y0:].any() or band[:, w:].any():
+                bad.append(("tile padding", k, tr, 0))
+        return bad
+
+    with ThreadPoolExecutor(NTHREADS) as ex:
+        bad = [b for res in ex.map(check_band, range(tile_rows)) for b in res]
+    assert not bad, f"{name}: {len(bad)} mismatching (path, plane, tile row, bytes): {bad[:8]}"
+    print(f"\n{name}: {len(planes)} planes x {h} rows x {w} px bit-exact on both paths "
+          f"({total_out / 1e6:.1f} MB of output tiles)")
+
+    # ---- one hop: GPU planes == what the reference's object code handed to save_raster()
+    if ref_thread is not None:
+        ref_thread.join()
+        res = ref_box["res"]
+        assert res["nplanes"] == 18 and (res["w"], res["h"]) == (w, h), res["log"]
+        assert tuple(res["gt"]) == tuple(gt)
+        ref_planes = res["planes"]
+
+        def check_ref(tr):
+            y0, y1 = tr * 256, min(h, tr * 256 + 256)
+            got = d_out[:, y0:y1, :w].cpu().numpy()
+            return [(k, tr) for j, k in enumerate(planes) if not np.array_equal(got[j], ref_planes[k, y0:y1])]
+
+        with ThreadPoolExecutor(NTHREADS) as ex:
+            bad = [b for r in ex.map(check_ref, range(tile_rows)) for b in r]
+        assert not bad, f"{name}: GPU planes differ from the reference's process_block() output: {bad[:8]}"
+        print(f"{name}: all 18 planes equal to oracle/_ref process_block() on the full block ({ref_box['s']:.0f} s on one core)")

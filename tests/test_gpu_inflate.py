@@ -232,63 +232,3 @@ def test_prefetch_overlaps_the_next_block_and_results_do_not_change(gpu_ctx, por
     check(gpu_ctx.block_tiles_deflate(srcs[1], 900, 700, blocks[1]["gt"], blocks[1]["hsg"], blocks[1]["soil_gt"]), wants[1])
     out = gpu_ctx.inflate_tiles(srcs[0], 900, 700)
     assert np.array_equal(out, blocks[0]["esa"])
-
-
-def test_full_tile_compressed_chain(gpu_ctx, port, tables):
-    """BASELINE config 2 size through the compressed-tile chain: a 36000 x 36000 land-cover tile as 1296 zlib tiles
-    of 1024 x 1024 in, the nine drained rasters as 9 x 19881 zlib tiles out.  Every output tile must be a valid
-    zlib stream of 65536 bytes (size-independent property); eight sampled tile rows (first, last = ragged, random)
-    are compared byte for byte with the oracle over the full width."""
-    import ctypes as C
-    from concurrent.futures import ThreadPoolExecutor
-    import torch
-    w = h = 36000
-    gt, sgt, hsx, hsy = synth.block_geometry(-114.0, 42.0, w, h)
-    esa = synth.esa_tile(w, h, seed=2234, device=torch.device("cuda:0")).cpu().numpy()
-    hsg = synth.hsg_tile(hsx, hsy, seed=3234)
-    T = 1024
-    tiles_x = tiles_y = (w + T - 1) // T
-
-    def one(i):
-        ty, tx = divmod(i, tiles_x)
-        t = np.zeros((T, T), dtype=np.uint8)
-        part = esa[ty * T:(ty + 1) * T, tx * T:(tx + 1) * T]
-        t[:part.shape[0], :part.shape[1]] = part
-        return zlib.compress(t.tobytes(), 6)
-
-    with ThreadPoolExecutor(max_workers=16) as ex:
-        streams = list(ex.map(one, range(tiles_x * tiles_y)))
-    sizes = np.array([len(z) for z in streams], dtype=np.uint32)
-    offsets = np.concatenate([[0], np.cumsum(sizes[:-1], dtype=np.uint64)]).astype(np.uint64)
-    src = capi.TileSource(T, T, tiles_x, tiles_y, 0, 0, np.frombuffer(b"".join(streams), dtype=np.uint8).copy(), offsets,
-                          sizes)
-    n_tile_rows, n_tile_cols = (h + 255) // 256, (w + 255) // 256
-    rng = np.random.default_rng(1)
-    sampled = sorted({0, 1, n_tile_rows - 1, n_tile_rows - 2} | set(int(v) for v in rng.integers(0, n_tile_rows, size=4)))
-    kept, count = {}, [0]
-
-    def on_strip(st):
-        blob = C.string_at(st.blob, st.blob_bytes)
-        for k in range(st.n_planes):
-            for tr in range(st.n_tile_rows):
-                for tx in range(st.tiles_x):
-                    i = (k * st.n_tile_rows + tr) * st.tiles_x + tx
-                    z = blob[st.offsets[i]: st.offsets[i] + st.sizes[i]]
-                    raw = zlib.decompress(z)                      # every tile: a valid stream of a whole tile
-                    assert len(raw) == 65536
-                    count[0] += 1
-                    if st.tile_row0 + tr in sampled:
-                        kept[(st.plane_ids[k], st.tile_row0 + tr, tx)] = raw
-        return 0
-
-    gpu_ctx.block_tiles_deflate(src, w, h, gt, hsg, sgt, plane_mask=capi.MASK_DRAINED, on_strip=on_strip)
-    assert count[0] == 9 * n_tile_rows * n_tile_cols
-    for tr in sampled:
-        y0, y1 = tr * 256, min(h, tr * 256 + 256)
-        want = port.block_rows(esa[y0:y1], gt, hsg, sgt, tables, y0=y0, y1=y1, h=h)[:9]
-        for k in range(9):
-            got = np.zeros((256, n_tile_cols * 256), dtype=np.uint8)
-            for tx in range(n_tile_cols):
-                got[:, tx * 256:(tx + 1) * 256] = np.frombuffer(kept[(k, tr, tx)], dtype=np.uint8).reshape(256, 256)
-            assert np.array_equal(got[:y1 - y0, :w], want[k]), f"plane {k}, tile row {tr}"
-            assert not got[y1 - y0:].any() and not got[:, w:].any(), "padding must be zero"

@@ -8,7 +8,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from gcn10_b200 import hostlib, lookups, synth
+from gcn10_b200 import hostlib, synth
+from tests import lookups
 from oracle import oracle as O
 from tests import fixtures
 

@@ -8,7 +8,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from gcn10_b200 import hostlib, lookups
+from gcn10_b200 import hostlib
+from tests import lookups
 from tests import fixtures, golden_io
 from tests.test_oracle_pinned import _effective_lut
 

@@ -12,7 +12,8 @@ import os
 import numpy as np
 import pytest
 
-from gcn10_b200 import lookups, synth
+from gcn10_b200 import synth
+from tests import lookups
 from oracle import oracle as O
 from tests import golden_io
 from tests.cases import SMALL_CASES, make_block, PX, PX_VRT, HSG_PX

@@ -15,7 +15,8 @@ import zlib
 import numpy as np
 import pytest
 
-from gcn10_b200 import lookups, synth
+from gcn10_b200 import synth
+from tests import lookups
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "harness", "tile_code_host.cpp")

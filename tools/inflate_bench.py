@@ -26,7 +26,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from gcn10_b200 import capi, lookups, synth  # noqa: E402
+from gcn10_b200 import capi, synth
+from tests import lookups  # noqa: E402
 import bench as B  # noqa: E402
 
 

@@ -17,7 +17,8 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from gcn10_b200 import capi, lookups, synth  # noqa: E402
+from gcn10_b200 import capi, synth
+from tests import lookups  # noqa: E402
 import bench as B  # noqa: E402
 
 
@@ -28,7 +29,6 @@ def main():
     ap.add_argument("--profile", default="worldcover")
     ap.add_argument("--planes", default="9")
     ap.add_argument("--tma", default="1")
-    ap.add_argument("--persistent", default="0")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--once", action="store_true", help="one launch per config, no timing loop (for ncu)")
     a = ap.parse_args()
@@ -50,9 +50,8 @@ def main():
             ptrs = [d_out[k].data_ptr() for k in range(18)]
             for tma in [int(x) for x in a.tma.split(",")]:
                 ctx.set_option("tma", tma)
-                for rpc, pers in [(int(x), int(q)) for q in a.persistent.split(",") for x in a.rows_per_cta.split(",")]:
+                for rpc in [int(x) for x in a.rows_per_cta.split(",")]:
                     ctx.set_option("rows_per_cta", rpc)
-                    ctx.set_option("persistent", pers)
 
                     def step():
                         ctx.block_device(d_esa.data_ptr(), w, h, w, gt, d_hsg.data_ptr(), hsx, hsy, hsx, sgt,
@@ -76,7 +75,7 @@ def main():
                     ts.sort()
                     ms = ts[len(ts) // 2]
                     by = float(w) * h * (1 + planes) + hsx * hsy
-                    print(json.dumps({"profile": prof, "planes": planes, "tma": tma, "persistent": pers, "rows_per_cta": rpc,
+                    print(json.dumps({"profile": prof, "planes": planes, "tma": tma, "rows_per_cta": rpc,
                                       "ms_med": round(ms, 4), "ms_min": round(ts[0], 4),
                                       "gpx_s": round(w * h / ms / 1e6, 1), "gb_s": round(by / ms / 1e6, 1),
                                       "frac_peak": round(by / ms / 1e6 / peak, 4)}), flush=True)

@@ -14,7 +14,8 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from gcn10_b200 import hostlib, lookups, synth  # noqa: E402
+from gcn10_b200 import hostlib, synth
+from tests import lookups  # noqa: E402
 from tests import fixtures  # noqa: E402
 
 
