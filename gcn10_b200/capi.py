@@ -29,7 +29,8 @@ EXPORTS = (
     "gcn10_cuda_launch_count", "gcn10_cuda_set_option", "gcn10_cuda_host_alloc", "gcn10_cuda_host_free",
     "gcn10_cuda_host_register", "gcn10_cuda_host_unregister", "gcn10_cuda_bind_host_thread",
     "gcn10_cuda_inflate_tiles", "gcn10_cuda_block_tiles_deflate", "gcn10_cuda_last_inflate_ms",
-    "gcn10_cuda_tiles_prefetch",
+    "gcn10_cuda_tiles_prefetch", "gcn10_cuda_block_async", "gcn10_cuda_wait", "gcn10_cuda_event_query",
+    "gcn10_cuda_pcie_probe",
 )
 
 _vp = C.c_void_p
@@ -130,6 +131,10 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     lib.gcn10_cuda_block.argtypes = blk
     lib.gcn10_cuda_block_rows.argtypes = blk[:4] + [C.c_int, C.c_int] + blk[4:]
     lib.gcn10_cuda_block_device.argtypes = blk + [_vp]
+    lib.gcn10_cuda_block_async.argtypes = blk + [C.POINTER(_vp)]
+    lib.gcn10_cuda_wait.argtypes = [_vp]
+    lib.gcn10_cuda_event_query.argtypes = [_vp]
+    lib.gcn10_cuda_pcie_probe.argtypes = [_vp, C.c_size_t, C.c_int, _dp]
     lib.gcn10_cuda_block_deflate.argtypes = blk[:12] + [TILE_SINK, _vp]
     lib.gcn10_cuda_block_deflate_rows.argtypes = blk[:4] + [C.c_int, C.c_int] + blk[4:12] + [TILE_SINK, _vp]
     lib.gcn10_cuda_index_maps.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp, _vp, _vp]
@@ -241,6 +246,40 @@ class Context:
             self.h, esa.ctypes.data, w, h, esa_pitch, _d6(gt), hsg.ctypes.data, hsx, hsy,
             hsg_pitch, _d6(soil_gt), plane_mask, ptrs, out.strides[1]))
         return out
+
+    def block_async(self, esa, gt, hsg, soil_gt, plane_mask=MASK_ALL, out=None):
+        """Queues a block and returns a handle; ``wait(handle)`` returns the uint8 [18,h,w] result.  The arrays
+        are kept alive by the handle (use page-locked arrays for copies that really overlap)."""
+        esa, esa_pitch = _rows(esa)
+        hsg, hsg_pitch = _rows(hsg)
+        h, w = esa.shape
+        hsy, hsx = hsg.shape
+        if out is None:
+            out = np.zeros((NPLANES, h, w), dtype=np.uint8)
+        ptrs = (_vp * NPLANES)()
+        for k in range(NPLANES):
+            ptrs[k] = out[k].ctypes.data if plane_mask & (1 << k) else None
+        ev = _vp()
+        self._check(self.lib.gcn10_cuda_block_async(
+            self.h, esa.ctypes.data, w, h, esa_pitch, _d6(gt), hsg.ctypes.data, hsx, hsy,
+            hsg_pitch, _d6(soil_gt), plane_mask, ptrs, out.strides[1], C.byref(ev)))
+        return dict(event=ev, out=out, keep=(esa, hsg, ptrs))
+
+    def query(self, handle) -> bool:
+        rc = self.lib.gcn10_cuda_event_query(handle["event"])
+        if rc < 0:
+            self._check(rc)
+        return rc == 1
+
+    def wait(self, handle):
+        ev, handle["event"] = handle["event"], None
+        self._check(self.lib.gcn10_cuda_wait(ev))
+        return handle["out"]
+
+    def pcie_probe(self, nbytes=256 << 20, reps=4):
+        g = (C.c_double * 3)()
+        self._check(self.lib.gcn10_cuda_pcie_probe(self.h, nbytes, reps, g))
+        return {"h2d_gbs": g[0], "d2h_gbs": g[1], "d2h_ship_kernel_gbs": g[2]}
 
     def block_rows(self, esa_rows, h, row0, gt, hsg, soil_gt, plane_mask=MASK_ALL):
         """Band call: esa_rows holds rows [row0, row0+len) of a block that is h rows tall."""

@@ -101,6 +101,7 @@ struct gcn10_ctx {
     int use_tma = 1;
     int inflate_probe = 0;      // measurement aid for tools/inflate_bench.py (see InflateParams::probe)
     int fused = 1;              // compressed-tile calls use cn_deflate_fused_kernel (0 = CN kernel + tile encoder)
+    int ship = 1;               // strips leave through ship_strip_kernel (0 = size read-back, then a D2H copy of that size)
     DevBuf fused_tab;           // idmap [256][16] | val [256][32] | lit9 [256][6] u64
     unsigned fused_mask = 0;    // plane mask the tables were built for (0 = none)
     int fused_ok = 0;           // the mask's value records fit the id space
@@ -124,6 +125,20 @@ struct gcn10_ctx {
     float last_inflate_ms = 0.f;
     float last_kernel_ms = 0.f;
     uint64_t launches = 0;
+    // asynchronous raw-plane blocks (gcn10_cuda_block_async): frame guard, per-stream end-of-block marks, timer events
+    cudaEvent_t frame_ready = nullptr;
+    cudaEvent_t tail[kMaxStreams] = {};
+    bool tail_valid[kMaxStreams] = {};
+    int pending_events = 0;             // blocks queued by gcn10_cuda_block_async and not yet waited for
+    std::vector<cudaEvent_t> timer_pool;
+};
+
+struct gcn10_event {
+    gcn10_ctx *ctx = nullptr;
+    int nstreams = 0;
+    int status = 0;                     // error met while queueing (reported by gcn10_cuda_wait)
+    std::vector<cudaEvent_t> timers;    // kernel start / end per strip
+    std::vector<cudaEvent_t> ends;      // behind the block's last copy, per stream
 };
 
 namespace {
@@ -234,6 +249,29 @@ void pack_lut_records(const int tables[GCN10_NVARIANTS][256][5], unsigned varian
 int auto_rows_per_cta(int planes) { return planes > 9 ? (GCN10_BULK_STORE ? 32 : 16) : 12; }
 
 int popcount9(unsigned m) { return __builtin_popcount(m & 0x1FFu); }
+
+// ---- strip hand-over ------------------------------------------------------------------------
+
+// A strip's compressed tiles leave the device without a host round trip: this kernel runs behind the encoder on
+// the strip's stream, reads the arena's fill level where the encoder left it and writes exactly that many bytes,
+// plus the offset / size tables, into page-locked host memory through its device mapping (coalesced 16-byte
+// stores = posted PCIe writes).  The host only waits for the event behind it.  If the host arena is too small
+// the copy stops at `h_cap`; the fill level in the table tells the host, which grows the arena and fetches the
+// strip with a plain copy.
+__global__ void __launch_bounds__(256)
+ship_strip_kernel(const uint4 *__restrict__ blob, const unsigned long long *__restrict__ cursor,
+                  const uint32_t *__restrict__ table, uint32_t table_words, uint4 *__restrict__ h_blob,
+                  unsigned long long h_cap, uint32_t *__restrict__ h_table)
+{
+    const unsigned long long used = min(*cursor, h_cap);
+    const size_t n16 = (size_t)((used + 15ull) >> 4);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+        h_blob[i] = blob[i];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < table_words; i += stride)
+        h_table[i] = table[i];
+}
+constexpr int kShipCtas = 32;
 
 // ---- kernel dispatch ------------------------------------------------------------------------
 
@@ -603,6 +641,9 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
     CUDA_TRY(cudaFuncSetAttribute((const void *)inflate_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->pre_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->frame_ready, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxStreams; i++)
+        CUDA_TRY(cudaEventCreateWithFlags(&c->tail[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CUDA_TRY(cudaEventCreate(&c->tslot[i].inf0));
         CUDA_TRY(cudaEventCreate(&c->tslot[i].inf1));
@@ -643,6 +684,11 @@ void gcn10_cuda_destroy(gcn10_ctx *c)
         if (c->tslot[i].done) cudaEventDestroy(c->tslot[i].done);
     }
     if (c->pre_stream) cudaStreamDestroy(c->pre_stream);
+    if (c->frame_ready) cudaEventDestroy(c->frame_ready);
+    for (int i = 0; i < kMaxStreams; i++)
+        if (c->tail[i]) cudaEventDestroy(c->tail[i]);
+    for (cudaEvent_t t : c->timer_pool)
+        cudaEventDestroy(t);
     for (int i = 0; i < kMaxStreams; i++) {
         release(c->slots[i].esa);
         release(c->slots[i].out);
@@ -663,6 +709,8 @@ int gcn10_cuda_set_luts(gcn10_ctx *c, const int tables[GCN10_NVARIANTS][256][5])
 {
     if (!c || !tables)
         return fail(GCN10_EINVAL, "NULL argument");
+    if (c->pending_events)
+        return fail(GCN10_EINVAL, "asynchronous blocks are pending on this context: gcn10_cuda_wait() for them first");
     CUDA_TRY(cudaSetDevice(c->device));
     memcpy(c->host_tables, tables, sizeof(c->host_tables));
     c->swz_shift = choose_swizzle(c->host_tables);
@@ -681,6 +729,7 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
     else if (!strcmp(key, "rows_per_cta") && value >= 0) c->rows_per_cta = (int)value;
     else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
     else if (!strcmp(key, "fused") && (value == 0 || value == 1)) c->fused = (int)value;
+    else if (!strcmp(key, "ship") && (value == 0 || value == 1)) c->ship = (int)value;
     else if (!strcmp(key, "inflate_probe") && value >= 0 && value <= 2) c->inflate_probe = (int)value;
     else if (!strcmp(key, "tuned_code") && (value == 0 || value == 1)) {
         c->tuned_code = (int)value;
@@ -723,6 +772,8 @@ int gcn10_cuda_index_maps(gcn10_ctx *c, int w, int h, const double gt[6], int hs
         return fail(GCN10_EINVAL, "NULL argument");
     if (w <= 0 || h <= 0 || hsx <= 0 || hsy <= 0)
         return fail(GCN10_EINVAL, "non-positive size");
+    if (c->pending_events)
+        return fail(GCN10_EINVAL, "asynchronous blocks are pending on this context: gcn10_cuda_wait() for them first");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->streams[0];
     int rc = launch_index_maps(c, w, h, gt, hsx, hsy, soil_gt, st);
@@ -748,6 +799,8 @@ int gcn10_cuda_block_device(gcn10_ctx *c,
         return rc;
     if (!c->have_lut)
         return fail(GCN10_ENOLUT, "gcn10_cuda_set_luts() has not been called");
+    if (c->pending_events)
+        return fail(GCN10_EINVAL, "asynchronous blocks are pending on this context: gcn10_cuda_wait() for them first");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->streams[0];
 
@@ -768,23 +821,24 @@ int gcn10_cuda_block_device(gcn10_ctx *c,
     return GCN10_OK;
 }
 
-int gcn10_cuda_block(gcn10_ctx *c,
-                     const uint8_t *esa, int w, int h, size_t esa_pitch, const double gt[6],
-                     const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
-                     unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch)
-{
-    return gcn10_cuda_block_rows(c, esa, w, h, 0, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask,
-                                 out, out_pitch);
-}
+// ---- raw planes back: enqueue / wait ----------------------------------------------------------------------------
+//
+// Everything a block needs is queued on the context's streams without the host waiting for any of it: the frame
+// (HSG window + fp64 index maps) on stream 0, guarded by an event the strip streams wait for; then the row strips
+// round-robin over the streams, each stream owning one staging slot (slot reuse is ordered by the stream itself).
+// A following block's frame waits, on the device, for the previous block's strips (they read the shared frame
+// buffers).  gcn10_cuda_wait() blocks for the block's last copies and adds up the kernel times.
 
-int gcn10_cuda_block_rows(gcn10_ctx *c,
-                          const uint8_t *esa, int w, int h, int row0, int nrows, size_t esa_pitch,
-                          const double gt[6],
-                          const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
-                          unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch)
+static int block_rows_enqueue(gcn10_ctx *c,
+                              const uint8_t *esa, int w, int h, int row0, int nrows, size_t esa_pitch,
+                              const double gt[6],
+                              const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                              unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch,
+                              gcn10_event **done)
 {
-    if (!c)
+    if (!c || !done)
         return fail(GCN10_EINVAL, "NULL context");
+    *done = nullptr;
     int rc = check_geometry(esa, w, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask, out, out_pitch);
     if (rc)
         return rc;
@@ -803,13 +857,27 @@ int gcn10_cuda_block_rows(gcn10_ctx *c,
     for (int i = 0; i < nplans; i++)
         nplanes += plans[i].np * plans[i].groups;
 
+    const size_t hsg_dpitch = round_up((size_t)hsx, 256);
+    const size_t dpitch = round_up((size_t)w, 256);
+    const int ns = c->nstreams;
+    const int strip = std::max(1, std::min(c->strip_rows, nrows));
+    const int nstrips = (nrows + strip - 1) / strip;
+    // (re)allocation frees device memory, which waits for the device by itself; sizes only ever grow
+    bool grow = c->hsg.cap < hsg_dpitch * (size_t)hsy;
+    for (int i = 0; i < ns; i++)
+        grow = grow || c->slots[i].esa.cap < dpitch * (size_t)strip ||
+               c->slots[i].out.cap < dpitch * (size_t)strip * (size_t)nplanes;
+    if (grow && (rc = gcn10_cuda_synchronize(c)))
+        return rc;
+
     cudaStream_t s0 = c->streams[0];
+    // the previous block's strips read the frame buffers this block is about to overwrite
+    for (int i = 1; i < kMaxStreams; i++)
+        if (c->tail_valid[i])
+            CUDA_TRY(cudaStreamWaitEvent(s0, c->tail[i], 0));
     for (int i = 0; i < nplans; i++)
         if ((rc = upload_lut(c, plans[i].variant_mask, i, s0)))
             return rc;
-
-    // whole-block state: index maps and the coarse HSG window (<= a few MB), on stream 0
-    const size_t hsg_dpitch = round_up((size_t)hsx, 256);
     if ((rc = ensure(c->hsg, hsg_dpitch * (size_t)hsy)))
         return rc;
     CUDA_TRY(cudaMemcpy2DAsync(c->hsg.p, hsg_dpitch, hsg, hsg_pitch, (size_t)hsx, (size_t)hsy,
@@ -819,65 +887,163 @@ int gcn10_cuda_block_rows(gcn10_ctx *c,
     CUtensorMap map;
     int tma_ok = 0;
     make_hsg_map(c, (const uint8_t *)c->hsg.p, hsx, hsy, hsg_dpitch, &map, &tma_ok);
-    CUDA_TRY(cudaStreamSynchronize(s0));
-
-    // row strips, round-robin over the streams; each stream owns one staging slot
-    const size_t dpitch = round_up((size_t)w, 256);
-    const int ns = c->nstreams;
-    const int strip = std::max(1, std::min(c->strip_rows, nrows));
+    CUDA_TRY(cudaEventRecord(c->frame_ready, s0));
     for (int i = 0; i < ns; i++) {
-        if ((rc = ensure(c->slots[i].esa, dpitch * (size_t)strip)))
+        if ((rc = ensure(c->slots[i].esa, dpitch * (size_t)strip)) ||
+            (rc = ensure(c->slots[i].out, dpitch * (size_t)strip * (size_t)nplanes)))
             return rc;
-        if ((rc = ensure(c->slots[i].out, dpitch * (size_t)strip * (size_t)nplanes)))
-            return rc;
-        c->slots[i].timed = false;
+        if (i)
+            CUDA_TRY(cudaStreamWaitEvent(c->streams[i], c->frame_ready, 0));
     }
-    float kernel_ms = 0.f;
-    int si = 0;
+
+    gcn10_event *ev = new (std::nothrow) gcn10_event();
+    if (!ev)
+        return fail(GCN10_ENOMEM, "event allocation failed");
+    ev->ctx = c;
+    ev->timers.resize(2 * (size_t)nstrips);
+    ev->ends.resize((size_t)ns);
+    auto take = [&](cudaEvent_t &t) {
+        if (!c->timer_pool.empty()) {
+            t = c->timer_pool.back();
+            c->timer_pool.pop_back();
+        }
+        else if (cudaEventCreate(&t) != cudaSuccess) {
+            t = nullptr;
+        }
+    };
+    for (auto &t : ev->timers)
+        take(t);
+    for (auto &t : ev->ends)
+        take(t);
+
+    int si = 0, sidx = 0;
     // y0 counts rows of the caller's band: esa / out row 0 is block row `row0`
-    for (int y0 = 0; y0 < nrows; y0 += strip, si = (si + 1) % ns) {
+    for (int y0 = 0; y0 < nrows && !rc; y0 += strip, si = (si + 1) % ns, sidx++) {
         const int rows = std::min(strip, nrows - y0);
         StripSlot &sl = c->slots[si];
         cudaStream_t st = c->streams[si];
-        if (sl.timed) {
-            // the slot's previous strip: its D2H copies must be complete before the buffers are reused
-            CUDA_TRY(cudaEventSynchronize(sl.done));
-            float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, sl.k0, sl.k1));
-            kernel_ms += ms;
-        }
-        CUDA_TRY(cudaMemcpy2DAsync(sl.esa.p, dpitch, esa + (size_t)y0 * esa_pitch, esa_pitch, (size_t)w,
-                                   (size_t)rows, cudaMemcpyHostToDevice, st));
+        cudaEvent_t k0 = ev->timers[2 * sidx], k1 = ev->timers[2 * sidx + 1];
+        cudaMemcpy2DAsync(sl.esa.p, dpitch, esa + (size_t)y0 * esa_pitch, esa_pitch, (size_t)w, (size_t)rows,
+                          cudaMemcpyHostToDevice, st);
         uint8_t *d_out[GCN10_NPLANES] = { nullptr };
         int k = 0;
         for (int i = 0; i < nplans; i++)
             for (int j = 0; j < plans[i].np * plans[i].groups; j++, k++)
                 d_out[plans[i].plane_ids[j]] = (uint8_t *)sl.out.p + (size_t)k * dpitch * (size_t)strip;
-        CUDA_TRY(cudaEventRecord(sl.k0, st));
-        for (int i = 0; i < nplans; i++)
-            if ((rc = launch_rows(c, plans[i], i, (const uint8_t *)sl.esa.p, dpitch, w, rows, row0 + y0,
-                                  (const uint8_t *)c->hsg.p, hsg_dpitch, hsx, hsy, map, tma_ok, d_out, dpitch, st)))
-                return rc;
-        CUDA_TRY(cudaEventRecord(sl.k1, st));
-        for (int p = 0; p < GCN10_NPLANES; p++)
+        if (k0)
+            cudaEventRecord(k0, st);
+        for (int i = 0; i < nplans && !rc; i++)
+            rc = launch_rows(c, plans[i], i, (const uint8_t *)sl.esa.p, dpitch, w, rows, row0 + y0,
+                             (const uint8_t *)c->hsg.p, hsg_dpitch, hsx, hsy, map, tma_ok, d_out, dpitch, st);
+        if (k1)
+            cudaEventRecord(k1, st);
+        for (int p = 0; p < GCN10_NPLANES && !rc; p++)
             if (d_out[p])
-                CUDA_TRY(cudaMemcpy2DAsync(out[p] + (size_t)y0 * out_pitch, out_pitch, d_out[p], dpitch, (size_t)w,
-                                           (size_t)rows, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaEventRecord(sl.done, st));
-        sl.timed = true;
+                cudaMemcpy2DAsync(out[p] + (size_t)y0 * out_pitch, out_pitch, d_out[p], dpitch, (size_t)w,
+                                  (size_t)rows, cudaMemcpyDeviceToHost, st);
     }
+    // the block is complete when every stream has passed this point
     for (int i = 0; i < ns; i++) {
-        StripSlot &sl = c->slots[i];
-        if (!sl.timed)
-            continue;
-        CUDA_TRY(cudaEventSynchronize(sl.done));
-        float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, sl.k0, sl.k1));
-        kernel_ms += ms;
-        sl.timed = false;
+        cudaEventRecord(c->tail[i], c->streams[i]);
+        c->tail_valid[i] = true;
+        if (ev->ends[i])
+            cudaEventRecord(ev->ends[i], c->streams[i]);
     }
-    c->last_kernel_ms = kernel_ms;
-    return GCN10_OK;
+    ev->nstreams = ns;
+    c->pending_events++;
+    const cudaError_t ce = cudaGetLastError();
+    if (!rc && ce != cudaSuccess)
+        rc = fail(GCN10_ECUDA, "queueing the block failed: %s", cudaGetErrorString(ce));
+    ev->status = rc;
+    *done = ev;
+    return GCN10_OK;            // a queueing error is reported by gcn10_cuda_wait, after the streams have drained
+}
+
+int gcn10_cuda_block_async(gcn10_ctx *c,
+                           const uint8_t *esa, int w, int h, size_t esa_pitch, const double gt[6],
+                           const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                           unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch,
+                           gcn10_event **done)
+{
+    return block_rows_enqueue(c, esa, w, h, 0, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask, out,
+                              out_pitch, done);
+}
+
+int gcn10_cuda_event_query(gcn10_event *ev)
+{
+    if (!ev || !ev->ctx)
+        return fail(GCN10_EINVAL, "NULL event");
+    gcn10_ctx *c = ev->ctx;
+    if (cudaSetDevice(c->device) != cudaSuccess)
+        return fail(GCN10_ECUDA, "cudaSetDevice failed");
+    for (int i = 0; i < ev->nstreams; i++) {
+        const cudaError_t e = ev->ends[i] ? cudaEventQuery(ev->ends[i]) : cudaStreamQuery(c->streams[i]);
+        if (e == cudaErrorNotReady)
+            return 0;
+        if (e != cudaSuccess)
+            return fail(GCN10_ECUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+    }
+    return 1;
+}
+
+int gcn10_cuda_wait(gcn10_event *ev)
+{
+    if (!ev || !ev->ctx)
+        return fail(GCN10_EINVAL, "NULL event");
+    gcn10_ctx *c = ev->ctx;
+    int rc = ev->status;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < ev->nstreams; i++) {
+        const cudaError_t e = ev->ends[i] ? cudaEventSynchronize(ev->ends[i]) : cudaStreamSynchronize(c->streams[i]);
+        if (e != cudaSuccess && !rc)
+            rc = fail(GCN10_ECUDA, "block failed on the device: %s", cudaGetErrorString(e));
+    }
+    float kernel_ms = 0.f;
+    for (size_t i = 0; i + 1 < ev->timers.size(); i += 2) {
+        float ms = 0.f;
+        if (!rc && ev->timers[i] && ev->timers[i + 1] &&
+            cudaEventElapsedTime(&ms, ev->timers[i], ev->timers[i + 1]) == cudaSuccess)
+            kernel_ms += ms;
+    }
+    cudaGetLastError();
+    for (cudaEvent_t t : ev->timers)
+        if (t)
+            c->timer_pool.push_back(t);
+    for (cudaEvent_t t : ev->ends)
+        if (t)
+            c->timer_pool.push_back(t);
+    if (!rc)
+        c->last_kernel_ms = kernel_ms;
+    if (--c->pending_events <= 0) {
+        c->pending_events = 0;
+        for (int i = 0; i < kMaxStreams; i++)
+            c->tail_valid[i] = false;       // (the newest block was waited for: every stream has drained)
+    }
+    delete ev;
+    return rc;
+}
+
+int gcn10_cuda_block(gcn10_ctx *c,
+                     const uint8_t *esa, int w, int h, size_t esa_pitch, const double gt[6],
+                     const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                     unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch)
+{
+    return gcn10_cuda_block_rows(c, esa, w, h, 0, h, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask,
+                                 out, out_pitch);
+}
+
+int gcn10_cuda_block_rows(gcn10_ctx *c,
+                          const uint8_t *esa, int w, int h, int row0, int nrows, size_t esa_pitch,
+                          const double gt[6],
+                          const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                          unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch)
+{
+    gcn10_event *ev = nullptr;
+    const int rc = block_rows_enqueue(c, esa, w, h, row0, nrows, esa_pitch, gt, hsg, hsx, hsy, hsg_pitch, soil_gt,
+                                      plane_mask, out, out_pitch, &ev);
+    if (rc)
+        return rc;
+    return gcn10_cuda_wait(ev);
 }
 
 int gcn10_cuda_block_deflate(gcn10_ctx *c,
@@ -912,6 +1078,8 @@ static int deflate_rows_impl(gcn10_ctx *c,
         return rc;
     if (!c->have_lut)
         return fail(GCN10_ENOLUT, "gcn10_cuda_set_luts() has not been called");
+    if (c->pending_events)
+        return fail(GCN10_EINVAL, "asynchronous blocks are pending on this context: gcn10_cuda_wait() for them first");
     CUDA_TRY(cudaSetDevice(c->device));
 
     LaunchPlan plans[2];
@@ -968,6 +1136,26 @@ static int deflate_rows_impl(gcn10_ctx *c,
     const int nstrips = (nrows + strip - 1) / strip;
     float kernel_ms = 0.f;
 
+    // behind the encoder on the strip's stream: either the ship kernel (exact bytes + tables straight into the
+    // page-locked arena, nothing for the host to do but wait), or the table read-back of the two-phase path
+    auto hand_over = [&](StripSlot &sl, cudaStream_t st) -> int {
+        CUDA_TRY(cudaEventRecord(sl.k1, st));
+        if (c->ship) {
+            ship_strip_kernel<<<kShipCtas, 256, 0, st>>>((const uint4 *)sl.blob.p, (const unsigned long long *)sl.table.p,
+                                                         (const uint32_t *)sl.table.p, (uint32_t)(table_bytes / 4),
+                                                         (uint4 *)sl.h_blob.p, (unsigned long long)(sl.h_blob.cap & ~(size_t)15),
+                                                         (uint32_t *)sl.h_table.p);
+            c->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        else {
+            CUDA_TRY(cudaMemcpyAsync(sl.h_table.p, sl.table.p, table_bytes, cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_TRY(cudaEventRecord(sl.enc_done, st));
+        sl.busy = true;
+        return GCN10_OK;
+    };
+
     auto issue = [&](int s) -> int {
         StripSlot &sl = c->slots[s % ns];
         cudaStream_t st = c->streams[s % ns];
@@ -1012,11 +1200,7 @@ static int deflate_rows_impl(gcn10_ctx *c,
                 cn_deflate_fused_kernel<18><<<dim3(tiles_x, tile_rows), kTile, fused_smem_bytes<18>(), st>>>(fp);
             c->launches++;
             CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaEventRecord(sl.k1, st));
-            CUDA_TRY(cudaMemcpyAsync(sl.h_table.p, sl.table.p, table_bytes, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaEventRecord(sl.enc_done, st));
-            sl.busy = true;
-            return GCN10_OK;
+            return hand_over(sl, st);
         }
         uint8_t *d_out[GCN10_NPLANES] = { nullptr };
         for (int k = 0; k < nplanes; k++)
@@ -1044,30 +1228,43 @@ static int deflate_rows_impl(gcn10_ctx *c,
         deflate_tiles_kernel<<<dim3(tiles_x, tile_rows, nplanes), kTile, kEncSmem, st>>>(ep);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(sl.k1, st));
-        CUDA_TRY(cudaMemcpyAsync(sl.h_table.p, sl.table.p, table_bytes, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaEventRecord(sl.enc_done, st));
-        sl.busy = true;
-        return GCN10_OK;
+        return hand_over(sl, st);
+    };
+
+    // an error inside the loop must not leave strips running on buffers the caller is about to reuse
+    auto bail = [&](int code) -> int {
+        for (int i = 0; i < ns; i++)
+            cudaStreamSynchronize(c->streams[i]);
+        for (int i = 0; i < ns; i++)
+            c->slots[i].busy = false;
+        return code;
     };
 
     for (int s = 0; s < std::min(ns, nstrips); s++)
         if ((rc = issue(s)))
-            return rc;
+            return bail(rc);
     for (int s = 0; s < nstrips; s++) {
         StripSlot &sl = c->slots[s % ns];
         cudaStream_t st = c->streams[s % ns];
-        CUDA_TRY(cudaEventSynchronize(sl.enc_done));
+        cudaError_t ce = cudaEventSynchronize(sl.enc_done);
+        if (ce != cudaSuccess)
+            return bail(fail(GCN10_ECUDA, "strip %d: %s", s, cudaGetErrorString(ce)));
         float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, sl.k0, sl.k1));
+        cudaEventElapsedTime(&ms, sl.k0, sl.k1);
         kernel_ms += ms;
         const size_t used = (size_t) * (const unsigned long long *)sl.h_table.p;
         if (used > blob_cap)
-            return fail(GCN10_ECUDA, "tile encoder overran its arena (%zu > %zu)", used, blob_cap);
-        if ((rc = ensure_host(sl.h_blob, used ? used : 16)))
-            return rc;
-        CUDA_TRY(cudaMemcpyAsync(sl.h_blob.p, sl.blob.p, used, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+            return bail(fail(GCN10_ECUDA, "tile encoder overran its arena (%zu > %zu)", used, blob_cap));
+        if (!c->ship || used > (sl.h_blob.cap & ~(size_t)15)) {
+            // two-phase path, or a strip that outgrew the host arena: (grow it and) copy exactly `used` bytes
+            if ((rc = ensure_host(sl.h_blob, used ? used + used / 4 : 16)))
+                return bail(rc);
+            ce = cudaMemcpyAsync(sl.h_blob.p, sl.blob.p, used, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess)
+                ce = cudaStreamSynchronize(st);
+            if (ce != cudaSuccess)
+                return bail(fail(GCN10_ECUDA, "strip %d copy: %s", s, cudaGetErrorString(ce)));
+        }
         gcn10_tile_strip ts;
         ts.tile_row0 = (row0 + sl.y0) / kTile;
         ts.n_tile_rows = (sl.rows + kTile - 1) / kTile;
@@ -1082,12 +1279,10 @@ static int deflate_rows_impl(gcn10_ctx *c,
         // full; the kernel indexes with the strip's own tile_rows, which is what n_tile_rows reports
         const int sink_rc = sink(user, &ts);
         sl.busy = false;
-        if (sink_rc) {
-            gcn10_cuda_synchronize(c);
-            return fail(GCN10_EINVAL, "tile sink returned %d", sink_rc);
-        }
+        if (sink_rc)
+            return bail(fail(GCN10_EINVAL, "tile sink returned %d", sink_rc));
         if (s + ns < nstrips && (rc = issue(s + ns)))
-            return rc;
+            return bail(rc);
     }
     c->last_kernel_ms = kernel_ms;
     return GCN10_OK;
@@ -1285,6 +1480,62 @@ int gcn10_cuda_last_inflate_ms(gcn10_ctx *c, float *ms)
     if (!c || !ms)
         return fail(GCN10_EINVAL, "NULL argument");
     *ms = c->last_inflate_ms;
+    return GCN10_OK;
+}
+
+int gcn10_cuda_pcie_probe(gcn10_ctx *c, size_t bytes, int reps, double gbs[3])
+{
+    if (!c || !gbs || bytes < 4096 || reps < 1)
+        return fail(GCN10_EINVAL, "bad argument");
+    if (c->pending_events)
+        return fail(GCN10_EINVAL, "asynchronous blocks are pending on this context: gcn10_cuda_wait() for them first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    bytes &= ~(size_t)15;
+    DevBuf d, cur;
+    HostBuf hb;
+    int rc;
+    if ((rc = ensure(d, bytes)) || (rc = ensure(cur, 16)) || (rc = ensure_host(hb, bytes))) {
+        release(d);
+        release(cur);
+        release_host(hb);
+        return rc;
+    }
+    memset(hb.p, 0x5A, bytes);
+    cudaStream_t st = c->streams[0];
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const unsigned long long n = bytes;
+    cudaMemcpyAsync(cur.p, &n, sizeof(n), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+    for (int leg = 0; leg < 3; leg++) {
+        for (int i = -1; i < reps; i++) {           // i = -1: warm-up
+            if (i == 0)
+                cudaEventRecord(e0, st);
+            if (leg == 0)
+                cudaMemcpyAsync(d.p, hb.p, bytes, cudaMemcpyHostToDevice, st);
+            else if (leg == 1)
+                cudaMemcpyAsync(hb.p, d.p, bytes, cudaMemcpyDeviceToHost, st);
+            else {
+                ship_strip_kernel<<<kShipCtas, 256, 0, st>>>((const uint4 *)d.p, (const unsigned long long *)cur.p, nullptr, 0u,
+                                                             (uint4 *)hb.p, (unsigned long long)bytes, nullptr);
+                c->launches++;
+            }
+        }
+        cudaEventRecord(e1, st);
+        cudaStreamSynchronize(st);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        gbs[leg] = ms > 0.f ? (double)bytes * reps / (ms * 1e-3) / 1e9 : 0.0;
+    }
+    const cudaError_t ce = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    release(d);
+    release(cur);
+    release_host(hb);
+    if (ce != cudaSuccess)
+        return fail(GCN10_ECUDA, "pcie probe: %s", cudaGetErrorString(ce));
     return GCN10_OK;
 }
 

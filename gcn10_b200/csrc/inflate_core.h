@@ -44,7 +44,9 @@ enum {
     kErrDistance = 6,       // distance reaches before the start of the tile
     kErrOverflow = 7,       // stream holds more bytes than the tile
     kErrInput = 8,          // ran past the end of the compressed tile
-    kErrShort = 9           // stream ended before the tile was full
+    kErrShort = 9,          // stream ended before the tile was full
+    kErrChecksum = 10       // the Adler-32 trailer does not match the decoded bytes (zlib: Z_DATA_ERROR, which GDAL
+                            // turns into the read error of raster.c:182-186)
 };
 
 // event reported by one step of the decode lane
@@ -378,6 +380,30 @@ GCN10_HD int read_zlib_header(DecodeLane &s, const uint32_t *ring, uint32_t firs
     if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u != 0u || (flg & 0x20u))
         return kErrZlibHeader;
     return 0;
+}
+
+// Adler-32 trailer (RFC 1950 2.2): the four bytes behind the final block, most significant first.  The
+// reader is byte-aligned first.  Returns false when the stream ends before the trailer does.
+GCN10_HD bool read_adler_trailer(DecodeLane &s, const uint32_t *ring, uint32_t *adler)
+{
+    const int drop = s.cnt & 7;
+    s.buf >>= drop;
+    s.cnt -= drop;
+    if (byte_pos(s) + 4u > s.in_end)
+        return false;
+    uint32_t v = 0;
+    for (int i = 0; i < 4; i++)
+        v = (v << 8) | get_bits(s, ring, 8);
+    *adler = v;
+    return true;
+}
+
+// Adler-32 of a stream continued over a piece of n bytes whose byte sum is a and whose position-weighted sum
+// sum((n - i) * d[i]) is b:  s1' = s1 + a, s2' = s2 + n * s1 + b  (mod 65521)
+GCN10_HD void adler_advance(uint32_t &s1, uint32_t &s2, uint32_t n, uint64_t a, uint64_t b)
+{
+    s2 = (uint32_t)(((uint64_t)s2 + (uint64_t)(n % 65521u) * s1 + b % 65521u) % 65521u);
+    s1 = (uint32_t)(((uint64_t)s1 + a) % 65521u);
 }
 
 // what read_block_header() asks its caller to do

@@ -51,6 +51,9 @@ struct InflateSmem {
     int meta[2][8];                     // n, event, stored_src, stored_len, decoder error, final flag
     volatile int writer_err;
     volatile uint32_t fl_pos[2], fl_len[2];     // ring pieces handed to the flusher warp (len 0 = quit)
+    uint32_t adler_want, adler_got;             // trailer of the stream (decoder warp) / sum over the decoded bytes (flusher warp)
+    int trailer_state;                          // 0 = the decoder never reached the trailer, 1 = read, 2 = stream ends before it
+    int final_err;                              // the writer warp's verdict
     int pad[3];
     uint8_t window[inflate::kWindow];
 };
@@ -135,6 +138,43 @@ __device__ __forceinline__ void inflate_flush(const uint8_t *window, const TileD
                 d.dst[(size_t)gy * d.pitch + gx] = window[p & (kWindow - 1)];
         }
     }
+}
+
+// Adler-32 over ring piece [p0, p0 + n) (p0 a multiple of 16), whole warp: per 16-byte group the byte sum and the
+// sum of k * d[k] come from dp4a; s1 / s2 stay uniform across the lanes.  zlib verifies this checksum when GDAL reads
+// a tile (raster.c:177-186 reports the failure); so does the flusher warp, on everything the stream decodes to.
+__device__ __forceinline__ void inflate_adler_piece(const uint8_t *window, uint32_t p0, uint32_t n, int lane,
+                                                    uint32_t &s1, uint32_t &s2)
+{
+    using inflate::kWindow;
+    uint32_t a = 0;
+    unsigned long long b = 0;
+    for (uint32_t g = lane; g * 16u < n; g += 32u) {
+        const uint32_t o = 16u * g, left = n - o;
+        const uint4 v = *reinterpret_cast<const uint4 *>(window + ((p0 + o) & (kWindow - 1)));
+        uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        if (left < 16u) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int valid = (int)left - 4 * j;
+                w[j] = valid >= 4 ? w[j] : (valid <= 0 ? 0u : w[j] & ((1u << (8 * valid)) - 1u));
+            }
+        }
+        uint32_t sum = 0, ksum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            sum = __dp4a(w[j], 0x01010101u, sum);
+            ksum = __dp4a(w[j], 0x03020100u + 0x04040404u * (uint32_t)j, ksum);
+        }
+        a += sum;
+        b += (unsigned long long)left * sum - ksum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    inflate::adler_advance(s1, s2, n, a, b);
 }
 
 // copy of one match by the whole warp: bytes [mp, mp + len) := bytes [mp - dist, ...) of the history ring
@@ -322,19 +362,30 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                     break;
             }
         }
+        // behind the final block: the Adler-32 trailer (compared with the flusher warp's sum at the end)
+        top_up(__shfl_sync(full, s.cons, 0));
+        if (lane == 0) {
+            uint32_t want = 0;
+            sm.trailer_state = s.err ? 0 : (read_adler_trailer(s, sm.ring, &want) ? 1 : 2);
+            sm.adler_want = want;
+        }
     }
     else if (warp == 2) {
         // ------------------------------------------------------------------ flusher warp: ring pieces -> plane
         bar_arrive_done(0);
         bar_arrive_done(1);
+        uint32_t s1 = 1u, s2 = 0u;
         for (int k = 0;; k ^= 1) {
             bar_sync_ready(k);
             const uint32_t pos = sm.fl_pos[k], len = sm.fl_len[k];
             if (len == 0)
                 break;
             inflate_flush(sm.window, d, pos, len, lane);
+            inflate_adler_piece(sm.window, pos, len, lane, s1, s2);
             bar_arrive_done(k);
         }
+        if (lane == 0)
+            sm.adler_got = (s2 << 16) | s1;
     }
     else {
         // ------------------------------------------------------------------ writer warp
@@ -471,7 +522,18 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
         }
         post(0, 0);
         if (lane == 0)
-            p.status[tile] = werr;
+            sm.final_err = werr;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int e = sm.final_err;
+        if (!e && !p.probe) {
+            if (sm.trailer_state == 2)
+                e = kErrInput;
+            else if (sm.trailer_state == 1 && sm.adler_want != sm.adler_got)
+                e = kErrChecksum;
+        }
+        p.status[tile] = e;
     }
 }
 

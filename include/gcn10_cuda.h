@@ -104,6 +104,33 @@ int gcn10_cuda_block(gcn10_ctx *ctx,
                      const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
                      unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch);
 
+/* Asynchronous form of gcn10_cuda_block(): queues the whole block -- upload of the HSG window, fp64 index maps, and
+ * per row strip the host->device copy, the fused kernel and the device->host copies of the planes -- on the context's
+ * streams and returns at once; the host thread is free to read the next block (load_raster of block i+1, cn.c:187)
+ * or write the previous one (save_raster, cn.c:363) meanwhile.  esa, hsg and the out[] planes must stay valid, and
+ * out[] must not be read, until gcn10_cuda_wait(*done) has returned; page-locked buffers (gcn10_cuda_host_alloc /
+ * _register) are what makes the copies truly asynchronous.  Several blocks may be queued on one context; they run in
+ * order.  Until every queued block has been waited for, the context accepts no other compute call.
+ *
+ *     gcn10_event *ev[2];
+ *     gcn10_cuda_block_async(ctx, esa[0], ..., out[0], pitch, &ev[0]);
+ *     gcn10_cuda_block_async(ctx, esa[1], ..., out[1], pitch, &ev[1]);     -- runs behind block 0
+ *     gcn10_cuda_wait(ev[0]);  save_raster(out[0][k], ...);  ...
+ */
+typedef struct gcn10_event gcn10_event;
+int gcn10_cuda_block_async(gcn10_ctx *ctx,
+                           const uint8_t *esa, int w, int h, size_t esa_pitch, const double gt[6],
+                           const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                           unsigned plane_mask, uint8_t *const out[GCN10_NPLANES], size_t out_pitch,
+                           gcn10_event **done);
+
+/* Blocks until the block behind `done` is complete in host memory, releases the event and returns the block's status
+ * (GCN10_OK or the error met while queueing / running it). */
+int gcn10_cuda_wait(gcn10_event *done);
+
+/* 1 = the block behind `done` has finished, 0 = still running, negative = error.  Does not release the event. */
+int gcn10_cuda_event_query(gcn10_event *done);
+
 /* Rows [row0, row0+nrows) of a w x h block: esa and out[k] point at row `row0` (the caller holds
  * only that band of the rasters), while gt / soil_gt / h still describe the WHOLE block so that the
  * fp64 index maps are the block's (a band with a shifted geotransform origin would not round the
@@ -181,8 +208,9 @@ typedef struct {
 
 /* Inflate the tiles of `src` on the GPU and return the w x h window as a raster in HOST memory
  * (the load_raster() half alone).  tile_status, if not NULL, receives tiles_x * tiles_y codes: 0 = ok,
- * 1..9 = the reason a tile could not be decoded (see inflate_core.h).  Returns GCN10_EDATA if any tile
- * failed (the window is then incomplete).  The Adler-32 trailer of the streams is not verified. */
+ * 1..10 = the reason a tile could not be decoded (see inflate_core.h; 10 = the stream's Adler-32 trailer does not
+ * match the decoded bytes, which zlib reports to GDAL as a data error).  Returns GCN10_EDATA if any tile failed (the
+ * window is then incomplete). */
 int gcn10_cuda_inflate_tiles(gcn10_ctx *ctx, const gcn10_tile_source *src, int w, int h,
                              uint8_t *out, size_t out_pitch, int *tile_status);
 
@@ -241,11 +269,18 @@ int gcn10_cuda_last_kernel_ms(gcn10_ctx *ctx, float *ms);
 int gcn10_cuda_launch_count(gcn10_ctx *ctx, uint64_t *launches);
 
 /* Tunables: "strip_rows" (rows per pipelined strip in the host-buffer calls), "streams" (1..8), "rows_per_cta"
- * (0 = automatic), "tma" (0 = always use the gather fallback for HSG staging), "fused" (0 = compressed-tile calls run the Curve Number kernel and the per-plane
- * tile encoder instead of the fused kernel), "tuned_code" (0 = tile streams use RFC 1951's fixed Huffman code instead
+ * (0 = automatic), "tma" (0 = always use the gather fallback for HSG staging), "fused" (0 = compressed-tile
+ * calls run the Curve Number kernel and the per-plane tile encoder instead of the fused kernel), "ship" (0 = a strip's
+ * compressed bytes are fetched with a size read-back and a copy instead of the ship kernel), "tuned_code" (0 = tile streams use RFC 1951's fixed Huffman code instead
  * of the tuned one), "inflate_probe" (measurement aid of tools/inflate_bench.py: 1 / 2 switch parts of the inflate
  * kernel's writer off; results are then invalid). */
 int gcn10_cuda_set_option(gcn10_ctx *ctx, const char *key, long value);
+
+/* Measures this GPU's host link with page-locked memory: gbs[0] = host->device and gbs[1] = device->host copy
+ * bandwidth (cudaMemcpyAsync of `bytes`, `reps` times, CUDA events), gbs[2] = device->host bandwidth of the kernel
+ * that ships the compressed strips (coalesced 16-byte stores into mapped host memory).  Diagnostic: bench.py runs it
+ * on one rank alone and on all ranks at once to record the fabric ceiling the end-to-end numbers sit under. */
+int gcn10_cuda_pcie_probe(gcn10_ctx *ctx, size_t bytes, int reps, double gbs[3]);
 
 /* Pins the calling host thread to the CPUs of the NUMA node the GPU hangs off (from
  * /sys/bus/pci/devices/<bus id>/numa_node and .../node<N>/cpulist), so that page-locked buffers

@@ -42,6 +42,21 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
         if (pos < out_len)
             out[pos] = b;
     };
+    // the flusher warp's checksum: finished 4 KB pieces of the ring, (byte sum, position-weighted sum) per piece
+    uint32_t s1 = 1, s2 = 0, summed = 0;
+    auto sum_pieces = [&](uint32_t upto, bool all) {
+        while (summed + 4096u <= upto || (all && summed < upto)) {
+            const uint32_t n = summed + 4096u <= upto ? 4096u : upto - summed;
+            uint64_t a = 0, b = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t d = window[(summed + i) & (kWindow - 1)];
+                a += d;
+                b += (uint64_t)(n - i) * d;
+            }
+            adler_advance(s1, s2, n, a, b);
+            summed += n;
+        }
+    };
 
     DecodeLane s;
     lane_init(s, first, first + size);
@@ -156,20 +171,34 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
                 }
                 nsym += (uint64_t)n;
                 out_base = pos;
+                sum_pieces(out_base, false);
             }
         }
         if (ev == kEvStored && !werr) {
             if (out_base + sl > out_len)
                 werr = kErrOverflow;
             else {
-                for (uint32_t i = 0; i < sl; i++)
+                for (uint32_t i = 0; i < sl; i++) {
                     emit(out_base + i, base[so + i]);
+                    if (((out_base + i + 1) & 4095u) == 0)
+                        sum_pieces(out_base + i + 1, false);
+                }
                 out_base += sl;
             }
         }
         if (ev == kEvEnd || (ev == kEvStored && fin)) {
             if (!werr && out_base != out_len)
                 werr = kErrShort;
+            if (!werr) {
+                // decoder lane: the trailer behind the final block; flusher: the sum over everything decoded
+                sum_pieces(out_base, true);
+                uint32_t want = 0;
+                top_up(s.cons);
+                if (!read_adler_trailer(s, ring, &want))
+                    werr = kErrInput;
+                else if (want != ((s2 << 16) | s1))
+                    werr = kErrChecksum;
+            }
             break;
         }
         if (ev == kEvError) {

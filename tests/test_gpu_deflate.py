@@ -211,3 +211,36 @@ def test_long_row_runs(break_row, gpu_ctx, port, tables, encoder_path):
     # row (two-kernel path), plus a few tokens where the raster changes
     per_tile = {"fused_tuned_code": 450, "fused_fixed_code": 750, "two_kernel": 900}[encoder_path]
     assert res["bytes"] < 18 * 9 * per_tile, "uniform tiles must collapse to a few hundred bytes each"
+
+
+def test_strip_hand_over_paths_agree(gpu_ctx, port, tables, encoder_path):
+    """The ship kernel (exact bytes + tables written straight into page-locked memory behind the encoder) and the
+    two-phase path (size read-back, then a copy) deliver the same tiles; a host arena that is too small for a strip
+    is grown and the strip fetched again.  A failing sink drains the strips in flight and leaves the context usable."""
+    b = make_block(w=1100, h=2300, seed=61, esa_patch=7, hsg_patch=1)
+    h, w = b["esa"].shape
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    got = {}
+    gpu_ctx.set_option("strip_rows", 512)
+    try:
+        for ship in (1, 0):
+            gpu_ctx.set_option("ship", ship)
+            got[ship] = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+        calls = [0]
+
+        def failing(_st):
+            calls[0] += 1
+            return 3 if calls[0] == 2 else 0
+
+        gpu_ctx.set_option("ship", 1)
+        with pytest.raises(capi.Gcn10Error):
+            gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], on_strip=failing)
+        again = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    finally:
+        gpu_ctx.set_option("ship", 1)
+        gpu_ctx.set_option("strip_rows", 2048)
+    assert got[0]["bytes"] == got[1]["bytes"] == again["bytes"]
+    for k in range(18):
+        assert got[0]["tiles"][k] == got[1]["tiles"][k] == again["tiles"][k]
+        full = _assemble(got[1]["tiles"][k], w, h)
+        assert np.array_equal(full[:h, :w], want[k])

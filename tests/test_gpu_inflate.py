@@ -149,6 +149,39 @@ def test_damaged_tiles_are_reported_not_fatal(gpu_ctx):
     assert np.array_equal(gpu_ctx.inflate_tiles(src, 1024, 512), grid)
 
 
+def test_adler32_mismatch_is_reported(gpu_ctx):
+    """A tile whose payload was altered without breaking the DEFLATE structure decodes to wrong land cover; zlib
+    (GDAL's codec, raster.c:177-186) rejects it by its Adler-32 trailer and so does the GPU inflater: status 10,
+    GCN10_EDATA, the other tiles unaffected."""
+    grid = _raster(768, 512, seed=17)
+    src = capi.TileSource.from_raster(grid, 256, 256, level=0)            # stored blocks: payload bytes are literals
+    blob = src.blob.copy()
+    blob[int(src.offsets[1]) + 7 + 4000] ^= 0x20                         # tile 1: one land-cover byte changed
+    blob[int(src.offsets[4]) + int(src.sizes[4]) - 1] ^= 0x01            # tile 4: trailer changed
+    bad = capi.TileSource(256, 256, src.tiles_x, src.tiles_y, 0, 0, blob, src.offsets, src.sizes)
+    rc, out, status = gpu_ctx.inflate_tiles(bad, 768, 512, want_status=True)
+    assert rc == -6
+    assert list(status) == [0, 10, 0, 0, 10, 0]
+    # Huffman-coded tiles: a flipped bit deep in a stream is either a structural error or a checksum error
+    src6 = capi.TileSource.from_raster(grid, 256, 256, level=6)
+    for k in range(12):
+        blob = src6.blob.copy()
+        t = k % 6
+        blob[int(src6.offsets[t]) + int(src6.sizes[t]) // 2 + k] ^= 1 << (k % 8)
+        rc, out, status = gpu_ctx.inflate_tiles(capi.TileSource(256, 256, 3, 2, 0, 0, blob, src6.offsets, src6.sizes),
+                                                768, 512, want_status=True)
+        if rc == 0:
+            assert np.array_equal(out, grid)
+        else:
+            assert status[t] != 0 and not np.delete(status, t).any()
+    assert np.array_equal(gpu_ctx.inflate_tiles(src6, 768, 512), grid)
+    # the chained call refuses the block (the reference skips a block whose land cover cannot be read, cn.c:188-192)
+    b = make_block(w=768, h=512, seed=17)
+    with pytest.raises(capi.Gcn10Error) as ei:
+        gpu_ctx.block_tiles_deflate(bad, 768, 512, b["gt"], b["hsg"], b["soil_gt"])
+    assert ei.value.code == -6
+
+
 def test_bad_arguments(gpu_ctx):
     grid = _raster(512, 512, seed=1)
     src = capi.TileSource.from_raster(grid, 256, 256)

@@ -154,3 +154,53 @@ def test_block_device_api(w, h, pitch_extra, gpu_ctx, port, tables):
     assert np.array_equal(got[:, guard:guard + h, :w], want)
     assert (got[:, guard:guard + h, w:] == 3).all(), "padding columns were written"
     assert (got[:, :guard] == 3).all() and (got[:, guard + h:] == 3).all(), "rows outside the block were written"
+
+
+def test_block_async_blocks_in_flight(gpu_ctx, port, tables):
+    """gcn10_cuda_block_async / gcn10_cuda_wait: three blocks of different shapes queued back to back on
+    one context from page-locked buffers, other compute calls refused meanwhile, results bit-exact."""
+    lib = gpu_ctx.lib
+    shapes = [(4111, 700, capi.MASK_ALL), (2048, 300, capi.MASK_DRAINED), (5000, 1300, 0b000010101 | (0b101 << 9))]
+    blocks, pins, handles = [], [], []
+    gpu_ctx.set_option("strip_rows", 256)
+    try:
+        for i, (w, h, mask) in enumerate(shapes):
+            b = make_block(w=w, h=h, seed=40 + i, shift=(0.0002 * i, 0.0003), margin=1)
+            e = capi.PinnedArray(lib, (h, w))
+            o = capi.PinnedArray(lib, (18, h, w))
+            e.array[:] = b["esa"]
+            o.array[:] = 9
+            pins += [e, o]
+            blocks.append((b, mask))
+            handles.append(gpu_ctx.block_async(e.array, b["gt"], b["hsg"], b["soil_gt"], plane_mask=mask, out=o.array))
+        with pytest.raises(capi.Gcn10Error):
+            gpu_ctx.index_maps(100, 100, blocks[0][0]["gt"], 10, 10, blocks[0][0]["soil_gt"])
+        with pytest.raises(capi.Gcn10Error):
+            gpu_ctx.set_luts(tables)
+        for (b, mask), hd in zip(blocks, handles):
+            got = gpu_ctx.wait(hd)
+            want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+            for k in range(18):
+                if mask & (1 << k):
+                    assert np.array_equal(got[k], want[k]), k
+                else:
+                    assert (got[k] == 9).all()
+        assert gpu_ctx.last_kernel_ms() > 0
+        # the context is free again
+        ci, _ = gpu_ctx.index_maps(100, 100, blocks[0][0]["gt"], 10, 10, blocks[0][0]["soil_gt"])
+        assert ci.shape == (100,)
+        # query: a finished block reports 1 before it is waited for
+        b, mask = blocks[1]
+        hd = gpu_ctx.block_async(pins[2].array, b["gt"], b["hsg"], b["soil_gt"], plane_mask=mask, out=pins[3].array)
+        gpu_ctx.lib.gcn10_cuda_synchronize(gpu_ctx.h)
+        assert gpu_ctx.query(hd)
+        gpu_ctx.wait(hd)
+    finally:
+        gpu_ctx.set_option("strip_rows", 2048)
+        for p in pins:
+            p.free()
+
+
+def test_pcie_probe(gpu_ctx):
+    r = gpu_ctx.pcie_probe(64 << 20, 2)
+    assert all(v > 0.5 for v in r.values()), r

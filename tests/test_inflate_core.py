@@ -163,13 +163,44 @@ def test_damaged_streams_terminate_with_an_error_or_wrong_bytes_never_overrun(ha
             ok = False
         if rc != 0:
             detected += 1
-        elif not ok:
-            # zlib catches more (Adler-32, incomplete codes); we may decode garbage, but only inside the tile
-            assert len(out) == len(data)
-    assert detected > 100
+        else:
+            # accepted = structure intact AND the Adler-32 trailer matches what was decoded: the bytes are right
+            # (zlib additionally rejects incomplete code sets, so `ok` may be False here)
+            assert out.tobytes() == data
+        if ok:
+            assert rc == 0
+    assert detected > 250
     for cut in (3, 10, len(stream) // 2, len(stream) - 5):
         rc, _, _ = run(harness, stream[:cut], len(data))
         assert rc != 0
+
+
+def test_adler32_trailer_is_verified(harness):
+    """Payload damage that leaves the Huffman structure valid is caught by the checksum, as zlib does for GDAL
+    (a read error at /root/reference/src/raster.c:182-186): status kErrChecksum = 10."""
+    data = CORPUS["small256"]
+    stored = bytearray(deflate(data, 0))                    # stored blocks: every payload byte is a literal
+    assert run(harness, bytes(stored), len(data))[0] == 0
+    bad = bytearray(stored)
+    bad[7 + 1000] ^= 0x10
+    rc, out, _ = run(harness, bytes(bad), len(data))
+    assert rc == 10 and out.tobytes() != data
+    for stream in (deflate(data, 6), deflate(data, 6, zlib.Z_FIXED), bytes(stored)):
+        for k in range(1, 5):                                # each byte of the trailer
+            bad = bytearray(stream)
+            bad[-k] ^= 0x01
+            assert run(harness, bytes(bad), len(data))[0] == 10
+        assert run(harness, stream[:-2], len(data))[0] == 8  # kErrInput: the stream ends inside the trailer
+    # a literal swapped for another literal of the same code length (Huffman-only stream, one flipped bit)
+    hs = deflate(data, 6, zlib.Z_HUFFMAN_ONLY)
+    hits = 0
+    for pos in range(len(hs) // 2, len(hs) // 2 + 40):
+        bad = bytearray(hs)
+        bad[pos] ^= 0x04
+        rc, out, _ = run(harness, bytes(bad), len(data))
+        assert rc != 0 or out.tobytes() == data
+        hits += rc == 10
+    assert hits > 0
 
 
 def test_symbol_statistics_are_exported(harness):
