@@ -30,7 +30,7 @@ EXPORTS = (
     "gcn10_cuda_host_register", "gcn10_cuda_host_unregister", "gcn10_cuda_bind_host_thread",
     "gcn10_cuda_inflate_tiles", "gcn10_cuda_block_tiles_deflate", "gcn10_cuda_last_inflate_ms",
     "gcn10_cuda_tiles_prefetch", "gcn10_cuda_block_async", "gcn10_cuda_wait", "gcn10_cuda_event_query",
-    "gcn10_cuda_pcie_probe",
+    "gcn10_cuda_pcie_probe", "gcn10_cuda_parts_prefetch", "gcn10_cuda_inflate_parts", "gcn10_cuda_block_parts_deflate",
 )
 
 _vp = C.c_void_p
@@ -108,6 +108,19 @@ class TileSource:
                                 self.sizes.ctypes.data)
 
 
+class TilePartStruct(C.Structure):
+    """gcn10_tile_part of include/gcn10_cuda.h."""
+    _fields_ = [("tiles", TileSourceStruct), ("dst_x", C.c_int), ("dst_y", C.c_int), ("w", C.c_int), ("h", C.c_int)]
+
+
+def parts_array(parts):
+    """[(TileSource, dst_x, dst_y, w, h), ...] -> ctypes array of gcn10_tile_part."""
+    arr = (TilePartStruct * len(parts))()
+    for i, (src, dx, dy, pw, ph) in enumerate(parts):
+        arr[i] = TilePartStruct(src.struct(), dx, dy, pw, ph)
+    return arr
+
+
 class Gcn10Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"gcn10cuda error {code}: {msg}")
@@ -154,6 +167,11 @@ def load(path: str = LIB_PATH) -> C.CDLL:
                                                    _vp, C.c_int, C.c_int, C.c_size_t, _dp, C.c_uint, TILE_SINK, _vp]
     lib.gcn10_cuda_last_inflate_ms.argtypes = [_vp, C.POINTER(C.c_float)]
     lib.gcn10_cuda_tiles_prefetch.argtypes = [_vp, C.POINTER(TileSourceStruct), C.c_int, C.c_int]
+    pp = C.POINTER(TilePartStruct)
+    lib.gcn10_cuda_parts_prefetch.argtypes = [_vp, pp, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.gcn10_cuda_inflate_parts.argtypes = [_vp, pp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]
+    lib.gcn10_cuda_block_parts_deflate.argtypes = [_vp, pp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _vp, C.c_int, C.c_int,
+                                                   C.c_size_t, _dp, C.c_uint, TILE_SINK, _vp]
     return lib
 
 
@@ -365,6 +383,45 @@ class Context:
         st = src.struct()
         self._check(self.lib.gcn10_cuda_block_tiles_deflate(
             self.h, C.byref(st), w, h, _d6(gt), hsg.ctypes.data, hsx, hsy, hsg_pitch, _d6(soil_gt), plane_mask,
+            cb, None))
+        return dict(tiles=tiles, bytes=total[0])
+
+    def inflate_parts(self, parts, fill, w, h, want_status=False):
+        """GPU inflate of a mosaic ([(TileSource, dst_x, dst_y, w, h), ...]) into a host raster uint8 [h, w]."""
+        out = np.zeros((h, w), dtype=np.uint8)
+        n = sum(p[0].tiles_x * p[0].tiles_y for p in parts)
+        status = np.full(n, -1, dtype=np.int32)
+        arr = parts_array(parts)
+        rc = self.lib.gcn10_cuda_inflate_parts(self.h, arr, len(parts), fill, w, h, out.ctypes.data, out.strides[0],
+                                               status.ctypes.data)
+        if want_status:
+            return rc, out, status
+        self._check(rc)
+        return out
+
+    def block_parts_deflate(self, parts, fill, w, h, gt, hsg, soil_gt, plane_mask=MASK_ALL):
+        """Mosaic form of block_tiles_deflate; same result layout."""
+        hsg, hsg_pitch = _rows(hsg)
+        hsy, hsx = hsg.shape
+        tiles = {}
+        total = [0]
+
+        def _sink(_user, sp):
+            st = sp.contents
+            total[0] += st.blob_bytes
+            blob = C.string_at(st.blob, st.blob_bytes)
+            for k in range(st.n_planes):
+                d = tiles.setdefault(st.plane_ids[k], {})
+                for tr in range(st.n_tile_rows):
+                    for tx in range(st.tiles_x):
+                        i = (k * st.n_tile_rows + tr) * st.tiles_x + tx
+                        d[(st.tile_row0 + tr, tx)] = blob[st.offsets[i]: st.offsets[i] + st.sizes[i]]
+            return 0
+
+        cb = TILE_SINK(_sink)
+        arr = parts_array(parts)
+        self._check(self.lib.gcn10_cuda_block_parts_deflate(
+            self.h, arr, len(parts), fill, w, h, _d6(gt), hsg.ctypes.data, hsx, hsy, hsg_pitch, _d6(soil_gt), plane_mask,
             cb, None))
         return dict(tiles=tiles, bytes=total[0])
 

@@ -288,7 +288,7 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
 
 // grid = (tiles_x, tile_rows), 256 threads, fused_smem_bytes<MAXP>() of dynamic shared memory
 template <int MAXP>
-__global__ void __launch_bounds__(kTile, 2)
+__global__ void __maxnreg__(120)
 cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
 {
     constexpr int VALB = MAXP <= 9 ? 16 : 32;

@@ -82,19 +82,20 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 // block's tiles can be uploaded and inflated while the current block's strips run: gcn10_cuda_tiles_prefetch)
 struct TileSlot {
     DevBuf in_blob, in_table, esa_full;
-    HostBuf h_status;           // [ntiles] status codes | [ntiles] launch order
+    HostBuf h_status;           // [ntiles] status codes | launch order | offsets (u64) | sizes (u32): page-locked staging
     cudaEvent_t inf0 = nullptr, inf1 = nullptr, done = nullptr;     // around the inflate kernel; behind the status copy
     bool pending = false;       // inflate issued, result not consumed yet
     uint64_t seq = 0;           // issue order of pending slots
     const void *key_blob = nullptr;
     size_t key_bytes = 0, ntiles = 0, dpitch = 0;
-    int key_w = 0, key_h = 0;
+    int key_w = 0, key_h = 0, key_parts = 0;
 };
 
 struct gcn10_ctx {
     int device = -1;
     int sm_count = 148;
     cudaStream_t streams[kMaxStreams] = {};
+    cudaStream_t ship_streams[kMaxStreams] = {};    // high priority: ship_strip_kernel of the slot with the same index
     int nstreams = 4;
     int strip_rows = 2048;
     int rows_per_cta = 0;       // 0 = auto (see auto_rows_per_cta)
@@ -258,7 +259,7 @@ int popcount9(unsigned m) { return __builtin_popcount(m & 0x1FFu); }
 // stores = posted PCIe writes).  The host only waits for the event behind it.  If the host arena is too small
 // the copy stops at `h_cap`; the fill level in the table tells the host, which grows the arena and fetches the
 // strip with a plain copy.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
 ship_strip_kernel(const uint4 *__restrict__ blob, const unsigned long long *__restrict__ cursor,
                   const uint32_t *__restrict__ table, uint32_t table_words, uint4 *__restrict__ h_blob,
                   unsigned long long h_cap, uint32_t *__restrict__ h_table)
@@ -271,7 +272,11 @@ ship_strip_kernel(const uint4 *__restrict__ blob, const unsigned long long *__re
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < table_words; i += stride)
         h_table[i] = table[i];
 }
-constexpr int kShipCtas = 32;
+// Small CTAs on a high-priority stream: 64 threads x <= 40 registers fit beside two resident CTAs of the fused
+// encoder (2 x 256 threads x 120 registers leave 4096 registers per SM), so a strip starts to leave while the next
+// strip's encoder already fills the SMs.
+constexpr int kShipThreads = 64;
+constexpr int kShipCtas = 2 * 148;
 
 // ---- kernel dispatch ------------------------------------------------------------------------
 
@@ -618,8 +623,12 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
         return fail(GCN10_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                     prop.major, prop.minor);
     }
-    for (int i = 0; i < kMaxStreams; i++)
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int i = 0; i < kMaxStreams; i++) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->ship_streams[i], cudaStreamNonBlocking, prio_hi));
+    }
     for (int i = 0; i < kMaxStreams; i++) {
         CUDA_TRY(cudaEventCreate(&c->slots[i].k0));
         CUDA_TRY(cudaEventCreate(&c->slots[i].k1));
@@ -701,6 +710,7 @@ void gcn10_cuda_destroy(gcn10_ctx *c)
         if (c->slots[i].k1) cudaEventDestroy(c->slots[i].k1);
         if (c->slots[i].done) cudaEventDestroy(c->slots[i].done);
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+        if (c->ship_streams[i]) cudaStreamDestroy(c->ship_streams[i]);
     }
     delete c;
 }
@@ -744,8 +754,10 @@ int gcn10_cuda_synchronize(gcn10_ctx *c)
     if (!c)
         return fail(GCN10_EINVAL, "NULL context");
     CUDA_TRY(cudaSetDevice(c->device));
-    for (int i = 0; i < kMaxStreams; i++)
+    for (int i = 0; i < kMaxStreams; i++) {
         CUDA_TRY(cudaStreamSynchronize(c->streams[i]));
+        CUDA_TRY(cudaStreamSynchronize(c->ship_streams[i]));
+    }
     return GCN10_OK;
 }
 
@@ -1141,17 +1153,21 @@ static int deflate_rows_impl(gcn10_ctx *c,
     auto hand_over = [&](StripSlot &sl, cudaStream_t st) -> int {
         CUDA_TRY(cudaEventRecord(sl.k1, st));
         if (c->ship) {
-            ship_strip_kernel<<<kShipCtas, 256, 0, st>>>((const uint4 *)sl.blob.p, (const unsigned long long *)sl.table.p,
-                                                         (const uint32_t *)sl.table.p, (uint32_t)(table_bytes / 4),
-                                                         (uint4 *)sl.h_blob.p, (unsigned long long)(sl.h_blob.cap & ~(size_t)15),
-                                                         (uint32_t *)sl.h_table.p);
+            cudaStream_t ss = c->ship_streams[&sl - c->slots];
+            CUDA_TRY(cudaStreamWaitEvent(ss, sl.k1, 0));
+            ship_strip_kernel<<<kShipCtas, kShipThreads, 0, ss>>>((const uint4 *)sl.blob.p, (const unsigned long long *)sl.table.p,
+                                                                  (const uint32_t *)sl.table.p, (uint32_t)(table_bytes / 4),
+                                                                  (uint4 *)sl.h_blob.p,
+                                                                  (unsigned long long)(sl.h_blob.cap & ~(size_t)15),
+                                                                  (uint32_t *)sl.h_table.p);
             c->launches++;
             CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(sl.enc_done, ss));
         }
         else {
             CUDA_TRY(cudaMemcpyAsync(sl.h_table.p, sl.table.p, table_bytes, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaEventRecord(sl.enc_done, st));
         }
-        CUDA_TRY(cudaEventRecord(sl.enc_done, st));
         sl.busy = true;
         return GCN10_OK;
     };
@@ -1233,8 +1249,10 @@ static int deflate_rows_impl(gcn10_ctx *c,
 
     // an error inside the loop must not leave strips running on buffers the caller is about to reuse
     auto bail = [&](int code) -> int {
-        for (int i = 0; i < ns; i++)
+        for (int i = 0; i < ns; i++) {
             cudaStreamSynchronize(c->streams[i]);
+            cudaStreamSynchronize(c->ship_streams[i]);
+        }
         for (int i = 0; i < ns; i++)
             c->slots[i].busy = false;
         return code;
@@ -1300,67 +1318,109 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
                              soil_gt, plane_mask, sink, user);
 }
 
-// Upload the compressed tiles of `src` and inflate them into sl.esa_full (pitch sl.dpitch) on the context's
-// upload stream, without waiting.  The per-tile status codes are in sl.h_status once that stream has drained.
-static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_source *src, int w, int h)
+// Upload the compressed tiles of every part and inflate them into sl.esa_full (pitch sl.dpitch) on the context's
+// upload stream, without waiting: ONE kernel launch for all parts (a 36-tile edge part launched on its own would
+// cost a whole tile's decode latency).  The per-tile status codes are in sl.h_status once that stream has drained.
+static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *parts, int nparts, int fill, int w, int h)
 {
-    if (!src || !src->offsets || !src->sizes || (!src->blob && src->blob_bytes))
+    if (!parts || nparts < 1)
         return fail(GCN10_EINVAL, "NULL argument");
-    if (w <= 0 || h <= 0 || src->tile_w <= 0 || src->tile_h <= 0 || src->tiles_x <= 0 || src->tiles_y <= 0)
+    if (nparts > kInflateMaxParts)
+        return fail(GCN10_EINVAL, "%d mosaic parts; at most %d are supported", nparts, kInflateMaxParts);
+    if (w <= 0 || h <= 0)
         return fail(GCN10_EINVAL, "non-positive size");
-    if ((long long)src->tile_w * src->tile_h > (1ll << 28))
-        return fail(GCN10_EINVAL, "tile of %d x %d pixels is too large", src->tile_w, src->tile_h);
-    if (src->x_off < 0 || src->y_off < 0 || (long long)src->x_off + w > (long long)src->tiles_x * src->tile_w ||
-        (long long)src->y_off + h > (long long)src->tiles_y * src->tile_h)
-        return fail(GCN10_EINVAL, "the %d x %d tile grid does not cover the %d x %d window at (%d, %d)", src->tiles_x,
-                    src->tiles_y, w, h, src->x_off, src->y_off);
-    const size_t ntiles = (size_t)src->tiles_x * src->tiles_y;
-    for (size_t i = 0; i < ntiles; i++)
-        if (src->sizes[i] && (src->offsets[i] > src->blob_bytes || src->sizes[i] > src->blob_bytes - src->offsets[i]))
-            return fail(GCN10_EINVAL, "tile %zu lies outside the blob", i);
+    size_t ntiles = 0, blob_total = 0;
+    long long covered = 0;
+    for (int k = 0; k < nparts; k++) {
+        const gcn10_tile_part &pt = parts[k];
+        const gcn10_tile_source *src = &pt.tiles;
+        if (!src->offsets || !src->sizes || (!src->blob && src->blob_bytes))
+            return fail(GCN10_EINVAL, "NULL argument");
+        if (pt.w <= 0 || pt.h <= 0 || src->tile_w <= 0 || src->tile_h <= 0 || src->tiles_x <= 0 || src->tiles_y <= 0)
+            return fail(GCN10_EINVAL, "non-positive size");
+        if ((long long)src->tile_w * src->tile_h > (1ll << 28))
+            return fail(GCN10_EINVAL, "tile of %d x %d pixels is too large", src->tile_w, src->tile_h);
+        if (pt.dst_x < 0 || pt.dst_y < 0 || (long long)pt.dst_x + pt.w > w || (long long)pt.dst_y + pt.h > h)
+            return fail(GCN10_EINVAL, "part %d (%d x %d at %d, %d) lies outside the %d x %d window", k, pt.w, pt.h, pt.dst_x,
+                        pt.dst_y, w, h);
+        if (src->x_off < 0 || src->y_off < 0 || (long long)src->x_off + pt.w > (long long)src->tiles_x * src->tile_w ||
+            (long long)src->y_off + pt.h > (long long)src->tiles_y * src->tile_h)
+            return fail(GCN10_EINVAL, "the %d x %d tile grid does not cover the %d x %d window at (%d, %d)", src->tiles_x,
+                        src->tiles_y, pt.w, pt.h, src->x_off, src->y_off);
+        const size_t n = (size_t)src->tiles_x * src->tiles_y;
+        for (size_t i = 0; i < n; i++)
+            if (src->sizes[i] && (src->offsets[i] > src->blob_bytes || src->sizes[i] > src->blob_bytes - src->offsets[i]))
+                return fail(GCN10_EINVAL, "tile %zu lies outside the blob", ntiles + i);
+        ntiles += n;
+        blob_total += round_up(src->blob_bytes, 16);
+        covered += (long long)pt.w * pt.h;
+    }
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->pre_stream;
     const size_t dpitch = round_up((size_t)w, 256);
     int rc;
     // the kernel's 512-byte input refills may run ~2 KB past a stream: keep that readable
-    if ((rc = ensure(sl.in_blob, round_up(src->blob_bytes, 256) + 4096)) ||
-        (rc = ensure(sl.in_table, ntiles * 20)) || (rc = ensure_host(sl.h_status, 2 * ntiles * sizeof(int))) ||
+    if ((rc = ensure(sl.in_blob, round_up(blob_total, 256) + 4096)) ||
+        (rc = ensure(sl.in_table, ntiles * 20)) ||
+        (rc = ensure_host(sl.h_status, ntiles * (2 * sizeof(int) + 12))) ||
         (rc = ensure(sl.esa_full, dpitch * (size_t)h)))
         return rc;
     unsigned long long *d_off = (unsigned long long *)sl.in_table.p;
     uint32_t *d_size = (uint32_t *)((uint8_t *)sl.in_table.p + ntiles * 8);
     int *d_status = (int *)((uint8_t *)sl.in_table.p + ntiles * 12);
     int *d_order = (int *)((uint8_t *)sl.in_table.p + ntiles * 16);
-    // longest streams first: a tile's decode time grows with its compressed size, and a block has only a
-    // few tiles per resident CTA slot (1296 tiles of 1024 x 1024 on 740 slots), so the order sets the tail
+    // page-locked staging: [status | order | offsets | sizes]
     int *h_order = (int *)sl.h_status.p + ntiles;
-    for (size_t i = 0; i < ntiles; i++)
-        h_order[i] = (int)i;
-    std::stable_sort(h_order, h_order + ntiles, [&](int a, int b) { return src->sizes[a] > src->sizes[b]; });
-    CUDA_TRY(cudaMemcpyAsync(d_order, h_order, ntiles * 4, cudaMemcpyHostToDevice, st));
-    if (src->blob_bytes)
-        CUDA_TRY(cudaMemcpyAsync(sl.in_blob.p, src->blob, src->blob_bytes, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_off, src->offsets, ntiles * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_size, src->sizes, ntiles * 4, cudaMemcpyHostToDevice, st));
+    unsigned long long *h_off = (unsigned long long *)((int *)sl.h_status.p + 2 * ntiles);
+    uint32_t *h_size = (uint32_t *)(h_off + ntiles);
+
     InflateParams ip;
     memset(&ip, 0, sizeof(ip));
+    // window pixels no part covers read as the fill value (GDAL initialises a VRT read with the band's nodata)
+    if (covered < (long long)w * h)
+        CUDA_TRY(cudaMemsetAsync(sl.esa_full.p, fill & 255, dpitch * (size_t)h, st));
+    size_t t0 = 0, b0 = 0;
+    for (int k = 0; k < nparts; k++) {
+        const gcn10_tile_part &pt = parts[k];
+        const gcn10_tile_source *src = &pt.tiles;
+        const size_t n = (size_t)src->tiles_x * src->tiles_y;
+        for (size_t i = 0; i < n; i++) {
+            h_off[t0 + i] = (unsigned long long)b0 + src->offsets[i];
+            h_size[t0 + i] = src->sizes[i];
+        }
+        if (src->blob_bytes)
+            CUDA_TRY(cudaMemcpyAsync((uint8_t *)sl.in_blob.p + b0, src->blob, src->blob_bytes, cudaMemcpyHostToDevice, st));
+        InflatePart &q = ip.part[k];
+        q.first_tile = (int)t0;
+        q.tiles_x = src->tiles_x;
+        q.tiles_y = src->tiles_y;
+        q.tile_w = src->tile_w;
+        q.tile_h = src->tile_h;
+        q.tw_shift = (src->tile_w & (src->tile_w - 1)) == 0 ? __builtin_ctz((unsigned)src->tile_w) : -1;
+        q.x_off = src->x_off;
+        q.y_off = src->y_off;
+        q.dst = (uint8_t *)sl.esa_full.p + (size_t)pt.dst_y * dpitch + pt.dst_x;
+        q.w = pt.w;
+        q.h = pt.h;
+        t0 += n;
+        b0 += round_up(src->blob_bytes, 16);
+    }
+    // longest streams first: a tile's decode time grows with its compressed size, and a block has only a
+    // few tiles per resident CTA slot, so the order sets the tail
+    for (size_t i = 0; i < ntiles; i++)
+        h_order[i] = (int)i;
+    std::stable_sort(h_order, h_order + ntiles, [&](int a, int b) { return h_size[a] > h_size[b]; });
+    CUDA_TRY(cudaMemcpyAsync(d_order, h_order, ntiles * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_off, h_off, ntiles * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_size, h_size, ntiles * 4, cudaMemcpyHostToDevice, st));
     ip.blob = (const uint8_t *)sl.in_blob.p;
     ip.offsets = d_off;
     ip.sizes = d_size;
-    ip.tiles_x = src->tiles_x;
-    ip.tiles_y = src->tiles_y;
-    ip.tile_w = src->tile_w;
-    ip.tile_h = src->tile_h;
-    ip.tw_shift = (src->tile_w & (src->tile_w - 1)) == 0 ? __builtin_ctz((unsigned)src->tile_w) : -1;
-    ip.x_off = src->x_off;
-    ip.y_off = src->y_off;
-    ip.dst = (uint8_t *)sl.esa_full.p;
     ip.pitch = dpitch;
-    ip.w = w;
-    ip.h = h;
     ip.status = d_status;
     ip.order = d_order;
     ip.probe = c->inflate_probe;
+    ip.nparts = nparts;
     CUDA_TRY(cudaEventRecord(sl.inf0, st));
     inflate_tiles_kernel<<<(unsigned)ntiles, kInflateThreads, kInflateSmem, st>>>(ip);
     c->launches++;
@@ -1370,13 +1430,25 @@ static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_source
     CUDA_TRY(cudaEventRecord(sl.done, st));
     sl.pending = true;
     sl.seq = ++c->tile_seq;
-    sl.key_blob = src->blob;
-    sl.key_bytes = src->blob_bytes;
+    sl.key_blob = parts[0].tiles.blob;
+    sl.key_bytes = blob_total;
+    sl.key_parts = nparts;
     sl.key_w = w;
     sl.key_h = h;
     sl.ntiles = ntiles;
     sl.dpitch = dpitch;
     return GCN10_OK;
+}
+
+static gcn10_tile_part whole_window_part(const gcn10_tile_source *src, int w, int h)
+{
+    gcn10_tile_part pt;
+    memset(&pt, 0, sizeof(pt));
+    if (src)
+        pt.tiles = *src;
+    pt.w = w;
+    pt.h = h;
+    return pt;
 }
 
 // waits for a slot's inflate, hands out the status codes, consumes the slot
@@ -1400,13 +1472,20 @@ static int finish_slot(gcn10_ctx *c, TileSlot &sl, int *tile_status)
 }
 
 // the slot a call works with: the oldest prefetched one that matches, else a free one (inflated now)
-static int acquire_slot(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h, TileSlot **out)
+static int acquire_slot(gcn10_ctx *c, const gcn10_tile_part *parts, int nparts, int fill, int w, int h, TileSlot **out)
 {
+    if (!parts || nparts < 1)
+        return fail(GCN10_EINVAL, "NULL argument");
+    size_t blob_total = 0, ntiles = 0;
+    for (int k = 0; k < nparts; k++) {
+        blob_total += round_up(parts[k].tiles.blob_bytes, 16);
+        ntiles += (size_t)std::max(parts[k].tiles.tiles_x, 0) * (size_t)std::max(parts[k].tiles.tiles_y, 0);
+    }
     TileSlot *hit = nullptr;
     for (int i = 0; i < 2; i++) {
         TileSlot &sl = c->tslot[i];
-        if (src && sl.pending && sl.key_blob == src->blob && sl.key_bytes == src->blob_bytes && sl.key_w == w &&
-            sl.key_h == h && sl.ntiles == (size_t)src->tiles_x * (size_t)src->tiles_y && (!hit || sl.seq < hit->seq))
+        if (sl.pending && sl.key_blob == parts[0].tiles.blob && sl.key_bytes == blob_total && sl.key_parts == nparts &&
+            sl.key_w == w && sl.key_h == h && sl.ntiles == ntiles && (!hit || sl.seq < hit->seq))
             hit = &sl;
     }
     if (!hit) {
@@ -1417,7 +1496,7 @@ static int acquire_slot(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h
             CUDA_TRY(cudaEventSynchronize(sl->done));
             sl->pending = false;
         }
-        int rc = inflate_to_device(c, *sl, src, w, h);
+        int rc = inflate_to_device(c, *sl, parts, nparts, fill, w, h);
         if (rc)
             return rc;
         hit = sl;
@@ -1426,25 +1505,33 @@ static int acquire_slot(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h
     return GCN10_OK;
 }
 
-int gcn10_cuda_tiles_prefetch(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h)
+int gcn10_cuda_parts_prefetch(gcn10_ctx *c, const gcn10_tile_part *parts, int nparts, int fill, int w, int h)
 {
     if (!c)
         return fail(GCN10_EINVAL, "NULL context");
     TileSlot *sl = !c->tslot[0].pending ? &c->tslot[0] : !c->tslot[1].pending ? &c->tslot[1] : nullptr;
     if (!sl)
         return fail(GCN10_EINVAL, "two prefetched blocks are already waiting; consume one first");
-    return inflate_to_device(c, *sl, src, w, h);
+    return inflate_to_device(c, *sl, parts, nparts, fill, w, h);
 }
 
-int gcn10_cuda_inflate_tiles(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h, uint8_t *out, size_t out_pitch,
-                             int *tile_status)
+int gcn10_cuda_tiles_prefetch(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h)
+{
+    if (!src)
+        return fail(GCN10_EINVAL, "NULL argument");
+    const gcn10_tile_part pt = whole_window_part(src, w, h);
+    return gcn10_cuda_parts_prefetch(c, &pt, 1, 0, w, h);
+}
+
+int gcn10_cuda_inflate_parts(gcn10_ctx *c, const gcn10_tile_part *parts, int nparts, int fill, int w, int h, uint8_t *out,
+                             size_t out_pitch, int *tile_status)
 {
     if (!c || !out)
         return fail(GCN10_EINVAL, "NULL argument");
     if (w > 0 && out_pitch < (size_t)w)
         return fail(GCN10_EINVAL, "pitch smaller than row width");
     TileSlot *sl = nullptr;
-    int rc = acquire_slot(c, src, w, h, &sl);
+    int rc = acquire_slot(c, parts, nparts, fill, w, h, &sl);
     if (rc)
         return rc;
     cudaStream_t st = c->pre_stream;
@@ -1453,7 +1540,17 @@ int gcn10_cuda_inflate_tiles(gcn10_ctx *c, const gcn10_tile_source *src, int w, 
     return finish_slot(c, *sl, tile_status);
 }
 
-int gcn10_cuda_block_tiles_deflate(gcn10_ctx *c, const gcn10_tile_source *esa_tiles, int w, int h, const double gt[6],
+int gcn10_cuda_inflate_tiles(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h, uint8_t *out, size_t out_pitch,
+                             int *tile_status)
+{
+    if (!src)
+        return fail(GCN10_EINVAL, "NULL argument");
+    const gcn10_tile_part pt = whole_window_part(src, w, h);
+    return gcn10_cuda_inflate_parts(c, &pt, 1, 0, w, h, out, out_pitch, tile_status);
+}
+
+int gcn10_cuda_block_parts_deflate(gcn10_ctx *c, const gcn10_tile_part *parts, int nparts, int fill, int w, int h,
+                                   const double gt[6],
                                    const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
                                    unsigned plane_mask, gcn10_tile_sink sink, void *user)
 {
@@ -1464,7 +1561,7 @@ int gcn10_cuda_block_tiles_deflate(gcn10_ctx *c, const gcn10_tile_source *esa_ti
     if (!c->have_lut)
         return fail(GCN10_ENOLUT, "gcn10_cuda_set_luts() has not been called");
     TileSlot *sl = nullptr;
-    int rc = acquire_slot(c, esa_tiles, w, h, &sl);
+    int rc = acquire_slot(c, parts, nparts, fill, w, h, &sl);
     if (rc)
         return rc;
     // a damaged tile must stop the block before any output tile reaches the sink (the reference skips a
@@ -1473,6 +1570,16 @@ int gcn10_cuda_block_tiles_deflate(gcn10_ctx *c, const gcn10_tile_source *esa_ti
         return rc;
     return deflate_rows_impl(c, nullptr, 0, (const uint8_t *)sl->esa_full.p, sl->dpitch, nullptr, w, h, 0, h, gt, hsg,
                              hsx, hsy, hsg_pitch, soil_gt, plane_mask, sink, user);
+}
+
+int gcn10_cuda_block_tiles_deflate(gcn10_ctx *c, const gcn10_tile_source *esa_tiles, int w, int h, const double gt[6],
+                                   const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                                   unsigned plane_mask, gcn10_tile_sink sink, void *user)
+{
+    if (!esa_tiles)
+        return fail(GCN10_EINVAL, "NULL argument");
+    const gcn10_tile_part pt = whole_window_part(esa_tiles, w, h);
+    return gcn10_cuda_block_parts_deflate(c, &pt, 1, 0, w, h, gt, hsg, hsx, hsy, hsg_pitch, soil_gt, plane_mask, sink, user);
 }
 
 int gcn10_cuda_last_inflate_ms(gcn10_ctx *c, float *ms)
@@ -1517,7 +1624,7 @@ int gcn10_cuda_pcie_probe(gcn10_ctx *c, size_t bytes, int reps, double gbs[3])
             else if (leg == 1)
                 cudaMemcpyAsync(hb.p, d.p, bytes, cudaMemcpyDeviceToHost, st);
             else {
-                ship_strip_kernel<<<kShipCtas, 256, 0, st>>>((const uint4 *)d.p, (const unsigned long long *)cur.p, nullptr, 0u,
+                ship_strip_kernel<<<kShipCtas, kShipThreads, 0, st>>>((const uint4 *)d.p, (const unsigned long long *)cur.p, nullptr, 0u,
                                                              (uint4 *)hb.p, (unsigned long long)bytes, nullptr);
                 c->launches++;
             }

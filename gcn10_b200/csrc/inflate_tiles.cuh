@@ -27,21 +27,31 @@
 
 namespace gcn10 {
 
-struct InflateParams {
-    const uint8_t *blob;                // device copy of the compressed tiles; readable 4 KB past the last one
-    const unsigned long long *offsets;  // [tiles_y][tiles_x] byte offset of a tile's zlib stream in blob
-    const uint32_t *sizes;              // [tiles_y][tiles_x] bytes; 0 = sparse tile (all zero, as GDAL reads it)
+constexpr int kInflateMaxParts = 9;     // a block window over a mosaic touches at most 3 x 3 sources of its own size
+
+// One source raster of a mosaic (a single GeoTIFF = one part covering the whole window): its tile grid and the
+// rectangle of the destination plane it fills.
+struct InflatePart {
+    int first_tile;                     // index of the part's first tile in offsets / sizes / status
     int tiles_x, tiles_y;               // tile grid handed over
     int tile_w, tile_h;                 // TIFF TileWidth / TileLength
     int tw_shift;                       // log2(tile_w) when it is a power of two, else -1
-    int x_off, y_off;                   // position of destination pixel (0, 0) inside the tile grid
-    uint8_t *dst;                       // destination plane (row 0 of the window)
-    size_t pitch;
-    int w, h;                           // window size: pixels outside are decoded but not stored
-    int *status;                        // [tiles_y][tiles_x] 0 or an inflate::kErr* code
+    int x_off, y_off;                   // position of the rectangle's pixel (0, 0) inside the tile grid
+    uint8_t *dst;                       // the rectangle's pixel (0, 0) in the destination plane
+    int w, h;                           // rectangle size: pixels outside are decoded but not stored
+};
+
+struct InflateParams {
+    const uint8_t *blob;                // device copy of the compressed tiles; readable 4 KB past the last one
+    const unsigned long long *offsets;  // per tile: byte offset of its zlib stream in blob
+    const uint32_t *sizes;              // per tile: bytes; 0 = sparse tile (all zero, as GDAL reads it)
+    size_t pitch;                       // of the destination plane
+    int *status;                        // per tile: 0 or an inflate::kErr* code
     const int *order;                   // launch order: CTA i takes tile order[i] (longest streams first), or NULL
     int probe;                          // measurement aid: 1 = the writer warp drops the batches (decoder speed alone),
                                         // 2 = the writer runs but does not flush the ring to the plane
+    int nparts;
+    InflatePart part[kInflateMaxParts];
 };
 
 struct InflateSmem {
@@ -243,27 +253,32 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = p.order ? p.order[blockIdx.x] : (int)blockIdx.x;
-    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    int pi = 0;
+    while (pi + 1 < p.nparts && tile >= p.part[pi + 1].first_tile)
+        pi++;
+    const InflatePart &pt = p.part[pi];
+    const int local = tile - pt.first_tile;
+    const int tx = local % pt.tiles_x, ty = local / pt.tiles_x;
 
     TileDst d;
-    d.dst = p.dst;
+    d.dst = pt.dst;
     d.pitch = p.pitch;
-    d.dx0 = tx * p.tile_w - p.x_off;
-    d.dy0 = ty * p.tile_h - p.y_off;
-    d.w = p.w;
-    d.h = p.h;
-    d.tile_w = p.tile_w;
-    d.tw_shift = p.tw_shift;
-    d.rows16 = (p.tile_w & 15) == 0;
+    d.dx0 = tx * pt.tile_w - pt.x_off;
+    d.dy0 = ty * pt.tile_h - pt.y_off;
+    d.w = pt.w;
+    d.h = pt.h;
+    d.tile_w = pt.tile_w;
+    d.tw_shift = pt.tw_shift;
+    d.rows16 = (pt.tile_w & 15) == 0;
 
     const uint32_t size = p.sizes[tile];
     if (size == 0) {
         // sparse tile: GDAL returns zeros for a tile without data
-        const int x0 = max(d.dx0, 0), x1 = min(d.dx0 + p.tile_w, p.w);
-        const int y0 = max(d.dy0, 0), y1 = min(d.dy0 + p.tile_h, p.h);
+        const int x0 = max(d.dx0, 0), x1 = min(d.dx0 + pt.tile_w, pt.w);
+        const int y0 = max(d.dy0, 0), y1 = min(d.dy0 + pt.tile_h, pt.h);
         for (int y = y0 + warp; y < y1; y += kInflateThreads / 32)
             for (int x = x0 + lane; x < x1; x += 32)
-                p.dst[(size_t)y * p.pitch + x] = 0;
+                pt.dst[(size_t)y * p.pitch + x] = 0;
         if (threadIdx.x == 0)
             p.status[tile] = 0;
         return;
@@ -272,7 +287,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
     const uint8_t *src = p.blob + p.offsets[tile];
     const uint8_t *base = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15);
     const uint32_t first = (uint32_t)(src - base);
-    const uint32_t out_end = (uint32_t)p.tile_w * (uint32_t)p.tile_h;
+    const uint32_t out_end = (uint32_t)pt.tile_w * (uint32_t)pt.tile_h;
     if (threadIdx.x == 0)
         sm.writer_err = 0;
     __syncthreads();

@@ -107,6 +107,34 @@ int gh_tiff_window_tiles_read(gh_tiff *t, const gh_tile_plan *plan, uint8_t *blo
                               int threads, char *err, size_t errlen);
 void gh_tiff_close(gh_tiff *t);
 
+/* ---- a raster as GDALOpen() sees it: one GeoTIFF or a VRT mosaic of GeoTIFFs (host_raster.c) ---------- */
+
+typedef struct gh_raster gh_raster;
+/* path: a GeoTIFF (see gh_tiff_open) or a GDAL .vrt whose first band is a 1:1 mosaic of GeoTIFF sources
+ * (<SimpleSource> / <ComplexSource> with equal SrcRect and DstRect sizes) -- the structure of the reference's
+ * landcover/esa_worldcover_2021.vrt, which its shipped config names as esa_data_path (raster.c:119). */
+int gh_raster_open(const char *path, gh_raster **out, char *err, size_t errlen);
+int gh_raster_size(const gh_raster *r, int *w, int *h);
+int gh_raster_geotransform(const gh_raster *r, double gt[6]);
+int gh_raster_is_mosaic(const gh_raster *r);
+int gh_raster_source_count(const gh_raster *r);
+int gh_raster_fill(const gh_raster *r);         /* value of pixels no source covers (VRT NoDataValue, else 0) */
+/* GDALRasterIO(GF_Read) of a window (raster.c:177-179), decoded on the host. */
+int gh_raster_read_window(gh_raster *r, int xoff, int yoff, int xcount, int ycount, uint8_t *dst, size_t pitch,
+                          int threads, char *err, size_t errlen);
+/* The window as compressed tiles, source by source, for gcn10_cuda_block_parts_deflate.  Returns 0 and fills
+ * parts[0..*nparts) when every source that touches the window is a tiled DEFLATE GeoTIFF without predictor; 1 when
+ * the window has to be decoded on the host instead (other formats, overlapping sources, more than max_parts
+ * sources); -1 when a source cannot be opened (err set: the read fails like GDAL's would). */
+typedef struct {
+    gh_tiff *ds;                /* borrowed: stays open inside the gh_raster */
+    gh_tile_plan plan;
+    int dst_x, dst_y, w, h;     /* the source's rectangle inside the window */
+} gh_raster_part;
+int gh_raster_window_parts(gh_raster *r, int xoff, int yoff, int xcount, int ycount, gh_raster_part *parts, int max_parts,
+                           int *nparts, char *err, size_t errlen);
+void gh_raster_close(gh_raster *r);
+
 /* What save_raster() produces (raster.c:204-219): 1 band Byte, TILED=YES (256x256),
  * COMPRESS=DEFLATE (zlib level 6, no predictor), geotransform + EPSG:4326 keys, no NoData tag. */
 int gh_tiff_write(const char *path, const uint8_t *data, int w, int h, size_t pitch, const double gt[6],

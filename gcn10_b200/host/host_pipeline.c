@@ -3,17 +3,27 @@
  * gh_process_block() is this program's process_block() (/root/reference/src/cn.c:134-384): same
  * inputs (block id -> bbox -> two raster windows), same 18 outputs with the same names, same log
  * lines and the same two-tier error convention (recoverable: log ERROR and skip the block; fatal:
- * exit(1) where the reference calls MPI_Abort).  What changes is the middle: instead of five CPU
- * passes per raster (cn.c:218-290) the block is streamed band by band (2048 rows, a multiple of the
- * 256-row GeoTIFF tiles).  Default path: a reader thread decodes land-cover band i+1 while the GPU runs
- * gcn10_cuda_block_deflate_rows() on band i -- Curve Numbers AND the DEFLATE tiles of save_raster()
- * (raster.c:204-219) are produced on the device -- and the worker only appends the compressed tiles to
- * the 18 GeoTIFFs.  With GCN10_HOST_DEFLATE=1 the raw planes come back instead
- * (gcn10_cuda_block_rows) and a zlib thread pool encodes them, overlapped with the next band.
+ * exit(1) where the reference calls MPI_Abort).  What changes is the middle.  Every GPU worker is a
+ * three-stage pipeline over the blocks it claims from the shared queue:
  *
- * gh_run_blocks() replaces the MPI round-robin of main.c:171: one worker thread and one gcn10_ctx
- * per GPU, block ids popped from a shared atomic counter; the join of the workers is the barrier
- * (main.c:187).  No data moves between workers, exactly as no data moves between ranks.
+ *   loader thread   block geometry (cn.c:155-184), the two window computations (raster.c:126-162), the HSG
+ *                   window, and the land cover AS IT LIES IN THE FILES: the compressed tiles of every source
+ *                   GeoTIFF that touches the window (a single file, or up to four files of a VRT mosaic), read
+ *                   into page-locked memory.  Runs up to two blocks ahead of the GPU; both rasters stay open
+ *                   for the whole run (the reference re-opens them per block, raster.c:119,180).
+ *   worker thread   gcn10_cuda_parts_prefetch(block i+1): upload + GPU inflate beside block i's strips;
+ *                   gcn10_cuda_block_parts_deflate(block i): Curve Numbers and the DEFLATE tiles of
+ *                   save_raster() (raster.c:204-219) on the device.
+ *   sink            the compressed tiles of the 18 rasters are appended to their GeoTIFFs on the I/O threads
+ *                   (files are created when the first strip arrives, i.e. after the land cover decoded cleanly,
+ *                   under a temporary name that is renamed on success).
+ *
+ * Land cover that is not tiled DEFLATE is decoded on the host band by band (gcn10_cuda_block_deflate_rows);
+ * with GCN10_HOST_DEFLATE=1 the raw planes come back instead and a zlib thread pool encodes them.
+ *
+ * gh_run_blocks() replaces the MPI round-robin of main.c:171: one worker and one gcn10_ctx per GPU, block ids
+ * popped from a shared atomic counter; the join of the workers is the barrier (main.c:187).  No data moves
+ * between workers, exactly as no data moves between ranks.
  */
 #define _GNU_SOURCE
 #include "gcn10_host.h"
@@ -30,7 +40,7 @@
 #include <sys/stat.h>
 #include <time.h>
 
-enum { BAND_ROWS = 2048, NPLANES = GCN10_NPLANES };
+enum { BAND_ROWS = 2048, BAND_STRIP_ROWS = 512, NPLANES = GCN10_NPLANES, MAX_PARTS = 9, LOAD_SLOTS = 3 };
 
 static const char *const k_conds[2] = { "drained", "undrained" };      /* cn.c:145 */
 static const char *const k_hcs[3] = { "p", "f", "g" };                 /* cn.c:146 */
@@ -43,10 +53,31 @@ typedef struct {
     int state;                      /* 0 free, 1 filled (waiting for its consumer), -1 read failed */
 } band_buf;
 
+/* one claimed block on its way to the GPU: what the loader thread prepares */
+typedef struct {
+    int state;                      /* 0 free, 1 loading, 2 ready, 3 end of queue */
+    int block_id;
+    int failed;                     /* 1: block not found / esa load failed, 2: hysogs load failed (already logged) */
+    gh_window we, wh;
+    uint8_t *hsg;
+    size_t hsg_cap;
+    int gpu_inflate;                /* the land cover is in `parts` as compressed tiles */
+    int nparts;
+    gcn10_tile_part parts[MAX_PARTS];
+    uint8_t *blob;                  /* pinned: the compressed tiles of all parts */
+    size_t blob_cap;
+    uint64_t *tile_off;
+    uint32_t *tile_size;
+    size_t tile_cap;
+    int prefetched;                 /* gcn10_cuda_parts_prefetch has been issued for it */
+    double t_read;
+} block_input;
+
 typedef struct worker {
     int index;                      /* worker number: the "rank" of the log lines */
     int device;                     /* its GPU */
     const gh_run_options *opt;
+    int io_threads;                 /* this worker's share of the I/O threads */
     gh_blocks *blocks;
     const int (*tables)[256][5];
     const int *ids;
@@ -56,21 +87,27 @@ typedef struct worker {
     gh_log *log;                    /* rank_<index>.log */
     gh_log *log0;                   /* worker 0's log: progress lines go there (log.c:199-207) */
     gcn10_ctx *ctx;
+    /* the two rasters, opened once (lazily) and shared by the loader and the band readers under rmu */
+    gh_raster *esa_r, *hsg_r;
+    pthread_mutex_t rmu;
+    /* loader -> worker ring */
+    block_input in[LOAD_SLOTS];
+    pthread_mutex_t lmu;
+    pthread_cond_t lcv;
     size_t pitch_cap;
     int have_planes;
     band_buf bands[2];
-    /* compressed land-cover tiles of a block (GPU-inflate path) */
-    uint8_t *tile_blob;             /* pinned */
-    size_t tile_blob_cap;
-    uint64_t *tile_off;
-    uint32_t *tile_size;
-    size_t tile_cap;
     /* encoder hand-off */
     pthread_mutex_t mu;
     pthread_cond_t cv;
     gh_tiffw *writers[NPLANES];
+    int writers_open;
+    char paths[NPLANES][PATH_MAX];
+    int out_w, out_h;
+    double out_gt[6];
+    int cur_block;
     size_t pitch;
-    int encode_failed;
+    atomic_int encode_failed;       /* set by I/O pool threads, read by the worker */
     int encoder_quit;
 } worker;
 
@@ -110,32 +147,6 @@ static int ensure_bands(worker *wk, size_t pitch, int need_planes)
     return 0;
 }
 
-/* encoder thread: compresses and appends filled bands in order */
-static void *encoder_main(void *arg)
-{
-    worker *wk = arg;
-    int turn = 0;
-    for (;;) {
-        pthread_mutex_lock(&wk->mu);
-        while (wk->bands[turn].state != 1 && !wk->encoder_quit)
-            pthread_cond_wait(&wk->cv, &wk->mu);
-        if (wk->bands[turn].state != 1 && wk->encoder_quit) {
-            pthread_mutex_unlock(&wk->mu);
-            return NULL;
-        }
-        pthread_mutex_unlock(&wk->mu);
-        band_buf *bb = &wk->bands[turn];
-        for (int k = 0; k < NPLANES; k++)
-            if (gh_tiffw_write_rows(wk->writers[k], bb->planes[k], wk->pitch, bb->y0, bb->rows, wk->opt->io_threads))
-                wk->encode_failed = 1;
-        pthread_mutex_lock(&wk->mu);
-        bb->state = 0;
-        pthread_cond_broadcast(&wk->cv);
-        pthread_mutex_unlock(&wk->mu);
-        turn ^= 1;
-    }
-}
-
 /* cn.c:293-360: "<outdir>/cn_<hc>_<arc>_<id>.tif", or "..._<id>_.tif" when the file exists and
  * overwrite is off */
 static void output_path(const worker *wk, int cond, int hi, int ai, int block_id, char *path, size_t n)
@@ -152,17 +163,81 @@ static void output_path(const worker *wk, int cond, int hi, int ai, int block_id
     }
 }
 
+
+/* The 18 output files of the current block (cn.c:293-360 names; raster.c:204-219 format), created when the first
+ * rows of output exist -- that is, after the land cover has been read and decoded without error.  The reference
+ * likewise returns before GDALCreate when the load fails (cn.c:188-192).  0 ok. */
+static int open_writers(worker *wk)
+{
+    if (wk->writers_open)
+        return 0;
+    char err[GH_ERRLEN] = "";
+    int opened = 0;
+    for (int k = 0; k < NPLANES; k++) {
+        if (gh_tiffw_open(wk->paths[k], wk->out_w, wk->out_h, wk->out_gt, &wk->writers[k], err, sizeof err)) {
+            gh_log_message(wk->log, "ERROR", err, 1);                               /* raster.c:220-223 */
+            break;
+        }
+        opened++;
+    }
+    if (opened < NPLANES) {
+        for (int k = 0; k < opened; k++) {
+            gh_tiffw_abort(wk->writers[k]);
+            wk->writers[k] = NULL;
+        }
+        return -1;
+    }
+    wk->writers_open = 1;
+    return 0;
+}
+
+/* encoder thread: compresses and appends filled bands in order */
+static void *encoder_main(void *arg)
+{
+    worker *wk = arg;
+    int turn = 0;
+    for (;;) {
+        pthread_mutex_lock(&wk->mu);
+        while (wk->bands[turn].state != 1 && !wk->encoder_quit)
+            pthread_cond_wait(&wk->cv, &wk->mu);
+        if (wk->bands[turn].state != 1 && wk->encoder_quit) {
+            pthread_mutex_unlock(&wk->mu);
+            return NULL;
+        }
+        pthread_mutex_unlock(&wk->mu);
+        band_buf *bb = &wk->bands[turn];
+        if (open_writers(wk))
+            atomic_store(&wk->encode_failed, 1);
+        for (int k = 0; k < NPLANES && !atomic_load(&wk->encode_failed); k++)
+            if (gh_tiffw_write_rows(wk->writers[k], bb->planes[k], wk->pitch, bb->y0, bb->rows, wk->io_threads))
+                atomic_store(&wk->encode_failed, 1);
+        pthread_mutex_lock(&wk->mu);
+        bb->state = 0;
+        pthread_cond_broadcast(&wk->cv);
+        pthread_mutex_unlock(&wk->mu);
+        turn ^= 1;
+    }
+}
+
 /* ---- GPU-deflate path: reader thread -> gcn10_cuda_block_deflate_rows -> append compressed tiles ---- */
 
 typedef struct {
     worker *wk;
-    gh_tiff *esa_ds;
     const gh_window *we;
     int w, h;
     size_t pitch;
     double t_read;
     char err[GH_ERRLEN];
 } reader_job;
+
+static int read_band(worker *wk, const gh_window *we, int y0, int rows, uint8_t *dst, size_t pitch, char *err, size_t errlen)
+{
+    pthread_mutex_lock(&wk->rmu);       /* the loader thread opens mosaic sources on the same handle */
+    int rc = gh_raster_read_window(wk->esa_r, we->xoff, we->yoff + y0, we->xcount, rows, dst, pitch, wk->io_threads, err,
+                                   errlen);
+    pthread_mutex_unlock(&wk->rmu);
+    return rc;
+}
 
 static void *reader_main(void *arg)
 {
@@ -180,8 +255,7 @@ static void *reader_main(void *arg)
             return NULL;
         int rows = rj->h - y0 < BAND_ROWS ? rj->h - y0 : BAND_ROWS;
         double t0 = now_s();
-        int rc = gh_tiff_read_window(rj->esa_ds, rj->we->xoff, rj->we->yoff + y0, rj->w, rows, bb->esa, rj->pitch,
-                                     wk->opt->io_threads, rj->err, sizeof rj->err);
+        int rc = read_band(wk, rj->we, y0, rows, bb->esa, rj->pitch, rj->err, sizeof rj->err);
         rj->t_read += now_s() - t0;
         bb->y0 = y0;
         bb->rows = rows;
@@ -209,7 +283,7 @@ static void sink_plane(void *arg, int k)
     for (int tr = 0; tr < st->n_tile_rows; tr++) {
         size_t base = ((size_t)k * st->n_tile_rows + tr) * (size_t)st->tiles_x;
         if (gh_tiffw_put_tile_row(tw, st->tile_row0 + tr, st->blob, st->offsets + base, st->sizes + base)) {
-            j->wk->encode_failed = 1;
+            atomic_store(&j->wk->encode_failed, 1);
             return;
         }
     }
@@ -219,23 +293,29 @@ static void sink_plane(void *arg, int k)
 static int tile_sink(void *user, const gcn10_tile_strip *st)
 {
     worker *wk = user;
+    if (open_writers(wk)) {
+        atomic_store(&wk->encode_failed, 1);
+        return 1;
+    }
     sink_job j = { wk, st };
-    gh_parallel_for(st->n_planes, wk->opt->io_threads > 0 ? wk->opt->io_threads : 1, sink_plane, &j);
-    return wk->encode_failed ? 1 : 0;
+    gh_parallel_for(st->n_planes, wk->io_threads > 0 ? wk->io_threads : 1, sink_plane, &j);
+    return atomic_load(&wk->encode_failed) ? 1 : 0;
 }
 
 /* returns 0 ok, 1 = land-cover read failed (recoverable tier) */
-static int bands_gpu_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const gh_window *we, const uint8_t *hsg,
-                             const gh_window *wh, size_t pitch, double *t_read, double *t_gpu)
+static int bands_gpu_deflate(worker *wk, int block_id, const gh_window *we, const uint8_t *hsg, const gh_window *wh,
+                             size_t pitch, double *t_read, double *t_gpu)
 {
     char msg[1024];
     const int w = we->xcount, h = we->ycount;
-    reader_job rj = { wk, esa_ds, we, w, h, pitch, 0.0, "" };
+    reader_job rj = { wk, we, w, h, pitch, 0.0, "" };
     pthread_t rd;
     wk->encoder_quit = 0;
     wk->bands[0].state = wk->bands[1].state = 0;
     if (pthread_create(&rd, NULL, reader_main, &rj) != 0)
         fatal(wk, "cannot start the reader thread");
+    /* a band is one call: cut it into several strips so that its copies and kernels overlap */
+    gcn10_cuda_set_option(wk->ctx, "strip_rows", BAND_STRIP_ROWS);
     int turn = 0, failed = 0;
     for (int y0 = 0; y0 < h; y0 += BAND_ROWS, turn ^= 1) {
         band_buf *bb = &wk->bands[turn];
@@ -252,7 +332,7 @@ static int bands_gpu_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const gh
         double t1 = now_s();
         int rc = gcn10_cuda_block_deflate_rows(wk->ctx, bb->esa, w, h, bb->y0, bb->rows, pitch, we->gt, hsg, wh->xcount,
                                                wh->ycount, (size_t)wh->xcount, wh->gt, GCN10_MASK_ALL, tile_sink, wk);
-        if (rc && !wk->encode_failed) {
+        if (rc && !atomic_load(&wk->encode_failed)) {
             snprintf(msg, sizeof msg, "cuda failure on block %d: %s", block_id, gcn10_cuda_last_error());
             fatal(wk, msg);                         /* CUDA errors are the fatal tier; there is no CPU path */
         }
@@ -261,9 +341,10 @@ static int bands_gpu_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const gh
         bb->state = 0;
         pthread_cond_broadcast(&wk->cv);
         pthread_mutex_unlock(&wk->mu);
-        if (wk->encode_failed)
+        if (atomic_load(&wk->encode_failed))
             break;
     }
+    gcn10_cuda_set_option(wk->ctx, "strip_rows", 2048);
     pthread_mutex_lock(&wk->mu);
     wk->encoder_quit = 1;
     pthread_cond_broadcast(&wk->cv);
@@ -273,62 +354,24 @@ static int bands_gpu_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const gh
     return failed;
 }
 
-/* ---- GPU-inflate path: the land-cover window goes to the device as the DEFLATE tiles of the file
- * (gcn10_cuda_block_tiles_deflate): no decode on the host at all.  Returns 0 ok, 1 = land-cover read or tile
- * decode failed (recoverable tier, raster.c:182-186) */
-static int block_gpu_tiles(worker *wk, int block_id, gh_tiff *esa_ds, const gh_window *we, const gh_tile_plan *plan,
-                           const uint8_t *hsg, const gh_window *wh, double *t_read, double *t_gpu)
+/* ---- GPU-inflate path: the land-cover window goes to the device as the DEFLATE tiles of the file(s)
+ * (gcn10_cuda_block_parts_deflate): no decode on the host at all.  Returns 0 ok, 1 = tile decode failed
+ * (recoverable tier, raster.c:182-186) */
+static int block_gpu_tiles(worker *wk, const block_input *in, double *t_gpu)
 {
-    char msg[1024], err[GH_ERRLEN] = "";
-    const size_t ntiles = (size_t)plan->tiles_x * (size_t)plan->tiles_y;
-    if (wk->tile_blob_cap < plan->blob_bytes + 16) {
-        gcn10_cuda_host_free(wk->tile_blob);
-        wk->tile_blob_cap = plan->blob_bytes + plan->blob_bytes / 4 + (1u << 20);
-        wk->tile_blob = gcn10_cuda_host_alloc(wk->tile_blob_cap);
-        if (!wk->tile_blob) {
-            wk->tile_blob_cap = 0;
-            snprintf(msg, sizeof msg, "pinned allocation failed for block %d: %s", block_id, gcn10_cuda_last_error());
-            fatal(wk, msg);
-        }
-    }
-    if (wk->tile_cap < ntiles) {
-        free(wk->tile_off);
-        free(wk->tile_size);
-        wk->tile_off = malloc(ntiles * sizeof *wk->tile_off);
-        wk->tile_size = malloc(ntiles * sizeof *wk->tile_size);
-        if (!wk->tile_off || !wk->tile_size)
-            fatal(wk, "out of memory for raster");
-        wk->tile_cap = ntiles;
-    }
-    double t0 = now_s();
-    if (gh_tiff_window_tiles_read(esa_ds, plan, wk->tile_blob, wk->tile_off, wk->tile_size, wk->opt->io_threads, err,
-                                  sizeof err)) {
-        gh_log_message(wk->log, "ERROR", err, 1);
-        return 1;
-    }
+    char msg[1024];
     double t1 = now_s();
-    *t_read += t1 - t0;
-    gcn10_tile_source src;
-    src.tile_w = plan->tile_w;
-    src.tile_h = plan->tile_h;
-    src.tiles_x = plan->tiles_x;
-    src.tiles_y = plan->tiles_y;
-    src.x_off = plan->x_in;
-    src.y_off = plan->y_in;
-    src.blob = wk->tile_blob;
-    src.blob_bytes = plan->blob_bytes;
-    src.offsets = wk->tile_off;
-    src.sizes = wk->tile_size;
-    int rc = gcn10_cuda_block_tiles_deflate(wk->ctx, &src, we->xcount, we->ycount, we->gt, hsg, wh->xcount, wh->ycount,
-                                            (size_t)wh->xcount, wh->gt, GCN10_MASK_ALL, tile_sink, wk);
+    int rc = gcn10_cuda_block_parts_deflate(wk->ctx, in->parts, in->nparts, gh_raster_fill(wk->esa_r), in->we.xcount,
+                                            in->we.ycount, in->we.gt, in->hsg, in->wh.xcount, in->wh.ycount,
+                                            (size_t)in->wh.xcount, in->wh.gt, GCN10_MASK_ALL, tile_sink, wk);
     *t_gpu += now_s() - t1;
     if (rc == GCN10_EDATA) {
         snprintf(msg, sizeof msg, "gdalrasterio error 3 (%s)", gcn10_cuda_last_error());
         gh_log_message(wk->log, "ERROR", msg, 1);
         return 1;
     }
-    if (rc && !wk->encode_failed) {
-        snprintf(msg, sizeof msg, "cuda failure on block %d: %s", block_id, gcn10_cuda_last_error());
+    if (rc && !atomic_load(&wk->encode_failed)) {
+        snprintf(msg, sizeof msg, "cuda failure on block %d: %s", in->block_id, gcn10_cuda_last_error());
         fatal(wk, msg);
     }
     return 0;
@@ -336,8 +379,8 @@ static int block_gpu_tiles(worker *wk, int block_id, gh_tiff *esa_ds, const gh_w
 
 /* ---- host-deflate path: raw planes back, zlib thread pool encodes band i while band i+1 is computed ---- */
 
-static int bands_host_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const gh_window *we, const uint8_t *hsg,
-                              const gh_window *wh, size_t pitch, double *t_read, double *t_gpu)
+static int bands_host_deflate(worker *wk, int block_id, const gh_window *we, const uint8_t *hsg, const gh_window *wh,
+                              size_t pitch, double *t_read, double *t_gpu)
 {
     char msg[1024], err[GH_ERRLEN] = "";
     const int w = we->xcount, h = we->ycount;
@@ -346,6 +389,7 @@ static int bands_host_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const g
     pthread_t enc;
     if (pthread_create(&enc, NULL, encoder_main, wk) != 0)
         fatal(wk, "cannot start the encoder thread");
+    gcn10_cuda_set_option(wk->ctx, "strip_rows", BAND_STRIP_ROWS);
     int turn = 0, failed = 0;
     for (int y0 = 0; y0 < h && !failed; y0 += BAND_ROWS, turn ^= 1) {
         band_buf *bb = &wk->bands[turn];
@@ -355,8 +399,7 @@ static int bands_host_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const g
             pthread_cond_wait(&wk->cv, &wk->mu);
         pthread_mutex_unlock(&wk->mu);
         double t0 = now_s();
-        if (gh_tiff_read_window(esa_ds, we->xoff, we->yoff + y0, w, rows, bb->esa, pitch, wk->opt->io_threads, err,
-                                sizeof err)) {
+        if (read_band(wk, we, y0, rows, bb->esa, pitch, err, sizeof err)) {
             gh_log_message(wk->log, "ERROR", err, 1);                               /* raster.c:182-186 */
             failed = 1;
             break;
@@ -377,6 +420,7 @@ static int bands_host_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const g
         pthread_cond_broadcast(&wk->cv);
         pthread_mutex_unlock(&wk->mu);
     }
+    gcn10_cuda_set_option(wk->ctx, "strip_rows", 2048);
     pthread_mutex_lock(&wk->mu);
     wk->encoder_quit = 1;
     pthread_cond_broadcast(&wk->cv);
@@ -385,80 +429,203 @@ static int bands_host_deflate(worker *wk, int block_id, gh_tiff *esa_ds, const g
     return failed;
 }
 
-static int gh_process_block(worker *wk, int block_id, int total_blocks)
-{
-    char msg[8192], err[GH_ERRLEN] = "";
-    double bbox[4];
-    double t_start = now_s();
+/* ---- the loader: everything of process_block() that happens before the first pixel is computed ---------- */
 
-    /* block geometry (cn.c:155-184) */
+static gh_raster *open_once(worker *wk, gh_raster **slot, const char *path)
+{
+    char err[GH_ERRLEN] = "";
+    if (!*slot && gh_raster_open(path, slot, err, sizeof err)) {
+        gh_log_message(wk->log, "ERROR", err, 1);                                   /* raster.c:121 */
+        *slot = NULL;
+    }
+    return *slot;
+}
+
+/* cn.c:155-203: bbox, land-cover window (+ its compressed tiles when the files allow it), soil window */
+static void load_block(worker *wk, block_input *in, int block_id)
+{
+    char msg[1024], err[GH_ERRLEN] = "";
+    double bbox[4], t[6];
+    int rw, rh;
+    in->block_id = block_id;
+    in->failed = 0;
+    in->gpu_inflate = 0;
+    in->nparts = 0;
+    in->prefetched = 0;
+    in->t_read = 0;
     if (gh_blocks_bbox(wk->blocks, block_id, bbox)) {
         snprintf(msg, sizeof msg, "block %d not found", block_id);                  /* cn.c:173 */
         gh_log_message(wk->log, "ERROR", msg, 1);
-        return -1;
+        in->failed = 3;
+        return;
     }
-
+    pthread_mutex_lock(&wk->rmu);
     /* land cover window (cn.c:187 -> raster.c:106-189) */
-    gh_tiff *esa_ds = NULL, *hsg_ds = NULL;
-    gh_window we, wh;
-    int rw, rh;
-    double t[6];
-    if (gh_tiff_open(wk->opt->cfg.esa_data_path, &esa_ds, err, sizeof err)) {
-        gh_log_message(wk->log, "ERROR", err, 1);
-        goto esa_failed;
+    if (!open_once(wk, &wk->esa_r, wk->opt->cfg.esa_data_path)) {
+        in->failed = 1;
+        goto out;
     }
-    gh_tiff_size(esa_ds, &rw, &rh);
-    gh_tiff_geotransform(esa_ds, t);
-    if (gh_raster_window(rw, rh, t, bbox, &we)) {
+    gh_raster_size(wk->esa_r, &rw, &rh);
+    gh_raster_geotransform(wk->esa_r, t);
+    if (gh_raster_window(rw, rh, t, bbox, &in->we)) {
         snprintf(msg, sizeof msg, "invalid raster bounds for %s", wk->opt->cfg.esa_data_path);   /* raster.c:143 */
         gh_log_message(wk->log, "ERROR", msg, 1);
-        goto esa_failed;
+        in->failed = 1;
+        goto out;
     }
-
     /* soil window (cn.c:195-196) */
-    if (gh_tiff_open(wk->opt->cfg.hysogs_data_path, &hsg_ds, err, sizeof err)) {
-        gh_log_message(wk->log, "ERROR", err, 1);
-        goto hsg_failed;
+    if (!open_once(wk, &wk->hsg_r, wk->opt->cfg.hysogs_data_path)) {
+        in->failed = 2;
+        goto out;
     }
-    gh_tiff_size(hsg_ds, &rw, &rh);
-    gh_tiff_geotransform(hsg_ds, t);
-    if (gh_raster_window(rw, rh, t, bbox, &wh)) {
+    gh_raster_size(wk->hsg_r, &rw, &rh);
+    gh_raster_geotransform(wk->hsg_r, t);
+    if (gh_raster_window(rw, rh, t, bbox, &in->wh)) {
         snprintf(msg, sizeof msg, "invalid raster bounds for %s", wk->opt->cfg.hysogs_data_path);
         gh_log_message(wk->log, "ERROR", msg, 1);
-        goto hsg_failed;
+        in->failed = 2;
+        goto out;
     }
-    uint8_t *hsg = malloc((size_t)wh.xcount * (size_t)wh.ycount);
-    if (!hsg)
-        fatal(wk, "out of memory for raster");                                      /* raster.c:171 */
-    if (gh_tiff_read_window(hsg_ds, wh.xoff, wh.yoff, wh.xcount, wh.ycount, hsg, (size_t)wh.xcount,
-                            wk->opt->io_threads, err, sizeof err)) {
+    const size_t hsg_bytes = (size_t)in->wh.xcount * (size_t)in->wh.ycount;
+    if (in->hsg_cap < hsg_bytes) {
+        free(in->hsg);
+        in->hsg = malloc(hsg_bytes);
+        in->hsg_cap = in->hsg ? hsg_bytes : 0;
+        if (!in->hsg)
+            fatal(wk, "out of memory for raster");                                  /* raster.c:171 */
+    }
+    double t0 = now_s();
+    if (gh_raster_read_window(wk->hsg_r, in->wh.xoff, in->wh.yoff, in->wh.xcount, in->wh.ycount, in->hsg,
+                              (size_t)in->wh.xcount, wk->io_threads, err, sizeof err)) {
         gh_log_message(wk->log, "ERROR", err, 1);
-        free(hsg);
-        goto hsg_failed;
+        in->failed = 2;
+        goto out;
     }
-    gh_tiff_close(hsg_ds);
-    hsg_ds = NULL;
 
-    const int w = we.xcount, h = we.ycount;
+    /* a tiled DEFLATE land-cover file (what GDAL writes for COMPRESS=DEFLATE TILED=YES, and what the ESA WorldCover
+     * files are) is handed to the GPU compressed; anything else is decoded later, band by band */
+    const char *hd = getenv("GCN10_HOST_DEFLATE"), *hi = getenv("GCN10_HOST_INFLATE");
+    const int host_side = (hd && *hd && *hd != '0') || (hi && *hi && *hi != '0');
+    gh_raster_part rp[MAX_PARTS];
+    int np = 0;
+    int prc = host_side ? 1 : gh_raster_window_parts(wk->esa_r, in->we.xoff, in->we.yoff, in->we.xcount, in->we.ycount, rp,
+                                                     MAX_PARTS, &np, err, sizeof err);
+    if (prc < 0) {
+        gh_log_message(wk->log, "ERROR", err, 1);
+        in->failed = 1;
+        goto out;
+    }
+    if (prc == 0) {
+        size_t ntiles = 0, bytes = 0;
+        for (int k = 0; k < np; k++) {
+            ntiles += (size_t)rp[k].plan.tiles_x * (size_t)rp[k].plan.tiles_y;
+            bytes += (rp[k].plan.blob_bytes + 15) & ~(size_t)15;
+        }
+        if (in->blob_cap < bytes + 16) {
+            gcn10_cuda_host_free(in->blob);
+            in->blob_cap = bytes + bytes / 4 + (1u << 20);
+            in->blob = gcn10_cuda_host_alloc(in->blob_cap);
+            if (!in->blob) {
+                in->blob_cap = 0;
+                snprintf(msg, sizeof msg, "pinned allocation failed for block %d: %s", block_id, gcn10_cuda_last_error());
+                fatal(wk, msg);
+            }
+        }
+        if (in->tile_cap < ntiles) {
+            free(in->tile_off);
+            free(in->tile_size);
+            in->tile_off = malloc(ntiles * sizeof *in->tile_off);
+            in->tile_size = malloc(ntiles * sizeof *in->tile_size);
+            if (!in->tile_off || !in->tile_size)
+                fatal(wk, "out of memory for raster");
+            in->tile_cap = ntiles;
+        }
+        size_t t_at = 0, b_at = 0;
+        for (int k = 0; k < np; k++) {
+            if (gh_tiff_window_tiles_read(rp[k].ds, &rp[k].plan, in->blob + b_at, in->tile_off + t_at, in->tile_size + t_at,
+                                          wk->io_threads, err, sizeof err)) {
+                gh_log_message(wk->log, "ERROR", err, 1);
+                in->failed = 1;
+                goto out;
+            }
+            gcn10_tile_part *cp = &in->parts[k];
+            cp->tiles.tile_w = rp[k].plan.tile_w;
+            cp->tiles.tile_h = rp[k].plan.tile_h;
+            cp->tiles.tiles_x = rp[k].plan.tiles_x;
+            cp->tiles.tiles_y = rp[k].plan.tiles_y;
+            cp->tiles.x_off = rp[k].plan.x_in;
+            cp->tiles.y_off = rp[k].plan.y_in;
+            cp->tiles.blob = in->blob + b_at;
+            cp->tiles.blob_bytes = rp[k].plan.blob_bytes;
+            cp->tiles.offsets = in->tile_off + t_at;
+            cp->tiles.sizes = in->tile_size + t_at;
+            cp->dst_x = rp[k].dst_x;
+            cp->dst_y = rp[k].dst_y;
+            cp->w = rp[k].w;
+            cp->h = rp[k].h;
+            t_at += (size_t)rp[k].plan.tiles_x * (size_t)rp[k].plan.tiles_y;
+            b_at += (rp[k].plan.blob_bytes + 15) & ~(size_t)15;
+        }
+        in->nparts = np;
+        in->gpu_inflate = np > 0;
+    }
+    in->t_read = now_s() - t0;
+out:
+    pthread_mutex_unlock(&wk->rmu);
+}
+
+static void *loader_main(void *arg)
+{
+    worker *wk = arg;
+    for (int k = 0;; k++) {
+        block_input *in = &wk->in[k % LOAD_SLOTS];
+        pthread_mutex_lock(&wk->lmu);
+        while (in->state != 0)
+            pthread_cond_wait(&wk->lcv, &wk->lmu);
+        in->state = 1;
+        pthread_mutex_unlock(&wk->lmu);
+        int i = atomic_fetch_add(wk->next, 1);                  /* replaces i = rank; i += size (main.c:171) */
+        int last = i >= wk->n_ids;
+        if (!last) {
+            char msg[64];
+            snprintf(msg, sizeof msg, "processing block %d", wk->ids[i]);          /* main.c:172-173 */
+            gh_log_message(wk->log, "INFO", msg, 1);
+            load_block(wk, in, wk->ids[i]);
+        }
+        pthread_mutex_lock(&wk->lmu);
+        in->state = last ? 3 : 2;
+        pthread_cond_broadcast(&wk->lcv);
+        pthread_mutex_unlock(&wk->lmu);
+        if (last)
+            return NULL;
+    }
+}
+
+/* cn.c:208-384 for a loaded block */
+static int gh_process_block(worker *wk, block_input *in, int total_blocks, double t_start)
+{
+    char msg[8192];
+    const int block_id = in->block_id;
+    if (in->failed) {
+        if (in->failed != 3) {
+            snprintf(msg, sizeof msg, "%s load failed for block %d", in->failed == 2 ? "hysogs" : "esa", block_id);
+            gh_log_message(wk->log, "ERROR", msg, 1);                               /* cn.c:189,198-199 */
+        }
+        return -1;
+    }
+    const gh_window *we = &in->we, *wh = &in->wh;
+    const int w = we->xcount, h = we->ycount;
     const size_t pitch = ((size_t)w + 255) / 256 * 256;
     const char *hd = getenv("GCN10_HOST_DEFLATE");
     const int host_deflate = hd && *hd && *hd != '0';
-    const char *hi = getenv("GCN10_HOST_INFLATE");
-    const int host_inflate = hi && *hi && *hi != '0';
-    /* a tiled DEFLATE land-cover file (what GDAL writes for COMPRESS=DEFLATE TILED=YES, and what the ESA WorldCover
-     * files are) is handed to the GPU compressed; anything else is decoded here, band by band */
-    gh_tile_plan plan;
-    const int gpu_inflate = !host_deflate && !host_inflate &&
-                            gh_tiff_window_tiles_plan(esa_ds, we.xoff, we.yoff, w, h, &plan) == 0;
-    if (!gpu_inflate && ensure_bands(wk, pitch, host_deflate)) {
+    if (!in->gpu_inflate && ensure_bands(wk, pitch, host_deflate)) {
         snprintf(msg, sizeof msg, "pinned allocation failed for block %d: %s", block_id, gcn10_cuda_last_error());
         fatal(wk, msg);
     }
     wk->pitch = pitch;
 
-    /* output directories and files (cn.c:236-256, 293-360) */
+    /* output directories and file names (cn.c:236-256, 293-360); the files themselves appear with the first rows */
     const char *root = (wk->opt->out_root && *wk->opt->out_root) ? wk->opt->out_root : ".";
-    char paths[NPLANES][PATH_MAX];
     for (int c = 0; c < 2; c++) {
         char outdir[PATH_MAX];
         snprintf(outdir, sizeof outdir, "%s/cn_rasters_%s", root, k_conds[c]);
@@ -467,43 +634,35 @@ static int gh_process_block(worker *wk, int block_id, int total_blocks)
             fatal(wk, msg);
         }
     }
-    int opened = 0;
-    for (int k = 0; k < NPLANES; k++) {
-        output_path(wk, k / 9, (k % 9) / 3, k % 3, block_id, paths[k], sizeof paths[k]);
-        if (gh_tiffw_open(paths[k], w, h, we.gt, &wk->writers[k], err, sizeof err)) {
-            gh_log_message(wk->log, "ERROR", err, 1);                               /* raster.c:220-223 */
-            break;
+    for (int k = 0; k < NPLANES; k++)
+        output_path(wk, k / 9, (k % 9) / 3, k % 3, block_id, wk->paths[k], sizeof wk->paths[k]);
+    wk->writers_open = 0;
+    wk->out_w = w;
+    wk->out_h = h;
+    memcpy(wk->out_gt, we->gt, sizeof wk->out_gt);
+    wk->cur_block = block_id;
+
+    atomic_store(&wk->encode_failed, 0);
+    double t_read = in->t_read, t_gpu = 0;
+    int failed = in->gpu_inflate ? block_gpu_tiles(wk, in, &t_gpu)
+                 : host_deflate ? bands_host_deflate(wk, block_id, we, in->hsg, wh, pitch, &t_read, &t_gpu)
+                                : bands_gpu_deflate(wk, block_id, we, in->hsg, wh, pitch, &t_read, &t_gpu);
+
+    if (failed || !wk->writers_open) {
+        if (wk->writers_open)
+            for (int k = 0; k < NPLANES; k++)
+                gh_tiffw_abort(wk->writers[k]);
+        wk->writers_open = 0;
+        if (failed) {
+            snprintf(msg, sizeof msg, "esa load failed for block %d", block_id);    /* cn.c:189 */
+            gh_log_message(wk->log, "ERROR", msg, 1);
         }
-        opened++;
-    }
-    if (opened < NPLANES) {
-        for (int k = 0; k < opened; k++)
-            gh_tiffw_abort(wk->writers[k]);
-        free(hsg);
-        gh_tiff_close(esa_ds);
-        return -1;
-    }
-
-    /* band loop */
-    wk->encode_failed = 0;
-    double t_read = 0, t_gpu = 0;
-    int failed = gpu_inflate ? block_gpu_tiles(wk, block_id, esa_ds, &we, &plan, hsg, &wh, &t_read, &t_gpu)
-                 : host_deflate ? bands_host_deflate(wk, block_id, esa_ds, &we, hsg, &wh, pitch, &t_read, &t_gpu)
-                                : bands_gpu_deflate(wk, block_id, esa_ds, &we, hsg, &wh, pitch, &t_read, &t_gpu);
-    free(hsg);
-    gh_tiff_close(esa_ds);
-
-    if (failed) {
-        for (int k = 0; k < NPLANES; k++)
-            gh_tiffw_abort(wk->writers[k]);
-        snprintf(msg, sizeof msg, "esa load failed for block %d", block_id);        /* cn.c:189 */
-        gh_log_message(wk->log, "ERROR", msg, 1);
         return -1;
     }
     int ok = 1;
     for (int k = 0; k < NPLANES; k++) {
-        if (gh_tiffw_close(wk->writers[k]) || wk->encode_failed) {
-            snprintf(msg, sizeof msg, "write error 3 on %s", paths[k]);             /* raster.c:221 */
+        if (gh_tiffw_close(wk->writers[k]) || atomic_load(&wk->encode_failed)) {
+            snprintf(msg, sizeof msg, "write error 3 on %s", wk->paths[k]);         /* raster.c:221 */
             gh_log_message(wk->log, "ERROR", msg, 1);
             ok = 0;
         }
@@ -515,33 +674,23 @@ static int gh_process_block(worker *wk, int block_id, int total_blocks)
         snprintf(msg, sizeof msg, "progress: completed block %d / total %d", block_id, total_blocks);
         gh_log_message(wk->log0, "INFO", msg, 0);                                   /* log.c:199-207 */
     }
+    wk->writers_open = 0;
     double dt = now_s() - t_start;
     snprintf(msg, sizeof msg,
-             "block %d: %d x %d px, 18 rasters in %.2f s (%.1f Mpx/s; decode %.2f s, gpu+copies %.2f s; %s deflate)%s",
+             "block %d: %d x %d px, 18 rasters in %.3f s (%.1f Mpx/s; read %.3f s [overlapped], gpu+copies+write %.3f s; %s deflate)%s",
              block_id, w, h, dt, (double)w * h / dt / 1e6, t_read, t_gpu, host_deflate ? "host" : "gpu",
-             gpu_inflate ? " [land cover inflated on the gpu]" : "");
+             in->gpu_inflate ? (in->nparts > 1 ? " [land cover: mosaic parts inflated on the gpu]"
+                                               : " [land cover inflated on the gpu]") : "");
     gh_log_message(wk->log, "INFO", msg, 0);
     return ok ? 0 : -1;
-
-hsg_failed:
-    gh_tiff_close(hsg_ds);
-    gh_tiff_close(esa_ds);
-    snprintf(msg, sizeof msg, "hysogs load failed for block %d", block_id);         /* cn.c:198-199 */
-    gh_log_message(wk->log, "ERROR", msg, 1);
-    return -1;
-esa_failed:
-    gh_tiff_close(esa_ds);
-    snprintf(msg, sizeof msg, "esa load failed for block %d", block_id);            /* cn.c:189 */
-    gh_log_message(wk->log, "ERROR", msg, 1);
-    return -1;
 }
 
 static void *worker_main(void *arg)
 {
     worker *wk = arg;
     char msg[256];
-    /* keep this worker (and the reader / encoder threads it spawns, which inherit the mask) on the
-     * NUMA node of its GPU so that the pinned band buffers are node-local */
+    /* keep this worker (and the loader / reader / encoder threads it spawns, which inherit the mask) on the
+     * NUMA node of its GPU so that the pinned buffers are node-local */
     int node = gcn10_cuda_bind_host_thread(wk->device);
     snprintf(msg, sizeof msg, "worker %d on gpu %d, numa node %d", wk->index, wk->device, node);
     gh_log_message(wk->log, "INFO", msg, 0);
@@ -551,26 +700,56 @@ static void *worker_main(void *arg)
     }
     pthread_mutex_init(&wk->mu, NULL);
     pthread_cond_init(&wk->cv, NULL);
-    for (;;) {
-        int i = atomic_fetch_add(wk->next, 1);                  /* replaces i = rank; i += size (main.c:171) */
-        if (i >= wk->n_ids)
+    pthread_mutex_init(&wk->rmu, NULL);
+    pthread_mutex_init(&wk->lmu, NULL);
+    pthread_cond_init(&wk->lcv, NULL);
+    pthread_t loader;
+    if (pthread_create(&loader, NULL, loader_main, wk) != 0)
+        fatal(wk, "cannot start the loader thread");
+    double t_prev = now_s();
+    for (int k = 0;; k++) {
+        block_input *in = &wk->in[k % LOAD_SLOTS], *nx = &wk->in[(k + 1) % LOAD_SLOTS];
+        pthread_mutex_lock(&wk->lmu);
+        while (in->state < 2)
+            pthread_cond_wait(&wk->lcv, &wk->lmu);
+        const int end = in->state == 3;
+        const int next_ready = nx->state == 2;
+        pthread_mutex_unlock(&wk->lmu);
+        if (end)
             break;
-        snprintf(msg, sizeof msg, "processing block %d", wk->ids[i]);              /* main.c:172-173 */
-        gh_log_message(wk->log, "INFO", msg, 1);
-        if (gh_process_block(wk, wk->ids[i], wk->n_ids) == 0)
+        /* the block after this one is already in memory: its upload + inflate run beside this block's strips */
+        if (next_ready && !nx->failed && nx->gpu_inflate && !nx->prefetched && in->gpu_inflate && !in->failed &&
+            gcn10_cuda_parts_prefetch(wk->ctx, nx->parts, nx->nparts, gh_raster_fill(wk->esa_r), nx->we.xcount,
+                                      nx->we.ycount) == GCN10_OK)
+            nx->prefetched = 1;
+        if (gh_process_block(wk, in, wk->n_ids, t_prev) == 0)
             atomic_fetch_add(wk->done, 1);
+        t_prev = now_s();
+        pthread_mutex_lock(&wk->lmu);
+        in->state = 0;
+        pthread_cond_broadcast(&wk->lcv);
+        pthread_mutex_unlock(&wk->lmu);
     }
+    pthread_join(loader, NULL);
     for (int b = 0; b < 2; b++) {
         gcn10_cuda_host_free(wk->bands[b].esa);
         for (int k = 0; k < NPLANES; k++)
             gcn10_cuda_host_free(wk->bands[b].planes[k]);
     }
-    gcn10_cuda_host_free(wk->tile_blob);
-    free(wk->tile_off);
-    free(wk->tile_size);
+    for (int i = 0; i < LOAD_SLOTS; i++) {
+        gcn10_cuda_host_free(wk->in[i].blob);
+        free(wk->in[i].tile_off);
+        free(wk->in[i].tile_size);
+        free(wk->in[i].hsg);
+    }
+    gh_raster_close(wk->esa_r);
+    gh_raster_close(wk->hsg_r);
     gcn10_cuda_destroy(wk->ctx);
     pthread_cond_destroy(&wk->cv);
     pthread_mutex_destroy(&wk->mu);
+    pthread_mutex_destroy(&wk->rmu);
+    pthread_cond_destroy(&wk->lcv);
+    pthread_mutex_destroy(&wk->lmu);
     return NULL;
 }
 
@@ -606,6 +785,11 @@ int gh_run_blocks(const gh_run_options *opt, const int *block_ids, int n_blocks)
              gpus < nworkers ? gpus : nworkers);
     gh_log_message(log0, "INFO", msg, 1);
 
+    /* the I/O threads are shared out between the workers */
+    int io_each = (opt->io_threads > 0 ? opt->io_threads : 4) / nworkers;
+    if (io_each < 1)
+        io_each = 1;
+
     atomic_int next = 0, done = 0;
     worker *wks = calloc((size_t)nworkers, sizeof *wks);
     pthread_t *th = calloc((size_t)nworkers, sizeof *th);
@@ -613,6 +797,7 @@ int gh_run_blocks(const gh_run_options *opt, const int *block_ids, int n_blocks)
         wks[i].index = i;
         wks[i].device = i % gpus;
         wks[i].opt = opt;
+        wks[i].io_threads = io_each;
         wks[i].blocks = blocks;
         wks[i].tables = tables;
         wks[i].ids = block_ids;

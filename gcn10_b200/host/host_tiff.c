@@ -577,6 +577,7 @@ enum { TILE = 256 };
 
 struct gh_tiffw {
     FILE *fp;
+    char *path, *tmp;           /* written as <path>.part, renamed on a successful close, removed otherwise */
     int w, h;
     int tiles_x, tiles_y;
     double gt[6];
@@ -632,15 +633,22 @@ int gh_tiffw_open(const char *path, int w, int h, const double gt[6], gh_tiffw *
     gh_tiffw *tw = calloc(1, sizeof *tw);
     if (!tw)
         return -1;
-    tw->fp = fopen(path, "wb");
-    if (tw->fp)
-        setvbuf(tw->fp, NULL, _IOFBF, 1 << 20);     /* tiles arrive as ~1.5 KB pieces: one write(2) per MB, not per tile */
+    /* A block that fails half way (read error, damaged tile, full disk) must not leave a truncated file under the
+     * reference's output name: with overwrite off a re-run would keep it and write beside it (cn.c:320-360). */
+    tw->path = strdup(path);
+    tw->tmp = malloc(strlen(path) + 6);
+    if (tw->path && tw->tmp) {
+        sprintf(tw->tmp, "%s.part", path);
+        tw->fp = fopen(tw->tmp, "wb");
+    }
     if (!tw->fp) {
         set_err(err, errlen, "write error 3 on %s (%s)", path, strerror(errno));     /* raster.c:221 */
+        free(tw->path);
+        free(tw->tmp);
         free(tw);
         return -1;
     }
-    setvbuf(tw->fp, NULL, _IOFBF, 1 << 20);
+    setvbuf(tw->fp, NULL, _IOFBF, 1 << 20);     /* tiles arrive as ~1.5 KB pieces: one write(2) per MB, not per tile */
     tw->w = w;
     tw->h = h;
     tw->tiles_x = (w + TILE - 1) / TILE;
@@ -787,6 +795,12 @@ int gh_tiffw_close(gh_tiffw *tw)
     }
     if (fclose(tw->fp) != 0)
         rc = -1;
+    if (rc == 0 && rename(tw->tmp, tw->path) != 0)
+        rc = -1;
+    if (rc != 0)
+        unlink(tw->tmp);
+    free(tw->path);
+    free(tw->tmp);
     free(tw->offsets);
     free(tw->counts);
     free(tw);
@@ -799,6 +813,10 @@ void gh_tiffw_abort(gh_tiffw *tw)
         return;
     if (tw->fp)
         fclose(tw->fp);
+    if (tw->tmp)
+        unlink(tw->tmp);
+    free(tw->path);
+    free(tw->tmp);
     free(tw->offsets);
     free(tw->counts);
     free(tw);

@@ -73,6 +73,17 @@ def load() -> C.CDLL:
     L.gh_tiffw_close.argtypes = [_vp]
     L.gh_tiffw_abort.argtypes = [_vp]
     L.gh_tiffw_abort.restype = None
+    L.gh_raster_open.argtypes = [C.c_char_p, C.POINTER(_vp), C.c_char_p, C.c_size_t]
+    L.gh_raster_size.argtypes = [_vp, _ip, _ip]
+    L.gh_raster_geotransform.argtypes = [_vp, _dp]
+    L.gh_raster_is_mosaic.argtypes = [_vp]
+    L.gh_raster_source_count.argtypes = [_vp]
+    L.gh_raster_fill.argtypes = [_vp]
+    L.gh_raster_read_window.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.c_int,
+                                        C.c_char_p, C.c_size_t]
+    L.gh_raster_window_parts.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _ip, C.c_char_p, C.c_size_t]
+    L.gh_raster_close.argtypes = [_vp]
+    L.gh_raster_close.restype = None
     L.gh_log_open.argtypes = [C.c_char_p, C.c_int]
     L.gh_log_open.restype = _vp
     L.gh_log_message.argtypes = [_vp, C.c_char_p, C.c_char_p, C.c_int]
@@ -226,6 +237,71 @@ class TilePlan(C.Structure):
     """gh_tile_plan of gcn10_host.h."""
     _fields_ = [("tile_w", C.c_int), ("tile_h", C.c_int), ("tx0", C.c_int), ("ty0", C.c_int), ("tiles_x", C.c_int),
                 ("tiles_y", C.c_int), ("x_in", C.c_int), ("y_in", C.c_int), ("blob_bytes", C.c_size_t)]
+
+
+class RasterPart(C.Structure):
+    """gh_raster_part of gcn10_host.h."""
+    _fields_ = [("ds", _vp), ("plan", TilePlan), ("dst_x", C.c_int), ("dst_y", C.c_int), ("w", C.c_int), ("h", C.c_int)]
+
+
+class Raster:
+    """gh_raster: a GeoTIFF or a VRT mosaic of GeoTIFFs, as GDALOpen() would present it (raster.c:119)."""
+
+    def __init__(self, path: str):
+        self.L = load()
+        h = _vp()
+        e = _err()
+        rc = self.L.gh_raster_open(os.fsencode(path), C.byref(h), e, ERRLEN)
+        if rc:
+            raise HostError(rc, e.value.decode())
+        self.h = h
+        w, hh = C.c_int(), C.c_int()
+        self.L.gh_raster_size(h, w, hh)
+        self.width, self.height = w.value, hh.value
+        gt = (C.c_double * 6)()
+        self.L.gh_raster_geotransform(h, gt)
+        self.gt = tuple(gt)
+        self.is_mosaic = bool(self.L.gh_raster_is_mosaic(h))
+        self.source_count = self.L.gh_raster_source_count(h)
+        self.fill = self.L.gh_raster_fill(h)
+
+    def read(self, xoff, yoff, xcount, ycount, threads=4) -> np.ndarray:
+        out = np.empty((ycount, xcount), dtype=np.uint8)
+        e = _err()
+        rc = self.L.gh_raster_read_window(self.h, xoff, yoff, xcount, ycount, out.ctypes.data, xcount, threads, e, ERRLEN)
+        if rc:
+            raise HostError(rc, e.value.decode())
+        return out
+
+    def window_parts(self, xoff, yoff, xcount, ycount, max_parts=9, threads=4):
+        """(rc, parts): rc 0 -> parts = [dict(dst_x, dst_y, w, h, tile_w, tile_h, tiles_x, tiles_y, x_in, y_in, blob,
+        offsets, sizes)] ready for capi.TileSource; rc 1 -> decode on the host; raises when a source is missing."""
+        arr = (RasterPart * max_parts)()
+        n = C.c_int()
+        e = _err()
+        rc = self.L.gh_raster_window_parts(self.h, xoff, yoff, xcount, ycount, arr, max_parts, C.byref(n), e, ERRLEN)
+        if rc < 0:
+            raise HostError(rc, e.value.decode())
+        parts = []
+        for k in range(n.value if rc == 0 else 0):
+            plan = arr[k].plan
+            nt = plan.tiles_x * plan.tiles_y
+            blob = np.zeros(max(plan.blob_bytes, 1), dtype=np.uint8)
+            offsets = np.zeros(nt, dtype=np.uint64)
+            sizes = np.zeros(nt, dtype=np.uint32)
+            r2 = self.L.gh_tiff_window_tiles_read(arr[k].ds, C.byref(plan), blob.ctypes.data, offsets.ctypes.data,
+                                                  sizes.ctypes.data, threads, e, ERRLEN)
+            if r2:
+                raise HostError(r2, e.value.decode())
+            parts.append(dict(dst_x=arr[k].dst_x, dst_y=arr[k].dst_y, w=arr[k].w, h=arr[k].h, tile_w=plan.tile_w,
+                              tile_h=plan.tile_h, tiles_x=plan.tiles_x, tiles_y=plan.tiles_y, x_in=plan.x_in,
+                              y_in=plan.y_in, blob=blob[:plan.blob_bytes], offsets=offsets, sizes=sizes))
+        return rc, parts
+
+    def close(self):
+        if self.h:
+            self.L.gh_raster_close(self.h)
+            self.h = None
 
 
 class TiffWriter:

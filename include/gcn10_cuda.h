@@ -236,6 +236,27 @@ int gcn10_cuda_block_tiles_deflate(gcn10_ctx *ctx, const gcn10_tile_source *esa_
  * cn.c:187.) */
 int gcn10_cuda_tiles_prefetch(gcn10_ctx *ctx, const gcn10_tile_source *src, int w, int h);
 
+/* Land cover that comes from a MOSAIC of tiled GeoTIFFs -- what the reference's shipped configuration opens:
+ * esa_data_path = landcover/esa_worldcover_2021.vrt, a GDAL VRT of 2651 36000 x 36000 files (raster.c:119).  With the
+ * VRT's pixel size a 3-degree block window is 36001 x 36001 and touches four files.  A part is one source file's share
+ * of the window: its tile grid (as in gcn10_tile_source; x_off / y_off locate the part's pixel (0, 0) inside the grid)
+ * and the rectangle of the window it fills.  All parts are uploaded and inflated by one kernel launch; window pixels
+ * that no part covers read as `fill` (the VRT band's NoDataValue).  Parts must not overlap.  At most 9 parts.
+ * The _parts_ calls are the general form of gcn10_cuda_tiles_prefetch / _inflate_tiles / _block_tiles_deflate. */
+typedef struct {
+    gcn10_tile_source tiles;
+    int dst_x, dst_y;           /* position of the part inside the block window */
+    int w, h;                   /* size of the part */
+} gcn10_tile_part;
+
+int gcn10_cuda_parts_prefetch(gcn10_ctx *ctx, const gcn10_tile_part *parts, int nparts, int fill, int w, int h);
+int gcn10_cuda_inflate_parts(gcn10_ctx *ctx, const gcn10_tile_part *parts, int nparts, int fill, int w, int h,
+                             uint8_t *out, size_t out_pitch, int *tile_status);
+int gcn10_cuda_block_parts_deflate(gcn10_ctx *ctx, const gcn10_tile_part *parts, int nparts, int fill, int w, int h,
+                                   const double gt[6],
+                                   const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
+                                   unsigned plane_mask, gcn10_tile_sink sink, void *user);
+
 /* Device time of the inflate kernel of the most recent gcn10_cuda_inflate_tiles /
  * gcn10_cuda_block_tiles_deflate call (CUDA events on the launching stream). */
 int gcn10_cuda_last_inflate_ms(gcn10_ctx *ctx, float *ms);

@@ -265,3 +265,51 @@ def test_prefetch_overlaps_the_next_block_and_results_do_not_change(gpu_ctx, por
     check(gpu_ctx.block_tiles_deflate(srcs[1], 900, 700, blocks[1]["gt"], blocks[1]["hsg"], blocks[1]["soil_gt"]), wants[1])
     out = gpu_ctx.inflate_tiles(srcs[0], 900, 700)
     assert np.array_equal(out, blocks[0]["esa"])
+
+
+def test_mosaic_parts(gpu_ctx, port, tables):
+    """A block window over a mosaic of four source files whose tile grids do not line up (the structure of the
+    reference's landcover/esa_worldcover_2021.vrt, where a 36001-pixel window spills one pixel into the
+    neighbouring 36000-pixel files): every part is inflated into its rectangle by one launch, pixels no part
+    covers read as the fill value, and the chained call gives the oracle's planes."""
+    w, h = 1531, 1203
+    b = make_block(w=w, h=h, seed=71)
+    esa = b["esa"]
+    cut_x, cut_y = 1530, 700                      # the last column comes from the right-hand neighbours
+    rects = [(0, 0, cut_x, cut_y), (cut_x, 0, w - cut_x, cut_y), (0, cut_y, cut_x, h - cut_y), (cut_x, cut_y, w - cut_x, h - cut_y)]
+    parts = []
+    for i, (x, y, pw, ph) in enumerate(rects):
+        # each source file holds more than the part: the window starts (ox, oy) pixels into its tile grid
+        ox, oy = 13 * i, 300 * (i % 2)
+        grid = synth.esa_tile(ox + pw + 9, oy + ph + 5, seed=100 + i, patch=40)
+        grid[oy:oy + ph, ox:ox + pw] = esa[y:y + ph, x:x + pw]
+        tw = (256, 240, 512, 1024)[i]
+        src = capi.TileSource.from_raster(grid, tw, tw if i != 1 else 112, x_off=ox, y_off=oy, level=6 if i else 1)
+        parts.append((src, x, y, pw, ph))
+    got = gpu_ctx.inflate_parts(parts, 0, w, h)
+    assert np.array_equal(got, esa)
+    want = port.block_rows(esa, b["gt"], b["hsg"], b["soil_gt"], tables)
+    res = gpu_ctx.block_parts_deflate(parts, 0, w, h, b["gt"], b["hsg"], b["soil_gt"])
+    for k in range(18):
+        full = _assemble(res["tiles"][k], w, h)
+        assert np.array_equal(full[:h, :w], want[k]), k
+    # a missing source: its rectangle reads as the fill value (VRT NoDataValue)
+    holed = esa.copy()
+    x, y, pw, ph = rects[2]
+    holed[y:y + ph, x:x + pw] = 80
+    got = gpu_ctx.inflate_parts([parts[0], parts[1], parts[3]], 80, w, h)
+    assert np.array_equal(got, holed)
+    # damaged tile in the second part: reported with its global tile number, GCN10_EDATA
+    src1 = parts[1][0]
+    blob = src1.blob.copy()
+    blob[int(src1.offsets[1])] = 0x79
+    bad = capi.TileSource(src1.tile_w, src1.tile_h, src1.tiles_x, src1.tiles_y, src1.x_off, src1.y_off, blob,
+                          src1.offsets, src1.sizes)
+    rc, _, status = gpu_ctx.inflate_parts([parts[0], (bad,) + parts[1][1:], parts[2], parts[3]], 0, w, h, want_status=True)
+    n0 = parts[0][0].tiles_x * parts[0][0].tiles_y
+    assert rc == -6 and status[n0 + 1] == 1 and np.count_nonzero(status) == 1
+    # parts outside the window / too many parts are refused
+    rc, _, _ = gpu_ctx.inflate_parts([(parts[0][0], 5, 0, cut_x, cut_y)], 0, cut_x, cut_y, want_status=True)
+    assert rc == -1
+    rc, _, _ = gpu_ctx.inflate_parts([parts[3]] * 10, 0, w, h, want_status=True)
+    assert rc == -1

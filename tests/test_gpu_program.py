@@ -138,3 +138,54 @@ def test_block_rows_bands_equal_whole_block(gpu_ctx, port, tables):
     for y0, n in [(0, 256), (256, 512), (768, 343), (1110, 1)]:
         got = gpu_ctx.block_rows(np.ascontiguousarray(b["esa"][y0:y0 + n]), 1111, y0, b["gt"], b["hsg"], b["soil_gt"])
         assert np.array_equal(got, want[:, y0:y0 + n]), (y0, n)
+
+
+def test_program_reads_a_vrt_mosaic(world, ref, tmp_path):
+    """esa_data_path = *.vrt, as in the reference's shipped config (landcover/esa_worldcover_2021.vrt, opened at
+    raster.c:119): the land cover is a 2 x 2 mosaic of GeoTIFFs whose borders (x = 1290, y = 1210) cross both block
+    windows, so every block is assembled from four sources -- on the GPU from their compressed tiles, and on the
+    host with GCN10_HOST_INFLATE=1.  The rasters must equal the reference's process_block() on the assembled raster."""
+    import shutil
+    from tests.test_host import write_vrt
+    root = world["root"]
+    vroot = tmp_path
+    esa, esa_t = world["esa"], world["esa_t"]
+    H, W = esa.shape
+    cx, cy = 1290, 1210
+    srcs = []
+    for r, (y0, y1) in enumerate([(0, cy), (cy, H)]):
+        for c, (x0, x1) in enumerate([(0, cx), (cx, W)]):
+            name = f"lc_{r}{c}.tif"
+            hostlib.tiff_write(str(vroot / name), esa[y0:y1, x0:x1],
+                               (esa_t[0] + x0 * PX, PX, 0, esa_t[3] - y0 * PX, 0, -PX))
+            srcs.append((name, 0, 0, x0, y0, x1 - x0, y1 - y0))
+    write_vrt(str(vroot / "mosaic.vrt"), W, H, esa_t, srcs)
+    fixtures.write_config(str(vroot / "config.txt"), str(vroot / "mosaic.vrt"), str(root / "hsg.tif"),
+                          str(root / "blocks.shp"), str(root / "lookups"), str(vroot / "logs"))
+    exe = hostlib.EXE_PATH
+    for host_inflate in ("0", "1"):
+        out = vroot / f"out{host_inflate}"
+        out.mkdir()
+        shutil.rmtree(vroot / "logs", ignore_errors=True)
+        r = subprocess.run([exe, "-c", str(vroot / "config.txt"), "-l", str(root / "blocks.txt"), "--gpus", "1", "-o",
+                            "--io-threads", "4", "--outdir", str(out)], cwd=str(vroot), capture_output=True, text=True,
+                           timeout=300, env=dict(os.environ, GCN10_HOST_INFLATE=host_inflate, GCN10_HOST_DEFLATE="0"))
+        assert r.returncode == 0, r.stderr
+        log = (vroot / "logs" / "rank_0.log").read_text()
+        assert ("mosaic parts inflated on the gpu" in log) == (host_inflate == "0")
+        for bid, x0, y0, x1, y1 in world["blocks"][:2]:
+            want = ref.run_block(esa, esa_t, world["hsg"], world["hsg_t"], (x0, y0, x1, y1), str(root / "lookups"),
+                                 block_id=bid)
+            for k, rel in enumerate(want["paths"]):
+                t = hostlib.Tiff(str(out / rel))
+                assert t.gt == want["gt"] and np.array_equal(t.read(), want["planes"][k]), (host_inflate, rel)
+                t.close()
+    # a source file that is missing: GDAL's read fails, the block is skipped, no output appears (cn.c:188-192)
+    os.remove(vroot / "lc_11.tif")
+    out = vroot / "out_missing"
+    out.mkdir()
+    r = subprocess.run([exe, "-c", str(vroot / "config.txt"), "-l", str(root / "blocks.txt"), "--gpus", "1", "-o",
+                        "--outdir", str(out)], cwd=str(vroot), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0
+    assert "gdal open failed" in r.stderr and "esa load failed for block 12" in r.stderr
+    assert not list(out.glob("cn_rasters_*/cn_*_12*"))

@@ -248,3 +248,151 @@ def test_window_tiles_are_the_files_zlib_streams(tmp_path):
     assert t2.window_tiles() is None
     assert np.array_equal(t2.read(), esa[:64, :64])
     t2.close()
+
+
+def write_vrt(path, w, h, gt, sources, kind="ComplexSource", nodata=0, remote_prefix=None):
+    """A VRT with the structure of /root/reference/landcover/esa_worldcover_2021.vrt: one Byte band, one
+    <ComplexSource> per file with SrcRect / DstRect, NODATA 0.  sources: (filename, src_x, src_y, dst_x, dst_y, w, h)."""
+    gts = ", ".join(f"{v:.16e}" for v in gt)
+    out = [f'<VRTDataset rasterXSize="{w}" rasterYSize="{h}">',
+           '  <SRS dataAxisToSRSAxisMapping="2,1">GEOGCS["WGS 84",AUTHORITY["EPSG","4326"]]</SRS>',
+           f'  <GeoTransform> {gts}</GeoTransform>',
+           '  <VRTRasterBand dataType="Byte" band="1">',
+           f'    <NoDataValue>{nodata}</NoDataValue>',
+           '    <ColorInterp>Palette</ColorInterp>']
+    for name, sx, sy, dx, dy, sw, sh in sources:
+        fn = (remote_prefix + os.path.basename(name)) if remote_prefix else name
+        rel = 0 if (remote_prefix or os.path.isabs(name)) else 1
+        out += [f'    <{kind} resampling="nearest">',
+                f'      <SourceFilename relativeToVRT="{rel}">{fn.replace("&", "&amp;")}</SourceFilename>',
+                '      <SourceBand>1</SourceBand>',
+                f'      <SourceProperties RasterXSize="{sw}" RasterYSize="{sh}" DataType="Byte" BlockXSize="256" BlockYSize="256" />',
+                f'      <SrcRect xOff="{sx}" yOff="{sy}" xSize="{sw}" ySize="{sh}" />',
+                f'      <DstRect xOff="{dx}" yOff="{dy}" xSize="{sw}" ySize="{sh}" />',
+                f'      <NODATA>{nodata}</NODATA>',
+                f'    </{kind}>']
+    out += ['  </VRTRasterBand>', '  <OverviewList resampling="nearest">2 4</OverviewList>', '</VRTDataset>']
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n")
+    return path
+
+
+VRT_PX = 8.3333333333330430e-05          # landcover/esa_worldcover_2021.vrt:3
+
+
+def test_vrt_mosaic_reader(tmp_path):
+    """esa_data_path = *.vrt (the reference's shipped config, raster.c:119): a 3 x 2 mosaic of 700 x 500 tiles with
+    one tile missing from the VRT (ocean: reads as NoDataValue) -- size, geotransform (the exact decimal string
+    GDAL writes), windows across source borders, host decode and compressed-tile parts."""
+    import zlib
+    from gcn10_b200 import synth
+    tw_, th_ = 700, 500
+    full = synth.esa_tile(3 * tw_, 2 * th_, 77, patch=60)
+    gt = (-180.0, VRT_PX, 0.0, 84.0, 0.0, -VRT_PX)
+    sources = []
+    for r in range(2):
+        for c in range(3):
+            if (r, c) == (1, 2):
+                full[r * th_:(r + 1) * th_, c * tw_:(c + 1) * tw_] = 0          # not in the mosaic
+                continue
+            name = f"tile & {r}_{c}.tif"
+            hostlib.tiff_write(str(tmp_path / name), full[r * th_:(r + 1) * th_, c * tw_:(c + 1) * tw_],
+                               (gt[0] + c * tw_ * VRT_PX, VRT_PX, 0, gt[3] - r * th_ * VRT_PX, 0, -VRT_PX))
+            sources.append((name, 0, 0, c * tw_, r * th_, tw_, th_))
+    vrt = write_vrt(str(tmp_path / "mosaic.vrt"), 3 * tw_, 2 * th_, gt, sources)
+    r = hostlib.Raster(vrt)
+    assert (r.width, r.height) == (3 * tw_, 2 * th_) and r.is_mosaic and r.source_count == 5 and r.fill == 0
+    assert r.gt == gt                                            # bit-exact: feeds the window arithmetic
+    for (xo, yo, xc, yc) in [(0, 0, 3 * tw_, 2 * th_), (650, 450, 101, 101), (699, 0, 2, 1000), (1390, 490, 30, 20),
+                             (1500, 600, 100, 100), (0, 499, 2100, 2)]:
+        assert np.array_equal(r.read(xo, yo, xc, yc), full[yo:yo + yc, xo:xo + xc]), (xo, yo, xc, yc)
+        rc, parts = r.window_parts(xo, yo, xc, yc)
+        assert rc == 0
+        got = np.zeros((yc, xc), dtype=np.uint8)
+        for p in parts:
+            grid = np.zeros((p["tiles_y"] * p["tile_h"], p["tiles_x"] * p["tile_w"]), dtype=np.uint8)
+            for i in range(p["tiles_y"] * p["tiles_x"]):
+                o, n = int(p["offsets"][i]), int(p["sizes"][i])
+                raw = zlib.decompress(p["blob"][o:o + n].tobytes())
+                a, b = divmod(i, p["tiles_x"])
+                grid[a * 256:(a + 1) * 256, b * 256:(b + 1) * 256] = np.frombuffer(raw, dtype=np.uint8).reshape(256, 256)
+            got[p["dst_y"]:p["dst_y"] + p["h"], p["dst_x"]:p["dst_x"] + p["w"]] = \
+                grid[p["y_in"]:p["y_in"] + p["h"], p["x_in"]:p["x_in"] + p["w"]]
+        assert np.array_equal(got, full[yo:yo + yc, xo:xo + xc])
+    with pytest.raises(hostlib.HostError):
+        r.read(0, 0, 3 * tw_ + 1, 10)
+    r.close()
+    # a plain GeoTIFF opens through the same call: one part
+    r1 = hostlib.Raster(str(tmp_path / "tile & 0_0.tif"))
+    assert not r1.is_mosaic and r1.source_count == 1
+    rc, parts = r1.window_parts(10, 20, 300, 300)
+    assert rc == 0 and len(parts) == 1 and (parts[0]["dst_x"], parts[0]["w"]) == (0, 300)
+    r1.close()
+
+
+def test_vrt_remote_sources_missing_files_and_bad_documents(tmp_path, monkeypatch):
+    from gcn10_b200 import synth
+    a = synth.esa_tile(300, 300, 3, patch=30)
+    os.makedirs(tmp_path / "tiles")
+    hostlib.tiff_write(str(tmp_path / "tiles" / "ESA_A.tif"), a, (0, 1, 0, 0, 0, -1))
+    src = [("ESA_A.tif", 0, 0, 0, 0, 300, 300), ("ESA_B.tif", 0, 0, 300, 0, 300, 300)]
+    # /vsicurl/ sources (what the shipped VRT names) are looked up by base name in GCN10_VRT_SOURCE_DIR
+    vrt = write_vrt(str(tmp_path / "remote.vrt"), 600, 300, (0, 1, 0, 0, 0, -1), src,
+                    remote_prefix="/vsicurl/https://esa-worldcover.s3.eu-central-1.amazonaws.com/v200/2021/map/")
+    monkeypatch.setenv("GCN10_VRT_SOURCE_DIR", str(tmp_path / "tiles"))
+    r = hostlib.Raster(vrt)
+    assert np.array_equal(r.read(0, 0, 300, 300), a)
+    with pytest.raises(hostlib.HostError) as e:                  # ESA_B.tif does not exist: the read fails (block skipped)
+        r.read(250, 0, 100, 100)
+    assert "gdal open failed" in e.value.msg
+    with pytest.raises(hostlib.HostError):
+        r.window_parts(250, 0, 100, 100)
+    r.close()
+    # SimpleSource, shifted SrcRect, NoDataValue as fill
+    vrt2 = write_vrt(str(tmp_path / "simple.vrt"), 400, 250, (5, 0.5, 0, 9, 0, -0.5),
+                     [(str(tmp_path / "tiles" / "ESA_A.tif"), 40, 50, 100, 0, 200, 250)], kind="SimpleSource", nodata=80)
+    r2 = hostlib.Raster(vrt2)
+    want = np.full((250, 400), 80, dtype=np.uint8)
+    want[:, 100:300] = a[50:300, 40:240]
+    assert r2.fill == 80 and np.array_equal(r2.read(0, 0, 400, 250), want)
+    r2.close()
+    # scaling sources and non-VRT XML are refused at open
+    bad = open(vrt2).read().replace('<DstRect xOff="100" yOff="0" xSize="200"', '<DstRect xOff="100" yOff="0" xSize="100"')
+    open(tmp_path / "scaled.vrt", "w").write(bad)
+    with pytest.raises(hostlib.HostError):
+        hostlib.Raster(str(tmp_path / "scaled.vrt"))
+    open(tmp_path / "junk.vrt", "w").write("<html></html>")
+    with pytest.raises(hostlib.HostError):
+        hostlib.Raster(str(tmp_path / "junk.vrt"))
+
+
+def test_reference_vrt_if_present():
+    vrt = "/root/reference/landcover/esa_worldcover_2021.vrt"
+    if not os.path.exists(vrt):
+        pytest.skip("reference tree not present")
+    r = hostlib.Raster(vrt)
+    assert (r.width, r.height) == (4320000, 1728000) and r.source_count == 2651 and r.fill == 0
+    assert r.gt == (-180.0, VRT_PX, 0.0, 84.0, 0.0, -VRT_PX)
+    # block 2234 (-114..-111, 39..42): the 36001 x 36001 window of SURVEY section 8
+    assert hostlib.raster_window(r.width, r.height, r.gt, (-114.0, 39.0, -111.0, 42.0))[:4] == (792000, 504000, 36001, 36001)
+    r.close()
+
+
+def test_geotiff_writer_leaves_no_partial_file(tmp_path):
+    """An output that is aborted or fails to close never appears under its final name (with overwrite off
+    a re-run would keep the junk file and write beside it, cn.c:320-360)."""
+    import zlib
+    z = zlib.compress(bytes(65536))
+    p = tmp_path / "cn_p_i_7.tif"
+    tw = hostlib.TiffWriter(str(p), 256, 512, (0, 1, 0, 0, 0, -1))
+    assert tw.put_tile_row(0, [z]) == 0
+    assert not p.exists()                                       # still under its temporary name
+    hostlib.load().gh_tiffw_abort(tw.h)
+    assert not p.exists() and not list(tmp_path.glob("cn_p_i_7*"))
+    tw = hostlib.TiffWriter(str(p), 256, 512, (0, 1, 0, 0, 0, -1))
+    tw.put_tile_row(0, [z])
+    assert tw.close() != 0 and not list(tmp_path.glob("cn_p_i_7*"))      # incomplete: removed
+    tw = hostlib.TiffWriter(str(p), 256, 512, (0, 1, 0, 0, 0, -1))
+    tw.put_tile_row(0, [z])
+    tw.put_tile_row(1, [z])
+    assert tw.close() == 0 and p.exists() and not (tmp_path / "cn_p_i_7.tif.part").exists()
