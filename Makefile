@@ -4,6 +4,7 @@
 #   make cuda       gcn10_b200/libgcn10cuda.so      (nvcc, sm_100a only)
 #   make host       gcn10_b200/host/gcn10           (gcc, links libgcn10cuda.so + zlib)
 #   make oracle     oracle/libcn_oracle.so and, when /root/reference exists, oracle/_ref/
+#   make integration  oracle/_ref/libgcn10_gpu_ref.so: integration/cn_gpu.c + the reference's raster.c + libgcn10cuda
 NVCC      ?= nvcc
 CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
@@ -13,7 +14,7 @@ CUDA_SO := gcn10_b200/libgcn10cuda.so
 CUDA_SRC := gcn10_b200/csrc/gcn10_cuda.cu
 CUDA_HDR := $(wildcard gcn10_b200/csrc/*.cuh) $(wildcard gcn10_b200/csrc/*.h) include/gcn10_cuda.h
 
-all: cuda host oracle
+all: cuda host oracle integration
 
 cuda: $(CUDA_SO)
 
@@ -26,9 +27,13 @@ host: cuda
 oracle:
 	$(MAKE) -s -C oracle all
 
+# the reference-side binding (integration/cn_gpu.c) built against the reference's own headers and raster.c
+integration: cuda
+	$(MAKE) -s -C integration all
+
 clean:
 	rm -f $(CUDA_SO) gcn10_b200/csrc/ptxas.log
 	$(MAKE) -s -C oracle clean
 	@if [ -f gcn10_b200/host/Makefile ]; then $(MAKE) -s -C gcn10_b200/host clean; fi
 
-.PHONY: all cuda host oracle clean
+.PHONY: all cuda host oracle integration clean

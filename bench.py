@@ -63,6 +63,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=1800)
     ap.add_argument("--ref-sample-rows", type=int, default=600)
+    ap.add_argument("--ship", type=int, default=None, choices=[0, 1], help="override the library's strip hand-over path")
+    ap.add_argument("--queue-blocks", type=int, default=64, help="blocks of the e2e.queue64 leg (0 = skip)")
+    ap.add_argument("--program-blocks", type=int, default=4, help="blocks of the e2e.program leg per GPU (0 = skip)")
     return ap.parse_args()
 
 
@@ -155,6 +158,11 @@ def run_reference_arm(args):
         cores = os.cpu_count() or 1
     rows = min(args.ref_sample_rows, args.tile)
     px_per_proc = args.tile * rows
+    # the reference's object code is loaded here, in the process the driver watches, before the ranks fork from it
+    from oracle import oracle as O
+    ref_loaded = None
+    if O.Ref.available():
+        ref_loaded = O.Ref()
     ctx = mp.get_context("fork")
     step_times = []
     kind = "reference"
@@ -183,7 +191,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t9 * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, {"sample_rows_per_process": rows, "processes": cores}),
+        "config": workload_config(args),
+        "sample_rows_per_process": rows, "processes": cores,
+        "reference_library": O.REF_SO if ref_loaded is not None else None,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -273,6 +283,8 @@ def run_ours(args):
 
     ctx = capi.Context(local_rank)
     ctx.set_luts(tables)
+    if args.ship is not None:
+        ctx.set_option("ship", args.ship)
     # host thread -> NUMA node of this GPU, before any pinned allocation (matters at N > 1: see DESIGN.md 6)
     numa_node = ctx.lib.gcn10_cuda_bind_host_thread(local_rank)
 
@@ -352,11 +364,41 @@ def run_ours(args):
     except Exception as e:  # extra information only
         all18 = {"error": repr(e)}
 
+    # ---- BASELINE configs[0]: lookup g_ii only (one plane: 1 B read + 1 B written per pixel)
+    config0 = None
+    try:
+        ptr0 = [0] * 18
+        ptr0[7] = d_out[0].data_ptr()
+
+        def step0():
+            ctx.block_device(d_esa.data_ptr(), w, h, w, gt, d_hsg.data_ptr(), hsx, hsy, hsx, sgt,
+                             1 << 7, ptr0, w, stream=stream.cuda_stream)
+        for _ in range(3):
+            step0()
+        barrier()
+        n0 = max(5, args.steps)
+        a0 = torch.cuda.Event(enable_timing=True)
+        b0 = torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(n0):
+            step0()
+        b0.record(stream)
+        barrier()
+        ms0 = max_over_ranks(a0.elapsed_time(b0)) / n0
+        bytes0 = px * 2 + hsx * hsy
+        config0 = {"workload": "BASELINE configs[0]: same tile, lookup g_ii only (drained), one plane", "planes": 1,
+                   "value": world * px / (ms0 * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms0,
+                   "achieved_gbs": bytes0 / (ms0 * 1e-3) / 1e9, "frac": bytes0 / (ms0 * 1e-3) / 1e9 / measured_peak()[0],
+                   "algorithmic_bytes_per_launch": bytes0, "kernel": "gcn10::cn_block_kernel<1,1>"}
+        step()      # leave the nine-plane result in d_out for the spot check below
+    except Exception as e:  # extra information only
+        config0 = {"error": repr(e)}
+
     # ---- end to end through the host-buffer C ABI (pinned host memory both ways)
     e2e = None
     e2e_steps = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 5)
     if e2e_steps > 0:
-        e2e = run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_over_ranks, e2e_steps)
+        e2e = run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_over_ranks, e2e_steps, group)
 
     clocks = sampler.stop() if rank == 0 else None
 
@@ -389,6 +431,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu,
             "output_gpixel_per_s": value * NVAR, "numa_node_rank0": numa_node, "all_18_planes": all18,
+            "config0": config0,
         }
         print_json(line)
     ctx.close()
@@ -396,7 +439,31 @@ def run_ours(args):
     return 0
 
 
-def run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_over_ranks, steps):
+def pcie_probe(ctx, group, barrier):
+    """The host link this end-to-end number sits under: copy bandwidth of one GPU alone (rank 0, the others idle) and
+    of all ranks at once (what the shared host fabric gives each GPU when N blocks' tile streams leave together)."""
+    nbytes, reps = 256 << 20, 4
+    alone = None
+    barrier()
+    if group.rank == 0:
+        alone = ctx.pcie_probe(nbytes, reps)
+    barrier()
+    mine = ctx.pcie_probe(nbytes, reps)
+    barrier()
+    out = {"bytes": nbytes, "alone": alone}
+    conc = {}
+    for k, v in mine.items():
+        conc[k + "_min"] = -group.max(-v)
+        conc[k + "_sum"] = group.sum(v)
+    out["concurrent"] = conc
+    if alone:
+        out["d2h_gbs_alone"] = alone["d2h_gbs"]
+        out["d2h_gbs_concurrent"] = conc["d2h_gbs_min"]
+        out["frac"] = conc["d2h_gbs_min"] / alone["d2h_gbs"]
+    return out
+
+
+def run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_over_ranks, steps, group):
     import numpy as np
     import psutil
 
@@ -480,7 +547,7 @@ def run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_o
         tiles_in = None
         try:
             tiles_in = run_e2e_tiles(args, ctx, capi, esa_pin.array, rows, w, gt6, sgt6, hsg_np, cb, nbytes, world,
-                                     barrier, max_over_ranks, steps)
+                                     barrier, max_over_ranks, steps, group)
         except Exception as e:  # extra leg: never take the benchmark down
             tiles_in = {"error": repr(e)}
 
@@ -498,6 +565,15 @@ def run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_o
             res = dict(deflate)
             res["tiles_in"] = tiles_in
         res["raw_planes"] = raw
+        try:
+            res["pcie"] = pcie_probe(ctx, group, barrier)
+            if res["pcie"].get("d2h_gbs_concurrent") and "d2h_bytes_per_step" in res and "ms_per_step" in res:
+                # share of the probed device->host ceiling that the tile streams of a step use
+                res["pcie"]["e2e_d2h_gbs_per_gpu"] = res["d2h_bytes_per_step"] / (res["ms_per_step"] * 1e-3) / 1e9
+                res["pcie"]["e2e_frac_of_concurrent_d2h"] = (res["pcie"]["e2e_d2h_gbs_per_gpu"] /
+                                                             res["pcie"]["d2h_gbs_concurrent"])
+        except Exception as e:
+            res["pcie"] = {"error": repr(e)}
         if note:
             res["note"] = note
         return res
@@ -507,7 +583,7 @@ def run_e2e(args, ctx, capi, d_esa, hsg_np, gt, sgt, w, h, world, barrier, max_o
 
 
 def run_e2e_tiles(args, ctx, capi, esa, rows, w, gt6, sgt6, hsg_np, cb, nbytes, world, barrier, max_over_ranks, steps,
-                  in_tile=1024, level=6):
+                  group, in_tile=1024, level=6):
     """Compressed tiles in, compressed tiles out (gcn10_cuda_block_tiles_deflate).  The tile bytes are produced
     once, outside the timed region, with zlib on the host: they stand for the bytes of the input GeoTIFF."""
     import ctypes as C
@@ -564,6 +640,7 @@ def run_e2e_tiles(args, ctx, capi, esa, rows, w, gt6, sgt6, hsg_np, cb, nbytes, 
             step()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        kernel_ms_step, inflate_ms_step = ctx.last_kernel_ms(), ctx.last_inflate_ms()
         # the same call for all 18 rasters of a block (both drainage conditions): what the gcn10 program asks for
         def step18():
             rc = lib.gcn10_cuda_block_tiles_deflate(ctx.h, C.byref(st), w, rows, gt6, hsg_np.ctypes.data, hsx, hsy, hsx,
@@ -583,13 +660,29 @@ def run_e2e_tiles(args, ctx, capi, esa, rows, w, gt6, sgt6, hsg_np, cb, nbytes, 
         all18 = {"planes": 18, "value": world * float(w) * rows / dt18 / 1e9, "unit": UNIT, "ms_per_step": dt18 * 1e3,
                  "d2h_bytes_per_step": int((nbytes[0] + nbytes[1]) / max(1, steps // 2))}
         nbytes[0], nbytes[1] = saved
+        d2h_step = int((nbytes[0] + nbytes[1]) / steps)
+        out_ratio = NVAR * float(w) * rows * steps / max(nbytes[0], 1)
+        queue64 = program = None
+        if args.queue_blocks > 0:
+            try:
+                queue64 = run_queue64(args, ctx, capi, blob_pin.array[:total], offsets, sizes, tiles_x, tiles_y, in_tile,
+                                      w, rows, cb, nbytes, group, barrier, max_over_ranks)
+            except Exception as e:
+                queue64 = {"error": repr(e)}
+        if args.program_blocks > 0:
+            try:
+                program = run_program_leg(args, blob_pin.array[:total], offsets, sizes, in_tile, w, rows, hsg_np, group,
+                                          barrier)
+            except Exception as e:
+                program = {"error": repr(e)}
         return {"value": world * float(w) * rows * steps / dt / 1e9, "unit": UNIT, "all_18_planes": all18,
+                "queue64": queue64, "program": program,
                 "h2d_bytes_per_step": int(total + offsets.nbytes + sizes.nbytes + hsg_np.size),
-                "d2h_bytes_per_step": int((nbytes[0] + nbytes[1]) / steps),
-                "steps": steps, "ms_per_step": dt / steps * 1e3, "kernel_ms_per_step": ctx.last_kernel_ms(),
-                "inflate_kernel_ms": ctx.last_inflate_ms(),
+                "d2h_bytes_per_step": d2h_step,
+                "steps": steps, "ms_per_step": dt / steps * 1e3, "kernel_ms_per_step": kernel_ms_step,
+                "inflate_kernel_ms": inflate_ms_step,
                 "input_compression_ratio": float(w) * rows / max(total, 1),
-                "output_compression_ratio": NVAR * float(w) * rows * steps / max(nbytes[0], 1),
+                "output_compression_ratio": out_ratio,
                 "input_tiles": [in_tile, in_tile, int(tiles_x * tiles_y)],
                 "path": "gcn10_cuda_block_tiles_deflate: pinned host DEFLATE tiles of the land-cover GeoTIFF (zlib "
                         f"level {level}, {in_tile} x {in_tile}) -> H2D / GPU inflate / fused Curve Number + tile DEFLATE "
@@ -599,6 +692,170 @@ def run_e2e_tiles(args, ctx, capi, esa, rows, w, gt6, sgt6, hsg_np, cb, nbytes, 
                         "the previous block's strips"}
     finally:
         blob_pin.free()
+
+
+def queue_blocks(n):
+    """The 8 x 8 grid of 3-degree blocks with SW corner (-114, 30) (SURVEY 8d config 4: lon -114..-90, lat 30..54;
+    it contains all 16 ids of the reference's src/test/blocks.txt): [(id, west, north)], row-major from the NW."""
+    with open(os.path.join(ROOT, "tests", "golden", "block_extents.json")) as f:
+        ext = {(int(w_), int(n_)): int(i) for i, w_, n_ in json.load(f)["blocks"]}
+    out = []
+    for north in range(54, 30, -3):
+        for west in range(-114, -90, 3):
+            out.append((ext[(west, north)], float(west), float(north)))
+    return out[:n]
+
+
+def run_queue64(args, ctx, capi, blob, offsets, sizes, tiles_x, tiles_y, in_tile, w, rows, cb, nbytes, group, barrier,
+                max_over_ranks, nvariants=8):
+    """BASELINE configs[3]: 64 blocks (8 x 8) handed out by the per-GPU block work queue -- every rank (GPU worker)
+    claims its next block with an atomic fetch-and-add on the job's store (dist.BlockQueue, the cross-process twin of
+    the atomic counter in host_pipeline.c; the reference's static round-robin is main.c:171), prefetches it (upload +
+    GPU inflate) beside the block it is working on and runs gcn10_cuda_block_tiles_deflate on it.  Strong scaling: the
+    64 blocks are the whole job at every N.  Each block has its own geotransform (so its own fp64 index maps), one of 8
+    HSG windows and one of 8 arrangements of the compressed land-cover tiles (the tile grid of the benchmark block
+    rotated by whole tiles: distinct rasters without compressing 64 x 1.3 GB on the host)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from gcn10_b200 import dist as gdist
+    from gcn10_b200 import synth
+    lib = ctx.lib
+    blocks = queue_blocks(args.queue_blocks)
+    off2, size2 = offsets.reshape(tiles_y, tiles_x), sizes.reshape(tiles_y, tiles_x)
+    srcs = []
+    for v in range(nvariants):
+        dy, dx = (5 * v) % tiles_y, (11 * v) % tiles_x
+        o = np.ascontiguousarray(np.roll(off2, (dy, dx), axis=(0, 1))).reshape(-1)
+        z = np.ascontiguousarray(np.roll(size2, (dy, dx), axis=(0, 1))).reshape(-1)
+        src = capi.TileSource(in_tile, in_tile, tiles_x, tiles_y, 0, 0, blob, o, z)
+        srcs.append((src, src.struct()))
+    hsgs = []
+    for v in range(nvariants):
+        gt_, sgt_, hsx, hsy = synth.block_geometry(0.0, 0.0, w, rows)
+        hsgs.append(np.ascontiguousarray(synth.hsg_tile(hsx, hsy, 5000 + v, args.profile)))
+    geo = []
+    for bid, west, north in blocks:
+        gt_, sgt_, hsx, hsy = synth.block_geometry(west, north, w, rows)
+        geo.append(((C.c_double * 6)(*gt_), (C.c_double * 6)(*sgt_), hsx, hsy))
+
+    def prefetch(k):
+        if lib.gcn10_cuda_tiles_prefetch(ctx.h, C.byref(srcs[k % nvariants][1]), w, rows):
+            raise RuntimeError(lib.gcn10_cuda_last_error().decode())
+
+    def process(k):
+        gt6, sgt6, hsx, hsy = geo[k]
+        hs = hsgs[(k // nvariants) % nvariants]
+        rc = lib.gcn10_cuda_block_tiles_deflate(ctx.h, C.byref(srcs[k % nvariants][1]), w, rows, gt6, hs.ctypes.data, hsx,
+                                                hsy, hsx, sgt6, capi.MASK_DRAINED, cb, None)
+        if rc:
+            raise RuntimeError(lib.gcn10_cuda_last_error().decode())
+
+    def run(name, n):
+        q = gdist.BlockQueue(group, n, name)
+        mine = []
+        cur = q.claim()
+        if cur is not None:
+            prefetch(cur)
+        while cur is not None:
+            nxt = q.claim()
+            if nxt is not None:
+                prefetch(nxt)
+            process(cur)
+            mine.append(cur)
+            cur = nxt
+        return mine
+
+    run("warm", min(len(blocks), 2 * group.world))
+    barrier()
+    nbytes[0] = nbytes[1] = 0
+    t0 = time.perf_counter()
+    mine = run("timed", len(blocks))
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    counts = group.gather_ints(len(mine))
+    d2h = group.sum(nbytes[0] + nbytes[1])
+    assert sum(counts) == len(blocks), counts
+    return {"workload": (f"BASELINE configs[3]: {len(blocks)} blocks (8 x 8 grid, SW corner -114/30, ids "
+                         f"{blocks[0][0]}..{blocks[-1][0]}) of {w} x {rows} px over the dynamic per-GPU block queue"),
+            "value": len(blocks) * float(w) * rows / dt / 1e9, "unit": UNIT, "scaling": "strong",
+            "blocks": len(blocks), "blocks_per_rank": counts, "seconds": dt, "ms_per_block": dt / len(blocks) * 1e3,
+            "distinct_land_cover_arrangements": nvariants, "distinct_hsg_windows": nvariants,
+            "d2h_bytes_total": int(d2h),
+            "claim": "atomic fetch-and-add on the rendezvous store (TCPStore.add), one block ahead for the prefetch"}
+
+
+def run_program_leg(args, blob, offsets, sizes, in_tile, w, rows, hsg_np, group, barrier):
+    """File to file: the gcn10 executable (C host program + libgcn10cuda) on a RAM disk.  One tiled DEFLATE GeoTIFF
+    holds the benchmark's compressed land-cover tiles; a GDAL VRT places it B times side by side (the structure of
+    the reference's landcover/esa_worldcover_2021.vrt), a shapefile holds the B block extents, and the program writes
+    all 18 GeoTIFFs of every block.  Per-block times are the program's own log lines (time between consecutive
+    blocks of a worker: read, GPU inflate, Curve Numbers, tile DEFLATE and the 18 file writes overlapped), the first
+    block of every worker (CUDA start-up) excluded.  Rank 0 launches it on all N GPUs; the other ranks wait."""
+    import re
+    import shutil
+
+    import numpy as np
+
+    from gcn10_b200 import hostlib
+    from tests import fixtures, lookups
+    barrier()
+    res = None
+    if group.rank == 0 and os.path.exists(hostlib.EXE_PATH):
+        nb = args.program_blocks * group.world
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        root = tempfile.mkdtemp(prefix="gcn10_program_", dir=base)
+        try:
+            px = 1.0 / 12000.0
+            lon0, lat0 = -114.0, 42.0
+            gt = (lon0, px, 0.0, lat0, 0.0, -px)
+            hostlib.write_tiled_deflate_tiff(os.path.join(root, "lc.tif"), w, rows, in_tile, in_tile, blob, offsets, sizes, gt)
+            from tests.fixtures import write_vrt
+            srcs = [("lc.tif", 0, 0, k * w, 0, w, rows) for k in range(nb)]
+            write_vrt(os.path.join(root, "lc.vrt"), nb * w, rows, gt, srcs)
+            hsy, hsx = hsg_np.shape
+            hostlib.tiff_write(os.path.join(root, "hsg.tif"), np.tile(hsg_np, (1, nb)), (lon0, 1.0 / 480.0, 0.0, lat0, 0.0, -1.0 / 480.0))
+            deg_w, deg_h = w * px, rows * px
+            blocks = [(100 + k, lon0 + k * deg_w, lat0 - deg_h, lon0 + (k + 1) * deg_w, lat0) for k in range(nb)]
+            fixtures.write_block_shapefile(os.path.join(root, "blocks.shp"), blocks)
+            lookups.write_default_lookups(os.path.join(root, "lookups"))
+            fixtures.write_config(os.path.join(root, "config.txt"), os.path.join(root, "lc.vrt"), os.path.join(root, "hsg.tif"),
+                                  os.path.join(root, "blocks.shp"), os.path.join(root, "lookups"), os.path.join(root, "logs"))
+            with open(os.path.join(root, "blocks.txt"), "w") as f:
+                f.write("\n".join(str(b[0]) for b in blocks) + "\n")
+            t0 = time.perf_counter()
+            r = subprocess.run([hostlib.EXE_PATH, "-c", os.path.join(root, "config.txt"), "-l", os.path.join(root, "blocks.txt"),
+                                "-o", "--gpus", str(group.world), "--outdir", os.path.join(root, "out")],
+                               cwd=root, capture_output=True, text=True, timeout=900,
+                               env=dict(os.environ, GCN10_HOST_INFLATE="0", GCN10_HOST_DEFLATE="0"))
+            wall = time.perf_counter() - t0
+            os.makedirs(os.path.join(root, "out"), exist_ok=True)
+            per_worker = {}
+            for fn in sorted(os.listdir(os.path.join(root, "logs"))):
+                for ln in open(os.path.join(root, "logs", fn)):
+                    m = re.search(r"block (\d+): (\d+) x (\d+) px, 18 rasters in ([0-9.]+) s", ln)
+                    if m:
+                        per_worker.setdefault(fn, []).append(float(m.group(4)))
+            warm = [t for ts in per_worker.values() for t in ts[1:]]
+            files = sum(len(fs) for _, _, fs in os.walk(os.path.join(root, "out")))
+            out_bytes = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(os.path.join(root, "out")) for f in fs)
+            res = {"returncode": r.returncode, "blocks": nb, "gpus": group.world, "rasters_written": files,
+                   "output_bytes": out_bytes, "wall_s_incl_startup": wall,
+                   "path": "gcn10 executable: VRT mosaic of a tiled DEFLATE GeoTIFF on /dev/shm -> 18 GeoTIFFs per block on /dev/shm"}
+            if warm:
+                warm.sort()
+                med = warm[len(warm) // 2]
+                nworkers = max(1, len(per_worker))
+                res.update({"ms_per_block_warm": med * 1e3, "warm_blocks": len(warm),
+                            "value": nworkers * float(w) * rows / med / 1e9, "unit": UNIT,
+                            "note": "value = workers x pixels / median warm per-block time (all 18 rasters per block)"})
+            if r.returncode != 0 or files != 18 * nb:
+                res["stderr_tail"] = r.stderr[-800:]
+        finally:
+            shutil.rmtree(root, ignore_errors=True)
+    barrier()
+    return res
 
 
 def load_tables_host(lookup_dir):

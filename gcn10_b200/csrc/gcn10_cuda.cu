@@ -86,7 +86,7 @@ struct TileSlot {
     cudaEvent_t inf0 = nullptr, inf1 = nullptr, done = nullptr;     // around the inflate kernel; behind the status copy
     bool pending = false;       // inflate issued, result not consumed yet
     uint64_t seq = 0;           // issue order of pending slots
-    const void *key_blob = nullptr;
+    const void *key_blob = nullptr, *key_off = nullptr;
     size_t key_bytes = 0, ntiles = 0, dpitch = 0;
     int key_w = 0, key_h = 0, key_parts = 0;
 };
@@ -1431,6 +1431,7 @@ static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *
     sl.pending = true;
     sl.seq = ++c->tile_seq;
     sl.key_blob = parts[0].tiles.blob;
+    sl.key_off = parts[0].tiles.offsets;
     sl.key_bytes = blob_total;
     sl.key_parts = nparts;
     sl.key_w = w;
@@ -1484,7 +1485,8 @@ static int acquire_slot(gcn10_ctx *c, const gcn10_tile_part *parts, int nparts, 
     TileSlot *hit = nullptr;
     for (int i = 0; i < 2; i++) {
         TileSlot &sl = c->tslot[i];
-        if (sl.pending && sl.key_blob == parts[0].tiles.blob && sl.key_bytes == blob_total && sl.key_parts == nparts &&
+        if (sl.pending && sl.key_blob == parts[0].tiles.blob && sl.key_off == parts[0].tiles.offsets &&
+            sl.key_bytes == blob_total && sl.key_parts == nparts &&
             sl.key_w == w && sl.key_h == h && sl.ntiles == ntiles && (!hit || sl.seq < hit->seq))
             hit = &sl;
     }

@@ -57,9 +57,46 @@ class Group:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
 
+    def gather_ints(self, value: int):
+        """[value of rank 0, value of rank 1, ...] on every rank."""
+        if not self.active:
+            return [int(value)]
+        t = self.torch.zeros(self.world, dtype=self.torch.int64,
+                             device=self.device if self.device is not None else "cpu")
+        t[self.rank] = int(value)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [int(v) for v in t.tolist()]
+
     def close(self):
         if self.active:
             self.dist.destroy_process_group()
+
+
+class BlockQueue:
+    """The per-GPU block work queue of north_star item (3) across the ranks of one torchrun job.
+
+    The reference hands blocks out statically, `for (i = rank; i < n; i += size)` (main.c:171); the gcn10 executable
+    replaces that with an atomic counter shared by its worker threads (host_pipeline.c, loader_main).  Between
+    PROCESSES the same counter lives in the rendezvous store: a claim is one atomic fetch-and-add
+    (`Store.add`), so a rank that finishes early simply takes the next block.  No data moves between ranks."""
+
+    def __init__(self, group: Group, n_blocks: int, name: str):
+        self.n = int(n_blocks)
+        self.key = f"gcn10/queue/{name}"
+        self.local = 0
+        self.store = None
+        if group.active:
+            from torch.distributed.distributed_c10d import _get_default_store
+            self.store = _get_default_store()
+
+    def claim(self):
+        """Index of the next unclaimed block, or None when the queue is empty."""
+        if self.store is not None:
+            i = int(self.store.add(self.key, 1)) - 1
+        else:
+            i = self.local
+            self.local += 1
+        return i if i < self.n else None
 
 
 def whole_job_rate(units_per_rank: float, group: Group, elapsed_s: float) -> float:

@@ -338,3 +338,54 @@ class TiffWriter:
         rc = self.L.gh_tiffw_close(self.h)
         self.h = None
         return rc
+
+
+def write_tiled_deflate_tiff(path: str, w: int, h: int, tile_w: int, tile_h: int, blob, offsets, sizes, gt):
+    """Assembles a tiled DEFLATE GeoTIFF (classic TIFF, Compression = 8, no predictor) from zlib streams that are
+    already compressed: blob[offsets[i] : offsets[i] + sizes[i]] is tile i, row-major over the ceil(w / tile_w) x
+    ceil(h / tile_h) grid.  Used by bench.py / tools to turn the benchmark's compressed land-cover tiles (1024 x
+    1024, the layout of the ESA WorldCover files) into the file the gcn10 executable reads, without re-encoding."""
+    import struct
+    tx, ty = (w + tile_w - 1) // tile_w, (h + tile_h - 1) // tile_h
+    n = tx * ty
+    assert len(offsets) == n and len(sizes) == n
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    pos = 8
+    file_off = []
+    for i in range(n):
+        file_off.append(pos)
+        pos += int(sizes[i])
+    pos += pos & 1
+    data_off = pos                                  # TileOffsets | TileByteCounts | scale | tiepoint | geokeys
+    off_offsets, off_counts = data_off, data_off + 4 * n
+    off_scale = off_counts + 4 * n
+    off_tie = off_scale + 24
+    off_keys = off_tie + 48
+    geokeys = [1, 1, 0, 3, 1024, 0, 1, 2, 1025, 0, 1, 1, 2048, 0, 1, 4326]
+    off_ifd = off_keys + 2 * len(geokeys)
+    off_ifd += off_ifd & 1
+    assert off_ifd + 512 < 2**32, "classic TIFF only"
+    entries = [(256, 4, 1, w), (257, 4, 1, h), (258, 3, 1, 8), (259, 3, 1, 8), (262, 3, 1, 1), (277, 3, 1, 1),
+               (284, 3, 1, 1), (322, 3, 1, tile_w), (323, 3, 1, tile_h),
+               (324, 4, n, file_off[0] if n == 1 else off_offsets), (325, 4, n, int(sizes[0]) if n == 1 else off_counts),
+               (339, 3, 1, 1), (33550, 12, 3, off_scale), (33922, 12, 6, off_tie), (34735, 3, len(geokeys), off_keys)]
+    with open(path, "wb") as f:
+        f.write(struct.pack("<2sHI", b"II", 42, off_ifd))
+        for i in range(n):
+            o, s_ = int(offsets[i]), int(sizes[i])
+            f.write(blob[o:o + s_].tobytes())
+        f.write(b"\0" * (data_off - f.tell()))
+        f.write(struct.pack(f"<{n}I", *file_off))
+        f.write(struct.pack(f"<{n}I", *[int(v) for v in sizes]))
+        f.write(struct.pack("<3d", gt[1], -gt[5], 0.0))
+        f.write(struct.pack("<6d", 0.0, 0.0, 0.0, gt[0], gt[3], 0.0))
+        f.write(struct.pack(f"<{len(geokeys)}H", *geokeys))
+        f.write(b"\0" * (off_ifd - f.tell()))
+        f.write(struct.pack("<H", len(entries)))
+        for tag, typ, cnt, val in entries:
+            if typ == 3 and cnt == 1:
+                f.write(struct.pack("<HHIHH", tag, typ, cnt, val, 0))
+            else:
+                f.write(struct.pack("<HHII", tag, typ, cnt, val))
+        f.write(struct.pack("<I", 0))
+    return path

@@ -225,7 +225,7 @@ int gcn10_cuda_block_tiles_deflate(gcn10_ctx *ctx, const gcn10_tile_source *esa_
 
 /* Starts the upload and the GPU inflate of a block's land-cover tiles and returns without waiting.  The next
  * gcn10_cuda_block_tiles_deflate / gcn10_cuda_inflate_tiles call on this context with the same tile source (same
- * blob pointer and size, same w x h) picks the result up instead of starting over, so a caller that knows its next
+ * blob and offsets pointers, same size, same w x h) picks the result up instead of starting over, so a caller that knows its next
  * block overlaps that block's upload + inflate with the current block's Curve Number strips:
  *
  *     gcn10_cuda_tiles_prefetch(ctx, &tiles[i + 1], w, h);

@@ -17,7 +17,18 @@ WORKER = textwrap.dedent("""
     g.barrier()
     elapsed = 1.0 + g.rank            # rank 1 is the slow one
     rate = dist.whole_job_rate(len(mine) * 10.0, g, elapsed)
-    out = dict(rank=g.rank, world=g.world, mine=mine, tmax=g.max(elapsed), rate=rate)
+    # the dynamic queue (bench.py e2e.queue64): rank 1 is slow, so rank 0 ends up with more blocks
+    import time
+    q = dist.BlockQueue(g, 23, "t")
+    claimed = []
+    while True:
+        i = q.claim()
+        if i is None:
+            break
+        claimed.append(i)
+        time.sleep(0.002 + 0.02 * g.rank)
+    counts = g.gather_ints(len(claimed))
+    out = dict(rank=g.rank, world=g.world, mine=mine, tmax=g.max(elapsed), rate=rate, claimed=claimed, counts=counts)
     g.barrier()
     g.close()
     print("RESULT " + json.dumps(out), flush=True)
@@ -46,6 +57,10 @@ def test_two_rank_gloo_sharding_and_timing(tmp_path):
     assert sorted(res[0]["mine"] + res[1]["mine"]) == ids                       # every block exactly once
     assert res[0]["tmax"] == res[1]["tmax"] == 2.0                              # max over ranks
     assert res[0]["rate"] == res[1]["rate"] == 170.0 / 2.0                      # all units / slowest rank
+    # dynamic queue: every block exactly once, the fast rank took more, both ranks agree on the counts
+    assert sorted(res[0]["claimed"] + res[1]["claimed"]) == list(range(23))
+    assert len(res[0]["claimed"]) > len(res[1]["claimed"]) >= 1
+    assert res[0]["counts"] == res[1]["counts"] == [len(res[0]["claimed"]), len(res[1]["claimed"])]
 
 
 def test_single_process_group_is_inert():
@@ -57,6 +72,8 @@ def test_single_process_group_is_inert():
         assert (g.rank, g.world, g.active) == (0, 1, False)
         assert g.max(3.5) == 3.5 and dist.whole_job_rate(7.0, g, 2.0) == 3.5
         assert dist.shard_blocks([1, 2, 3], 0, 1) == [1, 2, 3]
+        q = dist.BlockQueue(g, 3, "solo")
+        assert [q.claim() for _ in range(5)] == [0, 1, 2, None, None] and g.gather_ints(7) == [7]
         g.close()
     finally:
         os.environ.update(env)

@@ -146,7 +146,7 @@ def test_program_reads_a_vrt_mosaic(world, ref, tmp_path):
     windows, so every block is assembled from four sources -- on the GPU from their compressed tiles, and on the
     host with GCN10_HOST_INFLATE=1.  The rasters must equal the reference's process_block() on the assembled raster."""
     import shutil
-    from tests.test_host import write_vrt
+    from tests.fixtures import write_vrt
     root = world["root"]
     vroot = tmp_path
     esa, esa_t = world["esa"], world["esa_t"]

@@ -250,31 +250,7 @@ def test_window_tiles_are_the_files_zlib_streams(tmp_path):
     t2.close()
 
 
-def write_vrt(path, w, h, gt, sources, kind="ComplexSource", nodata=0, remote_prefix=None):
-    """A VRT with the structure of /root/reference/landcover/esa_worldcover_2021.vrt: one Byte band, one
-    <ComplexSource> per file with SrcRect / DstRect, NODATA 0.  sources: (filename, src_x, src_y, dst_x, dst_y, w, h)."""
-    gts = ", ".join(f"{v:.16e}" for v in gt)
-    out = [f'<VRTDataset rasterXSize="{w}" rasterYSize="{h}">',
-           '  <SRS dataAxisToSRSAxisMapping="2,1">GEOGCS["WGS 84",AUTHORITY["EPSG","4326"]]</SRS>',
-           f'  <GeoTransform> {gts}</GeoTransform>',
-           '  <VRTRasterBand dataType="Byte" band="1">',
-           f'    <NoDataValue>{nodata}</NoDataValue>',
-           '    <ColorInterp>Palette</ColorInterp>']
-    for name, sx, sy, dx, dy, sw, sh in sources:
-        fn = (remote_prefix + os.path.basename(name)) if remote_prefix else name
-        rel = 0 if (remote_prefix or os.path.isabs(name)) else 1
-        out += [f'    <{kind} resampling="nearest">',
-                f'      <SourceFilename relativeToVRT="{rel}">{fn.replace("&", "&amp;")}</SourceFilename>',
-                '      <SourceBand>1</SourceBand>',
-                f'      <SourceProperties RasterXSize="{sw}" RasterYSize="{sh}" DataType="Byte" BlockXSize="256" BlockYSize="256" />',
-                f'      <SrcRect xOff="{sx}" yOff="{sy}" xSize="{sw}" ySize="{sh}" />',
-                f'      <DstRect xOff="{dx}" yOff="{dy}" xSize="{sw}" ySize="{sh}" />',
-                f'      <NODATA>{nodata}</NODATA>',
-                f'    </{kind}>']
-    out += ['  </VRTRasterBand>', '  <OverviewList resampling="nearest">2 4</OverviewList>', '</VRTDataset>']
-    with open(path, "w") as f:
-        f.write("\n".join(out) + "\n")
-    return path
+from tests.fixtures import write_vrt  # noqa: E402
 
 
 VRT_PX = 8.3333333333330430e-05          # landcover/esa_worldcover_2021.vrt:3
