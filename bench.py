@@ -824,13 +824,13 @@ def run_program_leg(args, blob, offsets, sizes, in_tile, w, rows, hsg_np, group,
                                   os.path.join(root, "blocks.shp"), os.path.join(root, "lookups"), os.path.join(root, "logs"))
             with open(os.path.join(root, "blocks.txt"), "w") as f:
                 f.write("\n".join(str(b[0]) for b in blocks) + "\n")
+            os.makedirs(os.path.join(root, "out"), exist_ok=True)
             t0 = time.perf_counter()
             r = subprocess.run([hostlib.EXE_PATH, "-c", os.path.join(root, "config.txt"), "-l", os.path.join(root, "blocks.txt"),
                                 "-o", "--gpus", str(group.world), "--outdir", os.path.join(root, "out")],
                                cwd=root, capture_output=True, text=True, timeout=900,
                                env=dict(os.environ, GCN10_HOST_INFLATE="0", GCN10_HOST_DEFLATE="0"))
             wall = time.perf_counter() - t0
-            os.makedirs(os.path.join(root, "out"), exist_ok=True)
             per_worker = {}
             for fn in sorted(os.listdir(os.path.join(root, "logs"))):
                 for ln in open(os.path.join(root, "logs", fn)):

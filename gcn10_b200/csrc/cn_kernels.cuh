@@ -34,6 +34,15 @@ constexpr int kBoxCols = 256;          // TMA box: HSG columns staged per CTA (m
 constexpr int kBoxRows = 16;           // TMA box: HSG rows staged per CTA
 constexpr int kLutRecords = 256 * 8;   // (land cover, slot) -> 16-byte record
 constexpr int kLutBytes = kLutRecords * 16;
+// Launches of at most four planes per drainage condition (BASELINE configs[0]: g_ii alone) use 4-byte records:
+// with 16-byte records every pixel costs a 16-byte shared-memory read for one useful byte, and the 128 B/clk of an
+// SM's shared memory (8 px/clk) caps a one-plane launch at 0.58 ms per 36000^2 tile -- below the HBM rate.  Narrow
+// records are read with LDS.32 (32 px/clk).  Their row stride is 9 words so that the land-cover classes (multiples
+// of 10) do not all fall onto the same eight banks; no swizzle is needed.
+constexpr int kLut4Stride = 9;         // words per land-cover row of the narrow layout (slots 0..7 used, 8 = padding)
+constexpr int kLut4Bytes = 256 * kLut4Stride * 4;
+constexpr int kNarrowPlanes = 4;       // NP <= kNarrowPlanes -> narrow records
+__host__ __device__ constexpr int lut_bytes_for(int np) { return np <= kNarrowPlanes ? kLut4Bytes : kLutBytes; }
 constexpr int kSgInvalid = 5;          // soil-group slot whose record is all 255
 #ifndef GCN10_PREFETCH
 #define GCN10_PREFETCH 2
@@ -53,8 +62,9 @@ struct BlockParams {
     const uint8_t *hsg;         // coarse window
     size_t hsg_pitch;
     int hsx, hsy;
-    const uint4 *lut;           // kLutRecords records, see pack_lut_records()
-    int swz_shift;              // bank swizzle: slot = sg ^ ((lc >> swz_shift) & 7)
+    const uint4 *lut;           // kLutRecords 16-byte records or the narrow layout, see pack_lut_records()
+    int rec_bytes;              // 16 or 4 (narrow layout)
+    int swz_shift;              // bank swizzle of the 16-byte layout: slot = sg ^ ((lc >> swz_shift) & 7)
     int rows_per_cta;
     int use_tma;
     int group_drained[2];       // per output group: 1 = "drained" remap, 0 = "undrained"
@@ -186,9 +196,8 @@ __device__ __forceinline__ uint32_t soil_slot(uint32_t hv, int drained)
 //
 // Shared memory: [0, 32 KB) LUT records, then the kBoxRows x kBoxCols HSG tile, then one mbarrier.
 
-constexpr int kSmemHsgOff = kLutBytes;
-constexpr int kSmemBarOff = kSmemHsgOff + kBoxRows * kBoxCols;
-constexpr int kSmemBytes = kSmemBarOff + 16;
+__host__ __device__ constexpr int smem_hsg_off(int np) { return lut_bytes_for(np); }
+__host__ __device__ constexpr int smem_bar_off(int np) { return smem_hsg_off(np) + kBoxRows * kBoxCols; }
 // store path: with GCN10_BULK_STORE=1 (default) results are staged per row in shared memory and written with
 // cp.async.bulk (TMA engine, SASS UBLKCP: +3 % over per-thread STG.128, profiles/r01_kernel_sweeps.md);
 // GCN10_BULK_STORE=0 keeps the direct-store kernel
@@ -198,8 +207,16 @@ constexpr int kSmemBytes = kSmemBarOff + 16;
 #ifndef GCN10_STORE_HINT
 #define GCN10_STORE_HINT 1      // L2 evict-first cache hint on the bulk stores (+0.5 %: the planes are never re-read)
 #endif
-constexpr int kSmemStageOff = kSmemBarOff + 128;
-constexpr int smem_bytes_for(int planes) { return GCN10_BULK_STORE ? kSmemStageOff + 2 * planes * kStripPx : kSmemBytes; }
+__host__ __device__ constexpr int smem_stage_off(int np) { return smem_bar_off(np) + 128; }
+// Launches that write at most kNarrowPlanes planes keep the direct per-thread stores: with one to four 4 KB rows per
+// CTA and row, the per-row CTA barrier of the staged path costs more than the TMA stores save (one plane:
+// 0.93 ms staged vs 0.63 ms direct on B200), and without the stage eight CTAs fit an SM.
+__host__ __device__ constexpr bool bulk_store_for(int np, int groups) { return GCN10_BULK_STORE && np * groups > kNarrowPlanes; }
+// np = planes per drainage condition, groups = conditions in the launch
+constexpr int smem_bytes_for(int np, int groups)
+{
+    return bulk_store_for(np, groups) ? smem_stage_off(np) + 2 * np * groups * kStripPx : smem_bar_off(np) + 16;
+}
 
 template <int NP>
 __device__ __forceinline__ void transpose_store_word(const uint4 (&r)[4], uint32_t (&ow)[NP][4], int j)
@@ -224,27 +241,42 @@ __device__ __forceinline__ void transpose_store_word(const uint4 (&r)[4], uint32
     }
 }
 
+// the same 4 x 4 byte transpose for narrow records: one word per pixel holds its (up to four) planes
+template <int NP>
+__device__ __forceinline__ void transpose_store_word4(const uint32_t (&r)[4], uint32_t (&ow)[NP][4], int j)
+{
+    const uint32_t t0 = __byte_perm(r[0], r[1], 0x5140), t1 = __byte_perm(r[2], r[3], 0x5140);
+    ow[0][j] = __byte_perm(t0, t1, 0x5410);
+    if (NP > 1) ow[NP > 1 ? 1 : 0][j] = __byte_perm(t0, t1, 0x7632);
+    if (NP > 2) {
+        const uint32_t t2 = __byte_perm(r[0], r[1], 0x7362), t3 = __byte_perm(r[2], r[3], 0x7362);
+        ow[NP > 2 ? 2 : 0][j] = __byte_perm(t2, t3, 0x5410);
+        if (NP > 3) ow[NP > 3 ? 3 : 0][j] = __byte_perm(t2, t3, 0x7632);
+    }
+}
+
 #ifndef GCN10_MIN_CTAS
 #define GCN10_MIN_CTAS 1
 #endif
 template <int NP, int G>
-__global__ void __launch_bounds__(kThreads, GCN10_MIN_CTAS)
+__global__ void __launch_bounds__(kThreads, (NP * G <= kNarrowPlanes ? 5 : GCN10_MIN_CTAS))
 cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ CUtensorMap hsg_map)
 {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr bool kNarrow = NP <= kNarrowPlanes;
+    constexpr bool kBulk = bulk_store_for(NP, G);
+    constexpr int kLutSize = lut_bytes_for(NP);
+    constexpr int kSmemHsgOff = smem_hsg_off(NP), kSmemBarOff = smem_bar_off(NP), kSmemStageOff = smem_stage_off(NP);
+    constexpr int kSlotShift = kNarrow ? 2 : 4;     // per-pixel slot byte = slot * record bytes
     const uint32_t s_hsg = smem_u32(smem + kSmemHsgOff);
     const uint32_t s_bar = smem_u32(smem + kSmemBarOff);
 
     const int tid = threadIdx.x;
     const int x_first = blockIdx.x * kStripPx;
     const int w16 = p.w & ~(kVecPx - 1);            // the right edge (< 16 px) is cn_bytes_kernel's
-#if GCN10_BULK_STORE
-    // every thread stays for the per-row barrier; threads right of the raster recompute column group 0
+    // staged stores: every thread stays for the per-row barrier; threads right of the raster recompute column group 0
     const bool active = x_first + tid * kVecPx < w16;
-    const int x0 = active ? x_first + tid * kVecPx : x_first;
-#else
-    const int x0 = x_first + tid * kVecPx;
-#endif
+    const int x0 = (kBulk && !active) ? x_first : x_first + tid * kVecPx;
     const int y_begin = blockIdx.y * p.rows_per_cta;
     const int y_end = min(p.h, y_begin + p.rows_per_cta);
 
@@ -263,19 +295,15 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
     if (tid == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(s_bar, kLutBytes + (staged ? kBoxRows * kBoxCols : 0));
+        mbar_expect_tx(s_bar, kLutSize + (staged ? kBoxRows * kBoxCols : 0));
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"(smem_u32(smem)), "l"(p.lut), "r"(kLutBytes), "r"(s_bar) : "memory");
+                     :: "r"(smem_u32(smem)), "l"(p.lut), "r"(kLutSize), "r"(s_bar) : "memory");
         if (staged)
             tma_load_2d(s_hsg, &hsg_map, ci_min, cj_min, s_bar);
     }
 
-#if !GCN10_BULK_STORE
-    const bool active = x0 < w16;
-#else
     const uint32_t row_bytes = (uint32_t)(min(w16, x_first + kStripPx) - x_first);      // multiple of 16
     size_t row_off = (size_t)y_begin * p.out_pitch + x_first;
-#endif
 
     // software pipeline: the land-cover vectors (and HSG row indices) of the next kPrefetch rows are in
     // flight while the current row is looked up and stored; the first ones are issued before the wait
@@ -287,7 +315,7 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
     int cq[kPrefetch];
 #pragma unroll
     for (int s = 0; s < kPrefetch; s++) {
-        const bool in = y_begin + s < y_end && (GCN10_BULK_STORE || active);
+        const bool in = y_begin + s < y_end && (kBulk || active);
         eq[s] = in ? ldg_stream16(esa_ptr + (size_t)s * p.esa_pitch) : make_uint4(0, 0, 0, 0);
         cq[s] = in ? __ldg(rowp + s) : 0;
     }
@@ -295,10 +323,8 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
     __syncthreads();            // the mbarrier is initialised
     mbar_wait(s_bar, 0);
 
-#if !GCN10_BULK_STORE
-    if (!active)
+    if (!kBulk && !active)
         return;
-#endif
 
     const uint32_t swz_mask = 0x07070707u;
     uint32_t slot[G][4];            // per pixel: (slot << 4) in one byte, 4 pixels per word
@@ -343,7 +369,7 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
                     const uint32_t hv = staged ? (uint32_t)smem[row_s + cc[q]] : (uint32_t)__ldg(row_g + cc[q]);
 #pragma unroll
                     for (int g = 0; g < G; g++)
-                        acc[g] |= (soil_slot(hv, p.group_drained[g]) << 4) << (8 * q);
+                        acc[g] |= (soil_slot(hv, p.group_drained[g]) << kSlotShift) << (8 * q);
                 }
 #pragma unroll
                 for (int g = 0; g < G; g++)
@@ -352,11 +378,11 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
         }
 
         const uint32_t ew[4] = { e.x, e.y, e.z, e.w };
-        // bank swizzle term per pixel: ((lc >> swz_shift) & 7) << 4, byte-parallel
+        // bank swizzle term per pixel (16-byte records): ((lc >> swz_shift) & 7) << 4, byte-parallel
         uint32_t fz[4];
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            fz[j] = ((ew[j] >> p.swz_shift) & swz_mask) << 4;
+            fz[j] = kNarrow ? 0u : ((ew[j] >> p.swz_shift) & swz_mask) << 4;
 
 #pragma unroll
         for (int g = 0; g < G; g++) {
@@ -364,32 +390,44 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t sx = slot[g][j] ^ fz[j];
-                uint4 r[4];
+                if constexpr (kNarrow) {
+                    uint32_t r[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    // record offset = lc*128 + (slot ^ swizzle)*16
-                    const uint32_t lc = __byte_perm(ew[j], 0, 0x4440 | q);
-                    const uint32_t sb = __byte_perm(sx, 0, 0x4440 | q);
-                    r[q] = *reinterpret_cast<const uint4 *>(smem + (lc * 128u + sb));
+                    for (int q = 0; q < 4; q++) {
+                        // record offset = lc * 36 + slot * 4
+                        const uint32_t lc = __byte_perm(ew[j], 0, 0x4440 | q);
+                        const uint32_t sb = __byte_perm(sx, 0, 0x4440 | q);
+                        r[q] = *reinterpret_cast<const uint32_t *>(smem + (lc * (4u * kLut4Stride) + sb));
+                    }
+                    transpose_store_word4<NP>(r, ow, j);
                 }
-                transpose_store_word<NP>(r, ow, j);
+                else {
+                    uint4 r[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        // record offset = lc*128 + (slot ^ swizzle)*16
+                        const uint32_t lc = __byte_perm(ew[j], 0, 0x4440 | q);
+                        const uint32_t sb = __byte_perm(sx, 0, 0x4440 | q);
+                        r[q] = *reinterpret_cast<const uint4 *>(smem + (lc * 128u + sb));
+                    }
+                    transpose_store_word<NP>(r, ow, j);
+                }
             }
-#if GCN10_BULK_STORE
-            {
+            if constexpr (kBulk) {
                 uint8_t *stage = smem + kSmemStageOff + ((y - y_begin) & 1) * (NP * G * kStripPx) + g * NP * kStripPx;
 #pragma unroll
                 for (int k = 0; k < NP; k++)
                     *reinterpret_cast<uint4 *>(stage + k * kStripPx + tid * kVecPx) =
                         make_uint4(ow[k][0], ow[k][1], ow[k][2], ow[k][3]);
             }
-#else
+            else {
 #pragma unroll
-            for (int k = 0; k < NP; k++)
-                stg_stream16(p.out[g * NP + k] + out_off, ow[k][0], ow[k][1], ow[k][2], ow[k][3]);
-#endif
+                for (int k = 0; k < NP; k++)
+                    stg_stream16(p.out[g * NP + k] + out_off, ow[k][0], ow[k][1], ow[k][2], ow[k][3]);
+            }
         }
 
-#if GCN10_BULK_STORE
+        if constexpr (kBulk) {
         // generic-proxy writes -> visible to the async proxy; the row before last has left its stage
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (tid == 0)
@@ -413,14 +451,12 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         row_off += p.out_pitch;
-#endif
+        }
         esa_ptr += p.esa_pitch;
         out_off += p.out_pitch;
     }
-#if GCN10_BULK_STORE
-    if (tid == 0)
+    if (kBulk && tid == 0)
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all bulk stores of this CTA have completed
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -441,8 +477,10 @@ __global__ void cn_bytes_kernel(const __grid_constant__ BlockParams p, int x_beg
         const int cj = __ldg(p.row_idx + p.y_base + y);
         const uint32_t hv = __ldg(p.hsg + (size_t)cj * p.hsg_pitch + ci);
         for (int g = 0; g < groups; g++) {
-            const uint32_t s = soil_slot(hv, p.group_drained[g]) ^ ((lc >> p.swz_shift) & 7u);
-            const uint8_t *rec = reinterpret_cast<const uint8_t *>(p.lut + (lc * 8u + s));
+            const uint32_t sg = soil_slot(hv, p.group_drained[g]);
+            const uint8_t *rec = p.rec_bytes == 16
+                                     ? reinterpret_cast<const uint8_t *>(p.lut + (lc * 8u + (sg ^ ((lc >> p.swz_shift) & 7u))))
+                                     : reinterpret_cast<const uint8_t *>(p.lut) + 4u * (lc * kLut4Stride + sg);
             for (int k = 0; k < np; k++)
                 p.out[g * np + k][(size_t)y * p.out_pitch + x] = __ldg(rec + k);
         }

@@ -102,7 +102,8 @@ struct gcn10_ctx {
     int use_tma = 1;
     int inflate_probe = 0;      // measurement aid for tools/inflate_bench.py (see InflateParams::probe)
     int fused = 1;              // compressed-tile calls use cn_deflate_fused_kernel (0 = CN kernel + tile encoder)
-    int ship = 1;               // strips leave through ship_strip_kernel (0 = size read-back, then a D2H copy of that size)
+    int ship = 0;               // 1 = strips leave through ship_strip_kernel; 0 = size read-back, then a D2H copy of that size
+                                // (measured on B200: 11.8 vs 12.2 ms per block -- the copy engine does not compete for SMs)
     DevBuf fused_tab;           // idmap [256][16] | val [256][32] | lit9 [256][6] u64
     unsigned fused_mask = 0;    // plane mask the tables were built for (0 = none)
     int fused_ok = 0;           // the mask's value records fit the id space
@@ -192,6 +193,8 @@ inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // (cn.c:126-128,289)
 inline uint8_t cn_byte(int v) { return v < 255 ? (uint8_t)v : (uint8_t)GCN10_NODATA; }
 
+int popcount9(unsigned m) { return __builtin_popcount(m & 0x1FFu); }
+
 // Pick the bank-swizzle shift: spread the land-cover classes that actually have table rows over
 // the 8 16-byte bank groups of shared memory, so that neighbouring pixels of different classes
 // (same soil group) do not serialise their record fetches.
@@ -227,14 +230,16 @@ int choose_swizzle(const int tables[GCN10_NVARIANTS][256][5])
 // Record (lc, slot') = the CN bytes of the selected variants, in selection order, for land cover
 // lc and soil-group slot s = slot' ^ ((lc >> shift) & 7).  Slots 5..7 (invalid soil group, cn.c:123-124)
 // hold 255 everywhere.
+// With at most kNarrowPlanes selected variants the records are 4 bytes, rows kLut4Stride words apart, no swizzle.
 void pack_lut_records(const int tables[GCN10_NVARIANTS][256][5], unsigned variant_mask, int shift,
                       std::vector<uint8_t> &rec)
 {
+    const bool narrow = popcount9(variant_mask) <= kNarrowPlanes;
     rec.assign((size_t)kLutBytes, (uint8_t)GCN10_NODATA);
     for (int lc = 0; lc < 256; lc++) {
         for (int s = 0; s < 5; s++) {
             int slot = s ^ ((lc >> shift) & 7);
-            uint8_t *r = &rec[((size_t)lc * 8 + slot) * 16];
+            uint8_t *r = narrow ? &rec[((size_t)lc * kLut4Stride + s) * 4] : &rec[((size_t)lc * 8 + slot) * 16];
             int k = 0;
             for (int t = 0; t < GCN10_NVARIANTS; t++)
                 if (variant_mask & (1u << t))
@@ -247,9 +252,7 @@ void pack_lut_records(const int tables[GCN10_NVARIANTS][256][5], unsigned varian
 // co-resident CTAs inside a narrow band of rows and leave no tail wave, long ones amortise the per-CTA
 // prologue (LUT + HSG box fills).  Bulk-store kernel: 12 rows is best for <= 9 planes (2 CTAs/SM), 32 for
 // 10..18 planes (1 CTA/SM); direct-store kernel: 12 / 16.
-int auto_rows_per_cta(int planes) { return planes > 9 ? (GCN10_BULK_STORE ? 32 : 16) : 12; }
-
-int popcount9(unsigned m) { return __builtin_popcount(m & 0x1FFu); }
+int auto_rows_per_cta(int planes) { return planes > 9 ? (GCN10_BULK_STORE ? 32 : 16) : planes <= kNarrowPlanes ? 16 : 12; }
 
 // ---- strip hand-over ------------------------------------------------------------------------
 
@@ -421,6 +424,7 @@ int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t 
     p.hsx = hsx;
     p.hsy = hsy;
     p.lut = (const uint4 *)((const uint8_t *)c->lut.p + (size_t)lut_slot * kLutBytes);
+    p.rec_bytes = lp.np <= kNarrowPlanes ? 4 : 16;
     p.swz_shift = c->swz_shift;
     p.rows_per_cta = c->rows_per_cta > 0 ? c->rows_per_cta : auto_rows_per_cta(lp.np * lp.groups);
     p.use_tma = tma_ok;
@@ -443,7 +447,7 @@ int launch_rows(gcn10_ctx *c, const LaunchPlan &lp, int lut_slot, const uint8_t 
             p.rows_per_cta *= 2;
         dim3 grid((w16 + kStripPx - 1) / kStripPx, (rows + p.rows_per_cta - 1) / p.rows_per_cta);
         BlockKernel k = pick_kernel(lp.np, lp.groups);
-        k<<<grid, kThreads, smem_bytes_for(lp.np * lp.groups), st>>>(p, map);
+        k<<<grid, kThreads, smem_bytes_for(lp.np, lp.groups), st>>>(p, map);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         x_bytes = w16;
@@ -667,7 +671,7 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
     for (int np = 1; np <= 9; np++)
         for (int g = 1; g <= 2; g++)
             CUDA_TRY(cudaFuncSetAttribute((const void *)pick_kernel(np, g),
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(np * g)));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(np, g)));
     *out = c;
     return GCN10_OK;
 }

@@ -626,6 +626,10 @@ static int gh_process_block(worker *wk, block_input *in, int total_blocks, doubl
 
     /* output directories and file names (cn.c:236-256, 293-360); the files themselves appear with the first rows */
     const char *root = (wk->opt->out_root && *wk->opt->out_root) ? wk->opt->out_root : ".";
+    if (mkdir(root, 0755) != 0 && errno != EEXIST) {            /* --outdir may name a directory that does not exist yet */
+        snprintf(msg, sizeof msg, "failed to create output directory %s", root);
+        fatal(wk, msg);
+    }
     for (int c = 0; c < 2; c++) {
         char outdir[PATH_MAX];
         snprintf(outdir, sizeof outdir, "%s/cn_rasters_%s", root, k_conds[c]);

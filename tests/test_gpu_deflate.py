@@ -237,7 +237,7 @@ def test_strip_hand_over_paths_agree(gpu_ctx, port, tables, encoder_path):
             gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], on_strip=failing)
         again = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
     finally:
-        gpu_ctx.set_option("ship", 1)
+        gpu_ctx.set_option("ship", 0)
         gpu_ctx.set_option("strip_rows", 2048)
     assert got[0]["bytes"] == got[1]["bytes"] == again["bytes"]
     for k in range(18):
