@@ -51,6 +51,12 @@ constexpr int kSgInvalid = 5;          // soil-group slot whose record is all 25
 #define GCN10_STORE_POLICY 0
 #endif
 constexpr int kPrefetch = GCN10_PREFETCH;   // rows of land cover in flight per thread
+#ifndef GCN10_NARROW_PF
+#define GCN10_NARROW_PF 2
+#endif
+#ifndef GCN10_NARROW_CTAS
+#define GCN10_NARROW_CTAS 5
+#endif
 
 struct BlockParams {
     const uint8_t *esa;         // first row of this launch
@@ -259,11 +265,12 @@ __device__ __forceinline__ void transpose_store_word4(const uint32_t (&r)[4], ui
 #define GCN10_MIN_CTAS 1
 #endif
 template <int NP, int G>
-__global__ void __launch_bounds__(kThreads, (NP * G <= kNarrowPlanes ? 5 : GCN10_MIN_CTAS))
+__global__ void __launch_bounds__(kThreads, (NP * G <= kNarrowPlanes ? GCN10_NARROW_CTAS : GCN10_MIN_CTAS))
 cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ CUtensorMap hsg_map)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr bool kNarrow = NP <= kNarrowPlanes;
+    constexpr int kPF = (NP * G <= kNarrowPlanes) ? GCN10_NARROW_PF : kPrefetch;     // rows of land cover in flight
     constexpr bool kBulk = bulk_store_for(NP, G);
     constexpr int kLutSize = lut_bytes_for(NP);
     constexpr int kSmemHsgOff = smem_hsg_off(NP), kSmemBarOff = smem_bar_off(NP), kSmemStageOff = smem_stage_off(NP);
@@ -305,16 +312,16 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
     const uint32_t row_bytes = (uint32_t)(min(w16, x_first + kStripPx) - x_first);      // multiple of 16
     size_t row_off = (size_t)y_begin * p.out_pitch + x_first;
 
-    // software pipeline: the land-cover vectors (and HSG row indices) of the next kPrefetch rows are in
+    // software pipeline: the land-cover vectors (and HSG row indices) of the next kPF rows are in
     // flight while the current row is looked up and stored; the first ones are issued before the wait
     // on the shared-memory fills
     const uint8_t *esa_ptr = p.esa + (size_t)y_begin * p.esa_pitch + x0;
     size_t out_off = (size_t)y_begin * p.out_pitch + x0;
     const int32_t *rowp = p.row_idx + p.y_base + y_begin;
-    uint4 eq[kPrefetch];
-    int cq[kPrefetch];
+    uint4 eq[kPF];
+    int cq[kPF];
 #pragma unroll
-    for (int s = 0; s < kPrefetch; s++) {
+    for (int s = 0; s < kPF; s++) {
         const bool in = y_begin + s < y_end && (kBulk || active);
         eq[s] = in ? ldg_stream16(esa_ptr + (size_t)s * p.esa_pitch) : make_uint4(0, 0, 0, 0);
         cq[s] = in ? __ldg(rowp + s) : 0;
@@ -328,6 +335,11 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
 
     const uint32_t swz_mask = 0x07070707u;
     uint32_t slot[G][4];            // per pixel: (slot << 4) in one byte, 4 pixels per word
+    // one-condition narrow launches keep, per pixel, the shared-memory address of its soil group's column of the
+    // narrow table (16 registers): the lookup is then PRMT (class byte) + IMAD (class * 36 + column) + LDS.32
+    constexpr bool kColumns = kNarrow && G == 1;
+    uint32_t column[kColumns ? 16 : 1];
+    const uint32_t s_lut = smem_u32(smem);
     int cj_cur = INT_MIN;           // row_idx is clamped to >= 0, so this never matches
 #pragma unroll
     for (int g = 0; g < G; g++)
@@ -339,13 +351,13 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
         const uint4 e = eq[0];
         const int cj = cq[0];
 #pragma unroll
-        for (int s = 0; s + 1 < kPrefetch; s++) {
+        for (int s = 0; s + 1 < kPF; s++) {
             eq[s] = eq[s + 1];
             cq[s] = cq[s + 1];
         }
-        if (y + kPrefetch < y_end) {
-            eq[kPrefetch - 1] = ldg_stream16(esa_ptr + (size_t)kPrefetch * p.esa_pitch);
-            cq[kPrefetch - 1] = __ldg(rowp + kPrefetch);
+        if (y + kPF < y_end) {
+            eq[kPF - 1] = ldg_stream16(esa_ptr + (size_t)kPF * p.esa_pitch);
+            cq[kPF - 1] = __ldg(rowp + kPF);
         }
         rowp++;
 
@@ -374,6 +386,11 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
 #pragma unroll
                 for (int g = 0; g < G; g++)
                     slot[g][j] = acc[g];
+                if constexpr (kColumns) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        column[4 * j + q] = s_lut + ((acc[0] >> (8 * q)) & 0xFFu);
+                }
             }
         }
 
@@ -390,7 +407,16 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t sx = slot[g][j] ^ fz[j];
-                if constexpr (kNarrow) {
+                if constexpr (kColumns) {
+                    uint32_t r[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t lc = __byte_perm(ew[j], 0, 0x4440 | q);
+                        asm("ld.shared.u32 %0, [%1];" : "=r"(r[q]) : "r"(lc * (4u * kLut4Stride) + column[4 * j + q]));
+                    }
+                    transpose_store_word4<NP>(r, ow, j);
+                }
+                else if constexpr (kNarrow) {
                     uint32_t r[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
