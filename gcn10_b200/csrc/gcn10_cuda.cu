@@ -81,7 +81,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 // one compressed land-cover window on its way to / resident on the device (two per context, so that the next
 // block's tiles can be uploaded and inflated while the current block's strips run: gcn10_cuda_tiles_prefetch)
 struct TileSlot {
-    DevBuf in_blob, in_table, esa_full;
+    DevBuf in_blob, in_table, esa_full, scratch;   // scratch: whole-tile copies of the tiles the window clips
     HostBuf h_status;           // [ntiles] status codes | launch order | offsets (u64) | sizes (u32): page-locked staging
     cudaEvent_t inf0 = nullptr, inf1 = nullptr, done = nullptr;     // around the inflate kernel; behind the status copy
     bool pending = false;       // inflate issued, result not consumed yet
@@ -691,6 +691,7 @@ void gcn10_cuda_destroy(gcn10_ctx *c)
         release(c->tslot[i].in_blob);
         release(c->tslot[i].in_table);
         release(c->tslot[i].esa_full);
+        release(c->tslot[i].scratch);
         release_host(c->tslot[i].h_status);
         if (c->tslot[i].inf0) cudaEventDestroy(c->tslot[i].inf0);
         if (c->tslot[i].inf1) cudaEventDestroy(c->tslot[i].inf1);
@@ -1365,18 +1366,23 @@ static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *
     int rc;
     // the kernel's 512-byte input refills may run ~2 KB past a stream: keep that readable
     if ((rc = ensure(sl.in_blob, round_up(blob_total, 256) + 4096)) ||
-        (rc = ensure(sl.in_table, ntiles * 20)) ||
-        (rc = ensure_host(sl.h_status, ntiles * (2 * sizeof(int) + 12))) ||
+        (rc = ensure(sl.in_table, ntiles * 24)) ||
+        (rc = ensure_host(sl.h_status, ntiles * (3 * sizeof(int) + 12))) ||
         (rc = ensure(sl.esa_full, dpitch * (size_t)h)))
         return rc;
     unsigned long long *d_off = (unsigned long long *)sl.in_table.p;
     uint32_t *d_size = (uint32_t *)((uint8_t *)sl.in_table.p + ntiles * 8);
     int *d_status = (int *)((uint8_t *)sl.in_table.p + ntiles * 12);
     int *d_order = (int *)((uint8_t *)sl.in_table.p + ntiles * 16);
-    // page-locked staging: [status | order | offsets | sizes]
+    int *d_scratch = (int *)((uint8_t *)sl.in_table.p + ntiles * 20);
+    // page-locked staging: [status | order | offsets | sizes | scratch slots]
     int *h_order = (int *)sl.h_status.p + ntiles;
     unsigned long long *h_off = (unsigned long long *)((int *)sl.h_status.p + 2 * ntiles);
     uint32_t *h_size = (uint32_t *)(h_off + ntiles);
+    int *h_scratch = (int *)(h_size + ntiles);
+    // tiles that are not stored whole in the plane (clipped by their part's rectangle) keep a scratch copy: the
+    // inflater reads history older than its 8 KB ring back from where the bytes were flushed to
+    size_t nscratch = 0, scratch_stride = 0;
 
     InflateParams ip;
     memset(&ip, 0, sizeof(ip));
@@ -1394,6 +1400,13 @@ static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *
         }
         if (src->blob_bytes)
             CUDA_TRY(cudaMemcpyAsync((uint8_t *)sl.in_blob.p + b0, src->blob, src->blob_bytes, cudaMemcpyHostToDevice, st));
+        for (size_t i = 0; i < n; i++) {
+            const long long tx0 = (long long)(i % (size_t)src->tiles_x) * src->tile_w - src->x_off;
+            const long long ty0 = (long long)(i / (size_t)src->tiles_x) * src->tile_h - src->y_off;
+            const bool whole = tx0 >= 0 && ty0 >= 0 && tx0 + src->tile_w <= pt.w && ty0 + src->tile_h <= pt.h;
+            h_scratch[t0 + i] = (whole || !src->sizes[i]) ? -1 : (int)nscratch++;
+        }
+        scratch_stride = std::max(scratch_stride, round_up((size_t)src->tile_w * (size_t)src->tile_h, 256));
         InflatePart &q = ip.part[k];
         q.first_tile = (int)t0;
         q.tiles_x = src->tiles_x;
@@ -1417,6 +1430,12 @@ static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *
     CUDA_TRY(cudaMemcpyAsync(d_order, h_order, ntiles * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_off, h_off, ntiles * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_size, h_size, ntiles * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_scratch, h_scratch, ntiles * 4, cudaMemcpyHostToDevice, st));
+    if (nscratch && (rc = ensure(sl.scratch, nscratch * scratch_stride)))
+        return rc;
+    ip.scratch = (uint8_t *)sl.scratch.p;
+    ip.scratch_index = d_scratch;
+    ip.scratch_stride = scratch_stride;
     ip.blob = (const uint8_t *)sl.in_blob.p;
     ip.offsets = d_off;
     ip.sizes = d_size;

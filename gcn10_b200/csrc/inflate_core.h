@@ -24,7 +24,15 @@
 namespace gcn10 {
 namespace inflate {
 
-constexpr int kWindow = 32768;          // DEFLATE history (RFC 1951: distances <= 32768)
+// History.  DEFLATE reaches back 32768 bytes (RFC 1951), but 96 % of the matches of a land-cover tile stay within
+// 4 KB (run, pixel above, a few rows up).  The ring in shared memory therefore holds only the last kWindow bytes;
+// older history is read back from the tile's place in the destination plane, where the flusher warp has already put
+// it (L2 resident).  With an 8 KB ring a tile needs 18 KB of shared memory instead of 43 KB and eleven tiles fit an SM:
+// all 1296 tiles of a 36000 x 36000 block decode at once instead of in 1.75 waves.
+constexpr int kWindow = 8192;           // shared-memory history ring (power of two)
+constexpr int kPart = 1024;             // a batch is executed in parts: symbols whose last byte falls into the same
+                                        // kPart-aligned span of the batch's output (a part is < kPart + 258 bytes)
+constexpr int kPiece = 2048;            // the ring is flushed to the plane in pieces of this size, two in flight
 constexpr int kLlBits = 10;             // literal/length lookup width; longer codes take the canonical walk
 constexpr int kDBits = 9;               // distance lookup width
 constexpr int kRingWords = 512;         // compressed-input ring: 2 KB, refilled 512 B at a time by the warp
@@ -560,10 +568,13 @@ GCN10_HD uint32_t sym_is_match(uint32_t sym) { return sym >> 31; }
 GCN10_HD uint32_t sym_len(uint32_t sym) { return (sym >> 31) ? (sym & 0x1FFu) : 1u; }
 GCN10_HD uint32_t sym_dist(uint32_t sym) { return ((sym >> 16) & 0x7FFFu) + 1u; }
 
-// The executor hoists all literals of a batch in front of its matches; with the history ring indexed
-// modulo 32768 a literal up to kMaxBatchOut bytes further on lands on the byte 32768 positions behind it,
-// so a batch holding a match that reaches back into that zone is executed strictly in order instead.
-GCN10_HD bool sym_is_far(uint32_t sym) { return sym_is_match(sym) && sym_dist(sym) + (uint32_t)kMaxBatchOut > (uint32_t)kWindow; }
+// Execution rule of a part that covers output [p0, p1) (p1 - p0 < kPart + 258), shared by the writer warp and
+// the CPU harness.  When the part starts, the ring holds [p1 - kWindow, p0) and the plane holds every byte below
+// flushed_done, with flushed_done >= p0 - (3 * kPiece - 1) >= p1 - kWindow (pieces are handed over after every part,
+// at most two in flight).  So a source byte at position s comes from the ring when s >= p1 - kWindow and from the
+// plane otherwise.  Order inside a part: (1) all literals, (2) the matches that start below p1 - kWindow ("far":
+// their source ends below p0, so they depend on nothing in the part), (3) the other matches, in stream order.
+GCN10_HD bool byte_from_plane(uint32_t s, uint32_t p1) { return p1 > (uint32_t)kWindow && s < p1 - (uint32_t)kWindow; }
 
 }  // namespace inflate
 }  // namespace gcn10

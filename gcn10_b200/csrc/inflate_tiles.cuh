@@ -9,15 +9,19 @@
 //   decoder warp  tops up the 2 KB compressed-input ring (16-byte loads by all lanes); lane 0 owns the bit
 //                 reader and turns code words into batches of up to 32 LZ77 symbols (inflate_core.h); block
 //                 headers are parsed by lane 0, the Huffman lookup tables are filled by all 32 lanes.
-//   writer warp   executes the batches against a 32 KB history ring in shared memory: a warp scan of the
-//                 symbol lengths gives every symbol its output position, all literals are written at once,
-//                 matches are copied one after the other (32 or 128 bytes per step).
-//   flusher warp  writes finished 4 KB pieces of the ring to the land-cover plane in HBM with 16-byte stores,
-//                 clipped to the requested window, while the writer goes on (at most two pieces in flight).
-// The warps hand over through a double-buffered symbol queue and a two-deep piece queue, both guarded by named
-// barriers (bar.sync / bar.arrive with literal barrier numbers), so decoding batch k+1, executing batch k and
-// storing the bytes of earlier batches overlap.  Shared memory per CTA: 43 KB (history 32 KB, tables 7.6 KB,
-// input ring 2 KB, queues 0.5 KB) -> five tiles in flight per SM.
+//   writer warp   executes the batches against an 8 KB history ring in shared memory: a warp scan of the
+//                 symbol lengths gives every symbol its output position; per ~1 KB part of a batch all literals are
+//                 written at once, then the matches that reach back further than the ring (4 % of them: their
+//                 source is read back from the plane, where the flusher has put it), then the others one after the
+//                 other (32 or 128 bytes per step).
+//   flusher warp  writes finished 2 KB pieces of the ring to the land-cover plane in HBM with 16-byte stores,
+//                 clipped to the requested window, while the writer goes on (at most two pieces in flight), and
+//                 accumulates the stream's Adler-32.  Tiles that the window clips also go to a scratch copy, so
+//                 that their older history can be read back like that of any other tile.
+// The warps hand over through a double-buffered symbol queue and a two-deep piece queue, both guarded by
+// mbarriers in shared memory, so decoding batch k+1, executing batch k and storing the bytes of earlier batches
+// overlap.  Shared memory per CTA: 18 KB (history 8 KB, tables 7.6 KB, input ring 2 KB, queues 0.5 KB) -> eleven
+// tiles in flight per SM: the 1296 tiles of a 36000 x 36000 block are all resident at once.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -51,6 +55,9 @@ struct InflateParams {
     int probe;                          // measurement aid: 1 = the writer warp drops the batches (decoder speed alone),
                                         // 2 = the writer runs but does not flush the ring to the plane
     int nparts;
+    uint8_t *scratch;                   // private copies of the tiles the window clips (their older history)
+    const int *scratch_index;           // per tile: its slot in `scratch`, or -1 = the plane holds the whole tile
+    size_t scratch_stride;              // bytes per slot
     InflatePart part[kInflateMaxParts];
 };
 
@@ -65,35 +72,38 @@ struct InflateSmem {
     int trailer_state;                          // 0 = the decoder never reached the trailer, 1 = read, 2 = stream ends before it
     int final_err;                              // the writer warp's verdict
     int pad[3];
+    // hand-over between the warps: mbarriers (count 1: the elected lane of the producing warp arrives, the whole
+    // consuming warp waits).  Named barriers would do, but an SM has 16 per resident CTA slot at 4 CTAs, and eight
+    // of them per tile would cap the SM at seven tiles.
+    unsigned long long bar_full[2], bar_empty[2];       // decoder -> writer: batch b queued / writer -> decoder: consumed
+    unsigned long long bar_ready[2], bar_done[2];       // writer -> flusher: piece k posted / flusher -> writer: stored
     uint8_t window[inflate::kWindow];
 };
 
 constexpr int kInflateSmem = (int)sizeof(InflateSmem);
 constexpr int kInflateThreads = 96;      // decoder warp, writer warp, flusher warp
-constexpr uint32_t kFlushChunk = 4096;
+constexpr uint32_t kFlushChunk = inflate::kPiece;
 
 struct TileDst {
     uint8_t *dst;
     size_t pitch;
     int dx0, dy0, w, h, tile_w, tw_shift;
     bool rows16;                        // tile_w % 16 == 0: a 16-byte group never straddles tile rows
+    // where the tile's older history is read back from: its own rectangle of the plane, or -- for a tile that the
+    // window clips (its bytes are not all stored in the plane) -- a private scratch copy of the whole tile
+    uint8_t *hist;                      // address of tile pixel (0, 0)
+    size_t hist_pitch;
+    bool scratch;                       // hist is a scratch copy: the flusher fills it as well
 };
 
-enum { kBarFull0 = 1, kBarFull1 = 2, kBarEmpty0 = 3, kBarEmpty1 = 4 };
-
-// literal barrier numbers: with a register operand ptxas reserves all 16 named barriers for the CTA, which caps
-// the SM at four CTAs (64 barriers); five fit by shared memory
-template <int ID> __device__ __forceinline__ void bar_sync_id() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
-template <int ID> __device__ __forceinline__ void bar_arrive_id() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
-__device__ __forceinline__ void bar_sync_full(int b) { if (b) bar_sync_id<kBarFull1>(); else bar_sync_id<kBarFull0>(); }
-__device__ __forceinline__ void bar_arrive_full(int b) { if (b) bar_arrive_id<kBarFull1>(); else bar_arrive_id<kBarFull0>(); }
-__device__ __forceinline__ void bar_sync_empty(int b) { if (b) bar_sync_id<kBarEmpty1>(); else bar_sync_id<kBarEmpty0>(); }
-__device__ __forceinline__ void bar_arrive_empty(int b) { if (b) bar_arrive_id<kBarEmpty1>(); else bar_arrive_id<kBarEmpty0>(); }
-// writer <-> flusher: 5, 6 = "piece k is ready", 7, 8 = "piece k has been written out"
-__device__ __forceinline__ void bar_sync_ready(int k) { if (k) bar_sync_id<6>(); else bar_sync_id<5>(); }
-__device__ __forceinline__ void bar_arrive_ready(int k) { if (k) bar_arrive_id<6>(); else bar_arrive_id<5>(); }
-__device__ __forceinline__ void bar_sync_done(int k) { if (k) bar_sync_id<8>(); else bar_sync_id<7>(); }
-__device__ __forceinline__ void bar_arrive_done(int k) { if (k) bar_arrive_id<8>(); else bar_arrive_id<7>(); }
+// one-producer / one-consumer-warp mbarrier hand-over
+__device__ __forceinline__ void warp_signal(unsigned long long *bar, int lane)
+{
+    __syncwarp();
+    if (lane == 0)
+        mbar_arrive(smem_u32(bar));
+}
+__device__ __forceinline__ void warp_wait(unsigned long long *bar, uint32_t parity) { mbar_wait(smem_u32(bar), parity); }
 
 // The writer warp addresses the history ring through its 32-bit shared-memory address with explicit ld.shared /
 // st.shared: through a generic pointer the compiler rebuilds the shared window base (S2R SR_CgaCtaId + LEA) at
@@ -113,11 +123,27 @@ struct Ring {
     }
 };
 
+// byte `pos` of the tile as the flusher stored it (read around L1: it was written by another warp of this CTA)
+__device__ __forceinline__ uint32_t hist_byte(const TileDst &d, uint32_t pos)
+{
+    const uint32_t r = d.tw_shift >= 0 ? pos >> d.tw_shift : pos / (uint32_t)d.tile_w;
+    const uint32_t c = pos - r * (uint32_t)d.tile_w;
+    return (uint32_t)__ldcg(d.hist + (size_t)r * d.hist_pitch + c);
+}
+
 // history ring piece [p0, p0 + nbytes) -> plane (p0 is a multiple of 16); whole warp
 __device__ __forceinline__ void inflate_flush(const uint8_t *window, const TileDst &d, uint32_t p0, uint32_t nbytes,
                                               int lane)
 {
     using inflate::kWindow;
+    if (d.scratch) {
+        // the private copy takes every byte of the piece, clipped or not
+        for (uint32_t i = lane; i < nbytes; i += 32u) {
+            const uint32_t p = p0 + i;
+            const uint32_t r = d.tw_shift >= 0 ? p >> d.tw_shift : p / (uint32_t)d.tile_w;
+            d.hist[(size_t)r * d.hist_pitch + (p - r * (uint32_t)d.tile_w)] = window[p & (kWindow - 1)];
+        }
+    }
     if (d.rows16) {
         for (uint32_t g = lane; g * 16u < nbytes; g += 32u) {
             const uint32_t p = p0 + 16u * g;
@@ -244,6 +270,19 @@ __device__ __forceinline__ void inflate_copy(const Ring window, uint32_t mp, uin
     }
 }
 
+// a match whose source starts below the ring (p1 = end of the part, see inflate::byte_from_plane): the bytes come
+// from the plane / scratch copy where the flusher put them, or -- the tail of a source that straddles -- from the ring;
+// source and destination never overlap here (the source ends more than a ring length below the destination)
+__device__ __forceinline__ void inflate_copy_far(const Ring window, const TileDst &d, uint32_t mp, uint32_t len,
+                                                 uint32_t dist, uint32_t p1, int lane)
+{
+    for (uint32_t i = lane; i < len; i += 32u) {
+        const uint32_t s = mp - dist + i;
+        window.st8(mp + i, inflate::byte_from_plane(s, p1) ? hist_byte(d, s) : window.ld8(s));
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kInflateThreads)
 inflate_tiles_kernel(const __grid_constant__ InflateParams p)
 {
@@ -270,6 +309,17 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
     d.tile_w = pt.tile_w;
     d.tw_shift = pt.tw_shift;
     d.rows16 = (pt.tile_w & 15) == 0;
+    // older history: the tile's own rectangle of the plane when all of it is stored there, else a scratch copy
+    const int sidx = p.scratch_index ? p.scratch_index[tile] : -1;
+    d.scratch = sidx >= 0;
+    if (d.scratch) {
+        d.hist = p.scratch + (size_t)sidx * (size_t)p.scratch_stride;
+        d.hist_pitch = (size_t)pt.tile_w;
+    }
+    else {
+        d.hist = pt.dst + (ptrdiff_t)d.dy0 * (ptrdiff_t)p.pitch + d.dx0;
+        d.hist_pitch = p.pitch;
+    }
 
     const uint32_t size = p.sizes[tile];
     if (size == 0) {
@@ -288,8 +338,16 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
     const uint8_t *base = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15);
     const uint32_t first = (uint32_t)(src - base);
     const uint32_t out_end = (uint32_t)pt.tile_w * (uint32_t)pt.tile_h;
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         sm.writer_err = 0;
+        for (int k = 0; k < 2; k++) {
+            mbar_init(smem_u32(&sm.bar_full[k]), 1);
+            mbar_init(smem_u32(&sm.bar_empty[k]), 1);
+            mbar_init(smem_u32(&sm.bar_ready[k]), 1);
+            mbar_init(smem_u32(&sm.bar_done[k]), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     if (warp == 0) {
@@ -309,6 +367,9 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
         if (lane == 0)
             s.err = read_zlib_header(s, sm.ring, first);
         int b = 0;
+        uint32_t use = 0;               // hand-overs so far: buffer b = use & 1 is on its (use >> 1)-th use
+        // waiting for the phase BEFORE a barrier's first one returns at once: the first use of a buffer does not block
+        auto wait_empty = [&]() { warp_wait(&sm.bar_empty[b], ((use >> 1) + 1u) & 1u); };
         for (;;) {
             top_up(__shfl_sync(full, s.cons, 0));
             if (lane == 0 && !s.err && sm.writer_err)
@@ -352,7 +413,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                 }
             }
             else {
-                bar_sync_empty(b);
+                wait_empty();
                 acquired = true;
                 if (lane == 0)
                     n = decode_symbols(s, sm.ring, sm.t, sm.queue[b], &ev);
@@ -361,7 +422,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
             }
             if (post) {
                 if (!acquired)
-                    bar_sync_empty(b);
+                    wait_empty();
                 if (lane == 0) {
                     sm.meta[b][0] = n;
                     sm.meta[b][1] = ev;
@@ -370,9 +431,9 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                     sm.meta[b][4] = s.err;
                     sm.meta[b][5] = fin;
                 }
-                __syncwarp();
-                bar_arrive_full(b);
+                warp_signal(&sm.bar_full[b], lane);
                 b ^= 1;
+                use++;
                 if (ev == kEvEnd || ev == kEvError || (ev == kEvStored && fin))
                     break;
             }
@@ -387,17 +448,16 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
     }
     else if (warp == 2) {
         // ------------------------------------------------------------------ flusher warp: ring pieces -> plane
-        bar_arrive_done(0);
-        bar_arrive_done(1);
         uint32_t s1 = 1u, s2 = 0u;
-        for (int k = 0;; k ^= 1) {
-            bar_sync_ready(k);
+        for (uint32_t n = 0;; n++) {
+            const int k = (int)(n & 1u);
+            warp_wait(&sm.bar_ready[k], (n >> 1) & 1u);
             const uint32_t pos = sm.fl_pos[k], len = sm.fl_len[k];
             if (len == 0)
                 break;
             inflate_flush(sm.window, d, pos, len, lane);
             inflate_adler_piece(sm.window, pos, len, lane, s1, s2);
-            bar_arrive_done(k);
+            warp_signal(&sm.bar_done[k], lane);
         }
         if (lane == 0)
             sm.adler_got = (s2 << 16) | s1;
@@ -406,29 +466,35 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
         // ------------------------------------------------------------------ writer warp
         Ring window;
         window.base = (uint32_t)__cvta_generic_to_shared(sm.window);
-        bar_arrive_empty(0);
-        bar_arrive_empty(1);
         uint32_t out_base = 0, flushed = 0;
-        int npost = 0;
-        // hands ring piece [pos, pos + len) to the flusher warp (len 0: no more pieces); at most two are in flight
+        uint32_t npost = 0;
+        // hands ring piece [pos, pos + len) to the flusher warp (len 0: no more pieces).  At most two are in flight:
+        // slot k is reused only after its previous piece has been stored, which is also what keeps the ring positions
+        // the writer is about to overwrite -- and the plane bytes a far match reads -- valid (inflate_core.h)
         auto post = [&](uint32_t pos, uint32_t len) {
-            const int k = npost & 1;
-            bar_sync_done(k);
+            const int k = (int)(npost & 1u);
+            warp_wait(&sm.bar_done[k], ((npost >> 1) + 1u) & 1u);
             if (lane == 0) {
                 sm.fl_pos[k] = pos;
                 sm.fl_len[k] = len;
             }
-            __syncwarp();
-            bar_arrive_ready(k);
+            warp_signal(&sm.bar_ready[k], lane);
             npost++;
         };
+        auto post_upto = [&](uint32_t pos) {
+            while (flushed + kFlushChunk <= pos) {
+                if (p.probe != 2)
+                    post(flushed, kFlushChunk);
+                flushed += kFlushChunk;
+            }
+        };
         int werr = 0, b = 0;
-        for (;;) {
-            bar_sync_full(b);
+        for (uint32_t use = 0;; use++) {
+            warp_wait(&sm.bar_full[b], (use >> 1) & 1u);
             const int n = sm.meta[b][0], ev = sm.meta[b][1], derr = sm.meta[b][4], fin = sm.meta[b][5];
             const uint32_t so = (uint32_t)sm.meta[b][2], sl = (uint32_t)sm.meta[b][3];
             const uint32_t sym = lane < n ? sm.queue[b][lane] : 0u;
-            bar_arrive_empty(b);
+            warp_signal(&sm.bar_empty[b], lane);
             b ^= 1;
 
             if (n > 0 && !werr && p.probe == 1) {
@@ -447,38 +513,35 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                 const uint32_t start = out_base + inc - l;
                 const uint32_t total = __shfl_sync(full, inc, 31);
                 const unsigned bad = __ballot_sync(full, is_match && sym_dist(sym) > start);
-                const unsigned far = __ballot_sync(full, sym_is_far(sym));
                 if (out_base + total > out_end)
                     werr = kErrOverflow;
                 else if (bad)
                     werr = kErrDistance;
-                else if (!far) {
-                    if (lane < n && !is_match)
-                        window.st8(start, sym);
-                    __syncwarp();
-                    unsigned mm = __ballot_sync(full, is_match);
-                    while (mm) {
-                        const int owner = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        const uint32_t ms = __shfl_sync(full, sym, owner);
-                        const uint32_t mp = __shfl_sync(full, start, owner);
-                        inflate_copy(window, mp, ms & 0x1FFu, sym_dist(ms), lane);
-                    }
-                }
                 else {
-                    // A match reaches far back: hoisting ALL literals of the batch could overwrite history it still
-                    // reads.  The batch is cut behind every such match; inside a part the literals (all in front of the
-                    // far match that ends it) are hoisted as usual, then its matches run in order.
-                    unsigned rest = n >= 32 ? 0xffffffffu : (1u << n) - 1u;
-                    const unsigned matches = __ballot_sync(full, is_match);
-                    while (rest) {
-                        const unsigned f = far & rest;
-                        const int end = f ? __ffs(f) - 1 : 31 - __clz(rest);
-                        const unsigned part = rest & ((2u << end) - 1u);
-                        if (((part >> lane) & 1u) && !is_match)
+                    // The batch runs in parts (inflate_core.h): per part all literals at once, then the matches that
+                    // start below the ring (read back from the plane, independent of the part), then the others in
+                    // stream order; the finished pieces of the ring go to the flusher after every part.
+                    const uint32_t my_part = lane < n ? (inc - 1u) / (uint32_t)kPart : 0xFFFFFFFFu;
+                    const uint32_t nparts = (total - 1u) / (uint32_t)kPart + 1u;
+                    for (uint32_t pid = 0; pid < nparts; pid++) {
+                        const unsigned members = __ballot_sync(full, my_part == pid);
+                        if (!members)
+                            continue;
+                        const uint32_t p1 = out_base + __shfl_sync(full, inc, 31 - __clz(members));
+                        const bool mine = ((members >> lane) & 1u) != 0u;
+                        if (mine && !is_match)
                             window.st8(start, sym);
                         __syncwarp();
-                        unsigned mm = matches & part;
+                        const unsigned mm_all = __ballot_sync(full, mine && is_match);
+                        unsigned far = __ballot_sync(full, mine && is_match && byte_from_plane(start - sym_dist(sym), p1));
+                        unsigned mm = mm_all & ~far;
+                        while (far) {
+                            const int owner = __ffs(far) - 1;
+                            far &= far - 1;
+                            const uint32_t ms = __shfl_sync(full, sym, owner);
+                            const uint32_t mp = __shfl_sync(full, start, owner);
+                            inflate_copy_far(window, d, mp, ms & 0x1FFu, sym_dist(ms), p1, lane);
+                        }
                         while (mm) {
                             const int owner = __ffs(mm) - 1;
                             mm &= mm - 1;
@@ -486,16 +549,9 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                             const uint32_t mp = __shfl_sync(full, start, owner);
                             inflate_copy(window, mp, ms & 0x1FFu, sym_dist(ms), lane);
                         }
-                        rest &= ~part;
+                        post_upto(p1);
                     }
-                }
-                if (!werr) {
                     out_base += total;
-                    while (flushed + kFlushChunk <= out_base) {
-                        if (p.probe != 2)
-                            post(flushed, kFlushChunk);
-                        flushed += kFlushChunk;
-                    }
                 }
             }
             if (ev == kEvStored && !werr) {
@@ -505,16 +561,13 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                     // raw bytes: global -> history ring, flushed piecewise (a stored block can exceed the ring)
                     uint32_t done = 0;
                     while (done < sl) {
-                        const uint32_t m = min(sl - done, kFlushChunk);
+                        const uint32_t m = min(sl - done, (uint32_t)kPart);
                         for (uint32_t i = lane; i < m; i += 32u)
                             window.st8(out_base + i, base[so + done + i]);
                         __syncwarp();
                         out_base += m;
                         done += m;
-                        while (flushed + kFlushChunk <= out_base) {
-                            post(flushed, kFlushChunk);
-                            flushed += kFlushChunk;
-                        }
+                        post_upto(out_base);
                     }
                 }
             }
@@ -531,7 +584,7 @@ inflate_tiles_kernel(const __grid_constant__ InflateParams p)
                 break;
             }
         }
-        if (!werr && flushed < out_end) {
+        if (!werr && flushed < out_end && p.probe != 2) {
             __syncwarp();
             post(flushed, out_end - flushed);
         }

@@ -42,22 +42,30 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
         if (pos < out_len)
             out[pos] = b;
     };
-    // the flusher warp's checksum: finished 4 KB pieces of the ring, (byte sum, position-weighted sum) per piece
-    uint32_t s1 = 1, s2 = 0, summed = 0;
-    auto sum_pieces = [&](uint32_t upto, bool all) {
-        while (summed + 4096u <= upto || (all && summed < upto)) {
-            const uint32_t n = summed + 4096u <= upto ? 4096u : upto - summed;
-            uint64_t a = 0, b = 0;
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t d = window[(summed + i) & (kWindow - 1)];
-                a += d;
-                b += (uint64_t)(n - i) * d;
-            }
-            adler_advance(s1, s2, n, a, b);
-            summed += n;
+    // the flusher warp's checksum: (byte sum, position-weighted sum) of every piece it stores
+    uint32_t s1 = 1, s2 = 0;
+    auto sum_piece = [&](uint32_t from, uint32_t n) {
+        uint64_t a = 0, b = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t d = window[(from + i) & (kWindow - 1)];
+            a += d;
+            b += (uint64_t)(n - i) * d;
+        }
+        adler_advance(s1, s2, n, a, b);
+    };
+    // the plane as the flusher warp fills it: pieces of kPiece bytes, at most two in flight -- a piece counts as
+    // stored (readable by a far match) only once the writer has posted two younger ones, the guarantee the device has
+    std::vector<uint8_t> plane((size_t)out_len + kWindow + 64, 0xCD);
+    uint32_t posted = 0, plane_done = 0;
+    auto flush_upto = [&](uint32_t upto) {
+        while (posted + (uint32_t)kPiece <= upto) {
+            for (uint32_t i = 0; i < (uint32_t)kPiece; i++)
+                plane[posted + i] = window[(posted + i) & (kWindow - 1)];
+            sum_piece(posted, (uint32_t)kPiece);
+            posted += (uint32_t)kPiece;
+            plane_done = posted >= 2u * (uint32_t)kPiece ? posted - 2u * (uint32_t)kPiece : 0u;
         }
     };
-
     DecodeLane s;
     lane_init(s, first, first + size);
     top_up(first & ~3u);
@@ -113,11 +121,12 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
 
         // ---- writer warp
         if (n > 0 && !werr) {
-            uint32_t start[kQueue], pos = out_base;
+            uint32_t start[kQueue], end[kQueue], pos = out_base;
             bool bad = false;
             for (int k = 0; k < n; k++) {
                 start[k] = pos;
                 pos += sym_len(queue[k]);
+                end[k] = pos;
                 if (sym_is_match(queue[k]) && sym_dist(queue[k]) > start[k])
                     bad = true;
             }
@@ -126,52 +135,77 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
             else if (bad)
                 werr = kErrDistance;
             else {
-                // as the writer warp does it: the batch is cut behind every far match; inside a part all literals
-                // are written first, then the part's matches in order (one part = the whole batch without far matches)
-                int lo = 0;
-                while (lo < n) {
-                    int hi = lo;
-                    while (hi < n - 1 && !sym_is_far(queue[hi]))
-                        hi++;
+                // as the writer warp does it (inflate_core.h): the batch runs in parts; per part all literals first,
+                // then the matches that start below the ring (read from the plane), then the others in order
+                const uint32_t nparts = (pos - out_base - 1u) / (uint32_t)kPart + 1u;
+                for (uint32_t pid = 0; pid < nparts && !werr; pid++) {
+                    int lo = -1, hi = -1;
+                    for (int k = 0; k < n; k++)
+                        if ((end[k] - out_base - 1u) / (uint32_t)kPart == pid) {
+                            if (lo < 0)
+                                lo = k;
+                            hi = k;
+                        }
+                    if (lo < 0)
+                        continue;
+                    const uint32_t p1 = end[hi];
                     for (int k = lo; k <= hi; k++)
                         if (!sym_is_match(queue[k]))
                             emit(start[k], (uint8_t)(queue[k] & 255u));
-                    for (int k = lo; k <= hi; k++) {
-                        if (!sym_is_match(queue[k]))
-                            continue;
-                        nmatch++;
-                        const uint32_t len = queue[k] & 0x1FFu, dist = sym_dist(queue[k]), mp = start[k];
-                        if (dist >= len) {
-                            std::vector<uint8_t> tmp(len);
-                            for (uint32_t j = 0; j < len; j++)
-                                tmp[j] = window[(mp - dist + j) & (kWindow - 1)];
-                            for (uint32_t j = 0; j < len; j++)
-                                emit(mp + j, tmp[j]);
-                        }
-                        else if (dist >= 32u) {
-                            const uint32_t stepw = dist >= 128u ? 128u : 32u;
-                            for (uint32_t b = 0; b < len; b += stepw) {
-                                uint8_t tmp[128];
-                                const uint32_t m = len - b < stepw ? len - b : stepw;
-                                for (uint32_t j = 0; j < m; j++)
-                                    tmp[j] = window[(mp - dist + b + j) & (kWindow - 1)];
-                                for (uint32_t j = 0; j < m; j++)
-                                    emit(mp + b + j, tmp[j]);
+                    for (int pass = 0; pass < 2 && !werr; pass++)
+                        for (int k = lo; k <= hi && !werr; k++) {
+                            if (!sym_is_match(queue[k]))
+                                continue;
+                            const uint32_t len = queue[k] & 0x1FFu, dist = sym_dist(queue[k]), mp = start[k];
+                            const bool far = byte_from_plane(mp - dist, p1);
+                            if (far != (pass == 0))
+                                continue;
+                            nmatch++;
+                            if (far) {
+                                std::vector<uint8_t> tmp(len);
+                                for (uint32_t j = 0; j < len; j++) {
+                                    const uint32_t sp = mp - dist + j;
+                                    if (byte_from_plane(sp, p1)) {
+                                        if (sp >= plane_done)
+                                            werr = 99;              // would read a byte the flusher has not stored yet
+                                        tmp[j] = plane[sp];
+                                    }
+                                    else
+                                        tmp[j] = window[sp & (kWindow - 1)];
+                                }
+                                for (uint32_t j = 0; j < len; j++)
+                                    emit(mp + j, tmp[j]);
+                            }
+                            else if (dist >= len) {
+                                std::vector<uint8_t> tmp(len);
+                                for (uint32_t j = 0; j < len; j++)
+                                    tmp[j] = window[(mp - dist + j) & (kWindow - 1)];
+                                for (uint32_t j = 0; j < len; j++)
+                                    emit(mp + j, tmp[j]);
+                            }
+                            else if (dist >= 32u) {
+                                const uint32_t stepw = dist >= 128u ? 128u : 32u;
+                                for (uint32_t b = 0; b < len; b += stepw) {
+                                    uint8_t tmp[128];
+                                    const uint32_t m = len - b < stepw ? len - b : stepw;
+                                    for (uint32_t j = 0; j < m; j++)
+                                        tmp[j] = window[(mp - dist + b + j) & (kWindow - 1)];
+                                    for (uint32_t j = 0; j < m; j++)
+                                        emit(mp + b + j, tmp[j]);
+                                }
+                            }
+                            else {
+                                uint8_t pat[32];
+                                for (uint32_t j = 0; j < dist; j++)
+                                    pat[j] = window[(mp - dist + j) & (kWindow - 1)];
+                                for (uint32_t i = 0; i < len; i++)
+                                    emit(mp + i, pat[i % dist]);
                             }
                         }
-                        else {
-                            uint8_t pat[32];
-                            for (uint32_t j = 0; j < dist; j++)
-                                pat[j] = window[(mp - dist + j) & (kWindow - 1)];
-                            for (uint32_t i = 0; i < len; i++)
-                                emit(mp + i, pat[i % dist]);
-                        }
-                    }
-                    lo = hi + 1;
+                    flush_upto(p1);
                 }
                 nsym += (uint64_t)n;
                 out_base = pos;
-                sum_pieces(out_base, false);
             }
         }
         if (ev == kEvStored && !werr) {
@@ -180,8 +214,8 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
             else {
                 for (uint32_t i = 0; i < sl; i++) {
                     emit(out_base + i, base[so + i]);
-                    if (((out_base + i + 1) & 4095u) == 0)
-                        sum_pieces(out_base + i + 1, false);
+                    if (((out_base + i + 1) % (uint32_t)kPart) == 0 || i + 1 == sl)
+                        flush_upto(out_base + i + 1);
                 }
                 out_base += sl;
             }
@@ -191,7 +225,8 @@ extern "C" int gcn10_test_inflate(const uint8_t *stream, uint32_t size, uint32_t
                 werr = kErrShort;
             if (!werr) {
                 // decoder lane: the trailer behind the final block; flusher: the sum over everything decoded
-                sum_pieces(out_base, true);
+                if (posted < out_base)
+                    sum_piece(posted, out_base - posted);         // the last, partial piece
                 uint32_t want = 0;
                 top_up(s.cons);
                 if (!read_adler_trailer(s, ring, &want))
