@@ -327,6 +327,17 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
         cq[s] = in ? __ldg(rowp + s) : 0;
     }
 
+    // this thread's 16 HSG columns, relative to the staged box (one byte each): loaded once, not per HSG row
+    uint32_t box_col[4] = { 0, 0, 0, 0 };
+    if (kNarrow && staged && (kBulk || active)) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int4 c4 = __ldg(reinterpret_cast<const int4 *>(p.col_idx + x0) + j);
+            box_col[j] = (uint32_t)(c4.x - ci_min) | ((uint32_t)(c4.y - ci_min) << 8) | ((uint32_t)(c4.z - ci_min) << 16) |
+                         ((uint32_t)(c4.w - ci_min) << 24);
+        }
+    }
+
     __syncthreads();            // the mbarrier is initialised
     mbar_wait(s_bar, 0);
 
@@ -365,23 +376,37 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
             // new HSG row: gather this thread's 16 soil codes (cn.c:230) and turn them into
             // LUT slots for each drainage condition (cn.c:88-111)
             cj_cur = cj;
-            const int4 *cp = reinterpret_cast<const int4 *>(p.col_idx + x0);
             const uint8_t *row_g = p.hsg + (size_t)cj * p.hsg_pitch;
-            const int row_s = kSmemHsgOff + (cj - cj_min) * kBoxCols - ci_min;
+            const uint32_t row_s = s_hsg + (uint32_t)((cj - cj_min) * kBoxCols);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int4 c4 = __ldg(cp + j);
-                const int cc[4] = { c4.x, c4.y, c4.z, c4.w };
                 uint32_t acc[G];
 #pragma unroll
                 for (int g = 0; g < G; g++)
                     acc[g] = 0;
+                if (kNarrow && staged) {
+                    // the columns inside the staged box were packed into four registers before the row loop:
+                    // no global load is left on this path
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t hv = staged ? (uint32_t)smem[row_s + cc[q]] : (uint32_t)__ldg(row_g + cc[q]);
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t hv;
+                        asm("ld.shared.u8 %0, [%1];" : "=r"(hv) : "r"(row_s + ((box_col[j] >> (8 * q)) & 0xFFu)));
 #pragma unroll
-                    for (int g = 0; g < G; g++)
-                        acc[g] |= (soil_slot(hv, p.group_drained[g]) << kSlotShift) << (8 * q);
+                        for (int g = 0; g < G; g++)
+                            acc[g] |= (soil_slot(hv, p.group_drained[g]) << kSlotShift) << (8 * q);
+                    }
+                }
+                else {
+                    const int4 c4 = __ldg(reinterpret_cast<const int4 *>(p.col_idx + x0) + j);
+                    const int cc[4] = { c4.x, c4.y, c4.z, c4.w };
+                    const int row_off_s = kSmemHsgOff + (cj - cj_min) * kBoxCols - ci_min;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t hv = staged ? (uint32_t)smem[row_off_s + cc[q]] : (uint32_t)__ldg(row_g + cc[q]);
+#pragma unroll
+                        for (int g = 0; g < G; g++)
+                            acc[g] |= (soil_slot(hv, p.group_drained[g]) << kSlotShift) << (8 * q);
+                    }
                 }
 #pragma unroll
                 for (int g = 0; g < G; g++)

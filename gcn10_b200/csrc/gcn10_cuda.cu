@@ -252,7 +252,7 @@ void pack_lut_records(const int tables[GCN10_NVARIANTS][256][5], unsigned varian
 // co-resident CTAs inside a narrow band of rows and leave no tail wave, long ones amortise the per-CTA
 // prologue (LUT + HSG box fills).  Bulk-store kernel: 12 rows is best for <= 9 planes (2 CTAs/SM), 32 for
 // 10..18 planes (1 CTA/SM); direct-store kernel: 12 / 16.
-int auto_rows_per_cta(int planes) { return planes > 9 ? (GCN10_BULK_STORE ? 32 : 16) : planes <= kNarrowPlanes ? 16 : 12; }
+int auto_rows_per_cta(int planes) { return planes > 9 ? (GCN10_BULK_STORE ? 32 : 16) : planes <= kNarrowPlanes ? 24 : 12; }
 
 // ---- strip hand-over ------------------------------------------------------------------------
 
@@ -1357,7 +1357,12 @@ static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *
             if (src->sizes[i] && (src->offsets[i] > src->blob_bytes || src->sizes[i] > src->blob_bytes - src->offsets[i]))
                 return fail(GCN10_EINVAL, "tile %zu lies outside the blob", ntiles + i);
         ntiles += n;
-        blob_total += round_up(src->blob_bytes, 16);
+        // parts that address the same host buffer (several sources staged in one blob) share one device copy
+        bool shared = false;
+        for (int j = 0; j < k && !shared; j++)
+            shared = parts[j].tiles.blob == src->blob && parts[j].tiles.blob_bytes == src->blob_bytes;
+        if (!shared)
+            blob_total += round_up(src->blob_bytes, 16);
         covered += (long long)pt.w * pt.h;
     }
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1389,17 +1394,26 @@ static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *
     // window pixels no part covers read as the fill value (GDAL initialises a VRT read with the band's nodata)
     if (covered < (long long)w * h)
         CUDA_TRY(cudaMemsetAsync(sl.esa_full.p, fill & 255, dpitch * (size_t)h, st));
-    size_t t0 = 0, b0 = 0;
+    size_t t0 = 0, b_next = 0, part_base[kInflateMaxParts];
     for (int k = 0; k < nparts; k++) {
         const gcn10_tile_part &pt = parts[k];
         const gcn10_tile_source *src = &pt.tiles;
         const size_t n = (size_t)src->tiles_x * src->tiles_y;
+        int same = -1;
+        for (int j = 0; j < k && same < 0; j++)
+            if (parts[j].tiles.blob == src->blob && parts[j].tiles.blob_bytes == src->blob_bytes)
+                same = j;
+        const size_t b0 = same >= 0 ? part_base[same] : b_next;
+        part_base[k] = b0;
         for (size_t i = 0; i < n; i++) {
             h_off[t0 + i] = (unsigned long long)b0 + src->offsets[i];
             h_size[t0 + i] = src->sizes[i];
         }
-        if (src->blob_bytes)
-            CUDA_TRY(cudaMemcpyAsync((uint8_t *)sl.in_blob.p + b0, src->blob, src->blob_bytes, cudaMemcpyHostToDevice, st));
+        if (same < 0) {
+            if (src->blob_bytes)
+                CUDA_TRY(cudaMemcpyAsync((uint8_t *)sl.in_blob.p + b0, src->blob, src->blob_bytes, cudaMemcpyHostToDevice, st));
+            b_next += round_up(src->blob_bytes, 16);
+        }
         for (size_t i = 0; i < n; i++) {
             const long long tx0 = (long long)(i % (size_t)src->tiles_x) * src->tile_w - src->x_off;
             const long long ty0 = (long long)(i / (size_t)src->tiles_x) * src->tile_h - src->y_off;
@@ -1420,7 +1434,6 @@ static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *
         q.w = pt.w;
         q.h = pt.h;
         t0 += n;
-        b0 += round_up(src->blob_bytes, 16);
     }
     // longest streams first: a tile's decode time grows with its compressed size, and a block has only a
     // few tiles per resident CTA slot, so the order sets the tail
