@@ -65,6 +65,10 @@ def main():
     ap.add_argument("--variants", type=int, default=8)
     ap.add_argument("--check", type=int, default=1, help="oracle check of one tile row of each rank's first block")
     a = ap.parse_args()
+    # stdout carries exactly one JSON line: NCCL prints its version banner to stdout on the first collective
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank, local_rank, world = gdist.env_world()
     torch.cuda.set_device(local_rank)
@@ -276,7 +280,7 @@ def main():
             "d2h_bytes_total": int(d2h), "h2d_bytes_per_block": int(total + 2 * 36 * 22000),
             "window_shapes_rank0": shape_list, "parts_per_block_rank0": sorted(nparts_hist.items()),
             "setup_seconds": t_setup, "oracle_check": check_msg,
-        }), flush=True)
+        }), file=real_stdout, flush=True)
     ctx.close()
     blob_pin.free()
     group.close()
