@@ -87,6 +87,19 @@ typedef struct gh_tiff gh_tiff;
 int gh_tiff_open(const char *path, gh_tiff **out, char *err, size_t errlen);
 int gh_tiff_size(const gh_tiff *t, int *w, int *h);
 int gh_tiff_geotransform(const gh_tiff *t, double gt[6]);
+/* The file's GeoTIFF georeferencing tags (34735 GeoKeyDirectory, 34736 GeoDoubleParams, 34737 GeoAsciiParams) as they
+ * lie in it; the pointers stay valid while the dataset is open.  0 ok, 1 = the file has none.  The block pipeline
+ * hands them to its outputs, as the reference copies the source dataset's projection into every raster it writes
+ * (raster.c:164-165, 212-214).  A source tagged RasterPixelIsPoint gets GDAL's half-pixel shift in gh_tiff_geotransform. */
+typedef struct {
+    const uint16_t *keys;
+    size_t n_keys;
+    const double *doubles;
+    size_t n_doubles;
+    const char *ascii;
+    size_t n_ascii;
+} gh_geokeys;
+int gh_tiff_geokeys(const gh_tiff *t, gh_geokeys *out);
 /* Reads a pixel window into dst (row pitch in bytes); threads > 1 decodes tiles in parallel. */
 int gh_tiff_read_window(gh_tiff *t, int xoff, int yoff, int xcount, int ycount, uint8_t *dst, size_t pitch,
                         int threads, char *err, size_t errlen);
@@ -119,6 +132,8 @@ int gh_raster_geotransform(const gh_raster *r, double gt[6]);
 int gh_raster_is_mosaic(const gh_raster *r);
 int gh_raster_source_count(const gh_raster *r);
 int gh_raster_fill(const gh_raster *r);         /* value of pixels no source covers (VRT NoDataValue, else 0) */
+/* georeferencing tags of the raster (a mosaic: of its first source that is open); 0 ok, 1 = none */
+int gh_raster_geokeys(const gh_raster *r, gh_geokeys *out);
 /* GDALRasterIO(GF_Read) of a window (raster.c:177-179), decoded on the host. */
 int gh_raster_read_window(gh_raster *r, int xoff, int yoff, int xcount, int ycount, uint8_t *dst, size_t pitch,
                           int threads, char *err, size_t errlen);

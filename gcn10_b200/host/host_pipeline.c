@@ -178,6 +178,12 @@ static int open_writers(worker *wk)
             gh_log_message(wk->log, "ERROR", err, 1);                               /* raster.c:220-223 */
             break;
         }
+        /* the land cover's projection goes into every output (raster.c:164-165, 212-214) */
+        gh_geokeys gk;
+        pthread_mutex_lock(&wk->rmu);
+        if (wk->esa_r && gh_raster_geokeys(wk->esa_r, &gk) == 0)
+            gh_tiffw_set_geokeys(wk->writers[k], &gk);
+        pthread_mutex_unlock(&wk->rmu);
         opened++;
     }
     if (opened < NPLANES) {

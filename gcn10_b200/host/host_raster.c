@@ -340,6 +340,17 @@ int gh_raster_is_mosaic(const gh_raster *r) { return r->single == NULL; }
 int gh_raster_source_count(const gh_raster *r) { return r->single ? 1 : r->nsrc; }
 int gh_raster_fill(const gh_raster *r) { return r->fill; }
 
+int gh_raster_geokeys(const gh_raster *r, gh_geokeys *out)
+{
+    memset(out, 0, sizeof *out);
+    if (r->single)
+        return gh_tiff_geokeys(r->single, out);
+    for (int i = 0; i < r->nsrc; i++)
+        if (r->src[i].ds)
+            return gh_tiff_geokeys(r->src[i].ds, out);
+    return 1;
+}
+
 void gh_raster_close(gh_raster *r)
 {
     if (!r)

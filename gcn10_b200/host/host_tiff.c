@@ -40,46 +40,126 @@ static void set_err(char *err, size_t errlen, const char *fmt, ...)
 
 typedef void (*job_fn)(void *arg, int index);
 
+/* Every calling thread (a GPU worker, its loader, its band reader) owns a small pool of helper threads that lives as
+ * long as the caller: the tile sinks run a parallel-for per strip, 18 strips per block, and creating the helpers anew
+ * each time cost more than the work they did.  A job is "run fn(arg, i) for i in [0, n)"; indices are handed out under
+ * the pool's mutex, the caller takes part, and returns when all indices are done. */
 typedef struct {
+    pthread_mutex_t mu;
+    pthread_cond_t work, idle;
+    pthread_t *th;
+    int nthreads;               /* helpers */
     job_fn fn;
     void *arg;
-    int n;
-    int next;
-    pthread_mutex_t mu;
+    int n, next, active, generation, quit;
+    int limit;                  /* helpers allowed to join the current job */
 } job_pool;
 
-static void *job_worker(void *p)
+static pthread_key_t g_pool_key;
+static pthread_once_t g_pool_once = PTHREAD_ONCE_INIT;
+
+static void *pool_helper(void *p)
 {
     job_pool *jp = p;
+    int seen = 0;
+    pthread_mutex_lock(&jp->mu);
     for (;;) {
-        pthread_mutex_lock(&jp->mu);
-        int i = jp->next++;
-        pthread_mutex_unlock(&jp->mu);
-        if (i >= jp->n)
-            return NULL;
-        jp->fn(jp->arg, i);
+        while (!jp->quit && (jp->generation == seen || jp->next >= jp->n || jp->active >= jp->limit))
+            pthread_cond_wait(&jp->work, &jp->mu);
+        if (jp->quit)
+            break;
+        seen = jp->generation;
+        jp->active++;
+        while (jp->next < jp->n) {
+            int i = jp->next++;
+            pthread_mutex_unlock(&jp->mu);
+            jp->fn(jp->arg, i);
+            pthread_mutex_lock(&jp->mu);
+        }
+        jp->active--;
+        if (jp->active == 0)
+            pthread_cond_signal(&jp->idle);
     }
+    pthread_mutex_unlock(&jp->mu);
+    return NULL;
+}
+
+static void pool_destroy(void *p)
+{
+    job_pool *jp = p;
+    if (!jp)
+        return;
+    pthread_mutex_lock(&jp->mu);
+    jp->quit = 1;
+    pthread_cond_broadcast(&jp->work);
+    pthread_mutex_unlock(&jp->mu);
+    for (int t = 0; t < jp->nthreads; t++)
+        pthread_join(jp->th[t], NULL);
+    pthread_mutex_destroy(&jp->mu);
+    pthread_cond_destroy(&jp->work);
+    pthread_cond_destroy(&jp->idle);
+    free(jp->th);
+    free(jp);
+}
+
+static void pool_key_init(void) { pthread_key_create(&g_pool_key, pool_destroy); }
+
+/* the calling thread's pool, grown to at least `helpers` helper threads */
+static job_pool *pool_get(int helpers)
+{
+    pthread_once(&g_pool_once, pool_key_init);
+    job_pool *jp = pthread_getspecific(g_pool_key);
+    if (!jp) {
+        jp = calloc(1, sizeof *jp);
+        if (!jp)
+            return NULL;
+        pthread_mutex_init(&jp->mu, NULL);
+        pthread_cond_init(&jp->work, NULL);
+        pthread_cond_init(&jp->idle, NULL);
+        pthread_setspecific(g_pool_key, jp);
+    }
+    if (jp->nthreads < helpers) {
+        pthread_t *th = realloc(jp->th, sizeof(pthread_t) * (size_t)helpers);
+        if (!th)
+            return jp;
+        jp->th = th;
+        while (jp->nthreads < helpers) {
+            if (pthread_create(&jp->th[jp->nthreads], NULL, pool_helper, jp) != 0)
+                break;
+            jp->nthreads++;
+        }
+    }
+    return jp;
 }
 
 static void parallel_for(int n, int threads, job_fn fn, void *arg)
 {
     if (threads > n)
         threads = n;
-    if (threads <= 1) {
+    job_pool *jp = threads > 1 ? pool_get(threads - 1) : NULL;
+    if (!jp || jp->nthreads == 0) {
         for (int i = 0; i < n; i++)
             fn(arg, i);
         return;
     }
-    job_pool jp = { fn, arg, n, 0, PTHREAD_MUTEX_INITIALIZER };
-    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)threads);
-    int started = 0;
-    for (int t = 0; t < threads - 1; t++)
-        if (pthread_create(&th[started], NULL, job_worker, &jp) == 0)
-            started++;
-    job_worker(&jp);
-    for (int t = 0; t < started; t++)
-        pthread_join(th[t], NULL);
-    free(th);
+    pthread_mutex_lock(&jp->mu);
+    jp->fn = fn;
+    jp->arg = arg;
+    jp->n = n;
+    jp->next = 0;
+    jp->limit = threads - 1;
+    jp->generation++;
+    pthread_cond_broadcast(&jp->work);
+    while (jp->next < jp->n) {                 /* the caller works too */
+        int i = jp->next++;
+        pthread_mutex_unlock(&jp->mu);
+        fn(arg, i);
+        pthread_mutex_lock(&jp->mu);
+    }
+    while (jp->active > 0)
+        pthread_cond_wait(&jp->idle, &jp->mu);
+    jp->n = 0;                                  /* late wakers find nothing to do */
+    pthread_mutex_unlock(&jp->mu);
 }
 
 void gh_parallel_for(int n, int threads, void (*fn)(void *arg, int index), void *arg)
@@ -100,6 +180,15 @@ struct gh_tiff {
     uint64_t nchunks;
     int has_gt;
     double gt[6];
+    /* GeoTIFF georeferencing tags as they lie in the file (34735 key directory, 34736 double params, 34737 ascii
+     * params): handed to the outputs verbatim, as the reference copies the source's projection (raster.c:164-165,
+     * 212-214) */
+    uint16_t *geo_keys;
+    size_t n_geo_keys;
+    double *geo_doubles;
+    size_t n_geo_doubles;
+    char *geo_ascii;
+    size_t n_geo_ascii;
 };
 
 static uint16_t rd16(const gh_tiff *t, const unsigned char *p)
@@ -177,7 +266,7 @@ static int entry_values(gh_tiff *t, int type, uint64_t count, const unsigned cha
         uint64_t uv = 0;
         double dv = 0;
         switch (type) {
-        case 1: case 7: uv = p[0]; dv = (double)uv; break;
+        case 1: case 2: case 7: uv = p[0]; dv = (double)uv; break;
         case 3: uv = rd16(t, p); dv = (double)uv; break;
         case 4: case 13: uv = rd32(t, p); dv = (double)uv; break;
         case 16: case 18: uv = rd64(t, p); dv = (double)uv; break;
@@ -258,6 +347,38 @@ int gh_tiff_open(const char *path, gh_tiff **out, char *err, size_t errlen)
         case 33550: have_scale = entry_values(t, type, count, val, vlen, NULL, scale, 3) == 0 && count >= 2; break;
         case 33922: have_tie = entry_values(t, type, count, val, vlen, NULL, tie, 6) == 0 && count >= 6; break;
         case 34264: have_xf = entry_values(t, type, count, val, vlen, NULL, xf, 16) == 0 && count >= 16; break;
+        case 34735:
+            if (type == 3 && count >= 4 && count < 4096 && !t->geo_keys) {
+                uint64_t *tmp = malloc(sizeof(uint64_t) * (size_t)count);
+                t->geo_keys = malloc(sizeof(uint16_t) * (size_t)count);
+                if (tmp && t->geo_keys && entry_values(t, type, count, val, vlen, tmp, NULL, count) == 0) {
+                    for (uint64_t k = 0; k < count; k++)
+                        t->geo_keys[k] = (uint16_t)tmp[k];
+                    t->n_geo_keys = (size_t)count;
+                }
+                free(tmp);
+            }
+            break;
+        case 34736:
+            if (type == 12 && count > 0 && count < 4096 && !t->geo_doubles) {
+                t->geo_doubles = malloc(sizeof(double) * (size_t)count);
+                if (t->geo_doubles && entry_values(t, type, count, val, vlen, NULL, t->geo_doubles, count) == 0)
+                    t->n_geo_doubles = (size_t)count;
+            }
+            break;
+        case 34737:
+            if (type == 2 && count > 0 && count < 65536 && !t->geo_ascii) {
+                uint64_t *tmp = malloc(sizeof(uint64_t) * (size_t)count);
+                t->geo_ascii = malloc((size_t)count + 1);
+                if (tmp && t->geo_ascii && entry_values(t, type, count, val, vlen, tmp, NULL, count) == 0) {
+                    for (uint64_t k = 0; k < count; k++)
+                        t->geo_ascii[k] = (char)tmp[k];
+                    t->geo_ascii[count] = '\0';
+                    t->n_geo_ascii = (size_t)count;
+                }
+                free(tmp);
+            }
+            break;
         default: break;
         }
     }
@@ -302,6 +423,13 @@ int gh_tiff_open(const char *path, gh_tiff **out, char *err, size_t errlen)
         t->gt[0] = tie[3] - tie[0] * scale[0];
         t->gt[3] = tie[4] + tie[1] * scale[1];
         t->has_gt = 1;
+        /* GTRasterTypeGeoKey (1025) = RasterPixelIsPoint (2): the tiepoint names a pixel CENTRE; GDAL's geotransform
+         * is that of the pixel's corner, half a pixel up and to the left */
+        for (size_t k = 4; k + 3 < t->n_geo_keys; k += 4)
+            if (t->geo_keys[k] == 1025 && t->geo_keys[k + 1] == 0 && t->geo_keys[k + 3] == 2) {
+                t->gt[0] -= 0.5 * t->gt[1];
+                t->gt[3] -= 0.5 * t->gt[5];
+            }
     }
     else if (have_xf) {
         t->gt[0] = xf[3]; t->gt[1] = xf[0]; t->gt[2] = xf[1];
@@ -332,7 +460,24 @@ void gh_tiff_close(gh_tiff *t)
         close(t->fd);
     free(t->offsets);
     free(t->counts);
+    free(t->geo_keys);
+    free(t->geo_doubles);
+    free(t->geo_ascii);
     free(t);
+}
+
+int gh_tiff_geokeys(const gh_tiff *t, gh_geokeys *out)
+{
+    memset(out, 0, sizeof *out);
+    if (!t->n_geo_keys)
+        return 1;
+    out->keys = t->geo_keys;
+    out->n_keys = t->n_geo_keys;
+    out->doubles = t->geo_doubles;
+    out->n_doubles = t->n_geo_doubles;
+    out->ascii = t->geo_ascii;
+    out->n_ascii = t->n_geo_ascii;
+    return 0;
 }
 
 /* TIFF LZW: MSB-first variable width codes (9..12 bits), 256 = clear, 257 = end of information,
@@ -578,6 +723,12 @@ enum { TILE = 256 };
 struct gh_tiffw {
     FILE *fp;
     char *path, *tmp;           /* written as <path>.part, renamed on a successful close, removed otherwise */
+    uint16_t *geo_keys;         /* georeferencing tags copied from the land-cover source, or NULL = EPSG:4326 */
+    size_t n_geo_keys;
+    double *geo_doubles;
+    size_t n_geo_doubles;
+    char *geo_ascii;
+    size_t n_geo_ascii;
     int w, h;
     int tiles_x, tiles_y;
     double gt[6];
@@ -669,6 +820,41 @@ int gh_tiffw_open(const char *path, int w, int h, const double gt[6], gh_tiffw *
     return 0;
 }
 
+int gh_tiffw_set_geokeys(gh_tiffw *tw, const gh_geokeys *gk)
+{
+    if (!tw || !gk || !gk->keys || gk->n_keys < 4)
+        return -1;
+    free(tw->geo_keys);
+    free(tw->geo_doubles);
+    free(tw->geo_ascii);
+    tw->geo_keys = malloc(sizeof(uint16_t) * gk->n_keys);
+    tw->geo_doubles = gk->n_doubles ? malloc(sizeof(double) * gk->n_doubles) : NULL;
+    tw->geo_ascii = gk->n_ascii ? malloc(gk->n_ascii) : NULL;
+    if (!tw->geo_keys || (gk->n_doubles && !tw->geo_doubles) || (gk->n_ascii && !tw->geo_ascii)) {
+        free(tw->geo_keys);
+        free(tw->geo_doubles);
+        free(tw->geo_ascii);
+        tw->geo_keys = NULL;
+        tw->geo_doubles = NULL;
+        tw->geo_ascii = NULL;
+        tw->n_geo_keys = tw->n_geo_doubles = tw->n_geo_ascii = 0;
+        return -1;
+    }
+    memcpy(tw->geo_keys, gk->keys, sizeof(uint16_t) * gk->n_keys);
+    tw->n_geo_keys = gk->n_keys;
+    if (gk->n_doubles)
+        memcpy(tw->geo_doubles, gk->doubles, sizeof(double) * gk->n_doubles);
+    tw->n_geo_doubles = gk->n_doubles;
+    if (gk->n_ascii)
+        memcpy(tw->geo_ascii, gk->ascii, gk->n_ascii);
+    tw->n_geo_ascii = gk->n_ascii;
+    /* the outputs' tiepoint is the corner of pixel (0, 0): whatever the source said, they are PixelIsArea */
+    for (size_t k = 4; k + 3 < tw->n_geo_keys; k += 4)
+        if (tw->geo_keys[k] == 1025 && tw->geo_keys[k + 1] == 0)
+            tw->geo_keys[k + 3] = 1;
+    return 0;
+}
+
 int gh_tiffw_write_rows(gh_tiffw *tw, const uint8_t *data, size_t pitch, int y0, int nrows, int threads)
 {
     if (tw->failed || y0 != tw->next_tile_row * TILE || y0 + nrows > tw->h ||
@@ -750,12 +936,19 @@ int gh_tiffw_close(gh_tiffw *tw)
             2048, 0, 1, 4326,       /* GeographicTypeGeoKey   = WGS 84              */
             2054, 0, 1, 9102,       /* GeogAngularUnitsGeoKey = degree              */
         };
-        static const char ascii[] = "WGS 84|";
+        static const char ascii_default[] = "WGS 84|";
+        const uint16_t *keys = tw->geo_keys ? tw->geo_keys : geokeys;
+        const size_t nkeys = tw->geo_keys ? tw->n_geo_keys : sizeof geokeys / 2;
+        const char *ascii = tw->geo_keys ? tw->geo_ascii : ascii_default;
+        const size_t nascii = tw->geo_keys ? tw->n_geo_ascii : sizeof ascii_default;
+        const size_t ndbl = tw->geo_keys ? tw->n_geo_doubles : 0;
         if (tw->pos & 1) { fputc(0, tw->fp); tw->pos++; }
         uint64_t off_offsets = tw->pos, off_counts = off_offsets + 4 * nt, off_scale = off_counts + 4 * nt;
-        uint64_t off_tie = off_scale + 24, off_keys = off_tie + 48, off_ascii = off_keys + sizeof geokeys;
-        uint64_t off_ifd = (off_ascii + sizeof ascii + 1) & ~(uint64_t)1;
-        size_t tail = (size_t)(off_ifd - tw->pos) + 2 + 16 * 12 + 4;
+        uint64_t off_tie = off_scale + 24, off_keys = off_tie + 48, off_dbl = off_keys + 2 * nkeys;
+        uint64_t off_ascii = off_dbl + 8 * ndbl;
+        uint64_t off_ifd = (off_ascii + nascii + 1) & ~(uint64_t)1;
+        const int nent = 14 + 1 + (ndbl ? 1 : 0) + (nascii ? 1 : 0);
+        size_t tail = (size_t)(off_ifd - tw->pos) + 2 + (size_t)nent * 12 + 4;
         unsigned char *buf = calloc(1, tail), *p = buf;
         if (buf && off_ifd + 256 < 0xFFFFFFF0ull) {
             for (size_t i = 0; i < nt; i++) put32(&p, tw->offsets[i]);
@@ -763,10 +956,12 @@ int gh_tiffw_close(gh_tiffw *tw)
             put_f64(&p, tw->gt[1]); put_f64(&p, -tw->gt[5]); put_f64(&p, 0.0);
             put_f64(&p, 0.0); put_f64(&p, 0.0); put_f64(&p, 0.0);
             put_f64(&p, tw->gt[0]); put_f64(&p, tw->gt[3]); put_f64(&p, 0.0);
-            for (size_t i = 0; i < sizeof geokeys / 2; i++) put16(&p, geokeys[i]);
-            memcpy(p, ascii, sizeof ascii);
+            for (size_t i = 0; i < nkeys; i++) put16(&p, keys[i]);
+            for (size_t i = 0; i < ndbl; i++) put_f64(&p, tw->geo_doubles[i]);
+            if (nascii)
+                memcpy(p, ascii, nascii);
             p = buf + (off_ifd - tw->pos);
-            put16(&p, 16);
+            put16(&p, (uint16_t)nent);
             put_entry(&p, 256, 4, 1, (uint32_t)tw->w);
             put_entry(&p, 257, 4, 1, (uint32_t)tw->h);
             put_entry(&p, 258, 3, 1, 8);
@@ -781,8 +976,11 @@ int gh_tiffw_close(gh_tiffw *tw)
             put_entry(&p, 339, 3, 1, 1);                /* SampleFormat = unsigned */
             put_entry(&p, 33550, 12, 3, (uint32_t)off_scale);
             put_entry(&p, 33922, 12, 6, (uint32_t)off_tie);
-            put_entry(&p, 34735, 3, (uint32_t)(sizeof geokeys / 2), (uint32_t)off_keys);
-            put_entry(&p, 34737, 2, (uint32_t)sizeof ascii, (uint32_t)off_ascii);
+            put_entry(&p, 34735, 3, (uint32_t)nkeys, (uint32_t)off_keys);
+            if (ndbl)
+                put_entry(&p, 34736, 12, (uint32_t)ndbl, (uint32_t)off_dbl);
+            if (nascii)
+                put_entry(&p, 34737, 2, (uint32_t)nascii, (uint32_t)off_ascii);
             put32(&p, 0);
             if (fwrite(buf, 1, tail, tw->fp) == tail && fseek(tw->fp, 4, SEEK_SET) == 0) {
                 unsigned char o[4], *q = o;
@@ -799,6 +997,9 @@ int gh_tiffw_close(gh_tiffw *tw)
         rc = -1;
     if (rc != 0)
         unlink(tw->tmp);
+    free(tw->geo_keys);
+    free(tw->geo_doubles);
+    free(tw->geo_ascii);
     free(tw->path);
     free(tw->tmp);
     free(tw->offsets);
@@ -815,6 +1016,9 @@ void gh_tiffw_abort(gh_tiffw *tw)
         fclose(tw->fp);
     if (tw->tmp)
         unlink(tw->tmp);
+    free(tw->geo_keys);
+    free(tw->geo_doubles);
+    free(tw->geo_ascii);
     free(tw->path);
     free(tw->tmp);
     free(tw->offsets);

@@ -13,6 +13,10 @@ typedef struct gh_tiffw gh_tiffw;
 
 /* Creates path and reserves the header; tiles are appended with gh_tiffw_write_rows. */
 int gh_tiffw_open(const char *path, int w, int h, const double gt[6], gh_tiffw **out, char *err, size_t errlen);
+/* Georeferencing tags to write instead of the default EPSG:4326 keys (copied; GTRasterTypeGeoKey is forced to
+ * PixelIsArea because the tiepoint written is a pixel corner).  Call before gh_tiffw_close. */
+#include "gcn10_host.h"
+int gh_tiffw_set_geokeys(gh_tiffw *tw, const gh_geokeys *gk);
 /* Appends rows [y0, y0+nrows): y0 must continue where the previous call stopped and be a multiple
  * of 256; nrows must be a multiple of 256 except for the last band of the raster. */
 int gh_tiffw_write_rows(gh_tiffw *tw, const uint8_t *data, size_t pitch, int y0, int nrows, int threads);

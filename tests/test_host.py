@@ -372,3 +372,61 @@ def test_geotiff_writer_leaves_no_partial_file(tmp_path):
     tw.put_tile_row(0, [z])
     tw.put_tile_row(1, [z])
     assert tw.close() == 0 and p.exists() and not (tmp_path / "cn_p_i_7.tif.part").exists()
+
+
+def test_geokeys_travel_from_the_land_cover_to_the_outputs(tmp_path):
+    """The reference copies the source dataset's projection into every raster it writes (raster.c:164-165,
+    212-214): the GeoTIFF georeferencing tags of the input are re-emitted verbatim; a RasterPixelIsPoint source gets
+    GDAL's half-pixel shift on the way in and the output is tagged PixelIsArea."""
+    import struct
+    import zlib
+    L = hostlib.load()
+    src = tmp_path / "utm.tif"
+    a = np.arange(64 * 48, dtype=np.uint8).reshape(48, 64)
+    # a striped uncompressed TIFF with a projected CRS (EPSG:32612) and RasterPixelIsPoint
+    keys = [1, 1, 0, 3, 1024, 0, 1, 1, 1025, 0, 1, 2, 3072, 0, 1, 32612]
+    data = a.tobytes()
+    ifd_off = 8 + len(data)
+    scale_off = ifd_off + 2 + 12 * 11 + 4
+    tie_off = scale_off + 24
+    keys_off = tie_off + 48
+    ents = [(256, 4, 1, 64), (257, 4, 1, 48), (258, 3, 1, 8), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, 8),
+            (277, 3, 1, 1), (279, 4, 1, len(data)), (33550, 12, 3, scale_off), (33922, 12, 6, tie_off),
+            (34735, 3, len(keys), keys_off)]
+    with open(src, "wb") as f:
+        f.write(struct.pack("<2sHI", b"II", 42, ifd_off) + data + struct.pack("<H", len(ents)))
+        for tag, typ, cnt, val in ents:
+            f.write(struct.pack("<HHIHH", tag, typ, cnt, val, 0) if typ == 3 and cnt == 1 else struct.pack("<HHII", tag, typ, cnt, val))
+        f.write(struct.pack("<I", 0) + struct.pack("<3d", 10.0, 10.0, 0.0) + struct.pack("<6d", 0, 0, 0, 500000.0, 4100000.0, 0.0)
+                + struct.pack(f"<{len(keys)}H", *keys))
+    t = hostlib.Tiff(str(src))
+    assert t.gt == (500000.0 - 5.0, 10.0, 0.0, 4100000.0 + 5.0, 0.0, -10.0)        # PixelIsPoint: half a pixel up-left
+    assert np.array_equal(t.read(), a)
+
+    class GK(hostlib.C.Structure):
+        _fields_ = [("keys", hostlib.C.c_void_p), ("n_keys", hostlib.C.c_size_t), ("doubles", hostlib.C.c_void_p),
+                    ("n_doubles", hostlib.C.c_size_t), ("ascii", hostlib.C.c_void_p), ("n_ascii", hostlib.C.c_size_t)]
+    gk = GK()
+    L.gh_tiff_geokeys.argtypes = [hostlib.C.c_void_p, hostlib.C.POINTER(GK)]
+    L.gh_tiffw_set_geokeys.argtypes = [hostlib.C.c_void_p, hostlib.C.POINTER(GK)]
+    assert L.gh_tiff_geokeys(t.h, hostlib.C.byref(gk)) == 0 and gk.n_keys == len(keys)
+    out = tmp_path / "out.tif"
+    tw = hostlib.TiffWriter(str(out), 256, 256, t.gt)
+    assert L.gh_tiffw_set_geokeys(tw.h, hostlib.C.byref(gk)) == 0
+    tw.put_tile_row(0, [zlib.compress(bytes(65536))])
+    assert tw.close() == 0
+    t.close()
+    o = hostlib.Tiff(str(out))
+    assert o.gt == (499995.0, 10.0, 0.0, 4100005.0, 0.0, -10.0)                    # written as a corner: read back unshifted
+    gk2 = GK()
+    assert L.gh_tiff_geokeys(o.h, hostlib.C.byref(gk2)) == 0
+    got = list((hostlib.C.c_uint16 * gk2.n_keys).from_address(gk2.keys))
+    assert got == keys[:11] + [1] + keys[12:]                                       # same keys, RasterType -> PixelIsArea
+    o.close()
+    # a file without geokeys: the writer keeps its EPSG:4326 default
+    hostlib.tiff_write(str(tmp_path / "plain.tif"), a, (0, 1, 0, 0, 0, -1))
+    p = hostlib.Tiff(str(tmp_path / "plain.tif"))
+    gk3 = GK()
+    assert L.gh_tiff_geokeys(p.h, hostlib.C.byref(gk3)) == 0
+    assert 4326 in list((hostlib.C.c_uint16 * gk3.n_keys).from_address(gk3.keys))
+    p.close()

@@ -15,4 +15,4 @@ ncu --set full --clock-control none --import-source on -k regex:cn_block_kernel 
 python tools/one_block.py --reps 1 > $out/${tag}_plain_block.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:inflate_tiles_kernel -c 1 -o $out/${tag}_inflate python tools/one_block.py --reps 1 > $out/${tag}_ncu_inflate.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cn_deflate_fused_kernel -s 4 -c 1 -o $out/${tag}_fused python tools/one_block.py --reps 1 > $out/${tag}_ncu_fused.log 2>&1
-tail -2 $out/${tag}_ncu_*.log
+for f in $out/${tag}_ncu_*.log; do tail -n 2 "$f"; done
