@@ -57,6 +57,9 @@ constexpr int kPrefetch = GCN10_PREFETCH;   // rows of land cover in flight per 
 #ifndef GCN10_NARROW_CTAS
 #define GCN10_NARROW_CTAS 5
 #endif
+#ifndef GCN10_NARROW_DEPTH
+#define GCN10_NARROW_DEPTH 6    // land-cover rows in flight per thread in the direct-store narrow kernels (cp.async ring)
+#endif
 
 struct BlockParams {
     const uint8_t *esa;         // first row of this launch
@@ -218,10 +221,16 @@ __host__ __device__ constexpr int smem_stage_off(int np) { return smem_bar_off(n
 // CTA and row, the per-row CTA barrier of the staged path costs more than the TMA stores save (one plane:
 // 0.93 ms staged vs 0.63 ms direct on B200), and without the stage eight CTAs fit an SM.
 __host__ __device__ constexpr bool bulk_store_for(int np, int groups) { return GCN10_BULK_STORE && np * groups > kNarrowPlanes; }
+// The direct-store narrow kernels are latency bound on the land-cover stream (ncu: long-scoreboard stalls with two
+// rows prefetched into registers), so they keep GCN10_NARROW_DEPTH rows per thread in flight through a cp.async ring in
+// shared memory instead: every thread copies, waits for and reads back only its own 16 bytes -- no CTA barrier.
+__host__ __device__ constexpr bool deep_ring_for(int np, int groups) { return GCN10_NARROW_DEPTH > 0 && !bulk_store_for(np, groups) && np <= kNarrowPlanes; }
 // np = planes per drainage condition, groups = conditions in the launch
 constexpr int smem_bytes_for(int np, int groups)
 {
-    return bulk_store_for(np, groups) ? smem_stage_off(np) + 2 * np * groups * kStripPx : smem_bar_off(np) + 16;
+    return bulk_store_for(np, groups) ? smem_stage_off(np) + 2 * np * groups * kStripPx
+           : deep_ring_for(np, groups) ? smem_stage_off(np) + GCN10_NARROW_DEPTH * kStripPx
+                                       : smem_bar_off(np) + 16;
 }
 
 template <int NP>
@@ -272,6 +281,8 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
     constexpr bool kNarrow = NP <= kNarrowPlanes;
     constexpr int kPF = (NP * G <= kNarrowPlanes) ? GCN10_NARROW_PF : kPrefetch;     // rows of land cover in flight
     constexpr bool kBulk = bulk_store_for(NP, G);
+    constexpr bool kDeep = deep_ring_for(NP, G);
+    constexpr int kDepth = kDeep ? GCN10_NARROW_DEPTH : 1;
     constexpr int kLutSize = lut_bytes_for(NP);
     constexpr int kSmemHsgOff = smem_hsg_off(NP), kSmemBarOff = smem_bar_off(NP), kSmemStageOff = smem_stage_off(NP);
     constexpr int kSlotShift = kNarrow ? 2 : 4;     // per-pixel slot byte = slot * record bytes
@@ -323,8 +334,21 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
 #pragma unroll
     for (int s = 0; s < kPF; s++) {
         const bool in = y_begin + s < y_end && (kBulk || active);
-        eq[s] = in ? ldg_stream16(esa_ptr + (size_t)s * p.esa_pitch) : make_uint4(0, 0, 0, 0);
+        if (!kDeep)
+            eq[s] = in ? ldg_stream16(esa_ptr + (size_t)s * p.esa_pitch) : make_uint4(0, 0, 0, 0);
         cq[s] = in ? __ldg(rowp + s) : 0;
+    }
+    // deep ring: slot s of this thread at ring + s * 4 KB; one commit group per row, empty when the row does not exist
+    const uint32_t ring = smem_u32(smem) + (uint32_t)smem_stage_off(NP) + (uint32_t)tid * kVecPx;
+    uint32_t ring_slot = 0;
+    if constexpr (kDeep) {
+#pragma unroll
+        for (int s = 0; s < kDepth; s++) {
+            if (active && y_begin + s < y_end)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ring + (uint32_t)s * kStripPx),
+                             "l"(esa_ptr + (size_t)s * p.esa_pitch) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
     }
 
     // this thread's 16 HSG columns, relative to the staged box (one byte each): loaded once, not per HSG row
@@ -359,15 +383,31 @@ cn_block_kernel(const __grid_constant__ BlockParams p, const __grid_constant__ C
             slot[g][j] = 0;
 
     for (int y = y_begin; y < y_end; y++) {
-        const uint4 e = eq[0];
+        uint4 e;
+        if constexpr (kDeep) {
+            // the oldest of the kDepth rows in flight has landed; read it, then reuse its slot for row y + kDepth
+            asm volatile("cp.async.wait_group %0;" :: "n"(kDepth - 1) : "memory");
+            const uint32_t at = ring + ring_slot * kStripPx;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(at) : "memory");
+            if (y + kDepth < y_end)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(at),
+                             "l"(esa_ptr + (size_t)kDepth * p.esa_pitch) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            ring_slot = ring_slot + 1 == (uint32_t)kDepth ? 0u : ring_slot + 1;
+        }
+        else {
+            e = eq[0];
+        }
         const int cj = cq[0];
 #pragma unroll
         for (int s = 0; s + 1 < kPF; s++) {
-            eq[s] = eq[s + 1];
+            if (!kDeep)
+                eq[s] = eq[s + 1];
             cq[s] = cq[s + 1];
         }
         if (y + kPF < y_end) {
-            eq[kPF - 1] = ldg_stream16(esa_ptr + (size_t)kPF * p.esa_pitch);
+            if (!kDeep)
+                eq[kPF - 1] = ldg_stream16(esa_ptr + (size_t)kPF * p.esa_pitch);
             cq[kPF - 1] = __ldg(rowp + kPF);
         }
         rowp++;
