@@ -355,12 +355,18 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         // the soil cells under this thread's 16 pixel columns (the same for all its rows): at 25 pixels per cell
         // there are one or two; ksw = pixels that lie in the first one
         const int c0 = s_col[16 * g], c1 = s_col[16 * g + 15];
-        int ksw = 0;
-        while (ksw < 16 && s_col[16 * g + ksw] == c0)
-            ksw++;
-        bool two = true;
-        for (int k = ksw; k < 16; k++)
-            two = two && s_col[16 * g + k] == c1;
+        // (the column map is monotone: the pixels of the first cell are the leading ones)
+        int ksw = 0, n1 = 0;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+            const int4 cc = *reinterpret_cast<const int4 *>(s_col + 16 * g + 4 * k4);
+            ksw += (cc.x == c0) + (cc.y == c0) + (cc.z == c0) + (cc.w == c0);
+            n1 += (cc.x == c1) + (cc.y == c1) + (cc.z == c1) + (cc.w == c1);
+        }
+        const bool two = c0 == c1 || ksw + n1 == 16;
+        if (c0 == c1)
+            ksw = 16;
+        const uint32_t s_idmap32 = (uint32_t)__cvta_generic_to_shared(s_idmap);
         const uint32_t pad4 = 0x01010101u * kFusedPad;
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
@@ -397,7 +403,23 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                             if (k < nvalid)
                                 ew[k >> 2] |= (uint32_t)e[k] << (8 * (k & 3));
                     }
-                    if (two) {
+                    if (two && nvalid == 16) {
+                        // interior fast path: per pixel one PRMT (class byte), one select of the cell's map, one add and
+                        // one LDS.U8; four ids are packed with three PRMTs
+                        const uint32_t a0 = s_idmap32 + 256u * soil_class(code0[j]);
+                        const uint32_t a1 = s_idmap32 + 256u * soil_class(code1[j]);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; k4++) {
+                            uint32_t b[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t lc = __byte_perm(ew[k4], 0, 0x4440 | q);
+                                asm("ld.shared.u8 %0, [%1];" : "=r"(b[q]) : "r"((4 * k4 + q < ksw ? a0 : a1) + lc));
+                            }
+                            idw[k4] = __byte_perm(__byte_perm(b[0], b[1], 0x0040), __byte_perm(b[2], b[3], 0x0040), 0x5410);
+                        }
+                    }
+                    else if (two) {
                         const uint8_t *m0 = s_idmap + 256u * soil_class(code0[j]);
                         const uint8_t *m1 = s_idmap + 256u * soil_class(code1[j]);
 #pragma unroll

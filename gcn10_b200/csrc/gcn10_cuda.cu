@@ -252,7 +252,7 @@ void pack_lut_records(const int tables[GCN10_NVARIANTS][256][5], unsigned varian
 // co-resident CTAs inside a narrow band of rows and leave no tail wave, long ones amortise the per-CTA
 // prologue (LUT + HSG box fills).  Bulk-store kernel: 12 rows is best for <= 9 planes (2 CTAs/SM), 32 for
 // 10..18 planes (1 CTA/SM); direct-store kernel: 12 / 16.
-int auto_rows_per_cta(int planes) { return planes > 9 ? (GCN10_BULK_STORE ? 32 : 16) : planes <= kNarrowPlanes ? 24 : 12; }
+int auto_rows_per_cta(int planes) { return planes > 9 ? (GCN10_BULK_STORE ? 32 : 16) : planes <= kNarrowPlanes ? 32 : 12; }
 
 // ---- strip hand-over ------------------------------------------------------------------------
 
