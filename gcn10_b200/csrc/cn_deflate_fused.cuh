@@ -456,35 +456,52 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     // ---- 2. (thread r owns tile row r) word masks, per-id pixel counts / position-weight sums, work estimate
     {
         RowMasks m;
-        m.above = 0;
-        m.left = 0;
         const uint4 *rowv = reinterpret_cast<const uint4 *>(tile + tid * kTileStride);
         const uint4 *upv = rowv - kTileStride / 16;
-        uint32_t last = 0;
-        uint32_t cur = tile[tid * kTileStride], n = 0, xs = 0;
-        const uint32_t rowbase = (uint32_t)(kTileBytes - kTile * tid);      // N - i at x = 0
-#pragma unroll 2
-        for (int i = 0; i < kTile / 16; i++) {
-            const uint4 cv = rowv[i];
-            const uint4 uv = tid > 0 ? upv[i] : make_uint4(~cv.x, ~cv.y, ~cv.z, ~cv.w);
-            const uint32_t cw[4] = { cv.x, cv.y, cv.z, cv.w };
-            const uint32_t uw[4] = { uv.x, uv.y, uv.z, uv.w };
+        // (a) the two word masks, branch free: bit j of `above` = word j equals the word above it, bit j of `left` =
+        // word j is four copies of the last byte of word j - 1
+        {
+            uint32_t ab[2] = { 0, 0 }, lf[2] = { 0, 0 };
+            uint32_t last = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int j = 4 * i + k;
-                if (cw[k] == uw[k])
-                    m.above |= 1ull << j;
-                if (j > 0 && cw[k] == last * 0x01010101u)
-                    m.left |= 1ull << j;
-                last = cw[k] >> 24;
-                if (cw[k] == cur * 0x01010101u) {
-                    n += 4;
-                    xs += 16u * j + 6u;
+            for (int i = 0; i < kTile / 16; i++) {
+                const uint4 cv = rowv[i];
+                const uint4 uv = tid > 0 ? upv[i] : make_uint4(~cv.x, ~cv.y, ~cv.z, ~cv.w);
+                const uint32_t cw[4] = { cv.x, cv.y, cv.z, cv.w };
+                const uint32_t uw[4] = { uv.x, uv.y, uv.z, uv.w };
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int j = 4 * i + k;
+                    ab[j >> 5] |= (uint32_t)(cw[k] == uw[k]) << (j & 31);
+                    if (j > 0)
+                        lf[j >> 5] |= (uint32_t)(cw[k] == last * 0x01010101u) << (j & 31);
+                    last = cw[k] >> 24;
                 }
-                else {
+            }
+            m.above = (unsigned long long)ab[0] | ((unsigned long long)ab[1] << 32);
+            m.left = (unsigned long long)lf[0] | ((unsigned long long)lf[1] << 32);
+        }
+        // (b) per-id pixel counts and position-weight sums of the row, run by run.  Words that continue a run (the
+        // `left` bits) are skipped in one step; only the words in which something changes are looked at byte by byte,
+        // so that the 32 rows a warp handles in lockstep loop a dozen times instead of 64.
+        {
+            const uint32_t *roww = reinterpret_cast<const uint32_t *>(tile + tid * kTileStride);
+            const uint32_t rowbase = (uint32_t)(kTileBytes - kTile * tid);      // N - i at x = 0
+            uint32_t cur = roww[0] & 255u, n = 0, xs = 0;
+            int j = 0;
+            while (j < kTile / 4) {
+                if ((m.left >> j) & 1ull) {
+                    // (bit 0 is never set, so j > 0 here) c words equal to four copies of `cur`
+                    const uint32_t c = (uint32_t)min(ones_from(m.left, j), kTile / 4 - j);
+                    n += 4u * c;
+                    xs += 16u * (c * (uint32_t)j + c * (c - 1u) / 2u) + 6u * c;
+                    j += (int)c;
+                }
+                if (j < kTile / 4) {
+                    const uint32_t wv = roww[j];
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        const uint32_t v = (cw[k] >> (8 * b)) & 255u;
+                        const uint32_t v = (wv >> (8 * b)) & 255u;
                         if (v != cur) {
                             if (n) {
                                 atomicAdd(&s_cnt[cur], n);
@@ -495,13 +512,14 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                             xs = 0;
                         }
                         n += 1;
-                        xs += 4u * j + b;
+                        xs += 4u * (uint32_t)j + b;
                     }
+                    j++;
                 }
             }
+            atomicAdd(&s_cnt[cur], n);
+            atomicAdd(&s_w[cur], n * rowbase - xs);
         }
-        atomicAdd(&s_cnt[cur], n);
-        atomicAdd(&s_w[cur], n * rowbase - xs);
         s_masks[tid] = m;
         // Work items.  A row's parse is serial, so the longest row sets the latency of the whole CTA: rows with
         // many "new" words (neither a repeat of the row above nor the continuation of a run -- typically the first
