@@ -7,7 +7,7 @@ tag=${1:-r02}
 out=gpurun_out
 B="python bench.py --steps 2 --warmup 3 --e2e-steps 1 --no-cpu-baseline --queue-blocks 0 --program-blocks 0"
 $B > $out/${tag}_plain_bench.json 2> $out/${tag}_plain_bench.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gcn10|ship_strip" -c 400 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_ncu_bench.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"cn_block_kernel|index_map_kernel|cn_bytes_kernel|inflate_tiles_kernel|cn_deflate_fused_kernel|deflate_tiles_kernel|ship_strip_kernel" -c 400 --csv --log-file $out/${tag}_launches.csv $B > $out/${tag}_ncu_bench.log 2>&1
 python tools/kbench.py --planes 9 --rows-per-cta 0 --once > $out/${tag}_plain_k9.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:cn_block_kernel -c 1 -o $out/${tag}_cn_block_9 python tools/kbench.py --planes 9 --rows-per-cta 0 --once > $out/${tag}_ncu_k9.log 2>&1
 python tools/kbench.py --planes 1 --rows-per-cta 0 --once > $out/${tag}_plain_k1.log 2>&1 &&
