@@ -65,6 +65,7 @@ struct StripSlot {
     bool timed = false;
     // tile-deflate path
     DevBuf blob, table;         // compressed tiles; [cursor(16 B) | offsets u64[] | sizes u32[]]
+    DevBuf blob2, order;        // option "ordered": the strip re-laid in table order, and the scan's offsets
     HostBuf h_blob, h_table;    // page-locked mirrors
     cudaEvent_t enc_done = nullptr;
     int y0 = 0, rows = 0;
@@ -102,6 +103,7 @@ struct gcn10_ctx {
     int use_tma = 1;
     int inflate_probe = 0;      // measurement aid for tools/inflate_bench.py (see InflateParams::probe)
     int fused = 1;              // compressed-tile calls use cn_deflate_fused_kernel (0 = CN kernel + tile encoder)
+    int ordered = 0;            // 1 = strips are re-laid in table order before they leave the device
     int ship = 0;               // 1 = strips leave through ship_strip_kernel; 0 = size read-back, then a D2H copy of that size
                                 // (measured on B200: 11.8 vs 12.2 ms per block -- the copy engine does not compete for SMs)
     DevBuf fused_tab;           // idmap [256][16] | val [256][32] | lit9 [256][6] u64
@@ -280,6 +282,69 @@ ship_strip_kernel(const uint4 *__restrict__ blob, const unsigned long long *__re
 // strip's encoder already fills the SMs.
 constexpr int kShipThreads = 64;
 constexpr int kShipCtas = 2 * 148;
+
+// ---- ordered strips -------------------------------------------------------------------------
+
+// The encoders place a tile's streams wherever the arena's bump allocator stood when the tile's CTA finished.  With
+// the option "ordered" the strip is re-laid in table order -- [plane][tile row][tile column], every stream on a
+// 16-byte boundary -- before it leaves the device, so that the consumer can write a plane's share of the strip (or a
+// whole tile row of it) to its GeoTIFF with ONE write instead of one per tile.  Two small kernels behind the
+// encoder: an exclusive scan of the rounded sizes (one CTA) and a warp-per-tile copy.  The total is unchanged.
+__global__ void __launch_bounds__(1024)
+order_scan_kernel(const uint32_t *__restrict__ sizes, int n, unsigned long long *__restrict__ new_off)
+{
+    __shared__ unsigned long long s_part[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int i0 = tid * per, i1 = min(n, i0 + per);
+    unsigned long long sum = 0;
+    for (int i = i0; i < i1; i++)
+        sum += ((unsigned long long)sizes[i] + 15ull) & ~15ull;
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+            inc += t;
+    }
+    if (lane == 31)
+        s_part[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long v = s_part[lane], w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o)
+                w += t;
+        }
+        s_part[lane] = w - v;
+    }
+    __syncthreads();
+    unsigned long long at = s_part[warp] + inc - sum;
+    for (int i = i0; i < i1; i++) {
+        new_off[i] = at;
+        at += ((unsigned long long)sizes[i] + 15ull) & ~15ull;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+order_copy_kernel(const uint8_t *__restrict__ blob, unsigned long long *__restrict__ offsets, const uint32_t *__restrict__ sizes,
+                  const unsigned long long *__restrict__ new_off, uint8_t *__restrict__ blob2, int n)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(blob + offsets[i]);
+        uint4 *dst = reinterpret_cast<uint4 *>(blob2 + new_off[i]);
+        const uint32_t n16 = (sizes[i] + 15u) >> 4;
+        for (uint32_t k = lane; k < n16; k += 32u)
+            dst[k] = src[k];
+        __syncwarp();
+        if (lane == 0)
+            offsets[i] = new_off[i];
+    }
+}
 
 // ---- kernel dispatch ------------------------------------------------------------------------
 
@@ -707,6 +772,8 @@ void gcn10_cuda_destroy(gcn10_ctx *c)
         release(c->slots[i].esa);
         release(c->slots[i].out);
         release(c->slots[i].blob);
+        release(c->slots[i].blob2);
+        release(c->slots[i].order);
         release(c->slots[i].table);
         release_host(c->slots[i].h_blob);
         release_host(c->slots[i].h_table);
@@ -745,6 +812,7 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
     else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
     else if (!strcmp(key, "fused") && (value == 0 || value == 1)) c->fused = (int)value;
     else if (!strcmp(key, "ship") && (value == 0 || value == 1)) c->ship = (int)value;
+    else if (!strcmp(key, "ordered") && (value == 0 || value == 1)) c->ordered = (int)value;
     else if (!strcmp(key, "inflate_probe") && value >= 0 && value <= 2) c->inflate_probe = (int)value;
     else if (!strcmp(key, "tuned_code") && (value == 0 || value == 1)) {
         c->tuned_code = (int)value;
@@ -1138,6 +1206,7 @@ static int deflate_rows_impl(gcn10_ctx *c,
         if ((esa && (rc = ensure(sl.esa, dpitch * (size_t)strip))) ||
             (!fused && (rc = ensure(sl.out, dpitch * (size_t)strip * nplanes))) ||
             (rc = ensure(sl.blob, blob_cap)) || (rc = ensure(sl.table, table_bytes)) ||
+            (c->ordered && ((rc = ensure(sl.blob2, blob_cap)) || (rc = ensure(sl.order, ntile_slot * sizeof(unsigned long long))))) ||
             (rc = ensure_host(sl.h_table, table_bytes)))
             return rc;
         // the host mirror of the blob only has to hold what a strip really compresses to; start at 1/8 of
@@ -1157,10 +1226,21 @@ static int deflate_rows_impl(gcn10_ctx *c,
     // page-locked arena, nothing for the host to do but wait), or the table read-back of the two-phase path
     auto hand_over = [&](StripSlot &sl, cudaStream_t st) -> int {
         CUDA_TRY(cudaEventRecord(sl.k1, st));
+        if (c->ordered) {
+            const int n = nplanes * ((sl.rows + kTile - 1) / kTile) * tiles_x;
+            unsigned long long *d_offsets = (unsigned long long *)((uint8_t *)sl.table.p + 16);
+            const uint32_t *d_sizes = (const uint32_t *)((uint8_t *)sl.table.p + 16 + ntile_slot * sizeof(unsigned long long));
+            order_scan_kernel<<<1, 1024, 0, st>>>(d_sizes, n, (unsigned long long *)sl.order.p);
+            order_copy_kernel<<<2 * c->sm_count, 256, 0, st>>>((const uint8_t *)sl.blob.p, d_offsets, d_sizes,
+                                                              (const unsigned long long *)sl.order.p, (uint8_t *)sl.blob2.p, n);
+            c->launches += 2;
+            CUDA_TRY(cudaGetLastError());
+        }
+        const void *out_blob = c->ordered ? sl.blob2.p : sl.blob.p;
         if (c->ship) {
             cudaStream_t ss = c->ship_streams[&sl - c->slots];
             CUDA_TRY(cudaStreamWaitEvent(ss, sl.k1, 0));
-            ship_strip_kernel<<<kShipCtas, kShipThreads, 0, ss>>>((const uint4 *)sl.blob.p, (const unsigned long long *)sl.table.p,
+            ship_strip_kernel<<<kShipCtas, kShipThreads, 0, ss>>>((const uint4 *)out_blob, (const unsigned long long *)sl.table.p,
                                                                   (const uint32_t *)sl.table.p, (uint32_t)(table_bytes / 4),
                                                                   (uint4 *)sl.h_blob.p,
                                                                   (unsigned long long)(sl.h_blob.cap & ~(size_t)15),
@@ -1282,7 +1362,7 @@ static int deflate_rows_impl(gcn10_ctx *c,
             // two-phase path, or a strip that outgrew the host arena: (grow it and) copy exactly `used` bytes
             if ((rc = ensure_host(sl.h_blob, used ? used + used / 4 : 16)))
                 return bail(rc);
-            ce = cudaMemcpyAsync(sl.h_blob.p, sl.blob.p, used, cudaMemcpyDeviceToHost, st);
+            ce = cudaMemcpyAsync(sl.h_blob.p, c->ordered ? sl.blob2.p : sl.blob.p, used, cudaMemcpyDeviceToHost, st);
             if (ce == cudaSuccess)
                 ce = cudaStreamSynchronize(st);
             if (ce != cudaSuccess)

@@ -286,13 +286,10 @@ static void sink_plane(void *arg, int k)
     sink_job *j = arg;
     const gcn10_tile_strip *st = j->st;
     gh_tiffw *tw = j->wk->writers[st->plane_ids[k]];
-    for (int tr = 0; tr < st->n_tile_rows; tr++) {
-        size_t base = ((size_t)k * st->n_tile_rows + tr) * (size_t)st->tiles_x;
-        if (gh_tiffw_put_tile_row(tw, st->tile_row0 + tr, st->blob, st->offsets + base, st->sizes + base)) {
-            atomic_store(&j->wk->encode_failed, 1);
-            return;
-        }
-    }
+    /* the context runs with "ordered" strips: a plane's share of the strip is one contiguous piece of the blob */
+    size_t base = (size_t)k * st->n_tile_rows * (size_t)st->tiles_x;
+    if (gh_tiffw_put_tile_rows(tw, st->tile_row0, st->n_tile_rows, st->blob, st->offsets + base, st->sizes + base))
+        atomic_store(&j->wk->encode_failed, 1);
 }
 
 /* the 18 files are independent: their appends run on the I/O threads while the GPU works on the next strips */
@@ -704,7 +701,8 @@ static void *worker_main(void *arg)
     int node = gcn10_cuda_bind_host_thread(wk->device);
     snprintf(msg, sizeof msg, "worker %d on gpu %d, numa node %d", wk->index, wk->device, node);
     gh_log_message(wk->log, "INFO", msg, 0);
-    if (gcn10_cuda_create(wk->device, &wk->ctx) || gcn10_cuda_set_luts(wk->ctx, wk->tables)) {
+    if (gcn10_cuda_create(wk->device, &wk->ctx) || gcn10_cuda_set_luts(wk->ctx, wk->tables) ||
+        gcn10_cuda_set_option(wk->ctx, "ordered", 1)) {
         snprintf(msg, sizeof msg, "cannot initialise GPU %d: %s", wk->device, gcn10_cuda_last_error());
         fatal(wk, msg);
     }

@@ -908,6 +908,38 @@ int gh_tiffw_put_tile_row(gh_tiffw *tw, int tile_row, const uint8_t *blob, const
     return 0;
 }
 
+int gh_tiffw_put_tile_rows(gh_tiffw *tw, int tile_row0, int nrows, const uint8_t *blob, const uint64_t *offsets,
+                           const uint32_t *sizes)
+{
+    if (tw->failed || tile_row0 != tw->next_tile_row || nrows < 1 || tile_row0 + nrows > tw->tiles_y)
+        return -1;
+    const size_t n = (size_t)nrows * (size_t)tw->tiles_x;
+    /* laid out in table order with small gaps (the library's "ordered" strips)?  Then the whole share is one write;
+     * the gaps (< 16 bytes per tile, alignment padding) go into the file as unused bytes, which TIFF allows */
+    int ordered = 1;
+    for (size_t i = 0; i + 1 < n && ordered; i++)
+        ordered = offsets[i + 1] >= offsets[i] + sizes[i] && offsets[i + 1] - (offsets[i] + sizes[i]) < 64;
+    if (!ordered) {
+        for (int r = 0; r < nrows; r++)
+            if (gh_tiffw_put_tile_row(tw, tile_row0 + r, blob, offsets + (size_t)r * tw->tiles_x, sizes + (size_t)r * tw->tiles_x))
+                return -1;
+        return 0;
+    }
+    const uint64_t first = offsets[0], bytes = offsets[n - 1] + sizes[n - 1] - first;
+    if (tw->pos + bytes > 0xFFFFFFF0ull || fwrite(blob + first, 1, (size_t)bytes, tw->fp) != (size_t)bytes) {
+        tw->failed = 1;
+        return -1;
+    }
+    for (size_t i = 0; i < n; i++) {
+        const size_t ti = (size_t)tile_row0 * (size_t)tw->tiles_x + i;
+        tw->offsets[ti] = (uint32_t)(tw->pos + (offsets[i] - first));
+        tw->counts[ti] = sizes[i];
+    }
+    tw->pos += bytes;
+    tw->next_tile_row += nrows;
+    return 0;
+}
+
 static void put16(unsigned char **p, uint16_t v) { (*p)[0] = (unsigned char)v; (*p)[1] = (unsigned char)(v >> 8); *p += 2; }
 static void put32(unsigned char **p, uint32_t v) { for (int i = 0; i < 4; i++) (*p)[i] = (unsigned char)(v >> (8 * i)); *p += 4; }
 static void put_f64(unsigned char **p, double d) { uint64_t v; memcpy(&v, &d, 8); for (int i = 0; i < 8; i++) (*p)[i] = (unsigned char)(v >> (8 * i)); *p += 8; }

@@ -25,6 +25,10 @@ int gh_tiffw_write_rows(gh_tiffw *tw, const uint8_t *data, size_t pitch, int y0,
  * address `blob` for the tiles_x tiles of that row. */
 int gh_tiffw_put_tile_row(gh_tiffw *tw, int tile_row, const uint8_t *blob, const uint64_t *offsets,
                           const uint32_t *sizes);
+/* Several consecutive tile rows at once ([nrows][tiles_x] offsets / sizes).  When the tiles lie in `blob` in table
+ * order with at most alignment gaps between them (gcn10_cuda_set_option "ordered") they are written with one write. */
+int gh_tiffw_put_tile_rows(gh_tiffw *tw, int tile_row0, int nrows, const uint8_t *blob, const uint64_t *offsets,
+                           const uint32_t *sizes);
 /* Runs fn(arg, 0..n-1) on up to `threads` threads (the calling thread included). */
 void gh_parallel_for(int n, int threads, void (*fn)(void *arg, int index), void *arg);
 /* Writes the tile tables, georeferencing and IFD; 0 ok. */

@@ -293,7 +293,9 @@ int gcn10_cuda_launch_count(gcn10_ctx *ctx, uint64_t *launches);
  * (0 = automatic), "tma" (0 = always use the gather fallback for HSG staging), "fused" (0 = compressed-tile
  * calls run the Curve Number kernel and the per-plane tile encoder instead of the fused kernel), "ship" (1 = a strip's
  * compressed bytes leave through a kernel that writes them into mapped page-locked memory, instead of the default
- * size read-back + copy-engine transfer), "tuned_code" (0 = tile streams use RFC 1951's fixed Huffman code instead
+ * size read-back + copy-engine transfer), "ordered" (1 = every strip is re-laid on the device in table order -- [plane][tile row][tile column], streams on
+ * 16-byte boundaries, offsets ascending -- so that a consumer can write a plane's share of a strip with one write),
+ * "tuned_code" (0 = tile streams use RFC 1951's fixed Huffman code instead
  * of the tuned one), "inflate_probe" (measurement aid of tools/inflate_bench.py: 1 / 2 switch parts of the inflate
  * kernel's writer off; results are then invalid). */
 int gcn10_cuda_set_option(gcn10_ctx *ctx, const char *key, long value);

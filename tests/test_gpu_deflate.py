@@ -244,3 +244,37 @@ def test_strip_hand_over_paths_agree(gpu_ctx, port, tables, encoder_path):
         assert got[0]["tiles"][k] == got[1]["tiles"][k] == again["tiles"][k]
         full = _assemble(got[1]["tiles"][k], w, h)
         assert np.array_equal(full[:h, :w], want[k])
+
+
+def test_ordered_strips(gpu_ctx, port, tables, encoder_path):
+    """Option "ordered": every strip arrives laid out in table order ([plane][tile row][tile column], 16-byte
+    aligned, offsets ascending, no bytes unaccounted for) and decodes to the same rasters."""
+    b = make_block(w=1100, h=1500, seed=63, esa_patch=20, hsg_patch=2)
+    h, w = b["esa"].shape
+    want = port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], tables)
+    plain = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    seen = []
+
+    def on_strip(st):
+        n = st.n_planes * st.n_tile_rows * st.tiles_x
+        offs = np.ctypeslib.as_array(st.offsets, (n,)).astype(np.int64)
+        sizes = np.ctypeslib.as_array(st.sizes, (n,)).astype(np.int64)
+        assert offs[0] == 0 and (offs % 16 == 0).all()
+        assert (offs[1:] == offs[:-1] + (sizes[:-1] + 15) // 16 * 16).all()
+        assert offs[-1] + (sizes[-1] + 15) // 16 * 16 == st.blob_bytes
+        seen.append(n)
+        return 0
+
+    gpu_ctx.set_option("strip_rows", 512)
+    gpu_ctx.set_option("ordered", 1)
+    try:
+        gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], on_strip=on_strip)
+        res = gpu_ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+    finally:
+        gpu_ctx.set_option("ordered", 0)
+        gpu_ctx.set_option("strip_rows", 2048)
+    assert len(seen) == 3 and res["bytes"] == plain["bytes"]
+    for k in range(18):
+        assert res["tiles"][k] == plain["tiles"][k]
+        full = _assemble(res["tiles"][k], w, h)
+        assert np.array_equal(full[:h, :w], want[k])

@@ -430,3 +430,41 @@ def test_geokeys_travel_from_the_land_cover_to_the_outputs(tmp_path):
     assert L.gh_tiff_geokeys(p.h, hostlib.C.byref(gk3)) == 0
     assert 4326 in list((hostlib.C.c_uint16 * gk3.n_keys).from_address(gk3.keys))
     p.close()
+
+
+def test_geotiff_writer_takes_several_ordered_tile_rows_in_one_write(tmp_path):
+    """gh_tiffw_put_tile_rows: tiles laid out in table order with alignment gaps (the library's "ordered" strips) go to
+    the file with one write; any other layout falls back to tile-by-tile appends.  Both files decode to the raster."""
+    import zlib
+    from gcn10_b200 import synth
+    L = hostlib.load()
+    w, h = 700, 600
+    a = synth.esa_tile(w, h, 9, patch=30)
+    tx, ty = 3, 3
+    streams = []
+    for r in range(ty):
+        for c in range(tx):
+            t = np.zeros((256, 256), dtype=np.uint8)
+            part = a[r * 256:(r + 1) * 256, c * 256:(c + 1) * 256]
+            t[:part.shape[0], :part.shape[1]] = part
+            streams.append(zlib.compress(t.tobytes(), 6))
+    for name, order in (("ordered", list(range(9))), ("scattered", [4, 0, 8, 2, 6, 1, 7, 3, 5])):
+        blob = bytearray()
+        offs, sizes = [0] * 9, [0] * 9
+        for i in order:
+            while len(blob) % 16:
+                blob.append(0xAA)                      # alignment padding between the streams
+            offs[i], sizes[i] = len(blob), len(streams[i])
+            blob += streams[i]
+        buf = hostlib.C.create_string_buffer(bytes(blob), len(blob))
+        p = tmp_path / f"{name}.tif"
+        tw = hostlib.TiffWriter(str(p), w, h, (0, 1, 0, 0, 0, -1))
+        o = (hostlib.C.c_uint64 * 9)(*offs)
+        z = (hostlib.C.c_uint32 * 9)(*sizes)
+        assert L.gh_tiffw_put_tile_rows(tw.h, 0, 2, buf, o, z) == 0
+        assert L.gh_tiffw_put_tile_rows(tw.h, 2, 1, buf, hostlib.C.cast(hostlib.C.byref(o, 6 * 8), hostlib.C.POINTER(hostlib.C.c_uint64)),
+                                        hostlib.C.cast(hostlib.C.byref(z, 6 * 4), hostlib.C.POINTER(hostlib.C.c_uint32))) == 0
+        assert tw.close() == 0
+        t = hostlib.Tiff(str(p))
+        assert np.array_equal(t.read(), a), name
+        t.close()
