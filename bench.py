@@ -832,17 +832,20 @@ def run_program_leg(args, blob, offsets, sizes, in_tile, w, rows, hsg_np, group,
                                env=dict(os.environ, GCN10_HOST_INFLATE="0", GCN10_HOST_DEFLATE="0"))
             wall = time.perf_counter() - t0
             per_worker = {}
+            last_line = None
             for fn in sorted(os.listdir(os.path.join(root, "logs"))):
                 for ln in open(os.path.join(root, "logs", fn)):
                     m = re.search(r"block (\d+): (\d+) x (\d+) px, 18 rasters in ([0-9.]+) s", ln)
                     if m:
                         per_worker.setdefault(fn, []).append(float(m.group(4)))
+                        last_line = ln.strip()
             warm = [t for ts in per_worker.values() for t in ts[1:]]
             files = sum(len(fs) for _, _, fs in os.walk(os.path.join(root, "out")))
             out_bytes = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(os.path.join(root, "out")) for f in fs)
             res = {"returncode": r.returncode, "blocks": nb, "gpus": group.world, "rasters_written": files,
                    "output_bytes": out_bytes, "wall_s_incl_startup": wall,
-                   "path": "gcn10 executable: VRT mosaic of a tiled DEFLATE GeoTIFF on /dev/shm -> 18 GeoTIFFs per block on /dev/shm"}
+                   "path": "gcn10 executable: VRT mosaic of a tiled DEFLATE GeoTIFF on /dev/shm -> 18 GeoTIFFs per block on /dev/shm",
+                   "last_block_log_line": last_line}
             if warm:
                 warm.sort()
                 med = warm[len(warm) // 2]

@@ -291,8 +291,11 @@ constexpr int kShipCtas = 2 * 148;
 // whole tile row of it) to its GeoTIFF with ONE write instead of one per tile.  Two small kernels behind the
 // encoder: an exclusive scan of the rounded sizes (one CTA) and a warp-per-tile copy.  The total is unchanged.
 __global__ void __launch_bounds__(1024)
-order_scan_kernel(const uint32_t *__restrict__ sizes, int n, unsigned long long *__restrict__ new_off)
+order_scan_kernel(const uint32_t *__restrict__ sizes, int n, unsigned long long *__restrict__ new_off,
+                  const unsigned long long *__restrict__ cursor, unsigned long long cap2)
 {
+    if (*cursor > cap2)
+        return;                 // the strip does not fit the second arena: it leaves unordered
     __shared__ unsigned long long s_part[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (n + 1023) / 1024;
@@ -330,8 +333,11 @@ order_scan_kernel(const uint32_t *__restrict__ sizes, int n, unsigned long long 
 
 __global__ void __launch_bounds__(256)
 order_copy_kernel(const uint8_t *__restrict__ blob, unsigned long long *__restrict__ offsets, const uint32_t *__restrict__ sizes,
-                  const unsigned long long *__restrict__ new_off, uint8_t *__restrict__ blob2, int n)
+                  const unsigned long long *__restrict__ new_off, uint8_t *__restrict__ blob2, int n,
+                  const unsigned long long *__restrict__ cursor, unsigned long long cap2)
 {
+    if (*cursor > cap2)
+        return;
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
@@ -1201,12 +1207,15 @@ static int deflate_rows_impl(gcn10_ctx *c,
     const size_t ntile_slot = (size_t)nplanes * strip_tile_rows * tiles_x;
     const size_t blob_cap = ntile_slot * (size_t)round_up(kStoredBytes, 16);
     const size_t table_bytes = 16 + ntile_slot * (sizeof(unsigned long long) + sizeof(uint32_t));
+    // ordered strips: the second arena holds what a strip really compresses to (a quarter of the worst case, at least
+    // 16 MB); a strip that does not fit leaves unordered -- still a valid strip, the consumer only loses the single write
+    const size_t blob2_cap = std::min(blob_cap, std::max<size_t>(blob_cap / 4, (size_t)16 << 20));
     for (int i = 0; i < ns; i++) {
         StripSlot &sl = c->slots[i];
         if ((esa && (rc = ensure(sl.esa, dpitch * (size_t)strip))) ||
             (!fused && (rc = ensure(sl.out, dpitch * (size_t)strip * nplanes))) ||
             (rc = ensure(sl.blob, blob_cap)) || (rc = ensure(sl.table, table_bytes)) ||
-            (c->ordered && ((rc = ensure(sl.blob2, blob_cap)) || (rc = ensure(sl.order, ntile_slot * sizeof(unsigned long long))))) ||
+            (c->ordered && ((rc = ensure(sl.blob2, blob2_cap)) || (rc = ensure(sl.order, ntile_slot * sizeof(unsigned long long))))) ||
             (rc = ensure_host(sl.h_table, table_bytes)))
             return rc;
         // the host mirror of the blob only has to hold what a strip really compresses to; start at 1/8 of
@@ -1230,13 +1239,15 @@ static int deflate_rows_impl(gcn10_ctx *c,
             const int n = nplanes * ((sl.rows + kTile - 1) / kTile) * tiles_x;
             unsigned long long *d_offsets = (unsigned long long *)((uint8_t *)sl.table.p + 16);
             const uint32_t *d_sizes = (const uint32_t *)((uint8_t *)sl.table.p + 16 + ntile_slot * sizeof(unsigned long long));
-            order_scan_kernel<<<1, 1024, 0, st>>>(d_sizes, n, (unsigned long long *)sl.order.p);
+            order_scan_kernel<<<1, 1024, 0, st>>>(d_sizes, n, (unsigned long long *)sl.order.p,
+                                                  (const unsigned long long *)sl.table.p, (unsigned long long)blob2_cap);
             order_copy_kernel<<<2 * c->sm_count, 256, 0, st>>>((const uint8_t *)sl.blob.p, d_offsets, d_sizes,
-                                                              (const unsigned long long *)sl.order.p, (uint8_t *)sl.blob2.p, n);
+                                                              (const unsigned long long *)sl.order.p, (uint8_t *)sl.blob2.p, n,
+                                                              (const unsigned long long *)sl.table.p, (unsigned long long)blob2_cap);
             c->launches += 2;
             CUDA_TRY(cudaGetLastError());
         }
-        const void *out_blob = c->ordered ? sl.blob2.p : sl.blob.p;
+        const void *out_blob = c->ordered ? sl.blob2.p : sl.blob.p;      // (ship: ordered strips always fit, see below)
         if (c->ship) {
             cudaStream_t ss = c->ship_streams[&sl - c->slots];
             CUDA_TRY(cudaStreamWaitEvent(ss, sl.k1, 0));
@@ -1358,11 +1369,12 @@ static int deflate_rows_impl(gcn10_ctx *c,
         const size_t used = (size_t) * (const unsigned long long *)sl.h_table.p;
         if (used > blob_cap)
             return bail(fail(GCN10_ECUDA, "tile encoder overran its arena (%zu > %zu)", used, blob_cap));
-        if (!c->ship || used > (sl.h_blob.cap & ~(size_t)15)) {
+        if (!c->ship || used > (sl.h_blob.cap & ~(size_t)15) || (c->ordered && used > blob2_cap)) {
             // two-phase path, or a strip that outgrew the host arena: (grow it and) copy exactly `used` bytes
             if ((rc = ensure_host(sl.h_blob, used ? used + used / 4 : 16)))
                 return bail(rc);
-            ce = cudaMemcpyAsync(sl.h_blob.p, c->ordered ? sl.blob2.p : sl.blob.p, used, cudaMemcpyDeviceToHost, st);
+            ce = cudaMemcpyAsync(sl.h_blob.p, (c->ordered && used <= blob2_cap) ? sl.blob2.p : sl.blob.p, used,
+                                 cudaMemcpyDeviceToHost, st);
             if (ce == cudaSuccess)
                 ce = cudaStreamSynchronize(st);
             if (ce != cudaSuccess)
