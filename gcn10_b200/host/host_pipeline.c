@@ -301,7 +301,10 @@ static int tile_sink(void *user, const gcn10_tile_strip *st)
         return 1;
     }
     sink_job j = { wk, st };
-    gh_parallel_for(st->n_planes, wk->io_threads > 0 ? wk->io_threads : 1, sink_plane, &j);
+    /* one task per plane: with 16 threads two of 18 planes would wait for a second round, so from nine threads up
+     * every plane gets its own helper (they mostly sit in write(2)) */
+    const int nt = wk->io_threads >= 9 ? st->n_planes : (wk->io_threads > 0 ? wk->io_threads : 1);
+    gh_parallel_for(st->n_planes, nt, sink_plane, &j);
     return atomic_load(&wk->encode_failed) ? 1 : 0;
 }
 
