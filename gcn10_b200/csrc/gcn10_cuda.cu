@@ -700,8 +700,13 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
     }
     int prio_lo = 0, prio_hi = 0;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    // priorities: the strips of the block in hand outrank the prefetched inflate of the NEXT block (pre_stream stays
+    // at the lowest priority), so a block's first compressed tiles reach the copy engine as early as possible -- where
+    // the device->host link is the bottleneck (eight GPUs on one host fabric) the inflate then fills the gaps instead of
+    // delaying the stream of tiles; the ship kernels outrank both
+    const int prio_strip = prio_hi < prio_lo ? std::min(prio_lo - 1, prio_hi + 1) : prio_lo;
     for (int i = 0; i < kMaxStreams; i++) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->streams[i], cudaStreamNonBlocking, prio_strip));
         CUDA_TRY(cudaStreamCreateWithPriority(&c->ship_streams[i], cudaStreamNonBlocking, prio_hi));
     }
     for (int i = 0; i < kMaxStreams; i++) {
@@ -724,7 +729,7 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
                                   kInflateSmem));
     CUDA_TRY(cudaFuncSetAttribute((const void *)inflate_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->pre_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->pre_stream, cudaStreamNonBlocking, prio_lo));
     CUDA_TRY(cudaEventCreateWithFlags(&c->frame_ready, cudaEventDisableTiming));
     for (int i = 0; i < kMaxStreams; i++)
         CUDA_TRY(cudaEventCreateWithFlags(&c->tail[i], cudaEventDisableTiming));
