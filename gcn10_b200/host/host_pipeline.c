@@ -76,6 +76,7 @@ typedef struct {
 typedef struct worker {
     int index;                      /* worker number: the "rank" of the log lines */
     int device;                     /* its GPU */
+    int n_gpus;                     /* GPUs this run uses */
     const gh_run_options *opt;
     int io_threads;                 /* this worker's share of the I/O threads */
     gh_blocks *blocks;
@@ -704,8 +705,10 @@ static void *worker_main(void *arg)
     int node = gcn10_cuda_bind_host_thread(wk->device);
     snprintf(msg, sizeof msg, "worker %d on gpu %d, numa node %d", wk->index, wk->device, node);
     gh_log_message(wk->log, "INFO", msg, 0);
+    /* ordered strips: a plane's share of a strip is one write; ship kernel: from four GPUs on one host fabric its posted
+     * writes beat the copy engine's size read-back + copy (measured on 8 x B200: +4..7 %), below that the copy engine wins */
     if (gcn10_cuda_create(wk->device, &wk->ctx) || gcn10_cuda_set_luts(wk->ctx, wk->tables) ||
-        gcn10_cuda_set_option(wk->ctx, "ordered", 1)) {
+        gcn10_cuda_set_option(wk->ctx, "ordered", 1) || gcn10_cuda_set_option(wk->ctx, "ship", wk->n_gpus >= 4)) {
         snprintf(msg, sizeof msg, "cannot initialise GPU %d: %s", wk->device, gcn10_cuda_last_error());
         fatal(wk, msg);
     }
@@ -807,6 +810,7 @@ int gh_run_blocks(const gh_run_options *opt, const int *block_ids, int n_blocks)
     for (int i = 0; i < nworkers; i++) {
         wks[i].index = i;
         wks[i].device = i % gpus;
+        wks[i].n_gpus = gpus;
         wks[i].opt = opt;
         wks[i].io_threads = io_each;
         wks[i].blocks = blocks;
