@@ -16,7 +16,10 @@ bands in one thread per host core (the C call releases the GIL).  Cases = BASELI
   coastal_18      configs[2]: >= 50 % land cover 0 / 80, >= 30 % dual HSG 11..14, >= 20 % HSG 255
   g_ii_only       configs[0]: a single plane (drained, good, ARC II)
   vrt_36001       the real-VRT shape: 36001 x 36001 at pixel 8.3333333333330430e-05, origin (-3, 3) where an
-                  FMA-contracted index map would move 62 tie columns; ragged right edge
+                  FMA-contracted index map would move 62 tie columns; ragged right edge.  Its
+                  compressed chain runs the way the shipped landcover/esa_worldcover_2021.vrt lays the window out:
+                  FOUR source files (36000 x 36000 + a 1-pixel column + a 1-pixel row + a corner pixel, each with its own
+                  1024 x 1024 tile grid) through gcn10_cuda_block_parts_deflate
 
 Tolerance: none.
 """
@@ -44,7 +47,7 @@ CASES = {
     "g_ii_only": dict(w=36000, h=36000, px=PX, lon0=-111.0, lat0=39.0, profile="worldcover", mask=G_II,
                       seed=2235, level=1, ref=False),
     "vrt_36001": dict(w=36001, h=36001, px=PX_VRT, lon0=-3.0, lat0=3.0, profile="worldcover", mask=capi.MASK_ALL,
-                      seed=1500, level=1, ref=False),
+                      seed=1500, level=1, ref=False, mosaic=36000),
 }
 NTHREADS = max(4, len(os.sched_getaffinity(0)))
 IN_TILE = 1024          # the ESA WorldCover files' tile size (landcover/esa_worldcover_2021.vrt: BlockXSize)
@@ -121,7 +124,6 @@ def test_every_row_of_a_full_block(name, gpu_ctx, port, tables, lookup_dir):
         assert bool((d_out[:, :, w:] == 7).all()), "padding columns were written"
 
     # ---- path 2: compressed tiles in, compressed tiles out; the strips' bytes are kept as they arrive
-    src = _tile_source(esa, c["level"])
     tiles_x, tile_rows = (w + 255) // 256, (h + 255) // 256
     strips = []
 
@@ -132,7 +134,26 @@ def test_every_row_of_a_full_block(name, gpu_ctx, port, tables, lookup_dir):
                        C.string_at(st.blob, st.blob_bytes)))
         return 0
 
-    gpu_ctx.block_tiles_deflate(src, w, h, gt, hsg, sgt, plane_mask=mask, on_strip=on_strip)
+    if c.get("mosaic"):
+        # the window as the VRT assembles it: the block's own file and its east / south / south-east neighbours
+        m = c["mosaic"]
+        parts = []
+        for (y0, y1) in ((0, m), (m, h)):
+            for (x0, x1) in ((0, m), (m, w)):
+                # a neighbour file holds more than the strip the window needs: give it a 700-pixel body of other data
+                pad_x, pad_y = (0 if x0 == 0 else 700), (0 if y0 == 0 else 700)
+                grid = np.full((y1 - y0 + pad_y, x1 - x0 + pad_x), 30, dtype=np.uint8)
+                grid[:y1 - y0, :x1 - x0] = esa[y0:y1, x0:x1]
+                parts.append((_tile_source(grid, c["level"]), x0, y0, x1 - x0, y1 - y0))
+        cb = capi.TILE_SINK(lambda _u, sp: int(on_strip(sp.contents) or 0))
+        arr = capi.parts_array(parts)
+        hsg_c = np.ascontiguousarray(hsg)
+        rc = gpu_ctx.lib.gcn10_cuda_block_parts_deflate(
+            gpu_ctx.h, arr, len(parts), 0, w, h, (C.c_double * 6)(*gt), hsg_c.ctypes.data, hsx, hsy, hsx,
+            (C.c_double * 6)(*sgt), mask, cb, None)
+        assert rc == 0, gpu_ctx.lib.gcn10_cuda_last_error().decode()
+    else:
+        gpu_ctx.block_tiles_deflate(_tile_source(esa, c["level"]), w, h, gt, hsg, sgt, plane_mask=mask, on_strip=on_strip)
     by_row = {}
     for s in strips:
         assert s[2] == planes
