@@ -131,6 +131,8 @@ int gh_raster_size(const gh_raster *r, int *w, int *h);
 int gh_raster_geotransform(const gh_raster *r, double gt[6]);
 int gh_raster_is_mosaic(const gh_raster *r);
 int gh_raster_source_count(const gh_raster *r);
+int gh_raster_have_gdal(void);                  /* 1: built with the GDAL input backend (make GDAL=1) */
+const char *gh_raster_backend(const gh_raster *r);      /* "geotiff", "vrt" or "gdal" */
 int gh_raster_fill(const gh_raster *r);         /* value of pixels no source covers (VRT NoDataValue, else 0) */
 /* georeferencing tags of the raster (a mosaic: of its first source that is open); 0 ok, 1 = none */
 int gh_raster_geokeys(const gh_raster *r, gh_geokeys *out);

@@ -441,9 +441,16 @@ static int bands_host_deflate(worker *wk, int block_id, const gh_window *we, con
 static gh_raster *open_once(worker *wk, gh_raster **slot, const char *path)
 {
     char err[GH_ERRLEN] = "";
-    if (!*slot && gh_raster_open(path, slot, err, sizeof err)) {
+    if (*slot)
+        return *slot;
+    if (gh_raster_open(path, slot, err, sizeof err)) {
         gh_log_message(wk->log, "ERROR", err, 1);                                   /* raster.c:121 */
         *slot = NULL;
+    }
+    else if (strcmp(gh_raster_backend(*slot), "gdal") == 0) {
+        char msg[1024];
+        snprintf(msg, sizeof msg, "%s opened with gdal: windows are decoded on the host", path);
+        gh_log_message(wk->log, "INFO", msg, 0);
     }
     return *slot;
 }

@@ -16,9 +16,16 @@
  * no IFD.  /vsicurl/ and http(s) sources cannot be fetched here; they are looked up by base name in
  * $GCN10_VRT_SOURCE_DIR or next to the .vrt file, and a source that cannot be opened fails the read like GDAL's
  * RasterIO would (raster.c:182-186: the block is skipped).
+ *
+ * Built with -DGCN10_WITH_GDAL (host_raster_gdal.c), a path these readers do not take -- a /vsi... name, a file that
+ * is neither a VRT nor a TIFF they can decode -- is opened with GDAL itself, and GCN10_RASTER_BACKEND=gdal sends
+ * every input there.  Such a raster is read window by window on the host (no compressed tiles for the GPU).
  */
 #define _GNU_SOURCE
 #include "gcn10_host.h"
+#ifdef GCN10_WITH_GDAL
+#include "host_raster_gdal.h"
+#endif
 
 #include <ctype.h>
 #include <stdarg.h>
@@ -38,6 +45,9 @@ typedef struct {
 
 struct gh_raster {
     gh_tiff *single;            /* plain GeoTIFF */
+#ifdef GCN10_WITH_GDAL
+    gh_gdal *gdal;              /* opened by GDAL: neither single nor src is set */
+#endif
     int w, h;
     double gt[6];
     int fill;                   /* VRT: the band's NoDataValue (0 when absent) */
@@ -282,6 +292,37 @@ static int parse_vrt(const char *path, const char *xml, size_t len, gh_raster *r
     return 0;
 }
 
+/* ---- the optional GDAL backend ------------------------------------------------------------------------- */
+
+int gh_raster_have_gdal(void)
+{
+#ifdef GCN10_WITH_GDAL
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+static int open_with_gdal(const char *path, gh_raster *r, char *err, size_t errlen)
+{
+#ifdef GCN10_WITH_GDAL
+    return gh_gdal_open(path, &r->gdal, &r->w, &r->h, r->gt, err, errlen);
+#else
+    (void)r;
+    set_err(err, errlen, "gdal open failed: %s (this build has no GDAL backend: make GDAL=1)", path);
+    return -1;
+#endif
+}
+
+const char *gh_raster_backend(const gh_raster *r)
+{
+#ifdef GCN10_WITH_GDAL
+    if (r->gdal)
+        return "gdal";
+#endif
+    return r->single ? "geotiff" : "vrt";
+}
+
 int gh_raster_open(const char *path, gh_raster **out, char *err, size_t errlen)
 {
     *out = NULL;
@@ -290,9 +331,23 @@ int gh_raster_open(const char *path, gh_raster **out, char *err, size_t errlen)
     gh_raster *r = calloc(1, sizeof *r);
     if (!r)
         return -1;
+    const char *want = getenv("GCN10_RASTER_BACKEND");
+    if (want && strcmp(want, "gdal") == 0) {
+        if (open_with_gdal(path, r, err, errlen)) {
+            free(r);
+            return -1;
+        }
+        *out = r;
+        return 0;
+    }
     /* a VRT is XML: look at the first bytes instead of trusting the extension, like GDAL's driver probing */
     FILE *f = fopen(path, "rb");
     if (!f) {
+        /* not a local file (/vsicurl/..., a driver prefix): GDAL's business when it is there */
+        if (gh_raster_have_gdal() && open_with_gdal(path, r, err, errlen) == 0) {
+            *out = r;
+            return 0;
+        }
         set_err(err, errlen, "gdal open failed: %s", path);                 /* raster.c:121 */
         free(r);
         return -1;
@@ -318,6 +373,17 @@ int gh_raster_open(const char *path, gh_raster **out, char *err, size_t errlen)
         free(xml);
         if (rc) {
             gh_raster_close(r);
+            /* a VRT outside the subset above (warped, scaled, derived bands): GDAL reads it when it is there */
+            char gerr[256];
+            if (gh_raster_have_gdal() && (r = calloc(1, sizeof *r)) != NULL) {
+                if (open_with_gdal(path, r, gerr, sizeof gerr) == 0) {
+                    if (err && errlen)
+                        err[0] = '\0';
+                    *out = r;
+                    return 0;
+                }
+                free(r);
+            }
             return -1;
         }
         *out = r;
@@ -325,6 +391,14 @@ int gh_raster_open(const char *path, gh_raster **out, char *err, size_t errlen)
     }
     fclose(f);
     if (gh_tiff_open(path, &r->single, err, errlen)) {
+        /* not a TIFF this reader decodes (another format, LZW / ZSTD tiles, ...) */
+        char gerr[256];
+        if (gh_raster_have_gdal() && open_with_gdal(path, r, gerr, sizeof gerr) == 0) {
+            if (err && errlen)
+                err[0] = '\0';
+            *out = r;
+            return 0;
+        }
         free(r);
         return -1;
     }
@@ -336,13 +410,26 @@ int gh_raster_open(const char *path, gh_raster **out, char *err, size_t errlen)
 
 int gh_raster_size(const gh_raster *r, int *w, int *h) { *w = r->w; *h = r->h; return 0; }
 int gh_raster_geotransform(const gh_raster *r, double gt[6]) { memcpy(gt, r->gt, sizeof r->gt); return 0; }
-int gh_raster_is_mosaic(const gh_raster *r) { return r->single == NULL; }
-int gh_raster_source_count(const gh_raster *r) { return r->single ? 1 : r->nsrc; }
+static int is_gdal(const gh_raster *r)
+{
+#ifdef GCN10_WITH_GDAL
+    return r->gdal != NULL;
+#else
+    (void)r;
+    return 0;
+#endif
+}
+int gh_raster_is_mosaic(const gh_raster *r) { return !r->single && !is_gdal(r); }
+int gh_raster_source_count(const gh_raster *r) { return gh_raster_is_mosaic(r) ? r->nsrc : 1; }
 int gh_raster_fill(const gh_raster *r) { return r->fill; }
 
 int gh_raster_geokeys(const gh_raster *r, gh_geokeys *out)
 {
     memset(out, 0, sizeof *out);
+#ifdef GCN10_WITH_GDAL
+    if (r->gdal)
+        return 1;               /* the writer's EPSG:4326 default (host_raster_gdal.c) */
+#endif
     if (r->single)
         return gh_tiff_geokeys(r->single, out);
     for (int i = 0; i < r->nsrc; i++)
@@ -355,6 +442,9 @@ void gh_raster_close(gh_raster *r)
 {
     if (!r)
         return;
+#ifdef GCN10_WITH_GDAL
+    gh_gdal_close(r->gdal);
+#endif
     gh_tiff_close(r->single);
     for (int i = 0; i < r->nsrc; i++) {
         gh_tiff_close(r->src[i].ds);
@@ -415,6 +505,10 @@ static int intersect(const vrt_source *v, int xoff, int yoff, int xcount, int yc
 int gh_raster_read_window(gh_raster *r, int xoff, int yoff, int xcount, int ycount, uint8_t *dst, size_t pitch,
                           int threads, char *err, size_t errlen)
 {
+#ifdef GCN10_WITH_GDAL
+    if (r->gdal)
+        return gh_gdal_read_window(r->gdal, xoff, yoff, xcount, ycount, dst, pitch, err, errlen);
+#endif
     if (r->single)
         return gh_tiff_read_window(r->single, xoff, yoff, xcount, ycount, dst, pitch, threads, err, errlen);
     if (xoff < 0 || yoff < 0 || xcount <= 0 || ycount <= 0 || (long long)xoff + xcount > r->w ||
@@ -445,6 +539,10 @@ int gh_raster_window_parts(gh_raster *r, int xoff, int yoff, int xcount, int yco
     *nparts = 0;
     if (err && errlen)
         err[0] = '\0';
+#ifdef GCN10_WITH_GDAL
+    if (r->gdal)
+        return 1;                       /* GDAL hands out decoded pixels only */
+#endif
     if (r->single) {
         if (max_parts < 1 || gh_tiff_window_tiles_plan(r->single, xoff, yoff, xcount, ycount, &parts[0].plan))
             return 1;

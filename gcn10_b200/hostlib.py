@@ -38,13 +38,15 @@ class HostError(RuntimeError):
 _lib = None
 
 
-def load() -> C.CDLL:
+def load(path: str | None = None) -> C.CDLL:
+    """The host library (cached), or -- path given -- another build of it, e.g. one with the GDAL backend."""
     global _lib
-    if _lib is not None:
+    if path is None and _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise FileNotFoundError(f"{LIB_PATH} not built: run `make host`")
-    L = C.CDLL(LIB_PATH)
+    lib_path = path or LIB_PATH
+    if not os.path.exists(lib_path):
+        raise FileNotFoundError(f"{lib_path} not built: run `make host`")
+    L = C.CDLL(lib_path)
     L.gh_load_lookup_tables.argtypes = [C.c_char_p, _vp, C.c_char_p, C.c_size_t]
     L.gh_load_lookup_table.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, _vp, C.c_char_p, C.c_size_t]
     L.gh_raster_window.argtypes = [C.c_int, C.c_int, _dp, _dp, C.POINTER(Window)]
@@ -85,13 +87,17 @@ def load() -> C.CDLL:
     L.gh_raster_window_parts.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _ip, C.c_char_p, C.c_size_t]
     L.gh_raster_close.argtypes = [_vp]
     L.gh_raster_close.restype = None
+    L.gh_raster_backend.argtypes = [_vp]
+    L.gh_raster_backend.restype = C.c_char_p
+    L.gh_raster_have_gdal.argtypes = []
     L.gh_log_open.argtypes = [C.c_char_p, C.c_int]
     L.gh_log_open.restype = _vp
     L.gh_log_message.argtypes = [_vp, C.c_char_p, C.c_char_p, C.c_int]
     L.gh_log_message.restype = None
     L.gh_log_close.argtypes = [_vp]
     L.gh_log_close.restype = None
-    _lib = L
+    if path is None:
+        _lib = L
     return L
 
 
@@ -248,8 +254,8 @@ class RasterPart(C.Structure):
 class Raster:
     """gh_raster: a GeoTIFF or a VRT mosaic of GeoTIFFs, as GDALOpen() would present it (raster.c:119)."""
 
-    def __init__(self, path: str):
-        self.L = load()
+    def __init__(self, path: str, lib: C.CDLL | None = None):
+        self.L = lib or load()
         h = _vp()
         e = _err()
         rc = self.L.gh_raster_open(os.fsencode(path), C.byref(h), e, ERRLEN)
@@ -265,14 +271,16 @@ class Raster:
         self.is_mosaic = bool(self.L.gh_raster_is_mosaic(h))
         self.source_count = self.L.gh_raster_source_count(h)
         self.fill = self.L.gh_raster_fill(h)
+        self.backend = self.L.gh_raster_backend(h).decode()     # "geotiff", "vrt" or "gdal"
 
-    def read(self, xoff, yoff, xcount, ycount, threads=4) -> np.ndarray:
-        out = np.empty((ycount, xcount), dtype=np.uint8)
+    def read(self, xoff, yoff, xcount, ycount, threads=4, pitch=None) -> np.ndarray:
+        pitch = xcount if pitch is None else pitch
+        out = np.zeros((max(ycount, 0), max(pitch, 1)), dtype=np.uint8)
         e = _err()
-        rc = self.L.gh_raster_read_window(self.h, xoff, yoff, xcount, ycount, out.ctypes.data, xcount, threads, e, ERRLEN)
+        rc = self.L.gh_raster_read_window(self.h, xoff, yoff, xcount, ycount, out.ctypes.data, pitch, threads, e, ERRLEN)
         if rc:
             raise HostError(rc, e.value.decode())
-        return out
+        return out[:, :xcount]
 
     def window_parts(self, xoff, yoff, xcount, ycount, max_parts=9, threads=4):
         """(rc, parts): rc 0 -> parts = [dict(dst_x, dst_y, w, h, tile_w, tile_h, tiles_x, tiles_y, x_in, y_in, blob,

@@ -158,9 +158,11 @@ CPLErr GDALRasterIO(GDALRasterBandH band, GDALRWFlag rw, int xoff, int yoff, int
                     void *buf, int bxsize, int bysize, GDALDataType type, int pixel_space, int line_space)
 {
     fake_ds *ds = band;
-    (void)pixel_space; (void)line_space;
-    if (type != GDT_Byte || bxsize != xsize || bysize != ysize)
+    /* 0 = GDAL's default spacing (what raster.c passes): packed bytes, rows of bxsize */
+    if (type != GDT_Byte || bxsize != xsize || bysize != ysize || (pixel_space != 0 && pixel_space != 1) ||
+        (line_space != 0 && line_space < xsize))
         return CE_Failure;
+    const size_t row_bytes = line_space ? (size_t)line_space : (size_t)xsize;
     if (rw == GF_Read) {
         if (ds->kind != 0)
             return CE_Failure;
@@ -172,11 +174,12 @@ CPLErr GDALRasterIO(GDALRasterBandH band, GDALRWFlag rw, int xoff, int yoff, int
         g_lastread.ysize = ysize;
         if (ds->src->data) {
             for (int y = 0; y < ysize; y++)
-                memcpy((uint8_t *)buf + (size_t)y * xsize,
+                memcpy((uint8_t *)buf + (size_t)y * row_bytes,
                        ds->src->data + (size_t)(yoff + y) * ds->w + xoff, (size_t)xsize);
         }
         else {
-            memset(buf, 0, (size_t)xsize * ysize);
+            for (int y = 0; y < ysize; y++)
+                memset((uint8_t *)buf + (size_t)y * row_bytes, 0, (size_t)xsize);
         }
         return CE_None;
     }

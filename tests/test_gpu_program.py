@@ -189,3 +189,64 @@ def test_program_reads_a_vrt_mosaic(world, ref, tmp_path):
     assert r.returncode == 0
     assert "gdal open failed" in r.stderr and "esa load failed for block 12" in r.stderr
     assert not list(out.glob("cn_rasters_*/cn_*_12*"))
+
+
+def test_program_with_the_gdal_backend(world, ref, tmp_path):
+    """The optional GDAL input backend (host_raster_gdal.c, make GDAL=1) inside the whole program: gcn10 is rebuilt
+    here with -DGCN10_WITH_GDAL against the oracle's RAM stand-in for GDAL, the land cover is served by that GDAL under
+    a /vsicurl/ name no file has (the soil raster stays a GeoTIFF on disk, read by the built-in reader), and the 18
+    rasters per block must equal the reference's process_block().  The land cover then arrives as decoded pixels and
+    goes through the raster-in entry point (gcn10_cuda_block_deflate_rows)."""
+    host = os.path.join(os.path.dirname(hostlib.EXE_PATH))
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "refshim")
+    esa, esa_t = world["esa"], world["esa_t"]
+    root = world["root"]
+    esa.tofile(str(tmp_path / "esa.raw"))
+    # the stand-in's registry lives in the process: a constructor fills it from a raw file before main() runs
+    (tmp_path / "preload.c").write_text(
+        '#include <stdio.h>\n#include <stdlib.h>\n#include <stdint.h>\n#include "refshim.h"\n'
+        'void refshim_sink_deliver(refshim_sink *s, const char *p, const void *b, int w, int h)\n'
+        '{ (void)s; (void)p; (void)b; (void)w; (void)h; }\n'
+        'double refshim_now(void) { return 0.0; }\n'
+        '__attribute__((constructor)) static void preload(void)\n{\n'
+        '    const char *raw = getenv("REFSHIM_RAW"), *name = getenv("REFSHIM_NAME");\n'
+        '    if (!raw || !name) return;\n'
+        '    int w = atoi(getenv("REFSHIM_W")), h = atoi(getenv("REFSHIM_H"));\n'
+        '    double t[6];\n'
+        '    sscanf(getenv("REFSHIM_GT"), "%lf,%lf,%lf,%lf,%lf,%lf", &t[0], &t[1], &t[2], &t[3], &t[4], &t[5]);\n'
+        '    uint8_t *d = malloc((size_t)w * h);\n'
+        '    FILE *f = fopen(raw, "rb");\n'
+        '    if (!d || !f || fread(d, 1, (size_t)w * h, f) != (size_t)w * h) abort();\n'
+        '    fclose(f);\n'
+        '    refshim_add_raster(name, d, w, h, t);\n}\n')
+    exe = str(tmp_path / "gcn10_gdal")
+    srcs = [os.path.join(host, f) for f in ("gcn10_main.c", "host_pipeline.c", "host_core.c", "host_tiff.c", "host_raster.c",
+                                            "host_raster_gdal.c")]
+    cmd = ["gcc", "-std=gnu11", "-O2", "-fPIC", "-ffp-contract=off", "-pthread", "-DGCN10_WITH_GDAL",
+           "-I" + os.path.join(shim, "include"), "-I" + shim, "-o", exe, *srcs, os.path.join(shim, "fake_gdal.c"),
+           str(tmp_path / "preload.c"), "-L" + os.path.dirname(host), "-lgcn10cuda",
+           "-Wl,-rpath," + os.path.dirname(host), "-lz", "-lm", "-lstdc++"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    name = "/vsicurl/https://example.invalid/esa_worldcover.tif"
+    fixtures.write_config(str(tmp_path / "config.txt"), name, str(root / "hsg.tif"), str(root / "blocks.shp"),
+                          str(root / "lookups"), str(tmp_path / "logs"))
+    out = tmp_path / "out"
+    out.mkdir()
+    env = dict(os.environ, REFSHIM_RAW=str(tmp_path / "esa.raw"), REFSHIM_NAME=name, REFSHIM_W=str(esa.shape[1]),
+               REFSHIM_H=str(esa.shape[0]), REFSHIM_GT=",".join(repr(float(v)) for v in esa_t))
+    env.pop("GCN10_RASTER_BACKEND", None)
+    r = subprocess.run([exe, "-c", str(tmp_path / "config.txt"), "-l", str(root / "blocks.txt"), "--gpus", "1", "-o",
+                        "--io-threads", "4", "--outdir", str(out)], cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    log = (tmp_path / "logs" / "rank_0.log").read_text()
+    assert f"{name} opened with gdal" in log and "hsg.tif opened with gdal" not in log
+    assert "inflated on the gpu" not in log
+    for bid, x0, y0, x1, y1 in world["blocks"][:2]:
+        want = ref.run_block(esa, esa_t, world["hsg"], world["hsg_t"], (x0, y0, x1, y1), str(root / "lookups"),
+                             block_id=bid)
+        for k, rel in enumerate(want["paths"]):
+            t = hostlib.Tiff(str(out / rel))
+            assert t.gt == want["gt"] and np.array_equal(t.read(), want["planes"][k]), rel
+            t.close()
+    assert "esa load failed for block 13" in r.stderr and "block 99 not found" in r.stderr
