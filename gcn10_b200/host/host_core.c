@@ -306,7 +306,8 @@ int gh_blocks_open(const char *shp_path, gh_blocks **out, char *err, size_t errl
     uint32_t nrec = le32(dbf + 4);
     uint16_t hlen = le16(dbf + 8), rlen = le16(dbf + 10);
     int id_off = -1, id_len = 0, off = 1;       /* byte 0 of a record is the deletion flag */
-    for (size_t d = 32; d + 32 <= hlen && dbf[d] != 0x0D; d += 32) {
+    const size_t desc_end = hlen < dbf_len ? hlen : dbf_len;    /* a damaged header length must not reach past the file */
+    for (size_t d = 32; d + 32 <= desc_end && dbf[d] != 0x0D; d += 32) {
         char name[12] = { 0 };
         memcpy(name, dbf + d, 11);
         int flen = dbf[d + 16];
@@ -316,7 +317,7 @@ int gh_blocks_open(const char *shp_path, gh_blocks **out, char *err, size_t errl
         }
         off += flen;
     }
-    if (id_off < 0 || (size_t)hlen + (size_t)nrec * rlen > dbf_len + 1) {
+    if (id_off < 0 || rlen == 0 || id_off + id_len > (int)rlen || (size_t)hlen + (size_t)nrec * rlen > dbf_len + 1) {
         set_err(err, errlen, "ogr open failed: %s (attribute \"ID\" not found)", shp_path);
         free(shp);
         free(dbf);
@@ -324,14 +325,23 @@ int gh_blocks_open(const char *shp_path, gh_blocks **out, char *err, size_t errl
     }
 
     gh_blocks *b = calloc(1, sizeof *b);
-    b->ids = malloc(sizeof(int) * (nrec ? nrec : 1));
-    b->bbox = malloc(sizeof(double) * 4 * (nrec ? nrec : 1));
+    if (b) {
+        b->ids = malloc(sizeof(int) * (nrec ? (size_t)nrec : 1));
+        b->bbox = malloc(sizeof(double) * 4 * (nrec ? (size_t)nrec : 1));
+    }
+    if (!b || !b->ids || !b->bbox) {
+        set_err(err, errlen, "ogr open failed: %s (out of memory)", shp_path);
+        gh_blocks_close(b);
+        free(shp);
+        free(dbf);
+        return -1;
+    }
     size_t pos = 100;
     uint32_t i = 0;
     while (i < nrec && pos + 8 <= shp_len) {
-        uint32_t content = be32(shp + pos + 4) * 2u;    /* length in 16-bit words */
+        const size_t content = (size_t)be32(shp + pos + 4) * 2u;       /* length in 16-bit words */
         const unsigned char *rec = shp + pos + 8;
-        if (pos + 8 + content > shp_len)
+        if (content > shp_len - pos - 8)
             break;
         uint32_t shape = content >= 4 ? le32(rec) : 0;
         double *bb = b->bbox + 4 * (size_t)i;

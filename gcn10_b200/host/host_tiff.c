@@ -24,6 +24,7 @@
 #include <string.h>
 #include <unistd.h>
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 static void set_err(char *err, size_t errlen, const char *fmt, ...)
@@ -178,6 +179,7 @@ struct gh_tiff {
     int tiles_x, tiles_y;
     uint64_t *offsets, *counts;
     uint64_t nchunks;
+    uint64_t file_size;
     int has_gt;
     double gt[6];
     /* GeoTIFF georeferencing tags as they lie in the file (34735 key directory, 34736 double params, 34737 ascii
@@ -244,9 +246,12 @@ static int entry_values(gh_tiff *t, int type, uint64_t count, const unsigned cha
     size_t ts = type_size(type);
     if (!ts || count == 0)
         return -1;
-    const int is_inline = ts * (size_t)count <= valfield_len;    /* decided by the stored count */
+    const int is_inline = count <= valfield_len / ts;            /* decided by the stored count */
     if (count > max)
         count = max;
+    /* a table cannot be longer than the file that holds it (a damaged count must not size an allocation) */
+    if (!is_inline && count > t->file_size / ts)
+        return -1;
     size_t bytes = ts * (size_t)count;
     unsigned char *buf = malloc(bytes);
     if (!buf)
@@ -256,7 +261,7 @@ static int entry_values(gh_tiff *t, int type, uint64_t count, const unsigned cha
     }
     else {
         uint64_t off = t->big ? rd64(t, valfield) : rd32(t, valfield);
-        if (pread_all(t->fd, buf, bytes, off)) {
+        if (off > t->file_size || bytes > t->file_size - off || pread_all(t->fd, buf, bytes, off)) {
             free(buf);
             return -1;
         }
@@ -270,8 +275,8 @@ static int entry_values(gh_tiff *t, int type, uint64_t count, const unsigned cha
         case 3: uv = rd16(t, p); dv = (double)uv; break;
         case 4: case 13: uv = rd32(t, p); dv = (double)uv; break;
         case 16: case 18: uv = rd64(t, p); dv = (double)uv; break;
-        case 12: { uint64_t b = rd64(t, p); memcpy(&dv, &b, 8); uv = (uint64_t)dv; break; }
-        case 11: { uint32_t b = rd32(t, p); float f; memcpy(&f, &b, 4); dv = f; uv = (uint64_t)dv; break; }
+        case 12: { uint64_t b = rd64(t, p); memcpy(&dv, &b, 8); uv = dv >= 0.0 && dv < 1.8e19 ? (uint64_t)dv : 0; break; }
+        case 11: { uint32_t b = rd32(t, p); float f; memcpy(&f, &b, 4); dv = f; uv = dv >= 0.0 && dv < 1.8e19 ? (uint64_t)dv : 0; break; }
         default: free(buf); return -1;
         }
         if (u) u[i] = uv;
@@ -291,10 +296,12 @@ int gh_tiff_open(const char *path, gh_tiff **out, char *err, size_t errlen)
         return -1;
     t->fd = open(path, O_RDONLY);
     unsigned char hdr[16];
-    if (t->fd < 0 || pread_all(t->fd, hdr, 8, 0)) {
+    struct stat st;
+    if (t->fd < 0 || fstat(t->fd, &st) || st.st_size < 8 || pread_all(t->fd, hdr, 8, 0)) {
         set_err(err, errlen, "gdal open failed: %s", path);                 /* raster.c:121 */
         goto fail;
     }
+    t->file_size = (uint64_t)st.st_size;
     if (hdr[0] == 'I' && hdr[1] == 'I') t->swap = 0;
     else if (hdr[0] == 'M' && hdr[1] == 'M') t->swap = 1;
     else { set_err(err, errlen, "gdal open failed: %s (not a TIFF)", path); goto fail; }
@@ -314,6 +321,10 @@ int gh_tiff_open(const char *path, gh_tiff **out, char *err, size_t errlen)
     if (pread_all(t->fd, nb, t->big ? 8 : 2, ifd)) goto fail;
     uint64_t nent = t->big ? rd64(t, nb) : rd16(t, nb);
     size_t esz = t->big ? 20 : 12;
+    if (nent == 0 || nent > 65535 || ifd > t->file_size || esz * nent > t->file_size - ifd) {
+        set_err(err, errlen, "gdal open failed: %s (damaged TIFF directory)", path);
+        goto fail;
+    }
     unsigned char *ents = malloc(esz * (size_t)nent);
     if (!ents || pread_all(t->fd, ents, esz * (size_t)nent, ifd + (t->big ? 8 : 2))) { free(ents); goto fail; }
 
@@ -397,10 +408,16 @@ int gh_tiff_open(const char *path, gh_tiff **out, char *err, size_t errlen)
         t->tw = t->w;
         t->th = (rows_per_strip <= 0 || rows_per_strip > t->h) ? t->h : rows_per_strip;
     }
-    t->tiles_x = (t->w + t->tw - 1) / t->tw;
-    t->tiles_y = (t->h + t->th - 1) / t->th;
+    /* tile geometry out of a damaged directory: no division by zero, no tile that cannot be allocated */
+    if (t->tw <= 0 || t->th <= 0 || (uint64_t)t->tw * (uint64_t)t->th > (1ull << 33)) {
+        set_err(err, errlen, "gdal open failed: %s (bad tile size %d x %d)", path, t->tw, t->th);
+        free(ents);
+        goto fail;
+    }
+    t->tiles_x = (int)(((int64_t)t->w + t->tw - 1) / t->tw);
+    t->tiles_y = (int)(((int64_t)t->h + t->th - 1) / t->th);
     t->nchunks = (uint64_t)t->tiles_x * (uint64_t)t->tiles_y;
-    if (off_tag_count < t->nchunks) {
+    if (off_tag_count < t->nchunks || t->nchunks > t->file_size) {
         set_err(err, errlen, "gdal open failed: %s (offset table shorter than the tile grid)", path);
         free(ents);
         goto fail;
@@ -583,6 +600,9 @@ static void read_chunk(void *arg, int index)
         if (pread_all(t->fd, buf, take, t->offsets[ci])) j->failed = 1;
         if (take < raw) memset(buf + take, 0, raw - take);
     }
+    else if (t->offsets[ci] > t->file_size || n > t->file_size - t->offsets[ci]) {
+        j->failed = 1;                      /* the tile table points outside the file */
+    }
     else {
         comp = malloc((size_t)n);
         if (!comp || pread_all(t->fd, comp, (size_t)n, t->offsets[ci])) {
@@ -658,8 +678,10 @@ int gh_tiff_window_tiles_plan(const gh_tiff *t, int xoff, int yoff, int xcount, 
     size_t total = 0;
     for (int ty = 0; ty < plan->tiles_y; ty++)
         for (int tx = 0; tx < plan->tiles_x; tx++) {
-            uint64_t n = t->counts[(uint64_t)(plan->ty0 + ty) * (uint64_t)t->tiles_x + (uint64_t)(plan->tx0 + tx)];
-            if (n > 0xFFFFFFFFull)
+            const uint64_t ci = (uint64_t)(plan->ty0 + ty) * (uint64_t)t->tiles_x + (uint64_t)(plan->tx0 + tx);
+            uint64_t n = t->counts[ci];
+            /* a tile the file cannot hold: leave it to the host path, whose read fails like GDAL's would */
+            if (n > 0xFFFFFFFFull || t->offsets[ci] > t->file_size || n > t->file_size - t->offsets[ci])
                 return 1;
             total += (size_t)n;
         }

@@ -112,7 +112,7 @@ def load_lookup_tables(lookup_dir: str) -> np.ndarray:
     e = _err()
     rc = L.gh_load_lookup_tables(os.fsencode(lookup_dir), t.ctypes.data, e, ERRLEN)
     if rc:
-        raise HostError(rc, e.value.decode())
+        raise HostError(rc, e.value.decode(errors="replace"))
     return t
 
 
@@ -131,8 +131,8 @@ def parse_config(path: str) -> dict:
     e = _err()
     rc = L.gh_config_parse(os.fsencode(path), C.byref(cfg), e, ERRLEN)
     if rc:
-        raise HostError(rc, e.value.decode())
-    out = {k: getattr(cfg, k).decode() for k, _ in Config._fields_}
+        raise HostError(rc, e.value.decode(errors="replace"))
+    out = {k: getattr(cfg, k).decode(errors="replace") for k, _ in Config._fields_}
     L.gh_config_free(C.byref(cfg))
     return out
 
@@ -156,7 +156,7 @@ class Blocks:
         e = _err()
         rc = self.L.gh_blocks_open(os.fsencode(shp_path), C.byref(h), e, ERRLEN)
         if rc:
-            raise HostError(rc, e.value.decode())
+            raise HostError(rc, e.value.decode(errors="replace"))
         self.h = h
 
     def __len__(self):
@@ -184,7 +184,7 @@ def tiff_write(path: str, data: np.ndarray, gt, threads: int = 4):
     e = _err()
     rc = L.gh_tiff_write(os.fsencode(path), data.ctypes.data, w, h, w, (C.c_double * 6)(*gt), threads, e, ERRLEN)
     if rc:
-        raise HostError(rc, e.value.decode())
+        raise HostError(rc, e.value.decode(errors="replace"))
 
 
 class Tiff:
@@ -194,7 +194,7 @@ class Tiff:
         e = _err()
         rc = self.L.gh_tiff_open(os.fsencode(path), C.byref(h), e, ERRLEN)
         if rc:
-            raise HostError(rc, e.value.decode())
+            raise HostError(rc, e.value.decode(errors="replace"))
         self.h = h
         w, hh = C.c_int(), C.c_int()
         self.L.gh_tiff_size(h, w, hh)
@@ -210,7 +210,7 @@ class Tiff:
         e = _err()
         rc = self.L.gh_tiff_read_window(self.h, xoff, yoff, xcount, ycount, out.ctypes.data, xcount, threads, e, ERRLEN)
         if rc:
-            raise HostError(rc, e.value.decode())
+            raise HostError(rc, e.value.decode(errors="replace"))
         return out
 
     def window_tiles(self, xoff=0, yoff=0, xcount=None, ycount=None, threads=4):
@@ -230,7 +230,7 @@ class Tiff:
         rc = self.L.gh_tiff_window_tiles_read(self.h, C.byref(plan), blob.ctypes.data, offsets.ctypes.data,
                                               sizes.ctypes.data, threads, e, ERRLEN)
         if rc:
-            raise HostError(rc, e.value.decode())
+            raise HostError(rc, e.value.decode(errors="replace"))
         return dict(tile_w=plan.tile_w, tile_h=plan.tile_h, tiles_x=plan.tiles_x, tiles_y=plan.tiles_y, x_in=plan.x_in,
                     y_in=plan.y_in, blob=blob[:plan.blob_bytes], offsets=offsets, sizes=sizes)
 
@@ -260,7 +260,7 @@ class Raster:
         e = _err()
         rc = self.L.gh_raster_open(os.fsencode(path), C.byref(h), e, ERRLEN)
         if rc:
-            raise HostError(rc, e.value.decode())
+            raise HostError(rc, e.value.decode(errors="replace"))
         self.h = h
         w, hh = C.c_int(), C.c_int()
         self.L.gh_raster_size(h, w, hh)
@@ -279,7 +279,7 @@ class Raster:
         e = _err()
         rc = self.L.gh_raster_read_window(self.h, xoff, yoff, xcount, ycount, out.ctypes.data, pitch, threads, e, ERRLEN)
         if rc:
-            raise HostError(rc, e.value.decode())
+            raise HostError(rc, e.value.decode(errors="replace"))
         return out[:, :xcount]
 
     def window_parts(self, xoff, yoff, xcount, ycount, max_parts=9, threads=4):
@@ -290,7 +290,7 @@ class Raster:
         e = _err()
         rc = self.L.gh_raster_window_parts(self.h, xoff, yoff, xcount, ycount, arr, max_parts, C.byref(n), e, ERRLEN)
         if rc < 0:
-            raise HostError(rc, e.value.decode())
+            raise HostError(rc, e.value.decode(errors="replace"))
         parts = []
         for k in range(n.value if rc == 0 else 0):
             plan = arr[k].plan
@@ -301,7 +301,7 @@ class Raster:
             r2 = self.L.gh_tiff_window_tiles_read(arr[k].ds, C.byref(plan), blob.ctypes.data, offsets.ctypes.data,
                                                   sizes.ctypes.data, threads, e, ERRLEN)
             if r2:
-                raise HostError(r2, e.value.decode())
+                raise HostError(r2, e.value.decode(errors="replace"))
             parts.append(dict(dst_x=arr[k].dst_x, dst_y=arr[k].dst_y, w=arr[k].w, h=arr[k].h, tile_w=plan.tile_w,
                               tile_h=plan.tile_h, tiles_x=plan.tiles_x, tiles_y=plan.tiles_y, x_in=plan.x_in,
                               y_in=plan.y_in, blob=blob[:plan.blob_bytes], offsets=offsets, sizes=sizes))
@@ -322,7 +322,7 @@ class TiffWriter:
         e = _err()
         rc = self.L.gh_tiffw_open(os.fsencode(path), w, h, (C.c_double * 6)(*gt), C.byref(h_), e, ERRLEN)
         if rc:
-            raise HostError(rc, e.value.decode())
+            raise HostError(rc, e.value.decode(errors="replace"))
         self.h = h_
         self.tiles_x = (w + 255) // 256
 

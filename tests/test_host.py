@@ -3,6 +3,7 @@ reader, window arithmetic, config file, block list, shapefile extents, GeoTIFF w
 format.  Expected values come from the golden fixtures (reference object code) and the oracle."""
 import os
 import re
+import struct
 import subprocess
 
 import numpy as np
@@ -468,3 +469,100 @@ def test_geotiff_writer_takes_several_ordered_tile_rows_in_one_write(tmp_path):
         t = hostlib.Tiff(str(p))
         assert np.array_equal(t.read(), a), name
         t.close()
+
+
+def _ifd_entries(b):
+    ifd = struct.unpack_from("<I", b, 4)[0]
+    n = struct.unpack_from("<H", b, ifd)[0]
+    return ifd, {struct.unpack_from("<H", b, ifd + 2 + 12 * i)[0]: ifd + 2 + 12 * i for i in range(n)}
+
+
+def test_geotiff_reader_survives_damaged_directories(tmp_path):
+    """Input files are not trusted: a damaged TIFF directory (found by mutation fuzzing under ASan: zero tile sizes
+    divided, counts sized allocations) must be refused like GDAL refuses it -- an error, the block is skipped
+    (raster.c:121, cn.c:188-192) -- never a crash."""
+    a = (np.arange(300 * 520).reshape(300, 520) % 7 * 10).astype(np.uint8)
+    p = str(tmp_path / "ok.tif")
+    hostlib.tiff_write(p, a, (-114.0, PX, 0.0, 42.0, 0.0, -PX), threads=2)
+    good = open(p, "rb").read()
+    ifd, ent = _ifd_entries(good)
+
+    def damaged(edit):
+        b = bytearray(good)
+        edit(b)
+        q = str(tmp_path / "bad.tif")
+        open(q, "wb").write(b)
+        return q
+
+    cases = {
+        "tile width 0": lambda b: struct.pack_into("<I", b, ent[322] + 8, 0),
+        "tile length 0": lambda b: struct.pack_into("<I", b, ent[323] + 8, 0),
+        "tile width type unknown": lambda b: struct.pack_into("<H", b, ent[322] + 2, 99),
+        "huge tile": lambda b: (struct.pack_into("<HI", b, ent[322] + 2, 4, 1), struct.pack_into("<I", b, ent[322] + 8, 0x7FFFFFFF),
+                                struct.pack_into("<HI", b, ent[323] + 2, 4, 1), struct.pack_into("<I", b, ent[323] + 8, 0x7FFFFFFF)),
+        "directory offset outside the file": lambda b: struct.pack_into("<I", b, 4, 0xFFFFFF00),
+        "directory longer than the file": lambda b: struct.pack_into("<H", b, ifd, 0xFFFF),
+        "offset table outside the file": lambda b: struct.pack_into("<I", b, ent[324] + 8, 0xFFFFFF00),
+        "image 2^31 wide": lambda b: struct.pack_into("<I", b, ent[256] + 8, 0x80000000),
+        "truncated": lambda b: b.__delitem__(slice(ifd + 20, None)),
+    }
+    for name, edit in cases.items():
+        with pytest.raises(hostlib.HostError) as e:
+            hostlib.Raster(damaged(edit))
+        assert "gdal open failed" in e.value.msg, name
+    # a count larger than the tile grid needs is tolerated: only the grid's entries are read
+    r = hostlib.Raster(damaged(lambda b: struct.pack_into("<I", b, ent[324] + 4, 0xFFFFFFFF)))
+    assert np.array_equal(r.read(0, 0, 520, 300), a)
+    r.close()
+    # tile tables that point outside the file: the file opens, the read fails, compressed tiles are not handed out
+    def far_tile(b):
+        off = struct.unpack_from("<I", b, ent[324] + 8)[0]
+        struct.pack_into("<I", b, off, 0xFFFFFF00)
+    r = hostlib.Raster(damaged(far_tile))
+    with pytest.raises(hostlib.HostError) as e:
+        r.read(0, 0, 520, 300)
+    assert "gdalrasterio error" in e.value.msg                      # raster.c:182
+    rc, parts = r.window_parts(0, 0, 520, 300)
+    assert rc == 1 and parts == []
+    r.close()
+    def long_tile(b):
+        cnt = struct.unpack_from("<I", b, ent[325] + 8)[0]
+        struct.pack_into("<I", b, cnt, 0xFFFFFFF0)
+    r = hostlib.Raster(damaged(long_tile))
+    with pytest.raises(hostlib.HostError):
+        r.read(0, 0, 520, 300)
+    assert r.window_parts(0, 0, 520, 300)[0] == 1
+    r.close()
+
+
+def test_shapefile_reader_survives_damaged_attribute_tables(tmp_path):
+    """Same for the block shapefile (cn.c:155-184 reads it through OGR): header lengths, record lengths and field
+    widths out of a damaged .dbf must not index past the file."""
+    shp = str(tmp_path / "b.shp")
+    fixtures.write_block_shapefile(shp, [(2234, -114.0, 39.0, -111.0, 42.0), (7, 0.0, 0.0, 3.0, 3.0)])
+    dbf_path = str(tmp_path / "b.dbf")
+    good = open(dbf_path, "rb").read()
+    assert hostlib.Blocks(shp).bbox(7) == (0.0, 0.0, 3.0, 3.0)
+    cases = {
+        "header length beyond the file": lambda b: struct.pack_into("<H", b, 8, 0xFFF0),
+        "record length 0": lambda b: struct.pack_into("<H", b, 10, 0),
+        "record count absurd": lambda b: struct.pack_into("<I", b, 4, 0xFFFFFFFF),
+        "field wider than the record": lambda b: b.__setitem__(32 + 16, 255),
+        "no field terminator": lambda b: b.__setitem__(b.index(0x0D), 0x41),
+    }
+    for name, edit in cases.items():
+        b = bytearray(good)
+        edit(b)
+        open(dbf_path, "wb").write(b)
+        try:
+            blocks = hostlib.Blocks(shp)
+            blocks.bbox(2234)               # whatever it holds, reading it back must be safe
+        except hostlib.HostError as e:
+            assert "ogr open failed" in e.msg, name
+    # the geometry file: a record length that points far past the end stops the walk
+    open(dbf_path, "wb").write(good)
+    sb = bytearray(open(shp, "rb").read())
+    struct.pack_into(">I", sb, 100 + 4, 0x7FFFFFFF)
+    open(shp, "wb").write(sb)
+    blocks = hostlib.Blocks(shp)
+    assert len(blocks) == 0
