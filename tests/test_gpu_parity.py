@@ -204,3 +204,53 @@ def test_block_async_blocks_in_flight(gpu_ctx, port, tables):
 def test_pcie_probe(gpu_ctx):
     r = gpu_ctx.pcie_probe(64 << 20, 2)
     assert all(v > 0.5 for v in r.values()), r
+
+
+def test_contexts_in_concurrent_host_threads(port, tables):
+    """SURVEY 8(b) threading: a context per worker thread, no state shared between contexts.  Three threads, each with
+    its own context on cuda:0 and its own lookup tables (the third one's are permuted, so planes computed with the
+    wrong context's tables would show), run different blocks through the plain and the compressed path at once."""
+    import threading
+    import zlib
+    shapes = [dict(w=3100, h=900, seed=71), dict(w=1777, h=1301, seed=72, profile="coastal"),
+              dict(w=2500, h=1111, seed=73, shift=(0.0003, 0.0007), margin=1)]
+    other = tables.copy()
+    other[:, :, 1:5] = tables[::-1, :, 1:5][:, :, ::-1]
+    tabs = [tables, tables, other]
+    blocks = [make_block(**kw) for kw in shapes]
+    wants = [port.block_rows(b["esa"], b["gt"], b["hsg"], b["soil_gt"], t) for b, t in zip(blocks, tabs)]
+    errors = []
+    start = threading.Barrier(len(blocks))
+
+    def work(i):
+        try:
+            ctx = capi.Context(0)
+            ctx.set_luts(tabs[i])
+            b, want = blocks[i], wants[i]
+            start.wait()
+            for rep in range(3):
+                got = ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
+                if not np.array_equal(got, want):
+                    errors.append(f"thread {i} rep {rep}: block() differs")
+                res = ctx.block_deflate(b["esa"], b["gt"], b["hsg"], b["soil_gt"], capi.MASK_ALL)
+                h, w = b["esa"].shape
+                ntiles = 0
+                for k, d in res["tiles"].items():
+                    for (ty, tx), z in d.items():
+                        ntiles += 1
+                        t = np.frombuffer(zlib.decompress(z), dtype=np.uint8).reshape(256, 256)
+                        ref = want[k][ty * 256:(ty + 1) * 256, tx * 256:(tx + 1) * 256]
+                        if not np.array_equal(t[:ref.shape[0], :ref.shape[1]], ref):
+                            errors.append(f"thread {i} rep {rep}: tile {(k, ty, tx)} differs")
+                if ntiles != 18 * ((h + 255) // 256) * ((w + 255) // 256):
+                    errors.append(f"thread {i} rep {rep}: {ntiles} tiles")
+            ctx.close()
+        except Exception as e:                  # noqa: BLE001 -- reported below
+            errors.append(f"thread {i}: {e!r}")
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(blocks))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
