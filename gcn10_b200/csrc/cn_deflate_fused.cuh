@@ -34,7 +34,13 @@ constexpr int kFusedOutCap = 31 * 1024;         // shared-memory staging for the
 constexpr int kFusedIds = 256;
 constexpr int kFusedPad = 255;                  // record id of the zero padding right / below the raster
 constexpr int kFusedClasses = 3;                // distinct "which records need a 9-bit literal" patterns over the planes
-constexpr int kFusedSplitEst = 6;               // rows with at least this many "new" words are cut into four 64-pixel items
+#ifndef GCN10_FUSED_SPLIT_EST
+#define GCN10_FUSED_SPLIT_EST 6
+#endif
+#ifndef GCN10_FUSED_CKPT_STEP
+#define GCN10_FUSED_CKPT_STEP 3
+#endif
+constexpr int kFusedSplitEst = GCN10_FUSED_SPLIT_EST;               // rows with at least this many "new" words are cut into four 64-pixel items
 constexpr int kFusedMaxItems = 512;             // two items per thread at most
 constexpr int kFusedMaxSplitRows = (kFusedMaxItems - kTile) / 3;
 constexpr int kFusedRowMeta = kTile;            // byte offset of a row's 16 spare bytes inside its 272-byte tile row
@@ -206,17 +212,33 @@ __device__ __forceinline__ uint32_t fused_row_run(int nrows, unsigned long long 
     return pos;
 }
 
+// Checkpoints of the sizing pass.  The parse of an item is serial and the items are far from equal (a tile has some
+// 750 tokens in 130 items, the longest has 17), so the pass that writes the streams -- the expensive one -- does not
+// run on the items: the sizing pass notes, every `step` tokens, where the parse stands (pixel, bits so far), and the
+// writing pass runs on the pieces between the notes, a few tokens each, dealt out evenly to the 256 threads.  A token
+// boundary is a free place to cut: the greedy parse has no state, it goes on from there exactly as it would have.
+// An item has room for kFusedCkpt notes; when they are used up every other one is dropped and the step doubles.
+constexpr int kFusedCkpt = 7;
+constexpr int kFusedCkptStep = GCN10_FUSED_CKPT_STEP;
+constexpr int kFusedMaxSubs = 1024;             // pieces a tile may have (four per thread); more: the items are written
+
+struct FusedCkpt {
+    uint32_t *note;                             // [kFusedCkpt]: pixel | bits << 8
+    uint32_t count, step, next, ntok;
+};
+
 // Greedy parse of pixels [xa, xb) of one row of the id tile (a whole row, or one 64-pixel item of a long row).
 //   WRITE = false: returns the bits common to all planes; lit += 9-bit-literal counts per class
 //   WRITE = true : emits planes [lo, hi) ; `pos` = common bits before this item, lit = class counts before
 //                  it, obase[k] = byte offset of plane k's stream in `out` (16-byte aligned); the 19 header
 //                  bits are added here.
-template <bool WRITE, int MAXP, bool ONE = false, bool TMPL = false>
+//   CKPT  (sizing pass, pos = 0): notes the state of the parse in *ck as described above
+template <bool WRITE, int MAXP, bool ONE = false, bool TMPL = false, bool CKPT = false>
 __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, const RowMasks &m, const uint8_t *val,
                                                     const unsigned long long *lit9, unsigned long long clsbits,
                                                     unsigned long long &lit, uint32_t pos, uint32_t *out,
                                                     const uint32_t *obase, int lo, int hi, int xa, int xb,
-                                                    const FusedCode &code, const uint8_t *rank)
+                                                    const FusedCode &code, const uint8_t *rank, FusedCkpt *ck = nullptr)
 {
     constexpr int VALB = MAXP <= 9 ? 16 : 32;
     const bool tuned = code.header_bits != 0;
@@ -282,6 +304,19 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
             pos += tuned ? (uint32_t)code.lit_bits : 8u;
             x += 1;
         }
+        if (CKPT) {
+            if (++ck->ntok == ck->next && x < xb) {
+                if (ck->count == (uint32_t)kFusedCkpt) {
+                    ck->note[0] = ck->note[1];
+                    ck->note[1] = ck->note[3];
+                    ck->note[2] = ck->note[5];
+                    ck->count = 3;
+                    ck->step *= 2u;
+                }
+                ck->note[ck->count++] = (uint32_t)x | (pos << 8);
+                ck->next = ck->ntok + ck->step;
+            }
+        }
     }
     return pos;
 }
@@ -306,6 +341,9 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     uint16_t *s_perm = reinterpret_cast<uint16_t *>(outb + 8192);       // 1 KB  items in processing order: row | piece << 8
     uint32_t *s_ibits = reinterpret_cast<uint32_t *>(outb + 10240);     // 2 KB  per item slot (stream order): common bits
     unsigned long long *s_ilit = reinterpret_cast<unsigned long long *>(outb + 12288);   // 4 KB  ... 9-bit-literal counts
+    uint8_t *s_nsub = outb + 9216;                                      // 512 B per item slot: pieces of the writing pass
+    uint32_t *s_note = reinterpret_cast<uint32_t *>(outb + 16384);      // 14 KB per item slot: kFusedCkpt checkpoints
+    uint2 *s_desc = reinterpret_cast<uint2 *>(outb);                    // 8 KB  the pieces (once s_cnt / s_w are dead)
 
     __shared__ unsigned long long s_scan[kTile / 32][2];
     __shared__ uint32_t s_adler[18], s_nbytes[18], s_obase[18], s_stored[18];
@@ -322,6 +360,8 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
 #pragma unroll
     for (int k = 0; k < 18; k++)
         clsbits |= (unsigned long long)(p.cls[k] & 3u) << (2 * k);
+    // one bit position for all streams (see step 6): the writing pass can then run on checkpointed pieces
+    const bool fine = tuned && clsbits == 0ull;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = blockIdx.x, ty = blockIdx.y;
@@ -622,14 +662,25 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         const int xa = piece == 4 ? 0 : 64 * piece, xb = piece == 4 ? kTile : xa + 64;
         const RowMasks pm = s_masks[r];
         const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
-        unsigned long long lit = 0;
-        const uint32_t bits = rl == 0xFFFFu ? 0u
-                              : rl ? fused_row_run<false, MAXP, false, false>((int)rl, clsbits, lit, 0u, nullptr, nullptr, 0, 0, p.code)
-                                   : fused_parse_row<false, MAXP>(tile, r, pm, s_val, p.lit9, clsbits, lit, 0u, nullptr, nullptr, 0,
-                                                                  0, xa, xb, p.code, s_rank);
         const uint32_t slot = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta) + (piece & 3);
+        unsigned long long lit = 0;
+        uint32_t bits = 0, nsub = rl == 0xFFFFu ? 0u : 1u;
+        if (rl != 0u) {
+            if (rl != 0xFFFFu)
+                bits = fused_row_run<false, MAXP, false, false>((int)rl, clsbits, lit, 0u, nullptr, nullptr, 0, 0, p.code);
+        }
+        else if (fine) {
+            FusedCkpt ck = { s_note + slot * kFusedCkpt, 0u, (uint32_t)kFusedCkptStep, (uint32_t)kFusedCkptStep, 0u };
+            bits = fused_parse_row<false, MAXP, false, false, true>(tile, r, pm, s_val, p.lit9, clsbits, lit, 0u, nullptr, nullptr,
+                                                                    0, 0, xa, xb, p.code, s_rank, &ck);
+            nsub += ck.count;
+        }
+        else
+            bits = fused_parse_row<false, MAXP>(tile, r, pm, s_val, p.lit9, clsbits, lit, 0u, nullptr, nullptr, 0, 0, xa, xb,
+                                                p.code, s_rank);
         s_ibits[slot] = bits;
         s_ilit[slot] = lit;
+        s_nsub[slot] = (uint8_t)nsub;
         if (q)
             slot_b = slot;
         else
@@ -641,7 +692,10 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     {
         const uint32_t i0 = 2u * tid, i1 = 2u * tid + 1u;
         const uint32_t b0 = i0 < n_items ? s_ibits[i0] : 0u, b1 = i1 < n_items ? s_ibits[i1] : 0u;
-        const unsigned long long l0 = i0 < n_items ? s_ilit[i0] : 0ull, l1 = i1 < n_items ? s_ilit[i1] : 0ull;
+        // (fine: the second scan counts the pieces of the writing pass instead of 9-bit literals, which the tuned
+        // code does not have)
+        const unsigned long long l0 = i0 < n_items ? (fine ? (unsigned long long)s_nsub[i0] : s_ilit[i0]) : 0ull;
+        const unsigned long long l1 = i1 < n_items ? (fine ? (unsigned long long)s_nsub[i1] : s_ilit[i1]) : 0ull;
         unsigned long long inc0 = (unsigned long long)b0 + b1, inc1 = l0 + l1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -677,7 +731,15 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
     __syncthreads();
     // the items' stream positions move into registers: the staging area is about to be reused
     const uint32_t pos_a = s_ibits[slot_a], pos_b = s_ibits[slot_b];
-    const unsigned long long lit_a = s_ilit[slot_a], lit_b = s_ilit[slot_b];
+    const unsigned long long lit_a = fine ? 0ull : s_ilit[slot_a], lit_b = fine ? 0ull : s_ilit[slot_b];
+    // fine: the pieces of this thread's items -> (row | first pixel << 8 | last pixel << 16, bit position), in stream
+    // order at the index the scan gave them; every thread then takes pieces t, t + 256, ... (below, after step 5)
+    const bool use_fine = fine && s_total_lit <= (unsigned long long)kFusedMaxSubs;
+    uint32_t sub_a = 0, sub_b = 0;
+    if (use_fine) {
+        sub_a = (uint32_t)s_ilit[slot_a];
+        sub_b = (uint32_t)s_ilit[slot_b];
+    }
 
     // ---- 5. Adler-32 per plane: s1 = 1 + sum cnt[id] val[id], s2 = N + sum w[id] val[id]  (mod 65521)
     for (int k = warp; k < nsel; k += kTile / 32) {
@@ -699,6 +761,41 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         }
     }
     __syncthreads();
+    uint32_t pc0[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, pc1[4] = { 0, 0, 0, 0 };
+    if (use_fine) {
+        // (s_cnt / s_w are dead now: the descriptors may take their place)
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            const uint32_t item = q ? item1 : item0;
+            if (item == 0xFFFFu)
+                break;
+            const uint32_t r = item & 255u, piece = item >> 8;
+            const uint32_t xa = piece == 4u ? 0u : 64u * piece, xb = piece == 4u ? (uint32_t)kTile : xa + 64u;
+            const uint32_t slot = q ? slot_b : slot_a, base = q ? pos_b : pos_a, n = s_nsub[slot];
+            const uint32_t *note = s_note + slot * kFusedCkpt;
+            uint2 *d = s_desc + (q ? sub_b : sub_a);
+            uint32_t a = xa, at = base;
+            for (uint32_t j = 0; j < n; j++) {
+                const uint32_t nt = j + 1u < n ? note[j] : 0u;
+                const uint32_t b = j + 1u < n ? (nt & 255u) : xb;
+                d[j] = make_uint2(r | (a << 8) | ((b - 1u) << 16), at);
+                a = b;
+                at = base + (nt >> 8);
+            }
+        }
+        __syncthreads();
+        const uint32_t nsubs = (uint32_t)s_total_lit;
+#pragma unroll
+        for (int mth = 0; mth < 4; mth++) {
+            const uint32_t g = (uint32_t)tid + (uint32_t)kTile * mth;
+            if (g < nsubs) {
+                const uint2 d = s_desc[g];
+                pc0[mth] = d.x;
+                pc1[mth] = d.y;
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- 6. sizes, stored fallbacks, arena allocation, rounds
     if (tid == 0) {
@@ -772,6 +869,25 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
             for (uint32_t i = tid; i < span / 16 + 4; i += kTile)
                 reinterpret_cast<uint4 *>(outb)[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
+            if (use_fine) {
+                uint32_t d0 = pc0[0], d1 = pc0[1], d2 = pc0[2], d3 = pc0[3];
+                uint32_t e0 = pc1[0], e1 = pc1[1], e2 = pc1[2], e3 = pc1[3];
+#pragma unroll 1
+                for (int mth = 0; mth < 4 && d0 != 0xFFFFFFFFu; mth++) {
+                    const int r = d0 & 255u, xa = (d0 >> 8) & 255u, xb = (int)((d0 >> 16) & 255u) + 1;
+                    const RowMasks pm = s_masks[r];
+                    unsigned long long lw = 0ull;
+                    const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
+                    if (rl)
+                        fused_row_run<true, MAXP, true, true>((int)rl, clsbits, lw, e0, out, s_obase, lo, hi, p.code);
+                    else
+                        fused_parse_row<true, MAXP, true, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, e0, out, s_obase, lo, hi,
+                                                                xa, xb, p.code, s_rank);
+                    d0 = d1; d1 = d2; d2 = d3; d3 = 0xFFFFFFFFu;
+                    e0 = e1; e1 = e2; e2 = e3;
+                }
+            }
+            else {
 #pragma unroll 1
             for (int q = 0; q < 2; q++) {
                 const uint32_t item = q ? item1 : item0;
@@ -789,6 +905,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                 else
                     fused_parse_row<true, MAXP, true, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, q ? pos_b : pos_a, out,
                                                             s_obase, lo, hi, xa, xb, p.code, s_rank);
+            }
             }
             if (tuned) {
                 for (int i = tid; i < (p.code.header_bits + 31) >> 5; i += kTile)
@@ -832,7 +949,25 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                 int b = a;
                 while (b < hi && !s_stored[b])
                     b++;
-                if (a < b) {
+                if (a < b && use_fine) {
+                    uint32_t d0 = pc0[0], d1 = pc0[1], d2 = pc0[2], d3 = pc0[3];
+                    uint32_t e0 = pc1[0], e1 = pc1[1], e2 = pc1[2], e3 = pc1[3];
+#pragma unroll 1
+                    for (int mth = 0; mth < 4 && d0 != 0xFFFFFFFFu; mth++) {
+                        const int r = d0 & 255u, xa = (d0 >> 8) & 255u, xb = (int)((d0 >> 16) & 255u) + 1;
+                        const RowMasks pm = s_masks[r];
+                        unsigned long long lw = 0ull;
+                        const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
+                        if (rl)
+                            fused_row_run<true, MAXP, true, false>((int)rl, clsbits, lw, e0, out, s_obase, a, b, p.code);
+                        else
+                            fused_parse_row<true, MAXP, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, e0, out, s_obase, a, b, xa, xb,
+                                                              p.code, s_rank);
+                        d0 = d1; d1 = d2; d2 = d3; d3 = 0xFFFFFFFFu;
+                        e0 = e1; e1 = e2; e2 = e3;
+                    }
+                }
+                else if (a < b) {
 #pragma unroll 1
                     for (int q = 0; q < 2; q++) {
                         const uint32_t item = q ? item1 : item0;

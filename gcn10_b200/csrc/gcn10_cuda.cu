@@ -62,6 +62,7 @@ struct StripSlot {
     DevBuf esa;
     DevBuf out;                 // nplanes * strip_rows * pitch
     cudaEvent_t k0 = nullptr, k1 = nullptr, done = nullptr;
+    cudaEvent_t k2 = nullptr;   // tile-deflate path: behind everything the strip computes (encoder + re-ordering kernels)
     bool timed = false;
     // tile-deflate path
     DevBuf blob, table;         // compressed tiles; [cursor(16 B) | offsets u64[] | sizes u32[]]
@@ -86,6 +87,8 @@ struct TileSlot {
     HostBuf h_status;           // [ntiles] status codes | launch order | offsets (u64) | sizes (u32): page-locked staging
     cudaEvent_t inf0 = nullptr, inf1 = nullptr, done = nullptr;     // around the inflate kernel; behind the status copy
     bool pending = false;       // inflate issued, result not consumed yet
+    bool deferred = false;      // ... uploads issued, the kernel waits for the strips of the block in hand (launch_inflate)
+    InflateParams ip;           // the deferred launch
     uint64_t seq = 0;           // issue order of pending slots
     const void *key_blob = nullptr, *key_off = nullptr;
     size_t key_bytes = 0, ntiles = 0, dpitch = 0;
@@ -125,6 +128,7 @@ struct gcn10_ctx {
     // compressed-input path: the tiles' bytes, their tables and the inflated land-cover plane of a block
     TileSlot tslot[2];
     cudaStream_t pre_stream = nullptr;      // uploads + inflate kernels
+    int defer_inflate = 1;                  // option: hold a prefetched block's inflate kernel back (launch_inflate)
     uint64_t tile_seq = 0;
     float last_inflate_ms = 0.f;
     float last_kernel_ms = 0.f;
@@ -712,6 +716,7 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
     for (int i = 0; i < kMaxStreams; i++) {
         CUDA_TRY(cudaEventCreate(&c->slots[i].k0));
         CUDA_TRY(cudaEventCreate(&c->slots[i].k1));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->slots[i].k2, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->slots[i].done, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->slots[i].enc_done, cudaEventDisableTiming));
     }
@@ -791,6 +796,7 @@ void gcn10_cuda_destroy(gcn10_ctx *c)
         if (c->slots[i].enc_done) cudaEventDestroy(c->slots[i].enc_done);
         if (c->slots[i].k0) cudaEventDestroy(c->slots[i].k0);
         if (c->slots[i].k1) cudaEventDestroy(c->slots[i].k1);
+        if (c->slots[i].k2) cudaEventDestroy(c->slots[i].k2);
         if (c->slots[i].done) cudaEventDestroy(c->slots[i].done);
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
         if (c->ship_streams[i]) cudaStreamDestroy(c->ship_streams[i]);
@@ -819,6 +825,7 @@ int gcn10_cuda_set_option(gcn10_ctx *c, const char *key, long value)
         return fail(GCN10_EINVAL, "NULL argument");
     if (!strcmp(key, "strip_rows") && value >= 1) c->strip_rows = (int)value;
     else if (!strcmp(key, "streams") && value >= 1 && value <= kMaxStreams) c->nstreams = (int)value;
+    else if (!strcmp(key, "defer_inflate") && (value == 0 || value == 1)) c->defer_inflate = (int)value;
     else if (!strcmp(key, "rows_per_cta") && value >= 0) c->rows_per_cta = (int)value;
     else if (!strcmp(key, "tma") && (value == 0 || value == 1)) c->use_tma = (int)value;
     else if (!strcmp(key, "fused") && (value == 0 || value == 1)) c->fused = (int)value;
@@ -1154,6 +1161,8 @@ int gcn10_cuda_block_deflate(gcn10_ctx *c,
 // Strips of whole tile rows: [H2D of the land-cover rows ->] Curve Number kernel -> tile DEFLATE -> D2H of
 // the compressed tiles -> sink.  The land cover comes either from the caller's host raster (esa) or from a
 // device-resident plane (d_esa, valid once `esa_ready` has fired: the compressed-input path).
+static int launch_inflate(gcn10_ctx *c, TileSlot &sl, cudaEvent_t after);
+
 static int deflate_rows_impl(gcn10_ctx *c,
                              const uint8_t *esa, size_t esa_pitch, const uint8_t *d_esa, size_t d_esa_pitch,
                              cudaEvent_t esa_ready, int w, int h, int row0, int nrows,
@@ -1252,10 +1261,11 @@ static int deflate_rows_impl(gcn10_ctx *c,
             c->launches += 2;
             CUDA_TRY(cudaGetLastError());
         }
+        CUDA_TRY(cudaEventRecord(sl.k2, st));
         const void *out_blob = c->ordered ? sl.blob2.p : sl.blob.p;      // (ship: ordered strips always fit, see below)
         if (c->ship) {
             cudaStream_t ss = c->ship_streams[&sl - c->slots];
-            CUDA_TRY(cudaStreamWaitEvent(ss, sl.k1, 0));
+            CUDA_TRY(cudaStreamWaitEvent(ss, sl.k2, 0));
             ship_strip_kernel<<<kShipCtas, kShipThreads, 0, ss>>>((const uint4 *)out_blob, (const unsigned long long *)sl.table.p,
                                                                   (const uint32_t *)sl.table.p, (uint32_t)(table_bytes / 4),
                                                                   (uint4 *)sl.h_blob.p,
@@ -1285,6 +1295,11 @@ static int deflate_rows_impl(gcn10_ctx *c,
         if (!d_esa)
             CUDA_TRY(cudaMemcpy2DAsync(sl.esa.p, dpitch, esa + (size_t)y0 * esa_pitch, esa_pitch, (size_t)w, (size_t)rows,
                                        cudaMemcpyHostToDevice, st));
+        // The encoder kernels run in strip order, at most two at a time (the second fills the first one's last wave):
+        // launched side by side on all streams they would all finish together, and the copy of strip 0 -- the head of
+        // the chain of copies that ends the block -- would wait for the others.
+        if (s >= 2)
+            CUDA_TRY(cudaStreamWaitEvent(st, c->slots[(s - 2) % ns].k1, 0));
         CUDA_TRY(cudaEventRecord(sl.k0, st));
         if (fused) {
             FusedParams fp;
@@ -1359,8 +1374,20 @@ static int deflate_rows_impl(gcn10_ctx *c,
         return code;
     };
 
+    // the last strip is on its way: a prefetched block's inflate kernel may have the SMs behind it
+    auto release = [&](int s) -> int {
+        if (s != nstrips - 1)
+            return GCN10_OK;
+        for (int i = 0; i < 2; i++)
+            if (c->tslot[i].pending && c->tslot[i].deferred) {
+                int r2 = launch_inflate(c, c->tslot[i], c->slots[s % ns].k2);
+                if (r2)
+                    return r2;
+            }
+        return GCN10_OK;
+    };
     for (int s = 0; s < std::min(ns, nstrips); s++)
-        if ((rc = issue(s)))
+        if ((rc = issue(s)) || (rc = release(s)))
             return bail(rc);
     for (int s = 0; s < nstrips; s++) {
         StripSlot &sl = c->slots[s % ns];
@@ -1401,7 +1428,7 @@ static int deflate_rows_impl(gcn10_ctx *c,
         sl.busy = false;
         if (sink_rc)
             return bail(fail(GCN10_EINVAL, "tile sink returned %d", sink_rc));
-        if (s + ns < nstrips && (rc = issue(s + ns)))
+        if (s + ns < nstrips && ((rc = issue(s + ns)) || (rc = release(s + ns))))
             return bail(rc);
     }
     c->last_kernel_ms = kernel_ms;
@@ -1423,7 +1450,31 @@ int gcn10_cuda_block_deflate_rows(gcn10_ctx *c,
 // Upload the compressed tiles of every part and inflate them into sl.esa_full (pitch sl.dpitch) on the context's
 // upload stream, without waiting: ONE kernel launch for all parts (a 36-tile edge part launched on its own would
 // cost a whole tile's decode latency).  The per-tile status codes are in sl.h_status once that stream has drained.
-static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *parts, int nparts, int fill, int w, int h)
+// The inflate kernel of a slot whose uploads are on the upload stream already.  after != nullptr: not before that event
+// -- the inflater keeps every SM's shared memory and registers for milliseconds, so a prefetched block's kernel is held
+// back until the block in hand has issued its last strip (deflate_rows_impl) instead of starving the strips that
+// follow it.
+static int launch_inflate(gcn10_ctx *c, TileSlot &sl, cudaEvent_t after)
+{
+    if (!sl.deferred)
+        return GCN10_OK;
+    sl.deferred = false;
+    cudaStream_t st = c->pre_stream;
+    if (after)
+        CUDA_TRY(cudaStreamWaitEvent(st, after, 0));
+    CUDA_TRY(cudaEventRecord(sl.inf0, st));
+    inflate_tiles_kernel<<<(unsigned)sl.ntiles, kInflateThreads, kInflateSmem, st>>>(sl.ip);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(sl.inf1, st));
+    CUDA_TRY(cudaMemcpyAsync(sl.h_status.p, sl.ip.status, sl.ntiles * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(sl.done, st));
+    return GCN10_OK;
+}
+
+// defer: only the uploads are issued; launch_inflate() follows (at the latest when the slot is consumed)
+static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *parts, int nparts, int fill, int w, int h,
+                             bool defer = false)
 {
     if (!parts || nparts < 1)
         return fail(GCN10_EINVAL, "NULL argument");
@@ -1554,13 +1605,11 @@ static int inflate_to_device(gcn10_ctx *c, TileSlot &sl, const gcn10_tile_part *
     ip.order = d_order;
     ip.probe = c->inflate_probe;
     ip.nparts = nparts;
-    CUDA_TRY(cudaEventRecord(sl.inf0, st));
-    inflate_tiles_kernel<<<(unsigned)ntiles, kInflateThreads, kInflateSmem, st>>>(ip);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(sl.inf1, st));
-    CUDA_TRY(cudaMemcpyAsync(sl.h_status.p, d_status, ntiles * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaEventRecord(sl.done, st));
+    sl.ip = ip;
+    sl.ntiles = ntiles;
+    sl.deferred = true;
+    if (!defer && (rc = launch_inflate(c, sl, nullptr)))
+        return rc;
     sl.pending = true;
     sl.seq = ++c->tile_seq;
     sl.key_blob = parts[0].tiles.blob;
@@ -1589,6 +1638,9 @@ static gcn10_tile_part whole_window_part(const gcn10_tile_source *src, int w, in
 static int finish_slot(gcn10_ctx *c, TileSlot &sl, int *tile_status)
 {
     sl.pending = false;
+    int lrc = launch_inflate(c, sl, nullptr);               // (held back and never released: now)
+    if (lrc)
+        return lrc;
     CUDA_TRY(cudaEventSynchronize(sl.done));                // this slot only: a later prefetch keeps running
     const int *hs = (const int *)sl.h_status.p;
     size_t bad = 0, first_bad = 0;
@@ -1628,7 +1680,10 @@ static int acquire_slot(gcn10_ctx *c, const gcn10_tile_part *parts, int nparts, 
         TileSlot *sl = !c->tslot[0].pending ? &c->tslot[0] : !c->tslot[1].pending ? &c->tslot[1]
                        : c->tslot[0].seq < c->tslot[1].seq ? &c->tslot[0] : &c->tslot[1];
         if (sl->pending) {
-            CUDA_TRY(cudaEventSynchronize(sl->done));
+            if (sl->deferred)
+                sl->deferred = false;                       // never launched: its uploads drain in stream order
+            else
+                CUDA_TRY(cudaEventSynchronize(sl->done));
             sl->pending = false;
         }
         int rc = inflate_to_device(c, *sl, parts, nparts, fill, w, h);
@@ -1647,7 +1702,10 @@ int gcn10_cuda_parts_prefetch(gcn10_ctx *c, const gcn10_tile_part *parts, int np
     TileSlot *sl = !c->tslot[0].pending ? &c->tslot[0] : !c->tslot[1].pending ? &c->tslot[1] : nullptr;
     if (!sl)
         return fail(GCN10_EINVAL, "two prefetched blocks are already waiting; consume one first");
-    return inflate_to_device(c, *sl, parts, nparts, fill, w, h);
+    // The other slot holds a block that has not been run yet: the caller is about to run it (prefetch of block k + 1,
+    // then block k).  This block's inflate kernel then waits until that block has issued its last strip.
+    const TileSlot &other = c->tslot[sl == &c->tslot[0] ? 1 : 0];
+    return inflate_to_device(c, *sl, parts, nparts, fill, w, h, c->defer_inflate && other.pending);
 }
 
 int gcn10_cuda_tiles_prefetch(gcn10_ctx *c, const gcn10_tile_source *src, int w, int h)
@@ -1670,6 +1728,8 @@ int gcn10_cuda_inflate_parts(gcn10_ctx *c, const gcn10_tile_part *parts, int npa
     if (rc)
         return rc;
     cudaStream_t st = c->pre_stream;
+    if ((rc = launch_inflate(c, *sl, nullptr)))
+        return rc;
     CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, sl->esa_full.p, sl->dpitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return finish_slot(c, *sl, tile_status);

@@ -232,7 +232,10 @@ int gcn10_cuda_block_tiles_deflate(gcn10_ctx *ctx, const gcn10_tile_source *esa_
  *     gcn10_cuda_block_tiles_deflate(ctx, &tiles[i], w, h, ...);        -- prefetched in the previous iteration
  *
  * The memory behind src->blob / offsets / sizes must stay valid and unchanged until that call has returned.
- * At most two blocks can be waiting.  (Replaces nothing in the reference: its ranks read one block at a time,
+ * At most two blocks can be waiting.  When the other waiting block has not been run yet (the order above), the upload
+ * starts at once but the inflate kernel is queued behind that block's last strip: an inflate kernel occupies every SM
+ * for milliseconds, and started earlier it would hold up the strips whose copies end the block in hand (option
+ * "defer_inflate").  (Replaces nothing in the reference: its ranks read one block at a time,
  * cn.c:187.) */
 int gcn10_cuda_tiles_prefetch(gcn10_ctx *ctx, const gcn10_tile_source *src, int w, int h);
 
@@ -296,7 +299,8 @@ int gcn10_cuda_launch_count(gcn10_ctx *ctx, uint64_t *launches);
  * size read-back + copy-engine transfer), "ordered" (1 = every strip is re-laid on the device in table order -- [plane][tile row][tile column], streams on
  * 16-byte boundaries, offsets ascending -- so that a consumer can write a plane's share of a strip with one write),
  * "tuned_code" (0 = tile streams use RFC 1951's fixed Huffman code instead
- * of the tuned one), "inflate_probe" (measurement aid of tools/inflate_bench.py: 1 / 2 switch parts of the inflate
+ * of the tuned one), "defer_inflate" (0 = the inflate kernel of a prefetched block starts at once instead of behind
+ * the last strip of the block in hand), "inflate_probe" (measurement aid of tools/inflate_bench.py: 1 / 2 switch parts of the inflate
  * kernel's writer off; results are then invalid). */
 int gcn10_cuda_set_option(gcn10_ctx *ctx, const char *key, long value);
 

@@ -7,6 +7,7 @@ import json
 import os
 import sys
 import tempfile
+import time
 import zlib
 from concurrent.futures import ThreadPoolExecutor
 
@@ -26,6 +27,7 @@ def main():
     ap.add_argument("--tile", type=int, default=36000)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--planes", type=int, default=9, choices=[9, 18])
+    ap.add_argument("--streams", type=int, default=0, help="strip slots (0 = library default); 1 = strictly serial strips")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     tables = B.load_tables_host(lookups.write_default_lookups(tempfile.mkdtemp()))
@@ -60,11 +62,16 @@ def main():
         return 0
 
     mask = capi.MASK_DRAINED if a.planes == 9 else capi.MASK_ALL
+    if a.streams:
+        ctx.set_option("streams", a.streams)
     out = []
     for _ in range(a.reps):
         nb[0] = 0
+        t0 = time.perf_counter()
         ctx.block_tiles_deflate(src, w, h, gt, hsg, sgt, plane_mask=mask, on_strip=on_strip)
-        out.append({"inflate_ms": ctx.last_inflate_ms(), "fused_ms_sum_over_strips": ctx.last_kernel_ms(), "out_bytes": nb[0]})
+        wall = (time.perf_counter() - t0) * 1e3
+        out.append({"block_ms": round(wall, 3), "inflate_ms": ctx.last_inflate_ms(),
+                    "fused_ms_sum_over_strips": ctx.last_kernel_ms(), "out_bytes": nb[0]})
     print(json.dumps(out))
     ctx.close()
     pin.free()
