@@ -35,15 +35,21 @@ constexpr int kFusedIds = 256;
 constexpr int kFusedPad = 255;                  // record id of the zero padding right / below the raster
 constexpr int kFusedClasses = 3;                // distinct "which records need a 9-bit literal" patterns over the planes
 #ifndef GCN10_FUSED_SPLIT_EST
-#define GCN10_FUSED_SPLIT_EST 6
+#define GCN10_FUSED_SPLIT_EST 2
 #endif
 #ifndef GCN10_FUSED_CKPT_STEP
-#define GCN10_FUSED_CKPT_STEP 3
+#define GCN10_FUSED_CKPT_STEP 2
 #endif
-constexpr int kFusedSplitEst = GCN10_FUSED_SPLIT_EST;               // rows with at least this many "new" words are cut into four 64-pixel items
+#ifndef GCN10_FUSED_MIN_PIECE
+#define GCN10_FUSED_MIN_PIECE 8
+#endif
+constexpr int kFusedSplitEst = GCN10_FUSED_SPLIT_EST;   // rows with at least this many "new" words are cut into items
+constexpr int kFusedMinPiece = GCN10_FUSED_MIN_PIECE;   // ... of at least this many pixels
+constexpr int kFusedMaxCuts = 11;               // per row (the row's spare bytes hold them)
 constexpr int kFusedMaxItems = 512;             // two items per thread at most
-constexpr int kFusedMaxSplitRows = (kFusedMaxItems - kTile) / 3;
-constexpr int kFusedRowMeta = kTile;            // byte offset of a row's 16 spare bytes inside its 272-byte tile row
+constexpr int kFusedMaxExtra = kFusedMaxItems - kTile;  // items beyond one per row
+constexpr int kFusedRowMeta = kTile;            // byte offset of a row's 16 spare bytes inside its 272-byte tile row:
+                                                // u16 first item slot, u16 run length, u8 cuts, u8[11] cut pixels
 
 template <int MAXP>
 constexpr int fused_smem_bytes()
@@ -321,6 +327,15 @@ __device__ __forceinline__ uint32_t fused_parse_row(const uint8_t *tile, int r, 
     return pos;
 }
 
+// pixels [xa, xb) of item `piece` of tile row r (see step 2 of the kernel)
+__device__ __forceinline__ void fused_item_range(const uint8_t *tile, int r, uint32_t piece, int &xa, int &xb)
+{
+    const uint8_t *meta = tile + r * kTileStride + kFusedRowMeta + 4;
+    const uint32_t ncut = meta[0];
+    xa = piece ? (int)meta[piece] : 0;
+    xb = piece < ncut ? (int)meta[1u + piece] : kTile;
+}
+
 // grid = (tiles_x, tile_rows), 256 threads, fused_smem_bytes<MAXP>() of dynamic shared memory
 template <int MAXP>
 __global__ void __maxnreg__(120)
@@ -562,23 +577,68 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         }
         s_masks[tid] = m;
         // Work items.  A row's parse is serial, so the longest row sets the latency of the whole CTA: rows with
-        // many "new" words (neither a repeat of the row above nor the continuation of a run -- typically the first
-        // row of a soil cell) are cut into four 64-pixel items whose tokens stop at the item border (a few bits
-        // per cut).  Items are sorted by expected work so that the 32 items a warp parses in lockstep are alike.
+        // several "new" words (neither a repeat of the row above nor the continuation of a run -- typically the first
+        // row of a soil cell) are cut into items.  The cuts cost nothing: they are made at pixels that differ both from
+        // the pixel above and from the pixel to their left -- no match can run through such a pixel, so the greedy
+        // parse has a token boundary there anyway and goes on from it exactly as it would have.  Items are sorted by
+        // expected work so that the 32 items a warp parses in lockstep are alike.
         // Runs of rows that all repeat the row above them (the inside of a soil cell) become ONE item: the first row
         // of the run codes all of them as length-258 matches that run across the tile rows (fused_row_run), the
         // other rows of the run contribute nothing.
         const uint32_t est = (uint32_t)__popcll(~(m.above | m.left));
         const bool rep = tid > 0 && m.above == ~0ull;
         const unsigned repbal = __ballot_sync(0xffffffffu, rep);
-        // (the first kFusedMaxSplitRows long rows in row order, so that the streams do not depend on thread timing)
-        const bool cand = est >= (uint32_t)kFusedSplitEst;
-        const unsigned bal = __ballot_sync(0xffffffffu, cand);
-        if (lane == 0) {
-            s_scan[warp][1] = (unsigned long long)__popc(bal);
-            s_rep[warp] = repbal;
+        uint8_t *meta = tile + tid * kTileStride + kFusedRowMeta;
+        uint32_t ncut = 0;
+        if (!rep && est >= (uint32_t)kFusedSplitEst) {
+            const uint32_t *roww = reinterpret_cast<const uint32_t *>(tile + tid * kTileStride);
+            const uint32_t *upw = roww - kTileStride / 4;
+            unsigned long long newm = ~(m.above | m.left);      // only these words can hold such a pixel
+            uint32_t lastcut = 0;
+            while (newm && ncut < (uint32_t)kFusedMaxCuts) {
+                const int j = __ffsll((long long)newm) - 1;
+                newm &= newm - 1ull;
+                const uint32_t cw = roww[j];
+                const uint32_t uw = tid > 0 ? upw[j] : ~cw;
+                const uint32_t prev = j ? roww[j - 1] >> 24 : (~cw & 255u);
+                uint32_t nat = __vcmpne4(cw, uw) & __vcmpne4(cw, (cw << 8) | prev);     // 0xFF per pixel that qualifies
+                if (j == 0)
+                    nat &= 0xFFFFFF00u;                         // pixel 0 starts the row
+                while (nat && ncut < (uint32_t)kFusedMaxCuts) {
+                    const uint32_t b = (uint32_t)(__ffs((int)nat) - 1) >> 3;
+                    nat &= ~(0xFFu << (8u * b));
+                    const uint32_t x = 4u * (uint32_t)j + b;
+                    if (x - lastcut >= (uint32_t)kFusedMinPiece) {
+                        meta[5u + ncut++] = (uint8_t)x;
+                        lastcut = x;
+                    }
+                }
+            }
+        }
+        // at most kFusedMaxExtra items beyond one per row: if the rows want more, every row keeps its share
+        {
+            uint32_t sum = ncut, rows = ncut ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                rows += __shfl_xor_sync(0xffffffffu, rows, o);
+            }
+            if (lane == 0) {
+                s_scan[warp][1] = ((unsigned long long)rows << 32) | sum;
+                s_rep[warp] = repbal;
+            }
         }
         __syncthreads();
+        {
+            uint32_t sum = 0, rows = 0;
+            for (int wv = 0; wv < kTile / 32; wv++) {
+                sum += (uint32_t)s_scan[wv][1];
+                rows += (uint32_t)(s_scan[wv][1] >> 32);
+            }
+            if (sum > (uint32_t)kFusedMaxExtra)
+                ncut = min(ncut, (uint32_t)kFusedMaxExtra / rows);
+        }
+        meta[4] = (uint8_t)ncut;
         uint32_t runlen = 0;                    // 0: ordinary row; 0xFFFF: inside a run; else rows in the run it starts
         if (rep) {
             const bool prev = lane ? ((repbal >> (lane - 1)) & 1u) != 0u : (s_rep[warp - 1] >> 31) != 0u;
@@ -600,12 +660,8 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
             }
         }
         *reinterpret_cast<uint16_t *>(tile + tid * kTileStride + kFusedRowMeta + 2) = (uint16_t)runlen;
-        uint32_t rank = (uint32_t)__popc(bal & ((1u << lane) - 1u));
-        for (int wv = 0; wv < warp; wv++)
-            rank += (uint32_t)s_scan[wv][1];
-        const bool split = cand && rank < (uint32_t)kFusedMaxSplitRows;
-        const uint32_t nseg = split ? 4u : 1u;
-        const uint32_t key = runlen == 0xFFFFu ? 0u : runlen ? min(64u, 1u + runlen / 8u) : split ? (est + 3u) / 4u : est;
+        const uint32_t nseg = ncut + 1u;
+        const uint32_t key = runlen == 0xFFFFu ? 0u : runlen ? min(64u, 1u + runlen / 8u) : (est + ncut) / nseg;
         atomicAdd(&s_hist[64u - key], nseg);
         uint32_t inc = nseg;                    // first item slot of every row (stream order)
 #pragma unroll
@@ -644,7 +700,7 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         __syncthreads();
         const uint32_t at = atomicAdd(&s_hist[64u - key], nseg);
         for (uint32_t q = 0; q < nseg; q++)
-            s_perm[at + q] = (uint16_t)(tid | ((split ? q : 4u) << 8));
+            s_perm[at + q] = (uint16_t)(tid | (q << 8));
     }
     __syncthreads();
 
@@ -659,10 +715,11 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
         if (item == 0xFFFFu)
             break;
         const int r = item & 255u, piece = item >> 8;
-        const int xa = piece == 4 ? 0 : 64 * piece, xb = piece == 4 ? kTile : xa + 64;
+        int xa, xb;
+        fused_item_range(tile, r, (uint32_t)piece, xa, xb);
         const RowMasks pm = s_masks[r];
         const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
-        const uint32_t slot = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta) + (piece & 3);
+        const uint32_t slot = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta) + (uint32_t)piece;
         unsigned long long lit = 0;
         uint32_t bits = 0, nsub = rl == 0xFFFFu ? 0u : 1u;
         if (rl != 0u) {
@@ -770,7 +827,9 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
             if (item == 0xFFFFu)
                 break;
             const uint32_t r = item & 255u, piece = item >> 8;
-            const uint32_t xa = piece == 4u ? 0u : 64u * piece, xb = piece == 4u ? (uint32_t)kTile : xa + 64u;
+            int xai, xbi;
+            fused_item_range(tile, (int)r, piece, xai, xbi);
+            const uint32_t xa = (uint32_t)xai, xb = (uint32_t)xbi;
             const uint32_t slot = q ? slot_b : slot_a, base = q ? pos_b : pos_a, n = s_nsub[slot];
             const uint32_t *note = s_note + slot * kFusedCkpt;
             uint2 *d = s_desc + (q ? sub_b : sub_a);
@@ -894,7 +953,8 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                 if (item == 0xFFFFu)
                     break;
                 const int r = item & 255u, piece = item >> 8;
-                const int xa = piece == 4 ? 0 : 64 * piece, xb = piece == 4 ? kTile : xa + 64;
+                int xa, xb;
+                fused_item_range(tile, r, (uint32_t)piece, xa, xb);
                 const RowMasks pm = s_masks[r];
                 unsigned long long lw = q ? lit_b : lit_a;
                 const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
@@ -974,7 +1034,8 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
                         if (item == 0xFFFFu)
                             break;
                         const int r = item & 255u, piece = item >> 8;
-                        const int xa = piece == 4 ? 0 : 64 * piece, xb = piece == 4 ? kTile : xa + 64;
+                        int xa, xb;
+                fused_item_range(tile, r, (uint32_t)piece, xa, xb);
                         const RowMasks pm = s_masks[r];
                         unsigned long long lw = q ? lit_b : lit_a;
                         const uint32_t pw = q ? pos_b : pos_a;
