@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <vector>
 
@@ -100,7 +101,7 @@ struct gcn10_ctx {
     int sm_count = 148;
     cudaStream_t streams[kMaxStreams] = {};
     cudaStream_t ship_streams[kMaxStreams] = {};    // high priority: ship_strip_kernel of the slot with the same index
-    int nstreams = 4;
+    int nstreams = 8;
     int strip_rows = 2048;
     int rows_per_cta = 0;       // 0 = auto (see auto_rows_per_cta)
     int use_tma = 1;
@@ -691,6 +692,12 @@ int gcn10_cuda_create(int device, gcn10_ctx **out)
         return fail(GCN10_ENODEV, "device %d out of range (%d visible)", device, n);
     CUDA_TRY(cudaSetDevice(device));
     gcn10_ctx *c = new (std::nothrow) gcn10_ctx();
+    if (c) {
+        // development aid: the default of option "streams" from the environment
+        const char *e = getenv("GCN10_STREAMS");
+        if (e && atoi(e) >= 1 && atoi(e) <= kMaxStreams)
+            c->nstreams = atoi(e);
+    }
     if (!c)
         return fail(GCN10_ENOMEM, "context allocation failed");
     c->device = device;
@@ -1168,7 +1175,8 @@ static int deflate_rows_impl(gcn10_ctx *c,
                              cudaEvent_t esa_ready, int w, int h, int row0, int nrows,
                              const double gt[6],
                              const uint8_t *hsg, int hsx, int hsy, size_t hsg_pitch, const double soil_gt[6],
-                             unsigned plane_mask, gcn10_tile_sink sink, void *user)
+                             unsigned plane_mask, gcn10_tile_sink sink, void *user,
+                             const std::function<int()> &before_first_sink = nullptr)
 {
     if (!c)
         return fail(GCN10_EINVAL, "NULL context");
@@ -1232,9 +1240,9 @@ static int deflate_rows_impl(gcn10_ctx *c,
             (c->ordered && ((rc = ensure(sl.blob2, blob2_cap)) || (rc = ensure(sl.order, ntile_slot * sizeof(unsigned long long))))) ||
             (rc = ensure_host(sl.h_table, table_bytes)))
             return rc;
-        // the host mirror of the blob only has to hold what a strip really compresses to; start at 1/8 of
+        // the host mirror of the blob only has to hold what a strip really compresses to; start at 1/16 of
         // the worst case and grow on demand
-        if ((rc = ensure_host(sl.h_blob, std::max<size_t>(blob_cap / 8, 1 << 20))))
+        if ((rc = ensure_host(sl.h_blob, std::max<size_t>(blob_cap / 16, 1 << 20))))
             return rc;
         sl.busy = false;
         sl.timed = false;
@@ -1374,7 +1382,9 @@ static int deflate_rows_impl(gcn10_ctx *c,
         return code;
     };
 
-    // the last strip is on its way: a prefetched block's inflate kernel may have the SMs behind it
+    // the last strip is on its way: a prefetched block's inflate kernel may have the SMs behind it.  (Letting it go
+    // earlier -- once every strip slot is in use -- was measured: its CTAs keep the SMs until they retire, the encoder
+    // kernels of the remaining strips wait for milliseconds and the chain of copies runs dry; 10.6 ms against 7.5.)
     auto release = [&](int s) -> int {
         if (s != nstrips - 1)
             return GCN10_OK;
@@ -1412,6 +1422,10 @@ static int deflate_rows_impl(gcn10_ctx *c,
             if (ce != cudaSuccess)
                 return bail(fail(GCN10_ECUDA, "strip %d copy: %s", s, cudaGetErrorString(ce)));
         }
+        // (device land cover that was still being produced when the strips were queued: its verdict, before any
+        // strip reaches the caller)
+        if (s == 0 && before_first_sink && (rc = before_first_sink()))
+            return bail(rc);
         gcn10_tile_strip ts;
         ts.tile_row0 = (row0 + sl.y0) / kTile;
         ts.n_tile_rows = (sl.rows + kTile - 1) / kTile;
@@ -1759,12 +1773,25 @@ int gcn10_cuda_block_parts_deflate(gcn10_ctx *c, const gcn10_tile_part *parts, i
     int rc = acquire_slot(c, parts, nparts, fill, w, h, &sl);
     if (rc)
         return rc;
-    // a damaged tile must stop the block before any output tile reaches the sink (the reference skips a
-    // block whose land cover cannot be read, cn.c:188-192)
-    if ((rc = finish_slot(c, *sl, nullptr)))
+    // The strips are queued behind the inflate kernel on the device; the host does not wait for it first, so that the
+    // block's set-up (soil window upload, index maps, record tables) overlaps the kernel's tail.  A damaged tile must
+    // still stop the block before any output tile reaches the sink (the reference skips a block whose land cover cannot
+    // be read, cn.c:188-192): the inflater's verdict is read before the first strip is handed over.
+    if ((rc = launch_inflate(c, *sl, nullptr)))
         return rc;
-    return deflate_rows_impl(c, nullptr, 0, (const uint8_t *)sl->esa_full.p, sl->dpitch, nullptr, w, h, 0, h, gt, hsg,
-                             hsx, hsy, hsg_pitch, soil_gt, plane_mask, sink, user);
+    bool judged = false;
+    rc = deflate_rows_impl(c, nullptr, 0, (const uint8_t *)sl->esa_full.p, sl->dpitch, sl->done, w, h, 0, h, gt, hsg,
+                           hsx, hsy, hsg_pitch, soil_gt, plane_mask, sink, user, [&]() -> int {
+                               judged = true;
+                               return finish_slot(c, *sl, nullptr);
+                           });
+    if (!judged) {
+        // the call failed before its first strip (bad arguments, CUDA error): the slot is consumed all the same
+        const int frc = finish_slot(c, *sl, nullptr);
+        if (!rc)
+            rc = frc;
+    }
+    return rc;
 }
 
 int gcn10_cuda_block_tiles_deflate(gcn10_ctx *c, const gcn10_tile_source *esa_tiles, int w, int h, const double gt[6],

@@ -55,7 +55,7 @@ def test_strip_pipeline_shapes(strip_rows, streams, gpu_ctx, port, tables):
         got = gpu_ctx.block(b["esa"], b["gt"], b["hsg"], b["soil_gt"])
     finally:
         gpu_ctx.set_option("strip_rows", 2048)
-        gpu_ctx.set_option("streams", 4)
+        gpu_ctx.set_option("streams", 8)
     assert np.array_equal(got, want)
 
 
