@@ -446,7 +446,9 @@ def run_ours(args):
 def pcie_probe(ctx, group, barrier):
     """The host link this end-to-end number sits under: copy bandwidth of one GPU alone (rank 0, the others idle) and
     of all ranks at once (what the shared host fabric gives each GPU when N blocks' tile streams leave together)."""
-    nbytes, reps = 256 << 20, 4
+    # 1 GiB per copy, so that eight ranks' buffers do not sit in the host's last-level cache: with a reused 256 MB
+    # buffer the concurrent figure came out 3x above what the raw-plane and tile-stream legs sustain on the same box
+    nbytes, reps = 1 << 30, 3
     alone = None
     barrier()
     if group.rank == 0:
