@@ -13,14 +13,18 @@
 //   2. ONE LZ77 parse of the id tile (distances 256 = pixel above and 1 = run, as deflate_tiles.cuh): equal
 //      ids are equal bytes in every plane, so the token structure is valid for all planes at once;
 //   3. per plane only the literal bytes differ (and, through the 8/9-bit fixed-Huffman literal codes, the
-//      bit positions): a block scan of per-row (common bits, per-plane 9-bit-literal counts) places every
-//      row in every plane's stream; the second parse writes all planes' streams in one go;
+//      bit positions): a block scan of per-item (common bits, per-plane 9-bit-literal counts) places every
+//      item in every plane's stream; the second parse writes all planes' streams in one go;
 //   4. Adler-32 of every plane from per-id pixel counts and position-weight sums (run based).
 //
+// The parse of a row is serial, so how the rows are dealt out to the 256 threads decides the kernel's time.  Any
+// token boundary of the greedy parse is a free place to cut (the parse has no state): rows are cut into items at
+// pixels that no match can cross (step 2 of the kernel), and the sizing pass leaves checkpoints from which the
+// writing pass runs on pieces of a few tokens each (FusedCkpt).  Neither changes a bit of the streams.
+//
 // HBM traffic per pixel: 1 byte read + the compressed bytes (~0.2) instead of 1 + 2 * 9.  The planes are
-// never materialised; zlib streams are byte-identical to those of cn_block_kernel + deflate_tiles_kernel
-// whenever distinct records differ in the plane at hand (the id parse cannot see matches between different
-// records that happen to share a value in one plane, so streams can be a few bytes longer).
+// never materialised.  The id parse cannot see matches between different records that happen to share a value in
+// one plane, so a plane's stream can be a few bytes longer than deflate_tiles_kernel's for the same plane.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -948,24 +952,24 @@ cn_deflate_fused_kernel(const __grid_constant__ FusedParams p)
             }
             else {
 #pragma unroll 1
-            for (int q = 0; q < 2; q++) {
-                const uint32_t item = q ? item1 : item0;
-                if (item == 0xFFFFu)
-                    break;
-                const int r = item & 255u, piece = item >> 8;
-                int xa, xb;
-                fused_item_range(tile, r, (uint32_t)piece, xa, xb);
-                const RowMasks pm = s_masks[r];
-                unsigned long long lw = q ? lit_b : lit_a;
-                const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
-                if (rl == 0xFFFFu)
-                    continue;
-                if (rl)
-                    fused_row_run<true, MAXP, true, true>((int)rl, clsbits, lw, q ? pos_b : pos_a, out, s_obase, lo, hi, p.code);
-                else
-                    fused_parse_row<true, MAXP, true, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, q ? pos_b : pos_a, out,
-                                                            s_obase, lo, hi, xa, xb, p.code, s_rank);
-            }
+                for (int q = 0; q < 2; q++) {
+                    const uint32_t item = q ? item1 : item0;
+                    if (item == 0xFFFFu)
+                        break;
+                    const int r = item & 255u, piece = item >> 8;
+                    int xa, xb;
+                    fused_item_range(tile, r, (uint32_t)piece, xa, xb);
+                    const RowMasks pm = s_masks[r];
+                    unsigned long long lw = q ? lit_b : lit_a;
+                    const uint32_t rl = *reinterpret_cast<const uint16_t *>(tile + r * kTileStride + kFusedRowMeta + 2);
+                    if (rl == 0xFFFFu)
+                        continue;
+                    if (rl)
+                        fused_row_run<true, MAXP, true, true>((int)rl, clsbits, lw, q ? pos_b : pos_a, out, s_obase, lo, hi, p.code);
+                    else
+                        fused_parse_row<true, MAXP, true, true>(tile, r, pm, s_val, p.lit9, clsbits, lw, q ? pos_b : pos_a, out,
+                                                                s_obase, lo, hi, xa, xb, p.code, s_rank);
+                }
             }
             if (tuned) {
                 for (int i = tid; i < (p.code.header_bits + 31) >> 5; i += kTile)
