@@ -155,19 +155,24 @@ inline bool build_tile_code(const bool present[256], TileCode &tc)
     if (n_lit == 0)
         return false;
 
-    // model of a Curve Number tile's tokens, per 1000: the length symbols and end-of-block (index = symbol - 256)
-    std::vector<uint64_t> w(30, 0);
-    w[0] = 2;                                           // end of block
-    const uint64_t shortw[8] = { 60, 40, 30, 25, 20, 18, 16, 14 };     // lengths 3..10
-    for (int i = 0; i < 8; i++)
-        w[1 + i] = shortw[i];
-    for (int s = 265; s <= 268; s++)
-        w[s - 256] = 10;
-    for (int s = 269; s <= 283; s++)
-        w[s - 256] = 5;
-    w[284 - 256] = 120;                                 // 227..257: a single row that repeats the row above
-    w[285 - 256] = 250;                                 // 258: runs of such rows, coded across the tile rows
-    const uint64_t lit_weight = 300;
+    // model of a Curve Number tile's tokens, per 1000 tokens: the length symbols and end-of-block (index = symbol - 256).
+    // Measured, not guessed: tools/token_stats.py runs the kernel's parse (tests/harness/tile_code_host.cpp) over the
+    // record-id tiles of the synthetic WorldCover-like and coastal blocks of BASELINE.json (10 m land-cover patches over
+    // 25-pixel soil cells) and prints this table.  Two things carry it: the row-run tokens (258: the inside of a soil
+    // cell row, a fifth of all tokens) and the lengths 11..226, which together are a third of the tokens -- a soil cell
+    // is 25 pixels wide, a land-cover patch a few hundred.  The round-1 guess gave those 8 bits each and cost 4 % more
+    // bytes per block than this table, which is within 0.1 % of a code fitted to each block's own statistics.
+    static const uint64_t model[30] = { 2,                                  // end of block
+                                        12, 10, 109, 21, 4, 7, 3, 7,        // lengths 3..10
+                                        22, 9, 24, 16,                      // 11..18
+                                        13, 21, 18, 15,                     // 19..34
+                                        27, 22, 15, 19,                     // 35..66
+                                        23, 18, 15, 11,                     // 67..130
+                                        18, 12, 8,                          // 131..226
+                                        79,                                 // 227..257: a single row that repeats the row above
+                                        195 };                              // 258: runs of such rows, coded across the tile rows
+    std::vector<uint64_t> w(model, model + 30);
+    const uint64_t lit_weight = 230;                    // literals per 1000 tokens (same measurement)
     uint64_t nonlit_weight = 0;
     for (uint64_t f : w)
         nonlit_weight += f;

@@ -123,3 +123,95 @@ extern "C" uint32_t gcn10_test_tile_encode(const uint8_t *present, const uint8_t
     memcpy(out, b.data(), b.size());
     return (uint32_t)b.size();
 }
+
+// Token statistics of the fused kernel's parse of one 256 x 256 tile of record ids (cn_deflate_fused.cuh: rows that
+// repeat the row above, two or more in a row, become matches of length 258 that run across the tile rows; every other
+// row is parsed greedily -- pixel above, run, literal).  hist: [0] literals, [1] end-of-block, [2..30] length symbols
+// 257..285, [31] extra length bits, [32] matches at distance 256, [33] at distance 1.  tools/token_stats.py turns these
+// into the model table of build_tile_code().
+extern "C" void gcn10_test_tile_tokens(const uint8_t *tile, uint64_t *hist)
+{
+    auto add_match = [&](int len, bool above) {
+        int idx, e = 0;
+        if (len == 258)
+            idx = 28;
+        else {
+            const int l = len - 3;
+            if (l < 8)
+                idx = l;
+            else {
+                e = 29 - __builtin_clz((unsigned)l);
+                idx = 4 + 4 * e + ((l - (4 << e)) >> e);
+            }
+        }
+        hist[2 + idx]++;
+        hist[31] += (uint64_t)e;
+        hist[above ? 32 : 33]++;
+    };
+    int r = 0;
+    while (r < 256) {
+        const uint8_t *row = tile + 256 * r;
+        if (r > 0 && memcmp(row, row - 256, 256) == 0) {
+            int n = 1;
+            while (r + n < 256 && memcmp(row + 256 * n, row + 256 * (n - 1), 256) == 0)
+                n++;
+            if (n >= 2) {
+                const unsigned span = 256u * (unsigned)n;
+                unsigned q = span / 258u;
+                const unsigned rest = span - 258u * q;
+                int tail[2] = { (int)rest, 0 };
+                if (rest == 1u || rest == 2u) {
+                    q--;
+                    tail[0] = 129;
+                    tail[1] = 129 + (int)rest;
+                }
+                for (unsigned i = 0; i < q; i++)
+                    add_match(258, true);
+                for (int t = 0; t < 2; t++)
+                    if (tail[t])
+                        add_match(tail[t], true);
+                r += n;
+                continue;
+            }
+        }
+        int x = 0;
+        while (x < 256) {
+            int la = 0, lr = 0;
+            if (r > 0)
+                while (x + la < 256 && row[x + la] == row[x + la - 256])
+                    la++;
+            if (x > 0)
+                while (x + lr < 256 && row[x + lr] == row[x - 1])
+                    lr++;
+            const int len = la >= lr ? la : lr;
+            if (len >= 3) {
+                add_match(len, la >= lr);
+                x += len;
+            }
+            else {
+                hist[0]++;
+                x++;
+            }
+        }
+        r++;
+    }
+    hist[1]++;
+}
+
+// the code build_tile_code() designs for `present`: bits of the 29 length symbols, end-of-block, literals, header
+extern "C" int gcn10_test_tile_code_lengths(const uint8_t *present, int *len_bits /*[29]*/, int *eob_bits, int *lit_bits,
+                                            int *header_bits)
+{
+    bool p[256];
+    for (int v = 0; v < 256; v++)
+        p[v] = present[v] != 0;
+    TileCode tc;
+    if (!build_tile_code(p, tc))
+        return 1;
+    for (int i = 0; i < 29; i++)
+        len_bits[i] = tc.len_bits[i];
+    *eob_bits = tc.eob_bits;
+    *lit_bits = tc.lit_bits;
+    *header_bits = tc.header_bits;
+    return 0;
+}
