@@ -100,3 +100,48 @@ def test_smaller_than_the_fixed_code(harness):
     fixed = c.compress(tile.tobytes()) + c.flush()
     assert len(z) < len(fixed), (len(z), len(fixed))
     print("tuned", len(z), "zlib fixed", len(fixed), "zlib 6", len(zlib.compress(tile.tobytes(), 6)))
+
+
+def _tokens(lib, tile):
+    hist = np.zeros(34, dtype=np.uint64)
+    lib.gcn10_test_tile_tokens.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.gcn10_test_tile_tokens(np.ascontiguousarray(tile).ctypes.data, hist.ctypes.data)
+    return hist.astype(np.int64)
+
+
+def test_token_statistics_of_known_tiles(harness):
+    """The parse model behind the code's length table (tools/token_stats.py), on tiles whose tokens can be counted by
+    hand: the kernel's row-run rule (cn_deflate_fused.cuh: fused_row_run) and the greedy row parse."""
+    # one value: a literal and a run of 255 in row 0, then 255 rows that repeat the row above = 65280 bytes at distance
+    # 256 = 253 matches of 258 and one of 6
+    h = _tokens(harness, np.full((256, 256), 7, np.uint8))
+    assert h[0] == 1 and h[1] == 1
+    assert h[2 + 27] == 1 and h[2 + 28] == 253 and h[2 + 3] == 1 and h[2:31].sum() == 255
+    assert h[32] == 254 and h[33] == 1
+    # vertical stripes 25 pixels wide (soil cells): row 0 = 11 literals + 10 runs of 24 + one of 5, the rest repeats
+    t = np.tile((np.arange(256) // 25).astype(np.uint8), (256, 1))
+    h = _tokens(harness, t)
+    assert h[0] == 11 and h[33] == 11 and h[32] == 254
+    # every row differs from the row above in one cell: two matches above around a literal + run per row, no row-runs;
+    # row 0 has nothing above it: three literals, three runs
+    t = np.zeros((256, 256), np.uint8)
+    for r in range(256):
+        t[r, 100:125] = r % 2 + 1
+    h = _tokens(harness, t)
+    assert h[2 + 28] == 0, "no two rows in sequence repeat the row above"
+    assert h[0] == 3 + 255 and h[32] == 2 * 255 and h[33] == 3 + 255
+
+
+def test_length_table_follows_the_measured_model(harness):
+    """Symbols that the measured model makes frequent are short: the row-run token (258), the single repeated row
+    (227..257) and length 5 outrank the rest; nothing is longer than 12 bits (tuned_match_code packs a token into 27)."""
+    p = _present(_cn_values())
+    bits = (ctypes.c_int * 29)()
+    eob, lit, hdr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert harness.gcn10_test_tile_code_lengths(p.ctypes.data_as(ctypes.c_void_p), bits, ctypes.byref(eob),
+                                                ctypes.byref(lit), ctypes.byref(hdr)) == 0
+    b = list(bits)
+    assert b[28] == min(b) and b[28] <= 3 and b[27] <= 4 and b[2] <= 4
+    assert max(b + [eob.value]) <= 12
+    assert max(b[8:27]) <= 8, "lengths 11..226 are a third of all tokens"
+    assert lit.value == 7 and hdr.value <= 19 + 8 * 48
