@@ -820,7 +820,13 @@ def run_program_leg(args, blob, offsets, sizes, in_tile, w, rows, hsg_np, group,
     res = None
     if group.rank == 0 and os.path.exists(hostlib.EXE_PATH):
         nb = args.program_blocks * group.world
-        base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        # 18 rasters of ~25 MB per block + the inputs; a RAM disk that cannot hold them must not take the run down
+        need = nb * 560e6 + 200e6
+        bases = [d for d in ("/dev/shm", tempfile.gettempdir()) if os.path.isdir(d) and shutil.disk_usage(d).free > need]
+        if not bases:
+            barrier()
+            return {"skipped": f"no scratch directory with {need / 1e9:.1f} GB free for {nb} blocks"}
+        base = bases[0]
         root = tempfile.mkdtemp(prefix="gcn10_program_", dir=base)
         try:
             px = 1.0 / 12000.0
@@ -860,7 +866,7 @@ def run_program_leg(args, blob, offsets, sizes, in_tile, w, rows, hsg_np, group,
             out_bytes = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(os.path.join(root, "out")) for f in fs)
             res = {"returncode": r.returncode, "blocks": nb, "gpus": group.world, "rasters_written": files,
                    "output_bytes": out_bytes, "wall_s_incl_startup": wall,
-                   "path": "gcn10 executable: VRT mosaic of a tiled DEFLATE GeoTIFF on /dev/shm -> 18 GeoTIFFs per block on /dev/shm",
+                   "path": f"gcn10 executable: VRT mosaic of a tiled DEFLATE GeoTIFF on {base} -> 18 GeoTIFFs per block on {base}",
                    "last_block_log_line": last_line}
             if warm:
                 warm.sort()
@@ -871,6 +877,8 @@ def run_program_leg(args, blob, offsets, sizes, in_tile, w, rows, hsg_np, group,
                             "note": "value = workers x pixels / median warm per-block time (all 18 rasters per block)"})
             if r.returncode != 0 or files != 18 * nb:
                 res["stderr_tail"] = r.stderr[-800:]
+        except Exception as e:  # rank 0 must reach the barrier below whatever happens: the other ranks wait there
+            res = {"error": repr(e)}
         finally:
             shutil.rmtree(root, ignore_errors=True)
     barrier()
