@@ -855,7 +855,8 @@ def run_program_leg(args, blob, offsets, sizes, in_tile, w, rows, hsg_np, group,
             wall = time.perf_counter() - t0
             per_worker = {}
             last_line = None
-            for fn in sorted(os.listdir(os.path.join(root, "logs"))):
+            logs = os.path.join(root, "logs")
+            for fn in sorted(os.listdir(logs)) if os.path.isdir(logs) else []:
                 for ln in open(os.path.join(root, "logs", fn)):
                     m = re.search(r"block (\d+): (\d+) x (\d+) px, 18 rasters in ([0-9.]+) s", ln)
                     if m:
