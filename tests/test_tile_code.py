@@ -60,7 +60,7 @@ def test_code_for_the_shipped_tables(harness):
     p = _present(vals)
     lb, hb, l284, eob = (ctypes.c_int() for _ in range(4))
     assert harness.gcn10_test_tile_code(p.ctypes.data, lb, hb, l284, eob) == 0
-    assert lb.value <= 7, "the few dozen Curve Number values fit 7-bit literals"
+    assert lb.value == 8, "64 values: one leaf of the length tree, two bits deep, split into 64 code words"
     assert l284.value <= 4, "the repeated-row length bucket must be cheap"
     assert hb.value < 19 + 8 * 100, "header under 100 bytes"
 
@@ -144,4 +144,4 @@ def test_length_table_follows_the_measured_model(harness):
     assert b[28] == min(b) and b[28] <= 3 and b[27] <= 4 and b[2] <= 4
     assert max(b + [eob.value]) <= 12
     assert max(b[8:27]) <= 8, "lengths 11..226 are a third of all tokens"
-    assert lit.value == 7 and hdr.value <= 19 + 8 * 48
+    assert lit.value == 8 and hdr.value <= 19 + 8 * 48

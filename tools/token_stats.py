@@ -93,8 +93,7 @@ def main():
     assert lib.gcn10_test_tile_code_lengths(present.ctypes.data_as(ctypes.c_void_p), len_bits, ctypes.byref(eob),
                                             ctypes.byref(lit), ctypes.byref(hdr)) == 0
     today = [eob.value] + list(len_bits)
-    n_lit = int(present.sum())                                  # literals fill all but one m-bit prefix (tile_code.h)
-    m = next(k for k in range(1, 5) if (1 << lit.value) - (1 << (lit.value - k)) >= n_lit)
+    k = int(np.ceil(np.log2(max(int(present.sum()), 1))))          # the literals: one leaf split into 2^k code words
     print(f"code today: literals {lit.value} bits, header {hdr.value} bits, end-of-block + length symbols {today}")
     blend = np.zeros(31)
     for spec in a.profiles:
@@ -106,12 +105,13 @@ def main():
         fixed = hist[31] + 7 * hist[32] + hist[33]              # extra length bits, distance codes (+ 6 extra bits at 256)
         tail = (hdr.value + 7) // 8 + 4                         # header, Adler-32
 
-        def size(bits):
-            return ((hist[0] * lit.value + (sym * np.asarray(bits)).sum() + fixed) / tiles) / 8 + tail
-        fitted = np.asarray(huffman_depths(list(sym))) + m
+        def size(bits, lit_bits=lit.value):
+            return ((hist[0] * lit_bits + (sym * np.asarray(bits)).sum() + fixed) / tiles) / 8 + tail
+        joint = huffman_depths(list(sym) + [hist[0]])          # fitted to this block: the literals as one more leaf
+        lit_fit, fitted = joint[-1] + k, np.asarray(joint[:-1])
         print(f"{spec}: {tokens / tiles:.0f} tokens per tile ({hist[0] / tiles:.0f} literals, {hist[32] / tiles:.0f} "
               f"above, {hist[33] / tiles:.0f} runs); bytes per stream: today {size(today):.1f}, fitted to this block "
-              f"{size(fitted):.1f}")
+              f"{size(fitted, lit_fit):.1f}")
         blend += np.concatenate(([hist[0]], sym)) / tokens * 1000 / len(a.profiles)
     print("per 1000 tokens: literals %d; end-of-block and length symbols 257..285:" % round(blend[0]))
     print("   ", [max(2, int(round(x))) for x in blend[1:]])
