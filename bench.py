@@ -668,13 +668,14 @@ def run_e2e_tiles(args, ctx, capi, esa, rows, w, gt6, sgt6, hsg_np, cb, nbytes, 
             step18()
         barrier()
         dt18 = max_over_ranks(time.perf_counter() - t0) / steps
+        bytes18 = nbytes[0] + nbytes[1]          # of the timed steps only (the call below is one more block)
         # (the block the last step prefetched is still waiting: run it, untimed, so that the next leg starts clean)
         rc = lib.gcn10_cuda_block_tiles_deflate(ctx.h, C.byref(st), w, rows, gt6, hsg_np.ctypes.data, hsx, hsy, hsx, sgt6,
                                                 capi.MASK_ALL, cb, None)
         if rc:
             raise RuntimeError(lib.gcn10_cuda_last_error().decode())
         all18 = {"planes": 18, "value": world * float(w) * rows / dt18 / 1e9, "unit": UNIT, "ms_per_step": dt18 * 1e3,
-                 "d2h_bytes_per_step": int((nbytes[0] + nbytes[1]) / steps)}
+                 "d2h_bytes_per_step": int(bytes18 / steps)}
         nbytes[0], nbytes[1] = saved
         d2h_step = int((nbytes[0] + nbytes[1]) / steps)
         out_ratio = NVAR * float(w) * rows * steps / max(nbytes[0], 1)
