@@ -821,8 +821,8 @@ def run_program_leg(args, blob, offsets, sizes, in_tile, w, rows, hsg_np, group,
     res = None
     if group.rank == 0 and os.path.exists(hostlib.EXE_PATH):
         nb = args.program_blocks * group.world
-        # 18 rasters of ~25 MB per block + the inputs; a RAM disk that cannot hold them must not take the run down
-        need = nb * 560e6 + 200e6
+        # 18 rasters of ~22 MB per block + the inputs; a RAM disk that cannot hold them must not take the run down
+        need = nb * 450e6 + 200e6
         bases = [d for d in ("/dev/shm", tempfile.gettempdir()) if os.path.isdir(d) and shutil.disk_usage(d).free > need]
         if not bases:
             barrier()
