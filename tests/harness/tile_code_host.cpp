@@ -215,3 +215,46 @@ extern "C" int gcn10_test_tile_code_lengths(const uint8_t *present, int *len_bit
     *header_bits = tc.header_bits;
     return 0;
 }
+
+// What-if model (tools/token_stats.py, DESIGN.md "Next"): the same two distances, but the greedy parse runs over the
+// tile as ONE stream of 65536 bytes, so a match may run on from the end of a row into the next one (the kernel's
+// matches stop at row ends; only whole repeated rows are chained).  Same histogram layout as gcn10_test_tile_tokens.
+extern "C" void gcn10_test_tile_tokens_stream(const uint8_t *t, uint64_t *hist, int run_on_tie)
+{
+    const int n = 65536;
+    int p = 0;
+    while (p < n) {
+        int la = 0, lr = 0;
+        if (p >= 256)
+            while (p + la < n && la < 258 && t[p + la] == t[p + la - 256])
+                la++;
+        if (p >= 1)
+            while (p + lr < n && lr < 258 && t[p + lr] == t[p + lr - 1])
+                lr++;
+        const bool above = run_on_tie ? la > lr : la >= lr;
+        const int len = above ? la : lr;
+        if (len >= 3) {
+            int idx, e = 0;
+            if (len == 258)
+                idx = 28;
+            else {
+                const int l = len - 3;
+                if (l < 8)
+                    idx = l;
+                else {
+                    e = 29 - __builtin_clz((unsigned)l);
+                    idx = 4 + 4 * e + ((l - (4 << e)) >> e);
+                }
+            }
+            hist[2 + idx]++;
+            hist[31] += (uint64_t)e;
+            hist[above ? 32 : 33]++;
+            p += len;
+        }
+        else {
+            hist[0]++;
+            p++;
+        }
+    }
+    hist[1]++;
+}

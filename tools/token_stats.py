@@ -69,13 +69,15 @@ def block_tokens(lib, port, tables, profile, seed, rows, w=36000, h=36000):
     ids = ids.reshape(rows, w).astype(np.uint8)
     values = np.unique(planes)
     hist = np.zeros(34, np.uint64)
+    stream = np.zeros(34, np.uint64)                            # what-if: matches that run on across row ends
     for ty in range(rows // 256):
         for tx in range((w + 255) // 256):
             t = np.full((256, 256), 255, np.uint8)              # id of the padding right of the raster
             blk = ids[ty * 256:(ty + 1) * 256, tx * 256:(tx + 1) * 256]
             t[:, :blk.shape[1]] = blk
             lib.gcn10_test_tile_tokens(t.ctypes.data_as(ctypes.c_void_p), hist.ctypes.data_as(ctypes.c_void_p))
-    return hist.astype(np.float64), values
+            lib.gcn10_test_tile_tokens_stream(t.ctypes.data_as(ctypes.c_void_p), stream.ctypes.data_as(ctypes.c_void_p), 1)
+    return hist.astype(np.float64), values, stream.astype(np.float64)
 
 
 def main():
@@ -98,7 +100,7 @@ def main():
     blend = np.zeros(31)
     for spec in a.profiles:
         profile, seed = spec.split(":")
-        hist, _ = block_tokens(lib, port, tables, profile, int(seed), a.rows)
+        hist, _, stream = block_tokens(lib, port, tables, profile, int(seed), a.rows)
         tiles = hist[1]
         sym = np.concatenate(([hist[1]], hist[2:31]))
         tokens = hist[0] + hist[2:31].sum()
@@ -112,6 +114,11 @@ def main():
         print(f"{spec}: {tokens / tiles:.0f} tokens per tile ({hist[0] / tiles:.0f} literals, {hist[32] / tiles:.0f} "
               f"above, {hist[33] / tiles:.0f} runs); bytes per stream: today {size(today):.1f}, fitted to this block "
               f"{size(fitted, lit_fit):.1f}")
+        ssym = np.concatenate(([stream[1]], stream[2:31]))
+        sbytes = ((stream[0] * lit.value + (ssym * np.asarray(today)).sum() + stream[31] + 7 * stream[32] + stream[33])
+                  / tiles) / 8 + tail
+        print(f"    what-if, same code, greedy parse over the tile as one stream (matches run on across row ends, runs win "
+              f"ties): {(stream[0] + stream[2:31].sum()) / tiles:.0f} tokens, {sbytes:.1f} bytes per stream")
         blend += np.concatenate(([hist[0]], sym)) / tokens * 1000 / len(a.profiles)
     print("per 1000 tokens: literals %d; end-of-block and length symbols 257..285:" % round(blend[0]))
     print("   ", [max(2, int(round(x))) for x in blend[1:]])
